@@ -1,0 +1,807 @@
+// api.cu -- the C ABI declared in include/hs_gpu.h.
+#include <dirent.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+
+#include "device_utils.cuh"
+#include "engine.h"
+
+using namespace hs;
+
+#define HS_STR2(x) #x
+#define HS_STR(x) HS_STR2(x)
+
+namespace {
+
+void set_err(char* err, size_t errlen, const char* msg) {
+  if (err && errlen) {
+    strncpy(err, msg, errlen - 1);
+    err[errlen - 1] = 0;
+  }
+}
+
+template <typename F>
+int guarded(hs_ctx* ctx, char* err, size_t errlen, F&& f) {
+  try {
+    if (ctx) {
+      cudaError_t e = cudaSetDevice(ctx->device);
+      if (e != cudaSuccess) fail(HS_ECUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+      ctx->launches = 0;
+    }
+    f();
+    return HS_OK;
+  } catch (const hs::Error& e) {
+    set_err(err, errlen, e.what());
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
+    return HS_EINVAL;
+  }
+}
+
+void write_file_atomic(const std::string& dir, const std::string& name, const uint8_t* data, uint64_t size) {
+  const std::string tmp = dir + "/." + name + ".tmp";
+  const std::string fin = dir + "/" + name;
+  int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) fail(HS_EIO, "cannot create %s", tmp.c_str());
+  uint64_t done = 0;
+  while (done < size) {
+    ssize_t w = write(fd, data + done, size - done);
+    if (w <= 0) {
+      close(fd);
+      unlink(tmp.c_str());
+      fail(HS_EIO, "short write on %s", tmp.c_str());
+    }
+    done += (uint64_t)w;
+  }
+  close(fd);
+  if (rename(tmp.c_str(), fin.c_str()) != 0) {
+    unlink(tmp.c_str());
+    fail(HS_EIO, "cannot rename %s", tmp.c_str());
+  }
+}
+
+void mkdirs(const std::string& path) {
+  std::string cur;
+  for (size_t i = 0; i <= path.size(); i++) {
+    if (i == path.size() || path[i] == '/') {
+      if (!cur.empty()) mkdir(cur.c_str(), 0755);
+    }
+    if (i < path.size()) cur += path[i];
+  }
+}
+
+// Spark's DataPathFilter (util/PathUtils.scala:34-39): names starting with '_' or '.' are not data files
+void remove_data_files(const std::string& dir) {
+  DIR* d = opendir(dir.c_str());
+  if (!d) return;
+  while (dirent* e = readdir(d)) {
+    if (e->d_name[0] == '.' || e->d_name[0] == '_') continue;
+    unlink((dir + "/" + e->d_name).c_str());
+  }
+  closedir(d);
+}
+
+void fill_lineage(hs_ctx* ctx, Table& t, const hs_source_file* files, int n_files);
+void drop_deleted_rows(hs_ctx* ctx, Table& t, const int64_t* deleted, int ndeleted);
+
+// gather every column of `t` through idx (n_out rows)
+void gather_table(hs_ctx* ctx, Table& t, const uint32_t* d_idx, int64_t n_out) {
+  for (DevColumn& c : t.cols) {
+    Buf<uint8_t> nd(ctx, (size_t)n_out * c.width + 16);
+    launch_gather_plain(ctx, c.data.get(), d_idx, n_out, c.width, nd.get());
+    c.data = std::move(nd);
+    if (c.valid) {
+      Buf<uint8_t> nv(ctx, (size_t)n_out + 16);
+      launch_gather_plain(ctx, c.valid.get(), d_idx, n_out, 1, nv.get());
+      c.valid = std::move(nv);
+    }
+  }
+  t.nrows = n_out;
+}
+
+__global__ void k_fill_u64(uint64_t* out, int64_t n, uint64_t v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+__global__ void k_fill_u32(uint32_t* out, int64_t n, uint32_t v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+
+// CoveringIndex.createIndexData lineage (index/covering/CoveringIndex.scala:152-186): every row carries the id of the
+// source file it came from.
+void fill_lineage(hs_ctx* ctx, Table& t, const hs_source_file* files, int n_files) {
+  DevColumn dc;
+  dc.name = "_data_file_id";
+  dc.type = HS_TYPE_INT64;
+  dc.width = 8;
+  dc.schema.name = dc.name;
+  dc.schema.type = pq::INT64;
+  dc.schema.repetition = pq::OPTIONAL;
+  dc.data.alloc(ctx, (size_t)t.nrows * 8 + 16);
+  for (int f = 0; f < n_files; f++) {
+    const int64_t b = t.file_row_begin[f], n = t.file_row_begin[f + 1] - b;
+    if (n == 0) continue;
+    const int grid = (int)std::min<int64_t>(ceil_div(n, 256), ctx->sm_count * 8);
+    k_fill_u64<<<grid, 256, 0, ctx->stream>>>((uint64_t*)dc.data.get() + b, n, (uint64_t)files[f].file_id);
+    HS_LAUNCH_CHECK(ctx);
+  }
+  t.cols.push_back(std::move(dc));
+}
+
+// Rows whose `_data_file_id` is in `deleted` are dropped (CoveringIndexTrait.refreshIncremental, deleted files branch,
+// index/covering/CoveringIndexTrait.scala:78-94).
+void drop_deleted_rows(hs_ctx* ctx, Table& t, const int64_t* deleted, int ndeleted) {
+  int lc = -1;
+  for (size_t c = 0; c < t.cols.size(); c++)
+    if (t.cols[c].name == "_data_file_id") lc = (int)c;
+  if (lc < 0) fail(HS_EINVAL, "deleted_file_ids given but the source has no _data_file_id column (index built without lineage)");
+  const int64_t n = t.nrows;
+  if (n == 0) return;
+  Buf<uint32_t> mask(ctx, n);
+  Buf<uint64_t> offs(ctx, n + 1);
+  Buf<int64_t> d_del(ctx, ndeleted);
+  HS_CUDA(cudaMemcpyAsync(d_del.get(), deleted, sizeof(int64_t) * ndeleted, cudaMemcpyHostToDevice, ctx->stream));
+  k_fill_u32<<<(int)std::min<int64_t>(ceil_div(n, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(mask.get(), n, 1u);
+  HS_LAUNCH_CHECK(ctx);
+  launch_not_in_mask(ctx, (const int64_t*)t.cols[lc].data.get(), n, d_del.get(), ndeleted, mask.get());
+  exclusive_scan_u32_u64(ctx, mask.get(), n, offs.get());
+  uint64_t kept = 0;
+  HS_CUDA(cudaMemcpyAsync(&kept, offs.get() + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  Buf<uint32_t> idx(ctx, std::max<uint64_t>(1, kept));
+  launch_compact_indices(ctx, mask.get(), offs.get(), n, idx.get());
+  gather_table(ctx, t, idx.get(), (int64_t)kept);
+}
+
+std::vector<std::string> names_of(const char* const* a, int na, const char* const* b, int nb) {
+  std::vector<std::string> v;
+  for (int i = 0; i < na; i++) v.emplace_back(a[i]);
+  for (int i = 0; i < nb; i++) v.emplace_back(b[i]);
+  return v;
+}
+
+void finish_result(hs_ctx* ctx, EncodedFiles& enc, int output, const char* out_dir, int save_mode, hs_index_result* res,
+                   hs_stats* st) {
+  res->ctx = ctx;
+  res->output = output;
+  res->files = enc.files;
+  if (output == HS_OUT_DEVICE) {
+    res->d_arena = std::move(enc.arena);
+    return;
+  }
+  StageTimer t(ctx);
+  t.start();
+  res->h_arena.alloc(ctx, std::max<uint64_t>(enc.arena_bytes, 16), /*pinned=*/true);
+  if (enc.arena_bytes)
+    HS_CUDA(cudaMemcpyAsync(res->h_arena.get(), enc.arena.get(), enc.arena_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  t.stop();
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  st->ms_d2h += t.ms();
+  if (output == HS_OUT_FILES) {
+    if (!out_dir) fail(HS_EINVAL, "HS_OUT_FILES needs out_dir");
+    const std::string dir(out_dir);
+    mkdirs(dir);
+    if (save_mode == HS_SAVE_OVERWRITE) remove_data_files(dir);
+    std::vector<std::string> written;
+    try {
+      for (const OutFile& f : res->files) {
+        write_file_atomic(dir, f.name, res->h_arena.get() + f.offset, f.size);
+        written.push_back(dir + "/" + f.name);
+      }
+    } catch (...) {
+      for (auto& p : written) unlink(p.c_str());  // all-or-nothing
+      throw;
+    }
+    res->h_arena.release();
+  }
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int hs_abi_version(void) { return HS_ABI_VERSION; }
+
+const char* hs_build_info(void) {
+  return "hyperspace_b200 libhs_gpu 0.1.0; arch sm_100a; CUDA " HS_STR(CUDART_VERSION) "; nvcc -O3 -lineinfo";
+}
+
+int hs_init(int device_id, void* cuda_stream, hs_ctx** out, char* err, size_t errlen) {
+  if (!out) return HS_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "no CUDA device available (%s); libhs_gpu has no CPU fallback",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    set_err(err, errlen, buf);
+    cudaGetLastError();
+    return HS_ENODEVICE;
+  }
+  if (device_id < 0 || device_id >= count) {
+    set_err(err, errlen, "device id out of range");
+    return HS_EINVAL;
+  }
+  hs_ctx* ctx = new hs_ctx();
+  ctx->device = device_id;
+  int rc = guarded(nullptr, err, errlen, [&] {
+    HS_CUDA(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    HS_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) fail(HS_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device_id, prop.major, prop.minor);
+    if (cuda_stream) {
+      ctx->stream = (cudaStream_t)cuda_stream;
+      ctx->own_stream = false;
+    } else {
+      HS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+    HS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  });
+  if (rc != HS_OK) {
+    delete ctx;
+    return rc == HS_ECUDA ? HS_ENODEVICE : rc;
+  }
+  *out = ctx;
+  return HS_OK;
+}
+
+void hs_shutdown(hs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+void hs_trim(hs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->pool.trim();
+}
+
+void* hs_host_alloc(hs_ctx* ctx, size_t bytes) {
+  if (!ctx) return nullptr;
+  try {
+    cudaSetDevice(ctx->device);
+    return ctx->pool.get(bytes, true);
+  } catch (...) {
+    return nullptr;
+  }
+}
+
+void hs_host_free(hs_ctx* ctx, void* p) {
+  if (ctx && p) ctx->pool.put(p);
+}
+
+int hs_create_index(hs_ctx* ctx, const hs_index_spec* spec, hs_index_result** out, hs_stats* stats, char* err,
+                    size_t errlen) {
+  if (!ctx || !spec || !out) return HS_EINVAL;
+  *out = nullptr;
+  hs_stats st;
+  memset(&st, 0, sizeof st);
+  std::unique_ptr<hs_index_result> res(new hs_index_result());
+  int rc = guarded(ctx, err, errlen, [&] {
+    if (spec->n_indexed < 1) fail(HS_EINVAL, "at least one indexed column is required");
+    if (spec->n_files < 0 || (spec->n_files > 0 && !spec->files)) fail(HS_EINVAL, "bad source file list");
+    StageTimer total(ctx);
+    total.start();
+    std::vector<std::string> cols = names_of(spec->indexed_columns, spec->n_indexed, spec->included_columns, spec->n_included);
+    for (size_t i = 0; i < cols.size(); i++)
+      for (size_t j = i + 1; j < cols.size(); j++)
+        if (cols[i] == cols[j]) fail(HS_EINVAL, "duplicate column '%s' in index config", cols[i].c_str());
+    Table table;
+    load_sources(ctx, spec->files, spec->n_files, cols, &table, &st);
+    if (spec->lineage) fill_lineage(ctx, table, spec->files, spec->n_files);
+    if (spec->n_deleted_file_ids > 0) drop_deleted_rows(ctx, table, spec->deleted_file_ids, spec->n_deleted_file_ids);
+    if (ctx->world > 1) exchange_rows(ctx, table, spec->n_indexed, spec->num_buckets, &st);
+    IndexedRows rows;
+    index_rows(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
+
+    EncodeRequest req;
+    req.table = &rows.part;
+    req.d_perm = rows.sorted_perm;
+    req.d_sorted_keys = rows.sorted_keys;
+    req.plan = &rows.plan;
+    req.seg_offsets = rows.bucket_offsets;
+    req.rows_per_page = spec->rows_per_page;
+    req.rows_per_row_group = spec->rows_per_row_group;
+    const std::string uuid = spec->job_uuid ? spec->job_uuid : make_uuid();
+    req.seg_names.resize(spec->num_buckets);
+    for (int b = 0; b < spec->num_buckets; b++) {
+      // Spark FileFormatWriter: part-<task>-<jobUUID>_<bucket>.c000<codec ext>.parquet ; bucket id parsed back by
+      // BucketingUtils.getBucketId (relied on by actions/OptimizeAction.scala:110)
+      char nm[160];
+      snprintf(nm, sizeof nm, "part-%05d-%s_%05d.c000.parquet", b, uuid.c_str(), b);
+      req.seg_names[b] = nm;
+    }
+    EncodedFiles enc;
+    encode_segments(ctx, req, &enc, &st);
+    st.rows_out = rows.part.nrows;
+    finish_result(ctx, enc, spec->output, spec->out_dir, spec->save_mode, res.get(), &st);
+    total.stop();
+    st.ms_total = total.ms();
+    st.gpu_launches = ctx->launches;
+  });
+  if (stats) *stats = st;
+  if (rc == HS_OK) *out = res.release();
+  return rc;
+}
+
+int32_t hs_result_num_files(const hs_index_result* r) { return r ? (int32_t)r->files.size() : 0; }
+
+int hs_result_file(const hs_index_result* r, int32_t i, int32_t* bucket, const char** name, const void** data,
+                   uint64_t* size, int64_t* rows) {
+  if (!r || i < 0 || i >= (int32_t)r->files.size()) return HS_EINVAL;
+  const OutFile& f = r->files[i];
+  if (bucket) *bucket = f.bucket;
+  if (name) *name = f.name.c_str();
+  if (data) {
+    if (r->output == HS_OUT_DEVICE) *data = r->d_arena.get() + f.offset;
+    else if (r->output == HS_OUT_HOST) *data = r->h_arena.get() + f.offset;
+    else *data = nullptr;
+  }
+  if (size) *size = f.size;
+  if (rows) *rows = f.rows;
+  return HS_OK;
+}
+
+void hs_result_free(hs_index_result* r) {
+  if (!r) return;
+  if (r->ctx) {
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+  }
+  delete r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// read side
+// ---------------------------------------------------------------------------------------------------------------------
+
+static void batch_from_gather(hs_ctx* ctx, const Table& t, const std::vector<int>& col_idx, const uint32_t* d_idx,
+                              int64_t n_out, hs_batch* b) {
+  for (int ci : col_idx) {
+    const DevColumn& c = t.cols[ci];
+    Buf<uint8_t> d(ctx, (size_t)std::max<int64_t>(1, n_out) * c.width);
+    launch_gather_plain(ctx, c.data.get(), d_idx, n_out, c.width, d.get());
+    hs_batch::Col bc;
+    bc.name = c.name;
+    bc.type = c.type;
+    bc.data.alloc(ctx, (size_t)std::max<int64_t>(1, n_out) * c.width, true);
+    if (n_out) HS_CUDA(cudaMemcpyAsync(bc.data.get(), d.get(), (size_t)n_out * c.width, cudaMemcpyDeviceToHost, ctx->stream));
+    if (c.has_nulls) {
+      Buf<uint8_t> dv(ctx, (size_t)std::max<int64_t>(1, n_out));
+      launch_gather_plain(ctx, c.valid.get(), d_idx, n_out, 1, dv.get());
+      bc.valid.alloc(ctx, (size_t)std::max<int64_t>(1, n_out), true);
+      if (n_out) HS_CUDA(cudaMemcpyAsync(bc.valid.get(), dv.get(), (size_t)n_out, cudaMemcpyDeviceToHost, ctx->stream));
+      bc.has_valid = true;
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    b->cols.push_back(std::move(bc));
+  }
+  b->nrows = n_out;
+}
+
+__global__ void k_ranges_to_indices(const int64_t* __restrict__ bounds, const uint64_t* __restrict__ seg_offsets,
+                                    const uint64_t* __restrict__ out_offsets, int nseg, uint32_t* __restrict__ out_idx) {
+  // one CTA per segment
+  const int s = blockIdx.x;
+  if (s >= nseg) return;
+  const int64_t first = bounds[2 * s], last = bounds[2 * s + 1];
+  const uint64_t base = seg_offsets[s], o = out_offsets[s];
+  for (int64_t i = first + threadIdx.x; i < last; i += blockDim.x) out_idx[o + (i - first)] = (uint32_t)(base + i);
+}
+
+int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_stats* stats, char* err, size_t errlen) {
+  if (!ctx || !spec || !out) return HS_EINVAL;
+  *out = nullptr;
+  hs_stats st;
+  memset(&st, 0, sizeof st);
+  std::unique_ptr<hs_batch> res(new hs_batch());
+  res->ctx = ctx;
+  int rc = guarded(ctx, err, errlen, [&] {
+    StageTimer total(ctx);
+    total.start();
+    if (!spec->key_column) fail(HS_EINVAL, "key_column is required");
+    // columns to decode: key first, then the projection, then lineage when deletes must be filtered
+    std::vector<std::string> cols{spec->key_column};
+    std::vector<int> proj_idx;
+    for (int i = 0; i < spec->n_projected; i++) {
+      std::string nm = spec->projected_columns[i];
+      auto it = std::find(cols.begin(), cols.end(), nm);
+      if (it == cols.end()) {
+        cols.push_back(nm);
+        proj_idx.push_back((int)cols.size() - 1);
+      } else {
+        proj_idx.push_back((int)(it - cols.begin()));
+      }
+    }
+    int lineage_col = -1;
+    if (spec->n_deleted_file_ids > 0) {
+      auto it = std::find(cols.begin(), cols.end(), std::string("_data_file_id"));
+      if (it == cols.end()) {
+        cols.push_back("_data_file_id");
+        lineage_col = (int)cols.size() - 1;
+      } else {
+        lineage_col = (int)(it - cols.begin());
+      }
+    }
+    Table t;
+    load_sources(ctx, spec->files, spec->n_files, cols, &t, &st);
+    if (t.cols[0].type != HS_TYPE_INT64 && t.cols[0].type != HS_TYPE_INT32)
+      fail(HS_EUNSUPPORTED, "filter scan: key column must be int32/int64");
+    const int64_t n = t.nrows;
+    // widen an int32 key to int64 for the comparison kernels
+    Buf<int64_t> k64;
+    const int64_t* d_keys = (const int64_t*)t.cols[0].data.get();
+    StageTimer t_scan(ctx);
+    t_scan.start();
+    if (t.cols[0].type == HS_TYPE_INT32) fail(HS_EUNSUPPORTED, "filter scan on int32 keys not wired yet");
+    Buf<uint32_t> idx;
+    int64_t n_out = 0;
+    const bool sorted = spec->sorted_on_key && !t.cols[0].has_nulls && spec->n_deleted_file_ids == 0;
+    if (sorted) {
+      // K7: two binary searches per file
+      const int nseg = spec->n_files;
+      std::vector<uint64_t> seg(nseg + 1);
+      for (int f = 0; f <= nseg; f++) seg[f] = (uint64_t)t.file_row_begin[f];
+      Buf<uint64_t> d_seg(ctx, nseg + 1);
+      Buf<int64_t> d_bounds(ctx, 2 * std::max(1, nseg));
+      HS_CUDA(cudaMemcpyAsync(d_seg.get(), seg.data(), 8 * (nseg + 1), cudaMemcpyHostToDevice, ctx->stream));
+      launch_range_bounds(ctx, d_keys, d_seg.get(), nseg, spec->has_lo, spec->lo, spec->has_hi, spec->hi, d_bounds.get());
+      std::vector<int64_t> bounds(2 * std::max(1, nseg));
+      HS_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds.get(), 16 * nseg, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      std::vector<uint64_t> oo(nseg + 1, 0);
+      for (int f = 0; f < nseg; f++) oo[f + 1] = oo[f] + (uint64_t)(bounds[2 * f + 1] - bounds[2 * f]);
+      n_out = (int64_t)oo[nseg];
+      Buf<uint64_t> d_oo(ctx, nseg + 1);
+      HS_CUDA(cudaMemcpyAsync(d_oo.get(), oo.data(), 8 * (nseg + 1), cudaMemcpyHostToDevice, ctx->stream));
+      idx.alloc(ctx, std::max<int64_t>(1, n_out));
+      if (nseg) {
+        k_ranges_to_indices<<<nseg, 256, 0, ctx->stream>>>(d_bounds.get(), d_seg.get(), d_oo.get(), nseg, idx.get());
+        HS_LAUNCH_CHECK(ctx);
+      }
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+      // full predicate scan (appended source files under Hybrid Scan, or lineage NOT-IN filter)
+      Buf<uint32_t> mask(ctx, std::max<int64_t>(1, n));
+      Buf<uint64_t> offs(ctx, n + 1);
+      launch_filter_mask(ctx, d_keys, t.cols[0].has_nulls ? t.cols[0].valid.get() : nullptr, n, spec->has_lo, spec->lo,
+                         spec->has_hi, spec->hi, mask.get());
+      if (spec->n_deleted_file_ids > 0) {
+        Buf<int64_t> d_del(ctx, spec->n_deleted_file_ids);
+        HS_CUDA(cudaMemcpyAsync(d_del.get(), spec->deleted_file_ids, 8 * spec->n_deleted_file_ids, cudaMemcpyHostToDevice, ctx->stream));
+        launch_not_in_mask(ctx, (const int64_t*)t.cols[lineage_col].data.get(), n, d_del.get(), spec->n_deleted_file_ids, mask.get());
+        HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
+      exclusive_scan_u32_u64(ctx, mask.get(), n, offs.get());
+      uint64_t kept = 0;
+      HS_CUDA(cudaMemcpyAsync(&kept, offs.get() + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      n_out = (int64_t)kept;
+      idx.alloc(ctx, std::max<int64_t>(1, n_out));
+      launch_compact_indices(ctx, mask.get(), offs.get(), n, idx.get());
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    t_scan.stop();
+    batch_from_gather(ctx, t, proj_idx, idx.get(), n_out, res.get());
+    total.stop();
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    st.ms_sort += t_scan.ms();
+    st.rows_out = n_out;
+    st.ms_total = total.ms();
+    st.gpu_launches = ctx->launches;
+  });
+  if (stats) *stats = st;
+  if (rc == HS_OK) *out = res.release();
+  return rc;
+}
+
+// Orders the decoded rows of one join side bucket-major and key-sorted.  When every bucket holds exactly one file the
+// files are already sorted (they are index files) and only need to be visited in bucket order; otherwise the rows go
+// through K2-K4 again, which is what Spark's SortExec does for multi-file buckets.
+static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_files, const int32_t* buckets, int nb,
+                              const std::vector<std::string>& cols, Table* t, IndexedRows* rows, hs_stats* st,
+                              std::vector<uint64_t>* seg, const int64_t** d_keys, const uint32_t** d_perm, Buf<uint32_t>* iota) {
+  // reorder files by bucket so the decoded table is bucket-major
+  std::vector<int> order(n_files);
+  for (int i = 0; i < n_files; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return buckets[a] < buckets[b]; });
+  std::vector<hs_source_file> sorted_files(n_files);
+  std::vector<int> per_bucket(nb, 0);
+  for (int i = 0; i < n_files; i++) {
+    sorted_files[i] = files[order[i]];
+    if (buckets[order[i]] < 0 || buckets[order[i]] >= nb) fail(HS_EINVAL, "bucket id %d out of range", buckets[order[i]]);
+    per_bucket[buckets[order[i]]]++;
+  }
+  load_sources(ctx, sorted_files.data(), n_files, cols, t, st);
+  if (t->cols[0].type != HS_TYPE_INT64) fail(HS_EUNSUPPORTED, "bucket join: key column must be int64");
+  if (t->cols[0].has_nulls) fail(HS_EUNSUPPORTED, "bucket join: null join keys are not handled yet");
+  const bool single = std::all_of(per_bucket.begin(), per_bucket.end(), [](int c) { return c <= 1; });
+  if (single) {
+    seg->assign(nb + 1, 0);
+    int fi = 0;
+    for (int b = 0; b < nb; b++) {
+      (*seg)[b] = (uint64_t)t->file_row_begin[fi];
+      if (per_bucket[b]) fi++;
+    }
+    (*seg)[nb] = (uint64_t)t->nrows;
+    *d_keys = (const int64_t*)t->cols[0].data.get();
+    iota->alloc(ctx, std::max<int64_t>(1, t->nrows));
+    launch_iota_u32(ctx, iota->get(), t->nrows);
+    *d_perm = iota->get();
+  } else {
+    index_rows(ctx, *t, 1, nb, rows, st);
+    *seg = rows->bucket_offsets;
+    // materialise the sorted key column
+    Buf<uint8_t> sk(ctx, (size_t)std::max<int64_t>(1, rows->part.nrows) * 8);
+    launch_gather_plain(ctx, rows->part.cols[0].data.get(), rows->sorted_perm, rows->part.nrows, 8, sk.get());
+    rows->keys_alt.release();
+    t->cols.clear();
+    t->cols = std::move(rows->part.cols);
+    t->nrows = rows->part.nrows;
+    // keep the sorted keys in a column appended at the end
+    DevColumn kc;
+    kc.name = "__sorted_key";
+    kc.type = HS_TYPE_INT64;
+    kc.width = 8;
+    kc.data = std::move(sk);
+    t->cols.push_back(std::move(kc));
+    *d_keys = (const int64_t*)t->cols.back().data.get();
+    *d_perm = rows->sorted_perm;
+  }
+}
+
+__global__ void k_compose_u32(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int64_t n, uint32_t* out) {
+  // out[i] = a[b[i]]
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a[b[i]];
+}
+
+int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_stats* stats, char* err, size_t errlen) {
+  if (!ctx || !spec || !out) return HS_EINVAL;
+  *out = nullptr;
+  hs_stats st;
+  memset(&st, 0, sizeof st);
+  std::unique_ptr<hs_batch> res(new hs_batch());
+  res->ctx = ctx;
+  int rc = guarded(ctx, err, errlen, [&] {
+    StageTimer total(ctx);
+    total.start();
+    const int nb = spec->num_buckets;
+    if (nb < 1) fail(HS_EINVAL, "num_buckets must be positive");
+    std::vector<std::string> lcols{spec->left_key}, rcols{spec->right_key};
+    std::vector<int> lproj, rproj;
+    for (int i = 0; i < spec->n_left_columns; i++) {
+      std::string nm = spec->left_columns[i];
+      auto it = std::find(lcols.begin(), lcols.end(), nm);
+      if (it == lcols.end()) { lcols.push_back(nm); lproj.push_back((int)lcols.size() - 1); }
+      else lproj.push_back((int)(it - lcols.begin()));
+    }
+    for (int i = 0; i < spec->n_right_columns; i++) {
+      std::string nm = spec->right_columns[i];
+      auto it = std::find(rcols.begin(), rcols.end(), nm);
+      if (it == rcols.end()) { rcols.push_back(nm); rproj.push_back((int)rcols.size() - 1); }
+      else rproj.push_back((int)(it - rcols.begin()));
+    }
+    Table lt, rt;
+    IndexedRows lrows, rrows;
+    std::vector<uint64_t> lseg, rseg;
+    const int64_t *lkeys = nullptr, *rkeys = nullptr;
+    const uint32_t *lperm = nullptr, *rperm = nullptr;
+    Buf<uint32_t> liota, riota;
+    prepare_join_side(ctx, spec->left_files, spec->n_left, spec->left_buckets, nb, lcols, &lt, &lrows, &st, &lseg, &lkeys, &lperm, &liota);
+    prepare_join_side(ctx, spec->right_files, spec->n_right, spec->right_buckets, nb, rcols, &rt, &rrows, &st, &rseg, &rkeys, &rperm, &riota);
+    const int64_t nl = lt.nrows, nr = rt.nrows;
+    if (nr >= (1ll << 32) || nl >= (1ll << 32)) fail(HS_EUNSUPPORTED, "join side larger than 2^32-1 rows");
+    StageTimer t_join(ctx);
+    t_join.start();
+    Buf<uint64_t> d_lseg(ctx, nb + 1), d_rseg(ctx, nb + 1);
+    HS_CUDA(cudaMemcpyAsync(d_lseg.get(), lseg.data(), 8 * (nb + 1), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaMemcpyAsync(d_rseg.get(), rseg.data(), 8 * (nb + 1), cudaMemcpyHostToDevice, ctx->stream));
+    Buf<uint32_t> counts(ctx, std::max<int64_t>(1, nl)), first(ctx, std::max<int64_t>(1, nl));
+    Buf<uint64_t> offs(ctx, nl + 1);
+    launch_join_count(ctx, lkeys, d_lseg.get(), rkeys, d_rseg.get(), nb, nl, counts.get(), first.get());
+    exclusive_scan_u32_u64(ctx, counts.get(), nl, offs.get());
+    uint64_t total_out = 0;
+    HS_CUDA(cudaMemcpyAsync(&total_out, offs.get() + nl, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (total_out >= (1ull << 32)) fail(HS_EUNSUPPORTED, "join output larger than 2^32-1 rows per call");
+    Buf<uint32_t> li(ctx, std::max<uint64_t>(1, total_out)), ri(ctx, std::max<uint64_t>(1, total_out));
+    launch_join_emit(ctx, counts.get(), first.get(), offs.get(), nl, li.get(), ri.get());
+    // positions in sorted order -> rows of the partitioned tables
+    Buf<uint32_t> lrow(ctx, std::max<uint64_t>(1, total_out)), rrow(ctx, std::max<uint64_t>(1, total_out));
+    if (total_out) {
+      const int grid = (int)std::min<int64_t>(ceil_div((int64_t)total_out, 256), ctx->sm_count * 16);
+      k_compose_u32<<<grid, 256, 0, ctx->stream>>>(lperm, li.get(), (int64_t)total_out, lrow.get());
+      HS_LAUNCH_CHECK(ctx);
+      k_compose_u32<<<grid, 256, 0, ctx->stream>>>(rperm, ri.get(), (int64_t)total_out, rrow.get());
+      HS_LAUNCH_CHECK(ctx);
+    }
+    t_join.stop();
+    batch_from_gather(ctx, lt, lproj, lrow.get(), (int64_t)total_out, res.get());
+    batch_from_gather(ctx, rt, rproj, rrow.get(), (int64_t)total_out, res.get());
+    total.stop();
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    st.ms_sort += t_join.ms();
+    st.rows_out = (int64_t)total_out;
+    st.ms_total = total.ms();
+    st.gpu_launches = ctx->launches;
+  });
+  if (stats) *stats = st;
+  if (rc == HS_OK) *out = res.release();
+  return rc;
+}
+
+int64_t hs_batch_num_rows(const hs_batch* b) { return b ? b->nrows : 0; }
+int32_t hs_batch_num_columns(const hs_batch* b) { return b ? (int32_t)b->cols.size() : 0; }
+int hs_batch_column(const hs_batch* b, int32_t i, const char** name, int32_t* type, const void** data,
+                    const uint8_t** valid) {
+  if (!b || i < 0 || i >= (int32_t)b->cols.size()) return HS_EINVAL;
+  const hs_batch::Col& c = b->cols[i];
+  if (name) *name = c.name.c_str();
+  if (type) *type = c.type;
+  if (data) *data = c.data.get();
+  if (valid) *valid = c.has_valid ? c.valid.get() : nullptr;
+  return HS_OK;
+}
+void hs_batch_free(hs_batch* b) {
+  if (!b) return;
+  if (b->ctx) cudaSetDevice(b->ctx->device);
+  delete b;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel-level entry points
+// ---------------------------------------------------------------------------------------------------------------------
+
+static void upload_table(hs_ctx* ctx, const hs_host_column* keys, int nkeys, int64_t nrows, Table* t) {
+  t->nrows = nrows;
+  t->cols.resize(nkeys);
+  for (int k = 0; k < nkeys; k++) {
+    DevColumn& c = t->cols[k];
+    c.name = "k" + std::to_string(k);
+    c.type = keys[k].type;
+    c.width = type_width(c.type);
+    if (c.width == 0) fail(HS_EUNSUPPORTED, "key type %d is not handled by the GPU path", c.type);
+    c.data.alloc(ctx, (size_t)nrows * c.width + 16);
+    if (nrows) HS_CUDA(cudaMemcpyAsync(c.data.get(), keys[k].data, (size_t)nrows * c.width, cudaMemcpyHostToDevice, ctx->stream));
+    if (keys[k].valid) {
+      c.valid.alloc(ctx, (size_t)nrows + 16);
+      if (nrows) HS_CUDA(cudaMemcpyAsync(c.valid.get(), keys[k].valid, (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
+      c.has_nulls = true;
+    }
+  }
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+int hs_k_bucket_ids(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64_t nrows, int32_t num_buckets,
+                    int32_t* out_bucket, int64_t* out_hist, char* err, size_t errlen) {
+  if (!ctx) return HS_EINVAL;
+  return guarded(ctx, err, errlen, [&] {
+    if (num_buckets < 1 || num_buckets > kMaxBuckets) fail(HS_EUNSUPPORTED, "numBuckets must be in 1..%d", kMaxBuckets);
+    Table t;
+    upload_table(ctx, keys, nkeys, nrows, &t);
+    std::vector<KeyColumn> h_keys(nkeys);
+    for (int k = 0; k < nkeys; k++)
+      h_keys[k] = KeyColumn{t.cols[k].data.get(), t.cols[k].has_nulls ? t.cols[k].valid.get() : nullptr, t.cols[k].type, t.cols[k].width};
+    Buf<KeyColumn> d_keys(ctx, nkeys);
+    HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t ntiles = ceil_div(nrows, kPartTile);
+    Buf<uint16_t> bucket(ctx, std::max<int64_t>(1, nrows));
+    Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * num_buckets);
+    Buf<unsigned long long> ghist(ctx, num_buckets);
+    HS_CUDA(cudaMemsetAsync(ghist.get(), 0, 8 * num_buckets, ctx->stream));
+    launch_bucket_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, bucket.get(), tile_hist.get(), ghist.get());
+    std::vector<uint16_t> hb(nrows);
+    if (nrows) HS_CUDA(cudaMemcpyAsync(hb.data(), bucket.get(), 2 * nrows, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_hist) HS_CUDA(cudaMemcpyAsync(out_hist, ghist.get(), 8 * num_buckets, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out_bucket) for (int64_t i = 0; i < nrows; i++) out_bucket[i] = hb[i];
+  });
+}
+
+int hs_k_sort_perm(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64_t nrows, int32_t num_buckets,
+                   int64_t* out_perm, int64_t* out_bucket_offsets, char* err, size_t errlen) {
+  if (!ctx) return HS_EINVAL;
+  return guarded(ctx, err, errlen, [&] {
+    Table t;
+    upload_table(ctx, keys, nkeys, nrows, &t);
+    // carry the original row index through the partition as an extra column
+    DevColumn rid;
+    rid.name = "__row";
+    rid.type = HS_TYPE_INT32;
+    rid.width = 4;
+    rid.data.alloc(ctx, (size_t)nrows * 4 + 16);
+    launch_iota_u32(ctx, (uint32_t*)rid.data.get(), nrows);
+    t.cols.push_back(std::move(rid));
+    IndexedRows rows;
+    hs_stats st;
+    memset(&st, 0, sizeof st);
+    index_rows(ctx, t, nkeys, num_buckets, &rows, &st);
+    Buf<uint8_t> orig(ctx, (size_t)std::max<int64_t>(1, nrows) * 4);
+    launch_gather_plain(ctx, rows.part.cols[nkeys].data.get(), rows.sorted_perm, nrows, 4, orig.get());
+    std::vector<uint32_t> h(nrows);
+    if (nrows) HS_CUDA(cudaMemcpyAsync(h.data(), orig.get(), 4 * nrows, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < nrows; i++) out_perm[i] = h[i];
+    for (int b = 0; b <= num_buckets; b++) out_bucket_offsets[b] = (int64_t)rows.bucket_offsets[b];
+  });
+}
+
+int hs_synth_table(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, int32_t n_files,
+                   int32_t row_groups_per_file, int32_t output, hs_index_result** out, char* err, size_t errlen) {
+  if (!ctx || !out) return HS_EINVAL;
+  *out = nullptr;
+  std::unique_ptr<hs_index_result> res(new hs_index_result());
+  int rc = guarded(ctx, err, errlen, [&] {
+    if (ncols < 1 || ncols > 5 || n_files < 1 || row_groups_per_file < 1 || nrows < 0) fail(HS_EINVAL, "bad synthetic table shape");
+    if (output != HS_OUT_HOST && output != HS_OUT_DEVICE) fail(HS_EINVAL, "synthetic tables are returned in memory");
+    static const char* names[5] = {"k", "v1", "v2", "v3", "v4"};
+    static const int types[5] = {HS_TYPE_INT64, HS_TYPE_INT64, HS_TYPE_DOUBLE, HS_TYPE_INT32, HS_TYPE_FLOAT};
+    static const int ptypes[5] = {pq::INT64, pq::INT64, pq::DOUBLE, pq::INT32, pq::FLOAT};
+    Table t;
+    t.nrows = nrows;
+    t.cols.resize(ncols);
+    for (int c = 0; c < ncols; c++) {
+      DevColumn& dc = t.cols[c];
+      dc.name = names[c];
+      dc.type = types[c];
+      dc.width = type_width(types[c]);
+      dc.schema.name = names[c];
+      dc.schema.type = ptypes[c];
+      dc.schema.repetition = pq::OPTIONAL;
+      dc.data.alloc(ctx, (size_t)nrows * dc.width + 16);
+      launch_synth_column(ctx, c, first_row, nrows, dc.data.get());
+    }
+    // files are the segments; rows split evenly, row groups per file likewise (multiples of the page size)
+    const int64_t P = 131072;
+    std::vector<uint64_t> seg(n_files + 1, 0);
+    const int64_t per_file = ceil_div(nrows, n_files);
+    for (int f = 0; f < n_files; f++) seg[f + 1] = (uint64_t)std::min<int64_t>(nrows, (int64_t)(f + 1) * per_file);
+    SortPlan plan;
+    build_sort_plan(ctx, seg.data(), n_files, &plan);
+    Buf<uint32_t> iota(ctx, std::max<int64_t>(1, nrows));
+    launch_iota_u32(ctx, iota.get(), nrows);
+    EncodeRequest req;
+    req.table = &t;
+    req.d_perm = iota.get();
+    req.plan = &plan;
+    req.seg_offsets = seg;
+    req.rows_per_page = P;
+    req.rows_per_row_group = std::max<int64_t>(P, (int64_t)round_up((size_t)ceil_div(per_file, row_groups_per_file), (size_t)P));
+    req.seg_names.resize(n_files);
+    for (int f = 0; f < n_files; f++) {
+      char nm[64];
+      snprintf(nm, sizeof nm, "part-%05d.parquet", f);
+      req.seg_names[f] = nm;
+    }
+    EncodedFiles enc;
+    hs_stats st;
+    memset(&st, 0, sizeof st);
+    encode_segments(ctx, req, &enc, &st);
+    finish_result(ctx, enc, output, nullptr, HS_SAVE_OVERWRITE, res.get(), &st);
+  });
+  if (rc == HS_OK) *out = res.release();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,538 @@
+// engine.cu -- host orchestration of the covering-index data path on one GPU:
+//   load_sources   (H2D of file images, footer parse, K1 page walk + decode)
+//   index_rows     (K2 hash + histogram, K3 stable partition, K4 segmented radix sort)
+//   encode_segments(K5 gather fused with K6 PLAIN page encode into one file image per bucket)
+// Together they are the body of CoveringIndex.write (index/covering/CoveringIndex.scala:56-71) as executed by Spark
+// for the reference: scan -> project -> repartition(numBuckets, indexedColumns) -> sort within bucket -> bucketed
+// Parquet write (index/DataFrameWriterExtensions.scala:50-68).
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <random>
+
+#include "device_utils.cuh"
+#include "engine.h"
+
+namespace hs {
+
+std::string make_uuid() {
+  std::random_device rd;
+  std::mt19937_64 gen(((uint64_t)rd() << 32) ^ rd());
+  uint64_t a = gen(), b = gen();
+  char buf[40];
+  snprintf(buf, sizeof buf, "%08x-%04x-4%03x-%04x-%012llx", (unsigned)(a >> 32), (unsigned)((a >> 16) & 0xffff),
+           (unsigned)(a & 0xfff), (unsigned)(0x8000 | ((b >> 48) & 0x3fff)), (unsigned long long)(b & 0xffffffffffffull));
+  return buf;
+}
+
+namespace {
+
+int hs_type_of(const pq::SchemaColumn& c, const char* file) {
+  if (c.num_children > 0) fail(HS_EUNSUPPORTED, "%s: column '%s' is nested; only flat columns can be indexed", file, c.name.c_str());
+  if (c.repetition == pq::REPEATED) fail(HS_EUNSUPPORTED, "%s: column '%s' is repeated", file, c.name.c_str());
+  switch (c.type) {
+    case pq::BOOLEAN: return HS_TYPE_BOOL;
+    case pq::INT32: return HS_TYPE_INT32;
+    case pq::INT64: return HS_TYPE_INT64;
+    case pq::FLOAT: return HS_TYPE_FLOAT;
+    case pq::DOUBLE: return HS_TYPE_DOUBLE;
+    default:
+      fail(HS_EUNSUPPORTED, "%s: column '%s' has Parquet physical type %d; the GPU path handles BOOLEAN/INT32/INT64/FLOAT/DOUBLE",
+           file, c.name.c_str(), c.type);
+  }
+}
+
+bool iequals(const std::string& a, const std::string& b) {
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); i++)
+    if (tolower((unsigned char)a[i]) != tolower((unsigned char)b[i])) return false;
+  return true;
+}
+
+int find_column(const pq::FileMeta& fm, const std::string& name) {
+  for (size_t i = 0; i < fm.columns.size(); i++)
+    if (fm.columns[i].name == name) return (int)i;
+  for (size_t i = 0; i < fm.columns.size(); i++)  // Spark resolves names case-insensitively by default
+    if (iequals(fm.columns[i].name, name)) return (int)i;
+  return -1;
+}
+
+const char* decode_error_text(uint32_t code) {
+  switch (code) {
+    case DERR_BAD_HEADER: return "malformed page header";
+    case DERR_UNSUPPORTED_ENCODING: return "unsupported page encoding (PLAIN and PLAIN_/RLE_DICTIONARY are handled)";
+    case DERR_VALUE_COUNT: return "page value counts do not add up to the column chunk's num_values";
+    case DERR_COMPRESSED: return "compressed page (only UNCOMPRESSED is handled on the GPU path)";
+    case DERR_OVERRUN: return "page data shorter than its header claims";
+    case DERR_DICT_INDEX: return "dictionary index out of range or missing dictionary page";
+    case DERR_UNSUPPORTED_TYPE: return "unsupported physical type";
+  }
+  return "unknown decode error";
+}
+
+struct FileImage {
+  std::string what;
+  const uint8_t* dev = nullptr;
+  uint64_t size = 0;
+  pq::FileMeta meta;
+};
+
+void read_whole_file(const char* path, uint8_t* dst, uint64_t size) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) fail(HS_EIO, "cannot open %s", path);
+  uint64_t got = 0;
+  while (got < size) {
+    ssize_t r = read(fd, dst + got, size - got);
+    if (r <= 0) {
+      close(fd);
+      fail(HS_EIO, "short read on %s", path);
+    }
+    got += (uint64_t)r;
+  }
+  close(fd);
+}
+
+}  // namespace
+
+void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const std::vector<std::string>& columns,
+                  Table* out, hs_stats* stats) {
+  StageTimer t_h2d(ctx), t_plan(ctx), t_dec(ctx);
+  std::vector<FileImage> imgs(n_files);
+  // ---- sizes + device arena for host-supplied images --------------------------------------------------------
+  std::vector<uint64_t> sizes(n_files), dev_off(n_files, 0);
+  uint64_t arena_bytes = 0;
+  for (int f = 0; f < n_files; f++) {
+    const hs_source_file& sf = files[f];
+    if (sf.data == nullptr) {
+      if (!sf.path) fail(HS_EINVAL, "source file %d has neither data nor path", f);
+      struct stat st;
+      if (stat(sf.path, &st) != 0) fail(HS_EIO, "cannot stat %s", sf.path);
+      sizes[f] = (uint64_t)st.st_size;
+      imgs[f].what = sf.path;
+    } else {
+      sizes[f] = sf.size;
+      imgs[f].what = sf.path ? sf.path : ("<memory file " + std::to_string(f) + ">");
+    }
+    if (sizes[f] < 12) fail(HS_EFORMAT, "%s: too small to be a Parquet file", imgs[f].what.c_str());
+    imgs[f].size = sizes[f];
+    if (!(sf.data && sf.on_device)) {
+      dev_off[f] = arena_bytes;
+      arena_bytes += round_up(sizes[f], 16) + 16;
+    }
+  }
+  Buf<uint8_t> d_images;
+  if (arena_bytes) d_images.alloc(ctx, arena_bytes);
+  // ---- H2D + footers -----------------------------------------------------------------------------------------
+  t_h2d.start();
+  std::vector<Buf<uint8_t>> staging;  // pinned buffers for path-based files; kept until the copies have completed
+  std::vector<std::vector<uint8_t>> dev_footers(n_files);
+  for (int f = 0; f < n_files; f++) {
+    const hs_source_file& sf = files[f];
+    const uint8_t* host = nullptr;
+    if (sf.data && sf.on_device) {
+      if (((uintptr_t)sf.data & 15) != 0) fail(HS_EINVAL, "%s: device images must be 16-byte aligned", imgs[f].what.c_str());
+      imgs[f].dev = (const uint8_t*)sf.data;
+      uint8_t tail[8];
+      HS_CUDA(cudaMemcpyAsync(tail, imgs[f].dev + sizes[f] - 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      uint32_t flen;
+      memcpy(&flen, tail, 4);
+      if (memcmp(tail + 4, "PAR1", 4) != 0 || (uint64_t)flen + 12 > sizes[f])
+        fail(HS_EFORMAT, "%s: not a Parquet file", imgs[f].what.c_str());
+      dev_footers[f].resize(flen);
+      HS_CUDA(cudaMemcpyAsync(dev_footers[f].data(), imgs[f].dev + sizes[f] - 8 - flen, flen, cudaMemcpyDeviceToHost,
+                              ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      imgs[f].meta = pq::parse_footer_bytes(dev_footers[f].data(), flen, imgs[f].what.c_str());
+    } else {
+      if (sf.data) host = (const uint8_t*)sf.data;
+      else {
+        staging.emplace_back(ctx, sizes[f], /*pinned=*/true);
+        read_whole_file(sf.path, staging.back().get(), sizes[f]);
+        host = staging.back().get();
+      }
+      imgs[f].meta = pq::parse_footer(host, sizes[f], imgs[f].what.c_str());
+      imgs[f].dev = d_images.get() + dev_off[f];
+      HS_CUDA(cudaMemcpyAsync(d_images.get() + dev_off[f], host, sizes[f], cudaMemcpyHostToDevice, ctx->stream));
+    }
+    stats->bytes_in += (int64_t)sizes[f];
+  }
+  t_h2d.stop();
+
+  // ---- resolve columns, build chunk descriptors -----------------------------------------------------------------
+  t_plan.start();
+  const int ncols = (int)columns.size();
+  out->cols.clear();
+  out->cols.resize(ncols);
+  out->file_row_begin.assign(n_files + 1, 0);
+  std::vector<ChunkDesc> chunks;
+  std::vector<bool> col_optional(ncols, false);
+  int64_t nrows = 0;
+  for (int f = 0; f < n_files; f++) {
+    const pq::FileMeta& fm = imgs[f].meta;
+    const char* what = imgs[f].what.c_str();
+    std::vector<int> idx(ncols);
+    for (int c = 0; c < ncols; c++) {
+      idx[c] = find_column(fm, columns[c]);
+      if (idx[c] < 0) fail(HS_EINVAL, "%s: column '%s' not found", what, columns[c].c_str());
+      const pq::SchemaColumn& sc = fm.columns[idx[c]];
+      if (fm.nested) fail(HS_EUNSUPPORTED, "%s: nested schemas are not handled by the GPU path", what);
+      const int t = hs_type_of(sc, what);
+      DevColumn& dc = out->cols[c];
+      if (dc.type < 0) {
+        dc.name = columns[c];
+        dc.type = t;
+        dc.width = type_width(t);
+        dc.schema = sc;
+        dc.schema.name = columns[c];
+      } else if (dc.type != t) {
+        fail(HS_EINVAL, "%s: column '%s' changes type between source files", what, columns[c].c_str());
+      }
+      if (sc.repetition == pq::OPTIONAL) col_optional[c] = true;
+    }
+    out->file_row_begin[f] = nrows;
+    for (const pq::RowGroupMeta& rg : fm.row_groups) {
+      for (int c = 0; c < ncols; c++) {
+        const pq::ColumnChunkMeta& cm = rg.columns[idx[c]];
+        if (cm.codec != pq::UNCOMPRESSED)
+          fail(HS_EUNSUPPORTED, "%s: column '%s' uses compression codec %d; the GPU path reads UNCOMPRESSED pages only", what,
+               columns[c].c_str(), cm.codec);
+        if (cm.num_values != rg.num_rows)
+          fail(HS_EFORMAT, "%s: column '%s' has %lld values for %lld rows", what, columns[c].c_str(), (long long)cm.num_values,
+               (long long)rg.num_rows);
+        const int64_t start = cm.start();
+        if (start < 4 || (uint64_t)(start + cm.total_compressed_size) > imgs[f].size)
+          fail(HS_EFORMAT, "%s: column chunk of '%s' lies outside the file", what, columns[c].c_str());
+        ChunkDesc cd;
+        cd.data = imgs[f].dev + start;
+        cd.size = (uint64_t)cm.total_compressed_size;
+        cd.num_values = cm.num_values;
+        cd.row_base = nrows;
+        cd.col = c;
+        cd.phys_type = fm.columns[idx[c]].type;
+        cd.max_def = fm.columns[idx[c]].repetition == pq::OPTIONAL ? 1 : 0;
+        cd.file_index = f;
+        chunks.push_back(cd);
+      }
+      nrows += rg.num_rows;
+    }
+  }
+  out->file_row_begin[n_files] = nrows;
+  out->nrows = nrows;
+  if (nrows >= (1ll << 32)) fail(HS_EUNSUPPORTED, "more than 2^32-1 rows per GPU per call");
+  stats->rows_in += nrows;
+
+  std::vector<ColumnOut> h_cols(ncols);
+  for (int c = 0; c < ncols; c++) {
+    DevColumn& dc = out->cols[c];
+    dc.data.alloc(ctx, (size_t)nrows * dc.width + 16);
+    if (col_optional[c]) {
+      dc.valid.alloc(ctx, (size_t)nrows + 16);
+      HS_CUDA(cudaMemsetAsync(dc.valid.get(), 1, (size_t)nrows + 16, ctx->stream));
+    }
+    h_cols[c] = ColumnOut{dc.data.get(), col_optional[c] ? dc.valid.get() : nullptr, dc.width, dc.type};
+  }
+  const int n_chunks = (int)chunks.size();
+  t_plan.stop();
+  if (n_chunks == 0 || nrows == 0) {
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    stats->ms_h2d += t_h2d.ms();
+    return;
+  }
+  // ---- page walk -----------------------------------------------------------------------------------------
+  t_dec.start();
+  Buf<ChunkDesc> d_chunks(ctx, n_chunks);
+  Buf<int32_t> d_counts(ctx, n_chunks);
+  Buf<int64_t> d_offsets(ctx, n_chunks);
+  Buf<uint32_t> d_flags(ctx, 1 + ncols);  // [0] error word, [1..] per-column has-nulls
+  Buf<ColumnOut> d_cols(ctx, ncols);
+  HS_CUDA(cudaMemcpyAsync(d_chunks.get(), chunks.data(), sizeof(ChunkDesc) * n_chunks, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(d_cols.get(), h_cols.data(), sizeof(ColumnOut) * ncols, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemsetAsync(d_flags.get(), 0, sizeof(uint32_t) * (1 + ncols), ctx->stream));
+  launch_walk_pages(ctx, d_chunks.get(), n_chunks, d_counts.get(), nullptr, nullptr, d_flags.get(), 0);
+  std::vector<int32_t> counts(n_chunks);
+  HS_CUDA(cudaMemcpyAsync(counts.data(), d_counts.get(), sizeof(int32_t) * n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int64_t> offsets(n_chunks);
+  int64_t n_pages = 0;
+  for (int i = 0; i < n_chunks; i++) {
+    offsets[i] = n_pages;
+    n_pages += counts[i];
+  }
+  Buf<PageDesc> d_pages(ctx, std::max<int64_t>(1, n_pages));
+  HS_CUDA(cudaMemcpyAsync(d_offsets.get(), offsets.data(), sizeof(int64_t) * n_chunks, cudaMemcpyHostToDevice, ctx->stream));
+  launch_walk_pages(ctx, d_chunks.get(), n_chunks, d_counts.get(), d_offsets.get(), d_pages.get(), d_flags.get(), 1);
+  // ---- decode -----------------------------------------------------------------------------------------
+  launch_decode_pages(ctx, d_pages.get(), n_pages, d_cols.get(), d_flags.get() + 1, nullptr, d_flags.get());
+  std::vector<uint32_t> flags(1 + ncols);
+  HS_CUDA(cudaMemcpyAsync(flags.data(), d_flags.get(), sizeof(uint32_t) * (1 + ncols), cudaMemcpyDeviceToHost, ctx->stream));
+  t_dec.stop();
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (flags[0]) {
+    const uint32_t code = flags[0] >> 24, detail = flags[0] & 0xffffffu;
+    const int ecode = (code == DERR_COMPRESSED || code == DERR_UNSUPPORTED_ENCODING || code == DERR_UNSUPPORTED_TYPE)
+                          ? HS_EUNSUPPORTED
+                          : HS_EFORMAT;
+    fail(ecode, "Parquet decode failed: %s (detail %u)", decode_error_text(code), detail);
+  }
+  for (int c = 0; c < ncols; c++) out->cols[c].has_nulls = flags[1 + c] != 0;
+  stats->ms_h2d += t_h2d.ms();
+  stats->ms_plan += t_plan.ms();
+  stats->ms_decode += t_dec.ms();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+
+void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats) {
+  const int64_t nrows = table.nrows;
+  const int ncols = (int)table.cols.size();
+  if (num_buckets < 1 || num_buckets > kMaxBuckets)
+    fail(HS_EUNSUPPORTED, "numBuckets = %d; the GPU path handles 1..%d buckets", num_buckets, kMaxBuckets);
+  if (nkeys < 1 || nkeys > ncols) fail(HS_EINVAL, "bad number of indexed columns");
+  if (nrows >= (1ll << 32)) fail(HS_EUNSUPPORTED, "more than 2^32-1 rows per GPU per call");
+  StageTimer t_hash(ctx), t_part(ctx), t_sort(ctx);
+
+  // ---- K2: bucket ids + histograms -----------------------------------------------------------------------------
+  t_hash.start();
+  std::vector<KeyColumn> h_keys(nkeys);
+  for (int k = 0; k < nkeys; k++) {
+    DevColumn& c = table.cols[k];
+    h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width};
+  }
+  Buf<KeyColumn> d_keys(ctx, nkeys);
+  HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
+  const int64_t ntiles = ceil_div(nrows, kPartTile);
+  Buf<uint16_t> bucket(ctx, std::max<int64_t>(1, nrows));
+  Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * num_buckets);
+  Buf<unsigned long long> ghist(ctx, num_buckets);
+  out->d_bucket_offsets.alloc(ctx, num_buckets + 1);
+  HS_CUDA(cudaMemsetAsync(ghist.get(), 0, sizeof(unsigned long long) * num_buckets, ctx->stream));
+  launch_bucket_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, bucket.get(), tile_hist.get(), ghist.get());
+  launch_tile_offsets(ctx, tile_hist.get(), ntiles, num_buckets, ghist.get(),
+                      (unsigned long long*)out->d_bucket_offsets.get());
+  out->bucket_offsets.assign(num_buckets + 1, 0);
+  HS_CUDA(cudaMemcpyAsync(out->bucket_offsets.data(), out->d_bucket_offsets.get(), sizeof(uint64_t) * (num_buckets + 1),
+                          cudaMemcpyDeviceToHost, ctx->stream));
+  t_hash.stop();
+
+  // ---- K3: stable partition -----------------------------------------------------------------------------------
+  t_part.start();
+  Buf<uint32_t> dest(ctx, std::max<int64_t>(1, nrows));
+  launch_partition_dest(ctx, bucket.get(), nrows, num_buckets, tile_hist.get(), dest.get());
+  out->part.nrows = nrows;
+  out->part.cols.clear();
+  out->part.cols.resize(ncols);
+  for (int c = 0; c < ncols; c++) {
+    DevColumn& src = table.cols[c];
+    DevColumn& dst = out->part.cols[c];
+    dst.name = src.name;
+    dst.type = src.type;
+    dst.width = src.width;
+    dst.schema = src.schema;
+    dst.has_nulls = src.has_nulls;
+    dst.data.alloc(ctx, (size_t)nrows * src.width + 16);
+    launch_scatter_column(ctx, src.data.get(), dst.data.get(), dest.get(), nrows, src.width);
+    if (src.has_nulls) {
+      dst.valid.alloc(ctx, (size_t)nrows + 16);
+      launch_scatter_column(ctx, src.valid.get(), dst.valid.get(), dest.get(), nrows, 1);
+    }
+    src.data.release();  // stream-ordered: the pool only re-issues it to work enqueued after the scatter
+    src.valid.release();
+  }
+  t_part.stop();
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // bucket_offsets now valid on the host
+
+  // ---- K4: segmented sort on the indexed columns, last column first ---------------------------------------------
+  t_sort.start();
+  build_sort_plan(ctx, out->bucket_offsets.data(), num_buckets, &out->plan);
+  out->keys.alloc(ctx, std::max<int64_t>(1, nrows));
+  out->keys_alt.alloc(ctx, std::max<int64_t>(1, nrows));
+  out->perm.alloc(ctx, std::max<int64_t>(1, nrows));
+  out->perm_alt.alloc(ctx, std::max<int64_t>(1, nrows));
+  uint64_t* keys = out->keys.get();
+  uint64_t* keys_alt = out->keys_alt.get();
+  uint32_t* perm = out->perm.get();
+  uint32_t* perm_alt = out->perm_alt.get();
+  launch_iota_u32(ctx, perm, nrows);
+  Buf<unsigned long long> d_or_and(ctx, 2);
+  for (int k = nkeys - 1; k >= 0; k--) {
+    DevColumn& kc = out->part.cols[k];
+    const unsigned long long init[2] = {0ull, ~0ull};
+    HS_CUDA(cudaMemcpyAsync(d_or_and.get(), init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    launch_encode_keys(ctx, kc.data.get(), kc.type, k == nkeys - 1 ? nullptr : perm, nrows, keys, d_or_and.get());
+    unsigned long long or_and[2] = {0, 0};
+    HS_CUDA(cudaMemcpyAsync(or_and, d_or_and.get(), sizeof or_and, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint64_t varying = nrows ? (or_and[0] ^ or_and[1]) : 0;
+    segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying);
+    if (kc.has_nulls)  // nulls first: one more stable pass on the validity byte (0 = null)
+      segmented_sort_pass_by_table(ctx, &out->plan, keys, keys_alt, perm, perm_alt, kc.valid.get());
+  }
+  out->sorted_keys = keys;
+  out->sorted_perm = perm;
+  t_sort.stop();
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  stats->ms_hash += t_hash.ms();
+  stats->ms_partition += t_part.ms();
+  stats->ms_sort += t_sort.ms();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+
+void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, hs_stats* stats) {
+  const Table& table = *req.table;
+  const int ncols = (int)table.cols.size();
+  const int nseg = (int)req.seg_offsets.size() - 1;
+  int64_t P = req.rows_per_page > 0 ? req.rows_per_page : 131072;
+  P = (int64_t)round_up((size_t)P, kSortTile);
+  StageTimer t_plan(ctx), t_enc(ctx);
+  t_plan.start();
+  for (int c = 0; c < ncols; c++) {
+    const DevColumn& dc = table.cols[c];
+    if (dc.width != 4 && dc.width != 8)
+      fail(HS_EUNSUPPORTED, "column '%s': %d-byte values cannot be written by the GPU encoder yet", dc.name.c_str(), dc.width);
+    if (dc.has_nulls)
+      fail(HS_EUNSUPPORTED, "column '%s' contains nulls; the GPU encoder writes non-null columns only for now", dc.name.c_str());
+  }
+  std::vector<pq::SchemaColumn> schema(ncols);
+  for (int c = 0; c < ncols; c++) {
+    schema[c] = table.cols[c].schema;
+    schema[c].repetition = pq::OPTIONAL;  // Spark writes every column of a DataFrame read from Parquet as optional
+    schema[c].num_children = 0;
+    switch (table.cols[c].type) {
+      case HS_TYPE_INT32: schema[c].type = pq::INT32; break;
+      case HS_TYPE_INT64: schema[c].type = pq::INT64; break;
+      case HS_TYPE_FLOAT: schema[c].type = pq::FLOAT; break;
+      case HS_TYPE_DOUBLE: schema[c].type = pq::DOUBLE; break;
+    }
+  }
+  const std::string schema_json = pq::spark_schema_json(schema);
+
+  std::vector<uint8_t> skeleton;
+  std::vector<ByteCopy> copies;
+  std::vector<uint32_t> seg_page_begin(nseg + 1, 0);
+  std::vector<std::vector<uint64_t>> page_value_offset(ncols);
+  uint64_t cursor = 0;
+  uint32_t page_counter = 0;
+  auto emit = [&](uint64_t dst, size_t skel_begin) {
+    copies.push_back(ByteCopy{dst, (uint32_t)skel_begin, (uint32_t)(skeleton.size() - skel_begin)});
+  };
+  out->files.clear();
+  for (int s = 0; s < nseg; s++) {
+    seg_page_begin[s] = page_counter;
+    const int64_t n = (int64_t)(req.seg_offsets[s + 1] - req.seg_offsets[s]);
+    if (n == 0) continue;  // no file for an empty bucket
+    int64_t RG = !req.seg_rows_per_row_group.empty() ? req.seg_rows_per_row_group[s]
+                                                     : (req.rows_per_row_group > 0 ? req.rows_per_row_group : 4194304);
+    RG = std::max<int64_t>(P, RG / P * P);
+    const uint64_t file_off = round_up(cursor, 64);
+    cursor = file_off;
+    {
+      size_t b = skeleton.size();
+      skeleton.insert(skeleton.end(), {'P', 'A', 'R', '1'});
+      emit(cursor, b);
+      cursor += 4;
+    }
+    const int64_t npages = ceil_div(n, P);
+    for (int c = 0; c < ncols; c++) page_value_offset[c].resize(page_counter + npages);
+    std::vector<pq::OutRowGroup> rgs;
+    for (int64_t r0 = 0; r0 < n; r0 += RG) {
+      const int64_t r1 = std::min(n, r0 + RG);
+      pq::OutRowGroup g;
+      g.num_rows = r1 - r0;
+      g.file_offset = (int64_t)(cursor - file_off);
+      const uint64_t rg_begin = cursor;
+      for (int c = 0; c < ncols; c++) {
+        const int W = table.cols[c].width;
+        pq::OutChunk ch;
+        ch.type = schema[c].type;
+        ch.num_values = r1 - r0;
+        ch.data_page_offset = (int64_t)(cursor - file_off);
+        ch.null_count = 0;
+        ch.value_width = W;
+        const uint64_t chunk_begin = cursor;
+        for (int64_t p0 = r0; p0 < r1; p0 += P) {
+          const int64_t np = std::min(P, r1 - p0);
+          const size_t b = skeleton.size();
+          std::vector<uint8_t> defs;
+          pq::write_all_valid_def_levels(defs, np);
+          pq::write_data_page_header(skeleton, (int32_t)(defs.size() + (size_t)np * W), (int32_t)np, pq::ENC_PLAIN);
+          skeleton.insert(skeleton.end(), defs.begin(), defs.end());
+          emit(cursor, b);
+          cursor += skeleton.size() - b;
+          page_value_offset[c][page_counter + (p0 / P)] = cursor;
+          cursor += (uint64_t)np * W;
+        }
+        ch.total_size = (int64_t)(cursor - chunk_begin);
+        g.chunks.push_back(ch);
+      }
+      g.total_byte_size = (int64_t)(cursor - rg_begin);
+      rgs.push_back(std::move(g));
+    }
+    {
+      const size_t b = skeleton.size();
+      std::vector<uint8_t> footer = pq::write_footer(schema, rgs, n, schema_json);
+      skeleton.insert(skeleton.end(), footer.begin(), footer.end());
+      uint32_t flen = (uint32_t)footer.size();
+      const uint8_t* lp = (const uint8_t*)&flen;
+      skeleton.insert(skeleton.end(), lp, lp + 4);
+      skeleton.insert(skeleton.end(), {'P', 'A', 'R', '1'});
+      emit(cursor, b);
+      cursor += skeleton.size() - b;
+    }
+    OutFile of;
+    of.bucket = req.seg_ids.empty() ? s : req.seg_ids[s];
+    of.name = req.seg_names[s];
+    of.offset = file_off;
+    of.size = cursor - file_off;
+    of.rows = n;
+    out->files.push_back(std::move(of));
+    page_counter += (uint32_t)npages;
+  }
+  seg_page_begin[nseg] = page_counter;
+  if (skeleton.size() >= (1ull << 32)) fail(HS_EUNSUPPORTED, "index metadata exceeds 4 GiB");
+  out->arena_bytes = cursor;
+  out->arena.alloc(ctx, std::max<uint64_t>(cursor, 16) + 64);
+
+  // upload the plan
+  Buf<uint8_t> d_skel(ctx, std::max<size_t>(1, skeleton.size()));
+  Buf<ByteCopy> d_copies(ctx, std::max<size_t>(1, copies.size()));
+  Buf<uint32_t> d_page_begin(ctx, seg_page_begin.size());
+  Buf<uint64_t> d_pvo(ctx, std::max<size_t>(1, (size_t)ncols * page_counter));
+  if (!skeleton.empty())
+    HS_CUDA(cudaMemcpyAsync(d_skel.get(), skeleton.data(), skeleton.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!copies.empty())
+    HS_CUDA(cudaMemcpyAsync(d_copies.get(), copies.data(), copies.size() * sizeof(ByteCopy), cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(d_page_begin.get(), seg_page_begin.data(), seg_page_begin.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  for (int c = 0; c < ncols; c++)
+    if (page_counter)
+      HS_CUDA(cudaMemcpyAsync(d_pvo.get() + (size_t)c * page_counter, page_value_offset[c].data(), (size_t)page_counter * 8,
+                              cudaMemcpyHostToDevice, ctx->stream));
+  t_plan.stop();
+
+  // ---- K5+K6 -----------------------------------------------------------------------------------------
+  t_enc.start();
+  launch_scatter_bytes(ctx, d_copies.get(), (int64_t)copies.size(), d_skel.get(), out->arena.get());
+  for (int c = 0; c < ncols; c++) {
+    const DevColumn& dc = table.cols[c];
+    GatherColumn gc;
+    gc.src = dc.data.get();
+    gc.sorted_keys = nullptr;
+    gc.key_type = dc.type;
+    gc.width = dc.width;
+    gc.page_value_offset = d_pvo.get() + (size_t)c * page_counter;
+    if (c == 0 && req.d_sorted_keys && (dc.type == HS_TYPE_INT32 || dc.type == HS_TYPE_INT64)) gc.sorted_keys = req.d_sorted_keys;
+    launch_gather_encode(ctx, req.plan->tiles.get(), req.plan->ntiles, req.plan->seg_start.get(), req.d_perm, gc,
+                         d_page_begin.get(), P, out->arena.get());
+  }
+  t_enc.stop();
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host plan vectors are about to go out of scope
+  stats->ms_plan += t_plan.ms();
+  stats->ms_encode += t_enc.ms();
+  stats->bytes_out += (int64_t)cursor;
+  stats->files_out += (int32_t)out->files.size();
+}
+
+}  // namespace hs

@@ -1,0 +1,113 @@
+// engine.h -- host-side orchestration types shared by api.cu / engine.cu / exchange.cu.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "hs_common.h"
+#include "kernels.h"
+#include "parquet_meta.h"
+
+namespace hs {
+
+// A decoded (or partitioned) column resident in HBM.
+struct DevColumn {
+  std::string name;
+  int32_t type = -1;          // HS_TYPE_*
+  int32_t width = 0;
+  pq::SchemaColumn schema;    // Parquet leaf it came from (converted type carried into the index file)
+  Buf<uint8_t> data;          // nrows * width
+  Buf<uint8_t> valid;         // nrows bytes, only for optional columns
+  bool has_nulls = false;
+};
+
+struct Table {
+  int64_t nrows = 0;
+  std::vector<DevColumn> cols;
+  std::vector<int64_t> file_row_begin;  // nfiles+1: row range of every source file
+};
+
+// Rows in bucket-major, key-sorted order (result of K2-K4).
+struct IndexedRows {
+  Table part;                         // partitioned columns (bucket-major, source order inside a bucket)
+  std::vector<uint64_t> bucket_offsets;  // host, nb+1
+  Buf<uint64_t> d_bucket_offsets;     // device copy
+  SortPlan plan;
+  Buf<uint64_t> keys, keys_alt;       // sorted encoded first-key column (keys) + scratch
+  Buf<uint32_t> perm, perm_alt;       // perm[p] = partitioned row at sorted position p
+  uint64_t* sorted_keys = nullptr;    // points into keys or keys_alt
+  uint32_t* sorted_perm = nullptr;
+};
+
+struct OutFile {
+  int32_t bucket = 0;
+  std::string name;
+  uint64_t offset = 0;  // arena offset
+  uint64_t size = 0;
+  int64_t rows = 0;
+};
+
+struct StageTimes;
+
+// Source handling ----------------------------------------------------------------------------------------------
+struct LoadOptions {
+  const int64_t* d_row_window = nullptr;  // optional per-file [lo,hi) window (device)
+  bool allow_missing_lineage = true;
+};
+// Loads the projected columns of the source files into HBM (H2D of the file images when needed, footer parse on the
+// host, page walk + decode on the GPU).
+void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const std::vector<std::string>& columns,
+                  Table* out, hs_stats* stats);
+
+// K2-K4 on a decoded table whose first nkeys columns are the indexed columns.
+void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats);
+
+// K5+K6: encode every segment (bucket or source file) as one Parquet file image inside one device arena.
+struct EncodeRequest {
+  const Table* table = nullptr;            // column values (indexed by perm)
+  const uint32_t* d_perm = nullptr;        // sorted position -> row of `table`
+  const uint64_t* d_sorted_keys = nullptr; // optional: sorted encoded values of column 0 (integer key)
+  const SortPlan* plan = nullptr;          // tiles over the segments
+  std::vector<uint64_t> seg_offsets;       // host, nseg+1
+  std::vector<std::string> seg_names;      // file name per segment (empty segments produce no file)
+  std::vector<int32_t> seg_ids;            // bucket id per segment
+  int64_t rows_per_page = 0;
+  int64_t rows_per_row_group = 0;
+  std::vector<int64_t> seg_rows_per_row_group;  // optional per-segment override
+};
+struct EncodedFiles {
+  Buf<uint8_t> arena;       // device
+  uint64_t arena_bytes = 0;
+  std::vector<OutFile> files;
+};
+void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, hs_stats* stats);
+
+// multi-GPU exchange (exchange.cu): redistributes the rows of `table` so that this rank holds exactly the rows of
+// the buckets it owns (owner(b) = b % world).  No-op when world == 1.
+void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_stats* stats);
+void comm_destroy(hs_ctx* ctx);
+
+std::string make_uuid();
+
+}  // namespace hs
+
+struct hs_index_result {
+  hs_ctx* ctx = nullptr;
+  int output = HS_OUT_FILES;
+  hs::Buf<uint8_t> d_arena;
+  hs::Buf<uint8_t> h_arena;
+  std::vector<hs::OutFile> files;
+};
+
+struct hs_batch {
+  hs_ctx* ctx = nullptr;
+  int64_t nrows = 0;
+  struct Col {
+    std::string name;
+    int32_t type;
+    hs::Buf<uint8_t> data;
+    hs::Buf<uint8_t> valid;
+    bool has_valid = false;
+  };
+  std::vector<Col> cols;
+};

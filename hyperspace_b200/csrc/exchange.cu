@@ -1,0 +1,224 @@
+// exchange.cu -- the path's only exchange step: rows move to the GPU that owns their bucket.
+//
+// Replaces Spark's shuffle behind `indexData.repartition(numBuckets, indexedColumns)`
+// (index/covering/CoveringIndex.scala:60; on-the-fly variant covering/CoveringIndexRuleUtils.scala:413).
+// One process per GPU.  owner(bucket) = bucket % world.  Each rank partitions its decoded rows by owner with the same
+// stable counting sort as K3 (hash_partition.cu), all-gathers the world x world count matrix, and then moves every
+// column with ONE grouped ncclSend/ncclRecv all-to-all over NVLink.  NCCL is resolved with dlopen so that a
+// single-GPU deployment has no NCCL dependency and so that, inside a torch process, the already-loaded NCCL is used.
+#include <dlfcn.h>
+
+#include "device_utils.cuh"
+#include "engine.h"
+
+namespace {
+
+struct NcclUniqueId {
+  char internal[128];
+};
+typedef void* ncclComm_t;
+enum { kNcclUint8 = 1, kNcclUint64 = 5 };
+
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.handle) return api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) hs::fail(HS_ECOMM, "cannot load libnccl.so.2: %s", dlerror());
+#define HS_NCCL_SYM(field, sym)                                          \
+  api.field = (decltype(api.field))dlsym(api.handle, sym);               \
+  if (!api.field) hs::fail(HS_ECOMM, "libnccl is missing symbol %s", sym);
+  HS_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  HS_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  HS_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  HS_NCCL_SYM(AllGather, "ncclAllGather")
+  HS_NCCL_SYM(Send, "ncclSend")
+  HS_NCCL_SYM(Recv, "ncclRecv")
+  HS_NCCL_SYM(GroupStart, "ncclGroupStart")
+  HS_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  HS_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef HS_NCCL_SYM
+  return api;
+}
+
+#define HS_NCCL(expr)                                                                              \
+  do {                                                                                             \
+    int _r = (expr);                                                                               \
+    if (_r != 0) hs::fail(HS_ECOMM, "%s failed: %s", #expr, nccl().GetErrorString(_r));            \
+  } while (0)
+
+}  // namespace
+
+struct hs_comm_state {
+  ncclComm_t comm = nullptr;
+};
+
+namespace hs {
+
+void comm_destroy(hs_ctx* ctx) {
+  if (ctx->comm) {
+    if (ctx->comm->comm) nccl().CommDestroy(ctx->comm->comm);
+    delete ctx->comm;
+    ctx->comm = nullptr;
+  }
+}
+
+void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_stats* stats) {
+  const int world = ctx->world;
+  if (world <= 1) return;
+  if (!ctx->comm || !ctx->comm->comm) fail(HS_ECOMM, "hs_comm_init has not been called on this context");
+  const int64_t nrows = table.nrows;
+  const int ncols = (int)table.cols.size();
+  StageTimer t_part(ctx), t_x(ctx);
+  // ---- partition by owner rank (stable) -----------------------------------------------------------------------
+  t_part.start();
+  std::vector<KeyColumn> h_keys(nkeys);
+  for (int k = 0; k < nkeys; k++) {
+    DevColumn& c = table.cols[k];
+    h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width};
+  }
+  Buf<KeyColumn> d_keys(ctx, nkeys);
+  HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
+  const int64_t ntiles = ceil_div(nrows, kPartTile);
+  Buf<uint16_t> owner(ctx, std::max<int64_t>(1, nrows));
+  Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * world);
+  Buf<unsigned long long> ghist(ctx, world);
+  Buf<uint64_t> d_send_off(ctx, world + 1);
+  HS_CUDA(cudaMemsetAsync(ghist.get(), 0, 8 * world, ctx->stream));
+  launch_owner_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, owner.get(), tile_hist.get(), ghist.get());
+  launch_tile_offsets(ctx, tile_hist.get(), ntiles, world, ghist.get(), (unsigned long long*)d_send_off.get());
+  Buf<uint32_t> dest(ctx, std::max<int64_t>(1, nrows));
+  launch_partition_dest(ctx, owner.get(), nrows, world, tile_hist.get(), dest.get());
+  // ---- count matrix -----------------------------------------------------------------------------------------
+  Buf<uint64_t> d_matrix(ctx, (size_t)world * world);  // row r = counts rank r sends to each destination
+  HS_NCCL(nccl().AllGather(ghist.get(), d_matrix.get(), world, kNcclUint64, ctx->comm->comm, ctx->stream));
+  std::vector<uint64_t> matrix((size_t)world * world), send_off(world + 1);
+  HS_CUDA(cudaMemcpyAsync(matrix.data(), d_matrix.get(), 8 * (size_t)world * world, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(send_off.data(), d_send_off.get(), 8 * (world + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint64_t> recv_off(world + 1, 0);
+  for (int r = 0; r < world; r++) recv_off[r + 1] = recv_off[r] + matrix[(size_t)r * world + ctx->rank];
+  const int64_t n_recv = (int64_t)recv_off[world];
+  if (n_recv >= (1ll << 32)) fail(HS_EUNSUPPORTED, "more than 2^32-1 rows land on one GPU");
+  // any rank seeing nulls makes the column nullable everywhere
+  // (has_nulls flags travel as one more tiny all-gather folded into the matrix would be neater; a second call is fine)
+  Buf<uint64_t> d_nulls(ctx, (size_t)ncols), d_nulls_all(ctx, (size_t)ncols * world);
+  std::vector<uint64_t> h_nulls(ncols), h_nulls_all((size_t)ncols * world);
+  for (int c = 0; c < ncols; c++) h_nulls[c] = table.cols[c].has_nulls ? 1 : 0;
+  HS_CUDA(cudaMemcpyAsync(d_nulls.get(), h_nulls.data(), 8 * ncols, cudaMemcpyHostToDevice, ctx->stream));
+  HS_NCCL(nccl().AllGather(d_nulls.get(), d_nulls_all.get(), ncols, kNcclUint64, ctx->comm->comm, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(h_nulls_all.data(), d_nulls_all.get(), 8 * (size_t)ncols * world, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  // ---- scatter into send buffers -----------------------------------------------------------------------------
+  std::vector<Buf<uint8_t>> send_data(ncols), send_valid(ncols), recv_data(ncols), recv_valid(ncols);
+  std::vector<bool> any_nulls(ncols, false);
+  for (int c = 0; c < ncols; c++) {
+    for (int r = 0; r < world; r++) any_nulls[c] = any_nulls[c] || h_nulls_all[(size_t)r * ncols + c] != 0;
+    DevColumn& col = table.cols[c];
+    send_data[c].alloc(ctx, (size_t)nrows * col.width + 16);
+    launch_scatter_column(ctx, col.data.get(), send_data[c].get(), dest.get(), nrows, col.width);
+    recv_data[c].alloc(ctx, (size_t)n_recv * col.width + 16);
+    if (any_nulls[c]) {
+      send_valid[c].alloc(ctx, (size_t)nrows + 16);
+      if (col.valid) launch_scatter_column(ctx, col.valid.get(), send_valid[c].get(), dest.get(), nrows, 1);
+      else HS_CUDA(cudaMemsetAsync(send_valid[c].get(), 1, (size_t)nrows + 16, ctx->stream));
+      recv_valid[c].alloc(ctx, (size_t)n_recv + 16);
+    }
+    col.data.release();
+    col.valid.release();
+  }
+  t_part.stop();
+  // ---- the all-to-all -----------------------------------------------------------------------------------------
+  t_x.start();
+  HS_NCCL(nccl().GroupStart());
+  for (int c = 0; c < ncols; c++) {
+    const int W = table.cols[c].width;
+    for (int peer = 0; peer < world; peer++) {
+      const uint64_t scount = send_off[peer + 1] - send_off[peer];
+      const uint64_t rcount = recv_off[peer + 1] - recv_off[peer];
+      if (scount) {
+        HS_NCCL(nccl().Send(send_data[c].get() + send_off[peer] * W, scount * W, kNcclUint8, peer, ctx->comm->comm, ctx->stream));
+        if (any_nulls[c])
+          HS_NCCL(nccl().Send(send_valid[c].get() + send_off[peer], scount, kNcclUint8, peer, ctx->comm->comm, ctx->stream));
+      }
+      if (rcount) {
+        HS_NCCL(nccl().Recv(recv_data[c].get() + recv_off[peer] * W, rcount * W, kNcclUint8, peer, ctx->comm->comm, ctx->stream));
+        if (any_nulls[c])
+          HS_NCCL(nccl().Recv(recv_valid[c].get() + recv_off[peer], rcount, kNcclUint8, peer, ctx->comm->comm, ctx->stream));
+      }
+      if (peer != ctx->rank) stats->bytes_exchanged += (int64_t)(scount * (W + (any_nulls[c] ? 1 : 0)));
+    }
+  }
+  HS_NCCL(nccl().GroupEnd());
+  t_x.stop();
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < ncols; c++) {
+    table.cols[c].data = std::move(recv_data[c]);
+    table.cols[c].has_nulls = any_nulls[c];
+    if (any_nulls[c]) table.cols[c].valid = std::move(recv_valid[c]);
+  }
+  table.nrows = n_recv;
+  table.file_row_begin.clear();
+  stats->ms_partition += t_part.ms();
+  stats->ms_exchange += t_x.ms();
+}
+
+}  // namespace hs
+
+extern "C" {
+
+int hs_comm_unique_id(void* out_id128, char* err, size_t errlen) {
+  try {
+    NcclUniqueId id;
+    memset(&id, 0, sizeof id);
+    HS_NCCL(nccl().GetUniqueId(&id));
+    memcpy(out_id128, &id, 128);
+    return HS_OK;
+  } catch (const hs::Error& e) {
+    if (err && errlen) {
+      strncpy(err, e.what(), errlen - 1);
+      err[errlen - 1] = 0;
+    }
+    return e.code;
+  }
+}
+
+int hs_comm_init(hs_ctx* ctx, int rank, int world_size, const void* id128, char* err, size_t errlen) {
+  if (!ctx || world_size < 1 || rank < 0 || rank >= world_size) return HS_EINVAL;
+  try {
+    HS_CUDA(cudaSetDevice(ctx->device));
+    hs::comm_destroy(ctx);
+    ctx->rank = rank;
+    ctx->world = world_size;
+    if (world_size == 1) return HS_OK;
+    NcclUniqueId id;
+    memcpy(&id, id128, 128);
+    ctx->comm = new hs_comm_state();
+    HS_NCCL(nccl().CommInitRank(&ctx->comm->comm, world_size, id, rank));
+    return HS_OK;
+  } catch (const hs::Error& e) {
+    if (err && errlen) {
+      strncpy(err, e.what(), errlen - 1);
+      err[errlen - 1] = 0;
+    }
+    return e.code;
+  }
+}
+
+}  // extern "C"

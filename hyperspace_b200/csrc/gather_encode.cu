@@ -1,0 +1,142 @@
+// gather_encode.cu -- K5 payload gather fused with K6 PLAIN Parquet page encode, plus the synthetic-table generator.
+//
+// Replaces Spark's DynamicPartitionDataWriter -> ParquetOutputWriter (parquet-mr column writers) that the reference
+// reaches through DataSource.planForWriting (index/DataFrameWriterExtensions.scala:58-67; SURVEY.md 3.1 HOT LOOP 3).
+// The host lays every bucket file out up front (page headers, definition-level blocks and footers are tiny and are
+// serialised on the host into a "skeleton" byte stream); the kernel below writes each sorted value straight into its
+// page body inside the file image, so the index is encoded in the same pass that gathers the payload.  Page bodies
+// start at arbitrary byte offsets (Thrift headers have odd sizes): warp_store_unaligned assembles full-width stores
+// from neighbouring lanes.
+#include "device_utils.cuh"
+#include "kernels.h"
+
+namespace hs {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// inverse of sort_encode for the integer types
+__device__ __forceinline__ uint64_t sort_decode_int(int type, uint64_t e) {
+  return type == 1 ? (e ^ 0x8000000000000000ull) : (uint64_t)((uint32_t)e ^ 0x80000000u);
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) k_gather_encode(const SortTile* __restrict__ tiles,
+                                                             const uint64_t* __restrict__ seg_start,
+                                                             const uint32_t* __restrict__ perm, GatherColumn col,
+                                                             const uint32_t* __restrict__ bucket_page_begin,
+                                                             int64_t rows_per_page, uint8_t* __restrict__ arena) {
+  const SortTile t = tiles[blockIdx.x];
+  const uint64_t lr0 = t.start - seg_start[t.seg];
+  const uint32_t page0 = bucket_page_begin[t.seg];
+  const uint32_t iters = (t.count + kThreads - 1) / kThreads;
+  for (uint32_t it = 0; it < iters; it++) {
+    const uint32_t i = it * kThreads + threadIdx.x;
+    const bool active = i < t.count;
+    uint64_t v = 0;
+    uint8_t* dst = nullptr;
+    if (active) {
+      const uint64_t p = t.start + i;
+      if (col.sorted_keys) {
+        v = sort_decode_int(col.key_type, col.sorted_keys[p]);
+      } else {
+        const uint32_t src_row = perm[p];
+        v = W == 8 ? ((const uint64_t*)col.src)[src_row] : ((const uint32_t*)col.src)[src_row];
+      }
+      const uint64_t lr = lr0 + i;
+      const uint64_t page = lr / (uint64_t)rows_per_page;
+      const uint64_t in_page = lr - page * (uint64_t)rows_per_page;
+      dst = arena + col.page_value_offset[page0 + page] + in_page * W;
+    }
+    warp_store_unaligned<W>(dst, v, active);
+  }
+}
+
+// width-1 columns (BOOLEAN is bit-packed in PLAIN; handled by a byte-per-row staging column + k_pack_bits)
+template <typename T>
+__global__ void k_gather_plain(const T* __restrict__ src, const uint32_t* __restrict__ perm, int64_t n,
+                               T* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = src[perm[i]];
+}
+
+__global__ void k_scatter_bytes(const ByteCopy* __restrict__ copies, int64_t n, const uint8_t* __restrict__ skeleton,
+                                uint8_t* __restrict__ arena) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const ByteCopy c = copies[warp];
+  for (uint32_t i = lane; i < c.len; i += 32) arena[c.dst + i] = skeleton[c.src + i];
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void k_synth_column(int col, int64_t first_row, int64_t n, void* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const uint64_t i = (uint64_t)(first_row + j);
+    switch (col) {
+      case 0: ((uint64_t*)out)[j] = splitmix64(42, i); break;
+      case 1: ((int64_t*)out)[j] = (int64_t)(splitmix64(43, i) % 1000ull); break;
+      case 2: ((double*)out)[j] = (double)i * 1e-3; break;
+      case 3: ((int32_t*)out)[j] = (int32_t)(i % 100ull); break;
+      case 4: ((float*)out)[j] = (float)(i % 4096ull) * 0.25f; break;
+    }
+  }
+}
+
+inline int grid_for(hs_ctx* ctx, int64_t n, int threads, int per_sm) {
+  int64_t want = ceil_div(n, threads);
+  int64_t cap = (int64_t)ctx->sm_count * per_sm;
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+}  // namespace
+
+void launch_gather_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start,
+                          const uint32_t* perm, const GatherColumn& col, const uint32_t* bucket_page_begin,
+                          int64_t rows_per_page, uint8_t* arena) {
+  if (ntiles == 0) return;
+  if (col.width == 8)
+    k_gather_encode<8><<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, seg_start, perm, col, bucket_page_begin,
+                                                                        rows_per_page, arena);
+  else if (col.width == 4)
+    k_gather_encode<4><<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, seg_start, perm, col, bucket_page_begin,
+                                                                        rows_per_page, arena);
+  else
+    fail(HS_EUNSUPPORTED, "gather_encode: column width %d", col.width);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_gather_plain(hs_ctx* ctx, const void* src, const uint32_t* perm, int64_t n, int width, void* out) {
+  if (n == 0) return;
+  const int grid = grid_for(ctx, n, 256, 16);
+  switch (width) {
+    case 8: k_gather_plain<uint64_t><<<grid, 256, 0, ctx->stream>>>((const uint64_t*)src, perm, n, (uint64_t*)out); break;
+    case 4: k_gather_plain<uint32_t><<<grid, 256, 0, ctx->stream>>>((const uint32_t*)src, perm, n, (uint32_t*)out); break;
+    case 1: k_gather_plain<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)src, perm, n, (uint8_t*)out); break;
+    default: fail(HS_EINVAL, "gather: unsupported width %d", width);
+  }
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_scatter_bytes(hs_ctx* ctx, const ByteCopy* copies, int64_t n, const uint8_t* skeleton, uint8_t* arena) {
+  if (n == 0) return;
+  const int64_t threads = n * 32;
+  k_scatter_bytes<<<(unsigned)ceil_div(threads, 256), 256, 0, ctx->stream>>>(copies, n, skeleton, arena);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_synth_column(hs_ctx* ctx, int col, int64_t first_row, int64_t n, void* out) {
+  if (n == 0) return;
+  k_synth_column<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(col, first_row, n, out);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace hs

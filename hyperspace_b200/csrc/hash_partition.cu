@@ -1,0 +1,314 @@
+// hash_partition.cu -- K2 bucket hash + histogram, K3 stable partition into bucket-major order.
+//
+// Replaces Spark's ShuffleExchangeExec(HashPartitioning(indexedColumns, numBuckets)) behind
+// `indexData.repartition(numBuckets, indexedColumns)` (index/covering/CoveringIndex.scala:60): the map side computes
+// bucket = pmod(murmur3(keys, seed 42), n) per row; the "shuffle" on one GPU is a stable counting sort of row
+// indices by bucket id.  Stability makes the whole build deterministic: rows with equal keys keep source order,
+// which is also the oracle's tie order.
+//
+// Per 4096-row tile (256 threads x 16 rows, each warp owns 512 consecutive rows):
+//   k_bucket_hist     hashes the key columns, stores the bucket id (u16), counts per-warp histograms in shared memory
+//                     with __match_any_sync aggregation, and writes the tile histogram M[tile][bucket].
+//   k_tile_offsets_*  turn M into exclusive per-(tile, bucket) destinations (column scan in 3 small kernels).
+//   k_partition_dest  re-ranks the tile's rows (same match_any walk) and emits dest[row].
+//   k_scatter_column  out[dest[i]] = in[i] for each projected column.
+#include "device_utils.cuh"
+#include "kernels.h"
+
+namespace hs {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kItems = kPartTile / kThreads;   // 16 rows per thread
+constexpr int kWarpRows = kPartTile / kWarps;  // 512 consecutive rows per warp
+
+__device__ __forceinline__ uint64_t load_raw(const KeyColumn& k, int64_t row) {
+  switch (k.width) {
+    case 8: return ((const uint64_t*)k.data)[row];
+    case 4: return ((const uint32_t*)k.data)[row];
+    default: return ((const uint8_t*)k.data)[row];
+  }
+}
+
+__device__ __forceinline__ int32_t row_bucket(const KeyColumn* keys, int nkeys, int64_t row, int nb) {
+  uint32_t h = 42;
+  for (int k = 0; k < nkeys; k++) {
+    const KeyColumn kc = keys[k];
+    if (kc.valid && !kc.valid[row]) continue;  // null leaves the hash unchanged
+    h = mm3_hash_value(kc.type, load_raw(kc, row), h);
+  }
+  return spark_pmod(h, nb);
+}
+
+// Counts the warp's items into its private histogram with match_any aggregation and returns, for every item, its
+// rank among the warp's earlier items of the same bin.  cnt = this warp's histogram (nb entries, zeroed).
+template <int ITEMS>
+__device__ __forceinline__ void warp_rank(const uint16_t (&bin)[ITEMS], const bool (&act)[ITEMS], uint16_t* cnt,
+                                          uint16_t (&rank)[ITEMS]) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1;
+#pragma unroll
+  for (int j = 0; j < ITEMS; j++) {
+    const unsigned amask = __ballot_sync(0xffffffffu, act[j]);
+    if (act[j]) {
+      const unsigned peers = __match_any_sync(amask, bin[j]);
+      const uint16_t pre = cnt[bin[j]];
+      rank[j] = (uint16_t)(pre + __popc(peers & lt));
+      __syncwarp(amask);
+      if ((peers & lt) == 0) cnt[bin[j]] = (uint16_t)(pre + __popc(peers));
+    }
+    __syncwarp();
+  }
+}
+
+// owner_mod > 0: bin = bucket % owner_mod (the rank that owns the bucket) and the histogram has owner_mod bins
+__global__ void __launch_bounds__(kThreads) k_bucket_hist(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
+                                                           int num_buckets, int owner_mod, uint16_t* __restrict__ bucket,
+                                                           uint32_t* __restrict__ tile_hist,
+                                                           unsigned long long* __restrict__ global_hist) {
+  extern __shared__ uint16_t s_cnt[];  // [kWarps][nb]
+  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kWarps * nb; i += kThreads) s_cnt[i] = 0;
+  __syncthreads();
+  const int64_t tile = blockIdx.x;
+  const int64_t wbase = tile * kPartTile + (int64_t)warp * kWarpRows;
+  uint16_t bin[kItems], rank[kItems];
+  bool act[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    const int64_t row = wbase + j * 32 + lane;
+    act[j] = row < nrows;
+    bin[j] = 0;
+    if (act[j]) {
+      int32_t b = row_bucket(keys, nkeys, row, num_buckets);
+      if (owner_mod > 0) b %= owner_mod;
+      bin[j] = (uint16_t)b;
+      bucket[row] = bin[j];
+    }
+  }
+  warp_rank<kItems>(bin, act, s_cnt + warp * nb, rank);
+  __syncthreads();
+  for (int b = threadIdx.x; b < nb; b += kThreads) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) s += s_cnt[w * nb + b];
+    tile_hist[tile * nb + b] = s;
+    if (s) atomicAdd(&global_hist[b], (unsigned long long)s);
+  }
+}
+
+// ---- column scan of M[ntiles][nb] in chunks of kChunk tiles ---------------------------------------------------------
+constexpr int kChunk = 256;
+
+__global__ void k_chunk_sums(const uint32_t* __restrict__ tile_hist, int64_t ntiles, int nb,
+                             unsigned long long* __restrict__ chunk_sums) {
+  const int64_t chunk = blockIdx.y;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int64_t t0 = chunk * kChunk, t1 = min(t0 + kChunk, ntiles);
+  unsigned long long s = 0;
+  for (int64_t t = t0; t < t1; t++) s += tile_hist[t * nb + b];
+  chunk_sums[chunk * nb + b] = s;
+}
+
+// one thread per bucket: bucket base (exclusive scan over buckets of the global histogram) + prefix over chunks
+__global__ void k_chunk_scan(unsigned long long* __restrict__ chunk_sums, int64_t nchunks, int nb,
+                             const unsigned long long* __restrict__ global_hist,
+                             unsigned long long* __restrict__ bucket_offsets) {
+  extern __shared__ unsigned long long s_base[];  // nb + 1
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int b = 0; b < nb; b++) {
+      s_base[b] = run;
+      run += global_hist[b];
+    }
+    s_base[nb] = run;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b <= nb; b += blockDim.x) bucket_offsets[b] = s_base[b];
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    unsigned long long run = s_base[b];
+    for (int64_t c = 0; c < nchunks; c++) {
+      unsigned long long v = chunk_sums[c * nb + b];
+      chunk_sums[c * nb + b] = run;
+      run += v;
+    }
+  }
+}
+
+__global__ void k_chunk_apply(uint32_t* __restrict__ tile_hist, int64_t ntiles, int nb,
+                              const unsigned long long* __restrict__ chunk_sums) {
+  const int64_t chunk = blockIdx.y;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int64_t t0 = chunk * kChunk, t1 = min(t0 + kChunk, ntiles);
+  unsigned long long run = chunk_sums[chunk * nb + b];
+  for (int64_t t = t0; t < t1; t++) {
+    uint32_t v = tile_hist[t * nb + b];
+    tile_hist[t * nb + b] = (uint32_t)run;  // destinations are < 2^32 (row count checked by the caller)
+    run += v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_partition_dest(const uint16_t* __restrict__ bucket, int64_t nrows, int nb,
+                                                              const uint32_t* __restrict__ tile_offsets,
+                                                              uint32_t* __restrict__ dest) {
+  extern __shared__ uint16_t s_cnt[];  // [kWarps][nb]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kWarps * nb; i += kThreads) s_cnt[i] = 0;
+  __syncthreads();
+  const int64_t tile = blockIdx.x;
+  const int64_t wbase = tile * kPartTile + (int64_t)warp * kWarpRows;
+  uint16_t bin[kItems], rank[kItems];
+  bool act[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    const int64_t row = wbase + j * 32 + lane;
+    act[j] = row < nrows;
+    bin[j] = act[j] ? bucket[row] : 0;
+  }
+  warp_rank<kItems>(bin, act, s_cnt + warp * nb, rank);
+  __syncthreads();
+  // exclusive prefix over warps, in place
+  for (int b = threadIdx.x; b < nb; b += kThreads) {
+    uint16_t run = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) {
+      uint16_t v = s_cnt[w * nb + b];
+      s_cnt[w * nb + b] = run;
+      run = (uint16_t)(run + v);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    if (act[j]) {
+      const int64_t row = wbase + j * 32 + lane;
+      dest[row] = tile_offsets[tile * nb + bin[j]] + s_cnt[warp * nb + bin[j]] + rank[j];
+    }
+  }
+}
+
+template <typename T>
+__global__ void k_scatter(const T* __restrict__ in, T* __restrict__ out, const uint32_t* __restrict__ dest, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[dest[i]] = in[i];
+}
+
+__global__ void k_encode_keys(const void* __restrict__ in, int type, int width, const uint32_t* __restrict__ src,
+                              int64_t n, uint64_t* __restrict__ out, unsigned long long* __restrict__ or_and) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  uint64_t vor = 0, vand = ~0ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = src ? (int64_t)src[i] : i;
+    uint64_t raw = width == 8 ? ((const uint64_t*)in)[r] : width == 4 ? ((const uint32_t*)in)[r] : ((const uint8_t*)in)[r];
+    uint64_t e = sort_encode(type, raw);
+    out[i] = e;
+    vor |= e;
+    vand &= e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vor |= __shfl_xor_sync(0xffffffffu, (unsigned long long)vor, o);
+    vand &= __shfl_xor_sync(0xffffffffu, (unsigned long long)vand, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicOr(&or_and[0], (unsigned long long)vor);
+    atomicAnd(&or_and[1], (unsigned long long)vand);
+  }
+}
+
+__global__ void k_iota(uint32_t* out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint32_t)i;
+}
+
+inline int grid_for(hs_ctx* ctx, int64_t n, int threads, int per_sm) {
+  int64_t want = ceil_div(n, threads);
+  int64_t cap = (int64_t)ctx->sm_count * per_sm;
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+}  // namespace
+
+void launch_bucket_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets,
+                        uint16_t* bucket, uint32_t* tile_hist, unsigned long long* global_hist) {
+  if (nrows == 0) return;
+  const int64_t ntiles = ceil_div(nrows, kPartTile);
+  const size_t smem = (size_t)kWarps * num_buckets * sizeof(uint16_t);
+  static bool attr = false;
+  if (!attr) {
+    HS_CUDA(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kMaxBuckets * 2));
+    HS_CUDA(cudaFuncSetAttribute(k_partition_dest, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kMaxBuckets * 2));
+    attr = true;
+  }
+  k_bucket_hist<<<(unsigned)ntiles, kThreads, smem, ctx->stream>>>(d_keys, nkeys, nrows, num_buckets, 0, bucket,
+                                                                   tile_hist, global_hist);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_owner_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int world,
+                       uint16_t* owner, uint32_t* tile_hist, unsigned long long* global_hist) {
+  if (nrows == 0) return;
+  const int64_t ntiles = ceil_div(nrows, kPartTile);
+  const size_t smem = (size_t)kWarps * world * sizeof(uint16_t);
+  k_bucket_hist<<<(unsigned)ntiles, kThreads, smem, ctx->stream>>>(d_keys, nkeys, nrows, num_buckets, world, owner,
+                                                                   tile_hist, global_hist);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_tile_offsets(hs_ctx* ctx, uint32_t* tile_hist, int64_t ntiles, int num_buckets,
+                         const unsigned long long* global_hist, unsigned long long* bucket_offsets) {
+  const int64_t nchunks = std::max<int64_t>(1, ceil_div(ntiles, kChunk));
+  Buf<unsigned long long> chunk_sums(ctx, (size_t)nchunks * num_buckets);
+  dim3 grid((num_buckets + 127) / 128, (unsigned)nchunks);
+  k_chunk_sums<<<grid, 128, 0, ctx->stream>>>(tile_hist, ntiles, num_buckets, chunk_sums.get());
+  HS_LAUNCH_CHECK(ctx);
+  k_chunk_scan<<<1, 256, (num_buckets + 1) * sizeof(unsigned long long), ctx->stream>>>(
+      chunk_sums.get(), nchunks, num_buckets, global_hist, bucket_offsets);
+  HS_LAUNCH_CHECK(ctx);
+  k_chunk_apply<<<grid, 128, 0, ctx->stream>>>(tile_hist, ntiles, num_buckets, chunk_sums.get());
+  HS_LAUNCH_CHECK(ctx);
+  // chunk_sums returns to the pool here; the stream order keeps it alive until the kernels above have run because
+  // the pool only hands it out again to work enqueued later on the same stream.
+}
+
+void launch_partition_dest(hs_ctx* ctx, const uint16_t* bucket, int64_t nrows, int num_buckets,
+                           const uint32_t* tile_offsets, uint32_t* dest) {
+  if (nrows == 0) return;
+  const int64_t ntiles = ceil_div(nrows, kPartTile);
+  const size_t smem = (size_t)kWarps * num_buckets * sizeof(uint16_t);
+  k_partition_dest<<<(unsigned)ntiles, kThreads, smem, ctx->stream>>>(bucket, nrows, num_buckets, tile_offsets, dest);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_scatter_column(hs_ctx* ctx, const void* in, void* out, const uint32_t* dest, int64_t nrows, int width) {
+  if (nrows == 0) return;
+  const int grid = grid_for(ctx, nrows, 256, 16);
+  switch (width) {
+    case 8: k_scatter<uint64_t><<<grid, 256, 0, ctx->stream>>>((const uint64_t*)in, (uint64_t*)out, dest, nrows); break;
+    case 4: k_scatter<uint32_t><<<grid, 256, 0, ctx->stream>>>((const uint32_t*)in, (uint32_t*)out, dest, nrows); break;
+    case 1: k_scatter<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)in, (uint8_t*)out, dest, nrows); break;
+    default: fail(HS_EINVAL, "scatter: unsupported width %d", width);
+  }
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* src, int64_t nrows, uint64_t* out,
+                        unsigned long long* or_and) {
+  if (nrows == 0) return;
+  k_encode_keys<<<grid_for(ctx, nrows, 256, 16), 256, 0, ctx->stream>>>(in, type, type_width(type), src, nrows, out,
+                                                                         or_and);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_iota_u32(hs_ctx* ctx, uint32_t* out, int64_t n) {
+  if (n == 0) return;
+  k_iota<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(out, n);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace hs

@@ -1,0 +1,197 @@
+// hs_common.h -- context, error plumbing, pooled device/pinned buffers shared by every translation unit.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/hs_gpu.h"
+
+namespace hs {
+
+// Exception carrying an HS_E* code; converted to a return code + message at the C-ABI boundary.
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+#define HS_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      ::hs::fail(HS_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Size-keyed cache of device and pinned-host allocations: a 1 B-row build allocates >100 GB per call and
+// cudaMalloc/cudaHostAlloc of that size costs far more than the kernels, so buffers are recycled across calls.
+class BufferPool {
+ public:
+  void* get(size_t bytes, bool pinned) {
+    bytes = round_up(bytes ? bytes : 1, 1 << 16);
+    auto& free_map = pinned ? free_pinned_ : free_dev_;
+    auto it = free_map.lower_bound(bytes);
+    // accept a cached block up to 25% larger than asked
+    if (it != free_map.end() && it->first <= bytes + bytes / 4) {
+      void* p = it->second;
+      size_t sz = it->first;
+      free_map.erase(it);
+      live_[p] = {sz, pinned};
+      return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = pinned ? cudaHostAlloc(&p, bytes, cudaHostAllocDefault) : cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      trim();  // give cached blocks back and retry once
+      e = pinned ? cudaHostAlloc(&p, bytes, cudaHostAllocDefault) : cudaMalloc(&p, bytes);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(HS_ENOMEM, "%s of %zu bytes failed: %s", pinned ? "cudaHostAlloc" : "cudaMalloc", bytes,
+             cudaGetErrorString(e));
+      }
+    }
+    live_[p] = {bytes, pinned};
+    return p;
+  }
+  void put(void* p) {
+    if (!p) return;
+    auto it = live_.find(p);
+    if (it == live_.end()) return;
+    (it->second.pinned ? free_pinned_ : free_dev_).emplace(it->second.bytes, p);
+    live_.erase(it);
+  }
+  void trim() {
+    for (auto& kv : free_dev_) cudaFree(kv.second);
+    for (auto& kv : free_pinned_) cudaFreeHost(kv.second);
+    free_dev_.clear();
+    free_pinned_.clear();
+  }
+  ~BufferPool() {
+    trim();
+    for (auto& kv : live_) kv.second.pinned ? cudaFreeHost(kv.first) : cudaFree(kv.first);
+  }
+
+ private:
+  struct Live {
+    size_t bytes;
+    bool pinned;
+  };
+  std::multimap<size_t, void*> free_dev_, free_pinned_;
+  std::map<void*, Live> live_;
+};
+
+}  // namespace hs
+
+struct hs_comm_state;  // exchange.cu
+
+struct hs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;  // H2D/D2H overlap
+  int sm_count = 148;
+  hs::BufferPool pool;
+  int launches = 0;  // kernels launched by the current call (hs_stats.gpu_launches)
+  hs_comm_state* comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+namespace hs {
+
+// RAII handle on a pooled buffer.
+template <typename T>
+class Buf {
+ public:
+  Buf() = default;
+  Buf(hs_ctx* ctx, size_t n, bool pinned = false) { alloc(ctx, n, pinned); }
+  Buf(const Buf&) = delete;
+  Buf& operator=(const Buf&) = delete;
+  Buf(Buf&& o) noexcept { *this = std::move(o); }
+  Buf& operator=(Buf&& o) noexcept {
+    if (this != &o) {
+      release();
+      ctx_ = o.ctx_;
+      p_ = o.p_;
+      n_ = o.n_;
+      o.p_ = nullptr;
+      o.n_ = 0;
+    }
+    return *this;
+  }
+  ~Buf() { release(); }
+  void alloc(hs_ctx* ctx, size_t n, bool pinned = false) {
+    release();
+    ctx_ = ctx;
+    n_ = n;
+    p_ = static_cast<T*>(ctx->pool.get(n * sizeof(T), pinned));
+  }
+  void release() {
+    if (p_ && ctx_) ctx_->pool.put(p_);
+    p_ = nullptr;
+    n_ = 0;
+  }
+  T* get() const { return p_; }
+  T* detach() {
+    T* p = p_;
+    p_ = nullptr;
+    return p;
+  }
+  size_t size() const { return n_; }
+  T& operator[](size_t i) const { return p_[i]; }
+  explicit operator bool() const { return p_ != nullptr; }
+
+ private:
+  hs_ctx* ctx_ = nullptr;
+  T* p_ = nullptr;
+  size_t n_ = 0;
+};
+
+// CUDA-event stage timer on the ctx stream.
+struct StageTimer {
+  hs_ctx* ctx;
+  cudaEvent_t a = nullptr, b = nullptr;
+  explicit StageTimer(hs_ctx* c) : ctx(c) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  ~StageTimer() {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+  void start() { cudaEventRecord(a, ctx->stream); }
+  // records the end; the elapsed time is read later with ms() after a sync
+  void stop() { cudaEventRecord(b, ctx->stream); }
+  float ms() {
+    float t = 0;
+    cudaEventSynchronize(b);
+    cudaEventElapsedTime(&t, a, b);
+    return t;
+  }
+};
+
+#define HS_LAUNCH_CHECK(ctx)                \
+  do {                                      \
+    (ctx)->launches++;                      \
+    HS_CUDA(cudaGetLastError());            \
+  } while (0)
+
+}  // namespace hs

@@ -1,0 +1,156 @@
+// kernels.h -- host-callable launchers of the CUDA kernels (one .cu per stage).
+#pragma once
+#include "hs_common.h"
+
+namespace hs {
+
+// ---- Parquet decode (parquet_decode.cu) ---------------------------------------------------------------------------
+struct ChunkDesc {          // one per (file, row group, projected column)
+  const uint8_t* data;      // device pointer to the first page header of the chunk
+  uint64_t size;            // chunk bytes
+  int64_t num_values;       // values (rows) in the chunk
+  int64_t row_base;         // global row index of the row group's first row
+  int32_t col;              // projected column index
+  int32_t phys_type;        // pq::PhysType
+  int32_t max_def;          // 0 (required) or 1 (optional)
+  int32_t file_index;
+};
+
+struct PageDesc {           // one per data page
+  const uint8_t* data;      // page body
+  const uint8_t* dict;      // dictionary page body (PLAIN values) or nullptr
+  int64_t first_row;        // global row index of the page's first value
+  int32_t dict_count;
+  int32_t size;             // body bytes
+  int32_t num_values;
+  int32_t encoding;         // pq::Encoding of the values
+  int32_t page_type;        // DATA_PAGE / DATA_PAGE_V2
+  int32_t def_bytes;        // v2: definition_levels_byte_length, v1: -1 (length-prefixed block)
+  int32_t rep_bytes;        // v2
+  int32_t col, phys_type, max_def;
+  int32_t file_index;
+  int32_t pad;
+};
+
+struct ColumnOut {          // decoded column destination
+  void* data;               // num_rows values of `width` bytes (row order)
+  uint8_t* valid;           // one byte per row (pre-set to 1) or nullptr for required columns
+  int32_t width;
+  int32_t type;             // HS_TYPE_*
+};
+
+// device error word: 0 = ok, else (code << 24 | detail)
+enum DecodeError : uint32_t {
+  DERR_NONE = 0, DERR_BAD_HEADER = 1, DERR_UNSUPPORTED_ENCODING = 2, DERR_VALUE_COUNT = 3, DERR_COMPRESSED = 4,
+  DERR_OVERRUN = 5, DERR_DICT_INDEX = 6, DERR_UNSUPPORTED_TYPE = 7
+};
+
+// Walks the page headers of every chunk.  mode 0: page_counts[chunk] = number of data pages.
+// mode 1: fills pages[page_offsets[chunk] ...].
+void launch_walk_pages(hs_ctx* ctx, const ChunkDesc* chunks, int n_chunks, int32_t* page_counts,
+                       const int64_t* page_offsets, PageDesc* pages, uint32_t* d_error, int mode);
+// Decodes all pages into the column arrays.  row_window (optional, device, 2 x int64 per file: [lo, hi) global rows)
+// restricts decoding to pages that intersect the window of their file.
+void launch_decode_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, const ColumnOut* cols,
+                         uint32_t* col_has_nulls, const int64_t* row_window, uint32_t* d_error);
+
+// ---- hash / partition (hash_partition.cu) ---------------------------------------------------------------------------
+struct KeyColumn {
+  const void* data;
+  const uint8_t* valid;  // nullptr -> no nulls
+  int32_t type;
+  int32_t width;
+};
+
+constexpr int kPartTile = 4096;   // rows per partition tile (256 threads x 16)
+constexpr int kMaxBuckets = 4096;
+
+// bucket id per row + per-tile histograms M[tile][nb] + global histogram + OR/AND of the first key's sort encoding
+void launch_bucket_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets,
+                        uint16_t* bucket, uint32_t* tile_hist, unsigned long long* global_hist);
+// same, but bins are the owner ranks (bucket % world) -- the map side of the multi-GPU exchange
+void launch_owner_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int world,
+                       uint16_t* owner, uint32_t* tile_hist, unsigned long long* global_hist);
+// in-place: tile_hist[t][b] <- bucket_base[b] + sum_{t'<t} tile_hist[t'][b]   (bucket_base = exclusive scan of global hist)
+void launch_tile_offsets(hs_ctx* ctx, uint32_t* tile_hist, int64_t ntiles, int num_buckets,
+                         const unsigned long long* global_hist, unsigned long long* bucket_offsets /* nb+1 */);
+// dest[row] = stable position of the row in bucket-major order
+void launch_partition_dest(hs_ctx* ctx, const uint16_t* bucket, int64_t nrows, int num_buckets,
+                           const uint32_t* tile_offsets, uint32_t* dest);
+// out[dest[i]] = in[i]
+void launch_scatter_column(hs_ctx* ctx, const void* in, void* out, const uint32_t* dest, int64_t nrows, int width);
+// out[i] = sort_encode(in[src ? src[i] : i])  (+ global OR / AND reduction into or_and[0], or_and[1])
+void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* src, int64_t nrows, uint64_t* out,
+                        unsigned long long* or_and);
+void launch_iota_u32(hs_ctx* ctx, uint32_t* out, int64_t n);
+
+// ---- segmented radix sort (radix_sort.cu) ---------------------------------------------------------------------------
+constexpr int kSortTile = 4096;  // pairs per tile (256 threads x 16)
+struct SortTile {
+  uint32_t seg;
+  uint32_t count;
+  uint64_t start;  // global position of the tile's first pair
+};
+struct SortPlan {
+  int64_t n = 0;
+  int64_t ntiles = 0;
+  int32_t nseg = 0;
+  Buf<SortTile> tiles;          // device
+  Buf<uint32_t> seg_tile_begin; // device, nseg+1: first tile of each segment
+  Buf<uint64_t> seg_start;      // device, nseg+1: global start of each segment
+  Buf<uint32_t> tile_hist;      // device, ntiles x 256
+  std::vector<uint32_t> h_seg_tile_begin;  // host mirror of seg_tile_begin
+};
+// seg_offsets: host array of nseg+1 global offsets
+void build_sort_plan(hs_ctx* ctx, const uint64_t* seg_offsets, int nseg, SortPlan* plan);
+// Stable LSD radix sort of (key, val) pairs within each segment on the key bits set in `bit_mask` (bytes whose bits
+// are all constant are skipped).  Result is left in (keys, vals); (keys_alt, vals_alt) are scratch of the same size.
+void segmented_sort_pairs(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,
+                          uint32_t*& vals_alt, uint64_t bit_mask);
+// One extra stable pass on an external 8-bit digit: digit = digits[vals[i]]  (null flags for nullable 64-bit keys)
+void segmented_sort_pass_by_table(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,
+                                  uint32_t*& vals_alt, const uint8_t* digits);
+
+// ---- gather + Parquet encode (gather_encode.cu) -----------------------------------------------------------------
+struct GatherColumn {
+  const void* src;        // partitioned column values
+  const uint64_t* sorted_keys;  // when non-null: take the value from the sorted encoded keys (decode with key_type)
+  int32_t key_type;
+  int32_t width;
+  const uint64_t* page_value_offset;  // device: arena offset of the first value byte of each (bucket, page)
+};
+// For every sorted position p (tile by tile): value = src[perm[p]] written PLAIN into its page body in the arena.
+// page index of local row lr in bucket b = bucket_page_begin[b] + lr / rows_per_page.
+void launch_gather_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start,
+                          const uint32_t* perm, const GatherColumn& col, const uint32_t* bucket_page_begin,
+                          int64_t rows_per_page, uint8_t* arena);
+// Plain gather: out[i] = src[perm[i]]
+void launch_gather_plain(hs_ctx* ctx, const void* src, const uint32_t* perm, int64_t n, int width, void* out);
+struct ByteCopy {
+  uint64_t dst;  // arena offset
+  uint32_t src;  // offset into the skeleton byte stream
+  uint32_t len;
+};
+void launch_scatter_bytes(hs_ctx* ctx, const ByteCopy* copies, int64_t n, const uint8_t* skeleton, uint8_t* arena);
+// Synthetic table generator: rows [first_row, first_row+n) of column `col` (0..4) of table T
+void launch_synth_column(hs_ctx* ctx, int col, int64_t first_row, int64_t n, void* out);
+
+// ---- read side (read_side.cu) ---------------------------------------------------------------------------
+// per segment s: bounds[2s] = first index with key >= lo, bounds[2s+1] = first index with key > hi (segment-relative)
+void launch_range_bounds(hs_ctx* ctx, const int64_t* keys, const uint64_t* seg_offsets, int nseg, int has_lo,
+                         int64_t lo, int has_hi, int64_t hi, int64_t* bounds);
+// match counts of every left row against the right rows of the same bucket
+void launch_join_count(hs_ctx* ctx, const int64_t* lkeys, const uint64_t* lseg, const int64_t* rkeys,
+                       const uint64_t* rseg, int nseg, int64_t nl, uint32_t* counts, uint32_t* first_match);
+void launch_join_emit(hs_ctx* ctx, const uint32_t* counts, const uint32_t* first_match, const uint64_t* out_offsets,
+                      int64_t nl, uint32_t* out_li, uint32_t* out_ri);
+// exclusive scan of uint32 counts into uint64 offsets (n+1 entries; last = total)
+void exclusive_scan_u32_u64(hs_ctx* ctx, const uint32_t* in, int64_t n, uint64_t* out);
+// mask[i] = lo <= keys[i] <= hi (and file id not deleted); compaction index list
+void launch_filter_mask(hs_ctx* ctx, const int64_t* keys, const uint8_t* valid, int64_t n, int has_lo, int64_t lo,
+                        int has_hi, int64_t hi, uint32_t* mask);
+void launch_compact_indices(hs_ctx* ctx, const uint32_t* mask, const uint64_t* offsets, int64_t n, uint32_t* out_idx);
+void launch_not_in_mask(hs_ctx* ctx, const int64_t* file_ids, int64_t n, const int64_t* deleted, int ndeleted,
+                        uint32_t* mask /* and-ed in place */);
+
+}  // namespace hs

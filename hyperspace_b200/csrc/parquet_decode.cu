@@ -1,0 +1,497 @@
+// parquet_decode.cu -- K1: Parquet page walk + page decode on the GPU.
+//
+// Replaces the map stage Spark runs for the reference's createIndex (HOT LOOP 1):
+// FileSourceScanExec -> VectorizedParquetRecordReader, reached from `spark.read.parquet` upstream of
+// CreateAction (actions/CreateAction.scala:31) and from CoveringIndexTrait.scala:82-84,132 for refresh / optimize.
+//
+// Layout: whole Parquet file images live in HBM.  One thread per column chunk walks the Thrift page headers
+// (k_walk_pages) and emits a PageDesc per data page; one CTA per data page then decodes it (k_decode_pages):
+//   PLAIN fixed-width            unaligned little-endian loads -> coalesced stores
+//   PLAIN_/RLE_DICTIONARY        RLE/bit-packed hybrid index stream expanded warp-per-run, dictionary in smem
+//   definition levels (optional) same hybrid decoder at bit width 1, block scan -> dense value positions
+// Supported: data page v1 and v2, UNCOMPRESSED codec, BOOLEAN/INT32/INT64/FLOAT/DOUBLE, flat schemas.
+#include "device_utils.cuh"
+#include "kernels.h"
+#include "parquet_meta.h"
+#include "thrift_compact.h"
+
+namespace hs {
+
+namespace {
+
+struct PageHeaderInfo {
+  int32_t type = -1;
+  int32_t uncompressed_size = 0;
+  int32_t compressed_size = 0;
+  int32_t num_values = 0;
+  int32_t encoding = 0;
+  int32_t def_bytes = -1;
+  int32_t rep_bytes = 0;
+  int32_t is_compressed = 1;  // v2 default
+};
+
+// Parses one PageHeader; returns false on malformed input.  r.p is left at the first byte of the page body.
+__device__ bool parse_page_header(thrift::Reader& r, PageHeaderInfo& h) {
+  int16_t fid = 0;
+  for (;;) {
+    uint8_t t = r.field(fid);
+    if (r.bad) return false;
+    if (t == thrift::T_STOP) break;
+    switch (fid) {
+      case 1: h.type = (int32_t)r.zigzag(); break;
+      case 2: h.uncompressed_size = (int32_t)r.zigzag(); break;
+      case 3: h.compressed_size = (int32_t)r.zigzag(); break;
+      case 5:    // DataPageHeader
+      case 7:    // DictionaryPageHeader
+      case 8: {  // DataPageHeaderV2
+        if (t != thrift::T_STRUCT) return false;
+        int16_t f2 = 0;
+        for (;;) {
+          uint8_t t2 = r.field(f2);
+          if (r.bad) return false;
+          if (t2 == thrift::T_STOP) break;
+          if (fid == 5 || fid == 7) {
+            if (f2 == 1) h.num_values = (int32_t)r.zigzag();
+            else if (f2 == 2) h.encoding = (int32_t)r.zigzag();
+            else r.skip(t2);
+          } else {
+            if (f2 == 1) h.num_values = (int32_t)r.zigzag();
+            else if (f2 == 4) h.encoding = (int32_t)r.zigzag();
+            else if (f2 == 5) h.def_bytes = (int32_t)r.zigzag();
+            else if (f2 == 6) h.rep_bytes = (int32_t)r.zigzag();
+            else if (f2 == 7) h.is_compressed = (t2 == thrift::T_TRUE) ? 1 : 0;
+            else r.skip(t2);
+          }
+        }
+        break;
+      }
+      default: r.skip(t);
+    }
+  }
+  return !r.bad;
+}
+
+__device__ void set_error(uint32_t* d_error, uint32_t code, uint32_t detail) {
+  atomicCAS(d_error, 0u, (code << 24) | (detail & 0xffffffu));
+}
+
+__global__ void k_walk_pages(const ChunkDesc* __restrict__ chunks, int n_chunks, int32_t* __restrict__ page_counts,
+                             const int64_t* __restrict__ page_offsets, PageDesc* __restrict__ pages,
+                             uint32_t* d_error, int mode) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const ChunkDesc ch = chunks[c];
+  thrift::Reader r(ch.data, ch.data + ch.size);
+  const uint8_t* dict = nullptr;
+  int32_t dict_count = 0;
+  int64_t values_seen = 0;
+  int32_t n_pages = 0;
+  int64_t out = mode ? page_offsets[c] : 0;
+  while (r.p < r.end && values_seen < ch.num_values) {
+    PageHeaderInfo h;
+    if (!parse_page_header(r, h) || h.compressed_size < 0 || (int64_t)(r.end - r.p) < h.compressed_size) {
+      set_error(d_error, DERR_BAD_HEADER, (uint32_t)c);
+      break;
+    }
+    const uint8_t* body = r.p;
+    if (h.type == pq::DICTIONARY_PAGE) {
+      dict = body;
+      dict_count = h.num_values;
+    } else if (h.type == pq::DATA_PAGE || h.type == pq::DATA_PAGE_V2) {
+      if (mode) {
+        PageDesc pd;
+        pd.data = body;
+        pd.dict = dict;
+        pd.first_row = ch.row_base + values_seen;
+        pd.dict_count = dict_count;
+        pd.size = h.compressed_size;
+        pd.num_values = h.num_values;
+        pd.encoding = h.encoding;
+        pd.page_type = h.type;
+        pd.def_bytes = h.type == pq::DATA_PAGE_V2 ? h.def_bytes : -1;
+        pd.rep_bytes = h.type == pq::DATA_PAGE_V2 ? h.rep_bytes : 0;
+        pd.col = ch.col;
+        pd.phys_type = ch.phys_type;
+        pd.max_def = ch.max_def;
+        pd.file_index = ch.file_index;
+        pd.pad = 0;
+        pages[out + n_pages] = pd;
+      }
+      if (h.compressed_size != h.uncompressed_size) set_error(d_error, DERR_COMPRESSED, (uint32_t)c);
+      values_seen += h.num_values;
+      n_pages++;
+    }  // index pages and unknown page types are skipped
+    r.p = body + h.compressed_size;
+  }
+  if (values_seen != ch.num_values) set_error(d_error, DERR_VALUE_COUNT, (uint32_t)c);
+  if (!mode) page_counts[c] = n_pages;
+}
+
+// ---- RLE / bit-packed hybrid decoder, resumable, CTA-cooperative -----------------------------------------------------
+constexpr int kDecodeThreads = 256;
+constexpr int kRunTable = 128;      // run-table entries per refill
+constexpr int kMaxPerEntry = 256;   // values per entry (a warp expands one entry)
+constexpr int kTileRows = 2048;     // rows per tile on the nullable / dictionary paths
+constexpr int kSmemDict = 2048;     // dictionary entries cached in shared memory (8 B each)
+
+struct HybridState {  // lives in shared memory; mutated by thread 0 only
+  const uint8_t* p;
+  const uint8_t* end;
+  const uint8_t* run_data;  // bit-packed run: first byte
+  uint32_t bw;
+  uint32_t run_left;        // values left in the current run
+  uint32_t run_pos;         // values of the current bit-packed run already consumed
+  uint32_t run_value;       // RLE value
+  uint32_t run_is_rle;
+  uint32_t bad;
+};
+
+struct RunEntry {
+  const uint8_t* data;
+  uint32_t out_start;
+  uint32_t count;
+  uint32_t first;     // first value index inside the bit-packed run, or the RLE value
+  uint32_t is_rle;
+};
+
+struct HybridShared {
+  HybridState st;
+  RunEntry tab[kRunTable];
+  uint32_t n_runs;
+  uint32_t produced;
+};
+
+__device__ void hybrid_init(HybridState& st, const uint8_t* p, const uint8_t* end, uint32_t bw) {
+  st.p = p;
+  st.end = end;
+  st.bw = bw;
+  st.run_left = 0;
+  st.run_pos = 0;
+  st.run_value = 0;
+  st.run_is_rle = 1;
+  st.run_data = p;
+  st.bad = 0;
+}
+
+// thread 0: extend the run table to cover up to `want` more values
+__device__ void hybrid_fill_table(HybridShared& hs, uint32_t want) {
+  HybridState& st = hs.st;
+  uint32_t produced = 0, nr = 0;
+  while (produced < want && nr < kRunTable) {
+    if (st.run_left == 0) {
+      if (st.p >= st.end) {
+        st.bad = 1;
+        break;
+      }
+      // varint run header
+      uint32_t h = 0;
+      int shift = 0;
+      while (st.p < st.end) {
+        uint8_t b = *st.p++;
+        h |= (uint32_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) break;
+        shift += 7;
+        if (shift > 28) break;
+      }
+      if (h & 1) {  // bit-packed: (h >> 1) groups of 8 values
+        uint32_t groups = h >> 1;
+        st.run_is_rle = 0;
+        st.run_left = groups * 8;
+        st.run_pos = 0;
+        st.run_data = st.p;
+        st.p += (size_t)groups * st.bw;
+      } else {
+        st.run_is_rle = 1;
+        st.run_left = h >> 1;
+        uint32_t nbytes = (st.bw + 7) >> 3, v = 0;
+        for (uint32_t i = 0; i < nbytes && st.p < st.end; i++) v |= (uint32_t)(*st.p++) << (8 * i);
+        st.run_value = v;
+      }
+      if (st.run_left == 0) continue;  // empty run: legal but useless
+    }
+    uint32_t take = min(min(st.run_left, want - produced), (uint32_t)kMaxPerEntry);
+    RunEntry& e = hs.tab[nr++];
+    e.out_start = produced;
+    e.count = take;
+    e.is_rle = st.run_is_rle;
+    e.data = st.run_data;
+    e.first = st.run_is_rle ? st.run_value : st.run_pos;
+    st.run_left -= take;
+    st.run_pos += take;
+    produced += take;
+  }
+  hs.n_runs = nr;
+  hs.produced = produced;
+}
+
+// All threads: decode the next `count` values of the stream, calling sink(i, value) for i in [0, count).
+// Returns false when the stream ended early.
+template <typename Sink>
+__device__ bool hybrid_decode_next(HybridShared& hs, uint32_t count, Sink sink) {
+  uint32_t done = 0;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  while (done < count) {
+    __syncthreads();
+    if (threadIdx.x == 0) hybrid_fill_table(hs, count - done);
+    __syncthreads();
+    const uint32_t nr = hs.n_runs, produced = hs.produced, bw = hs.st.bw;
+    for (uint32_t e = warp; e < nr; e += nwarps) {
+      const RunEntry en = hs.tab[e];
+      for (uint32_t j = lane; j < en.count; j += 32) {
+        uint32_t v = en.is_rle ? en.first : extract_bits(en.data, (uint64_t)en.first + j, bw);
+        sink(done + en.out_start + j, v);
+      }
+    }
+    if (produced == 0) return false;
+    done += produced;
+  }
+  return true;
+}
+
+template <int W>
+__device__ __forceinline__ uint64_t load_value(const uint8_t* p) {
+  if (W == 8) return load_le64_unaligned(p);
+  if (W == 4) return load_le32_unaligned(p);
+  return *p;
+}
+template <int W>
+__device__ __forceinline__ void store_value(void* base, int64_t row, uint64_t v) {
+  if (W == 8) ((uint64_t*)base)[row] = v;
+  else if (W == 4) ((uint32_t*)base)[row] = (uint32_t)v;
+  else ((uint8_t*)base)[row] = (uint8_t)v;
+}
+
+struct DecodeShared {
+  HybridShared def;
+  HybridShared idx;
+  uint64_t dict[kSmemDict];
+  uint32_t tile_idx[kTileRows];
+  uint32_t tile_pos[kTileRows];
+  uint8_t tile_valid[kTileRows];
+  uint32_t warp_sums[40];
+  uint32_t flag;
+};
+
+// W = value width in bytes (8, 4) or 1 for BOOLEAN (bit-packed PLAIN, one output byte per row)
+template <int W>
+__device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* col_has_nulls, uint32_t* d_error,
+                            DecodeShared& sm) {
+  const int n = pg.num_values;
+  const uint8_t* p = pg.data;
+  const uint8_t* pend = pg.data + pg.size;
+  const bool is_dict = pg.encoding == pq::ENC_PLAIN_DICTIONARY || pg.encoding == pq::ENC_RLE_DICTIONARY;
+  if (!is_dict && pg.encoding != pq::ENC_PLAIN) {
+    if (threadIdx.x == 0) set_error(d_error, DERR_UNSUPPORTED_ENCODING, (uint32_t)pg.encoding);
+    return;
+  }
+  // ---- definition levels -----------------------------------------------------------------------------------
+  const uint8_t* def_p = nullptr;
+  const uint8_t* def_end = nullptr;
+  if (pg.page_type == pq::DATA_PAGE_V2) {
+    p += pg.rep_bytes;
+    if (pg.max_def > 0) {
+      def_p = p;
+      def_end = p + pg.def_bytes;
+    }
+    p += pg.def_bytes > 0 ? pg.def_bytes : 0;
+  } else if (pg.max_def > 0) {
+    uint32_t len = load_le32_unaligned(p);
+    def_p = p + 4;
+    def_end = def_p + len;
+    p = def_end;
+  }
+  if (p > pend) {
+    if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+    return;
+  }
+  // all-valid fast check: a single RLE run of ones covering the page
+  bool has_def = def_p != nullptr;
+  if (has_def) {
+    if (threadIdx.x == 0) {
+      uint32_t h = 0;
+      int shift = 0;
+      const uint8_t* q = def_p;
+      while (q < def_end) {
+        uint8_t b = *q++;
+        h |= (uint32_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) break;
+        shift += 7;
+        if (shift > 28) break;
+      }
+      sm.flag = (!(h & 1) && (h >> 1) >= (uint32_t)n && q < def_end && (*q & 1)) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (sm.flag) has_def = false;
+    __syncthreads();
+  }
+  // ---- dictionary -----------------------------------------------------------------------------------
+  uint32_t idx_bw = 0;
+  const bool dict_in_smem = is_dict && pg.dict_count <= kSmemDict;
+  if (is_dict) {
+    if (pg.dict == nullptr) {
+      if (threadIdx.x == 0) set_error(d_error, DERR_DICT_INDEX, 0);
+      return;
+    }
+    idx_bw = n > 0 && p < pend ? *p : 0;
+    p += 1;
+    if (idx_bw > 32) {
+      if (threadIdx.x == 0) set_error(d_error, DERR_UNSUPPORTED_ENCODING, idx_bw);
+      return;
+    }
+    if (dict_in_smem) {
+      for (int i = threadIdx.x; i < pg.dict_count; i += blockDim.x) {
+        uint64_t v;
+        if (W == 1) v = (pg.dict[i >> 3] >> (i & 7)) & 1;
+        else v = load_value<W>(pg.dict + (size_t)i * W);
+        sm.dict[i] = v;
+      }
+    }
+    if (threadIdx.x == 0) hybrid_init(sm.idx.st, p, pend, idx_bw);
+  }
+  if (has_def && threadIdx.x == 0) {
+    hybrid_init(sm.def.st, def_p, def_end, 1);
+    atomicOr(col_has_nulls, 1u);
+  }
+  __syncthreads();
+  const int64_t row0 = pg.first_row;
+  const uint32_t dict_count = (uint32_t)pg.dict_count;
+  auto dict_lookup = [&](uint32_t ix) -> uint64_t {
+    if (ix >= dict_count) {
+      set_error(d_error, DERR_DICT_INDEX, ix);
+      return 0;
+    }
+    if (dict_in_smem) return sm.dict[ix];
+    if (W == 1) return (pg.dict[ix >> 3] >> (ix & 7)) & 1;
+    return load_value<W>(pg.dict + (size_t)ix * W);
+  };
+
+  // ---- fast paths: no nulls in this page -----------------------------------------------------------------------
+  if (!has_def) {
+    if (!is_dict) {
+      if (W == 1) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) store_value<1>(co.data, row0 + i, (p[i >> 3] >> (i & 7)) & 1);
+      } else {
+        if ((int64_t)(pend - p) < (int64_t)n * W) {
+          if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+          return;
+        }
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n; i += blockDim.x) store_value<W>(co.data, row0 + i, load_value<W>(p + (size_t)i * W));
+      }
+    } else {
+      for (int base = 0; base < n; base += kTileRows) {
+        const uint32_t cnt = (uint32_t)min(kTileRows, n - base);
+        bool ok = hybrid_decode_next(sm.idx, cnt, [&](uint32_t i, uint32_t v) {
+          store_value<W>(co.data, row0 + base + i, dict_lookup(v));
+        });
+        if (!ok) {
+          if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+          return;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- general path: definition levels select which rows carry a value ---------------------------------------------
+  int64_t val_cursor = 0;  // dense values consumed so far
+  for (int base = 0; base < n; base += kTileRows) {
+    const uint32_t cnt = (uint32_t)min(kTileRows, n - base);
+    bool ok = hybrid_decode_next(sm.def, cnt, [&](uint32_t i, uint32_t v) { sm.tile_valid[i] = (uint8_t)(v != 0); });
+    __syncthreads();
+    if (!ok) {
+      if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+      return;
+    }
+    // exclusive positions of the valid rows: each thread owns kTileRows / blockDim consecutive rows
+    constexpr int kPer = kTileRows / kDecodeThreads;
+    uint32_t local = 0;
+    const uint32_t t0 = threadIdx.x * kPer;
+#pragma unroll
+    for (int k = 0; k < kPer; k++) local += (t0 + k < cnt) ? sm.tile_valid[t0 + k] : 0;
+    uint32_t total = 0;
+    uint32_t pre = block_exclusive_scan(local, sm.warp_sums, &total);
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+      if (t0 + k < cnt) {
+        sm.tile_pos[t0 + k] = pre;
+        pre += sm.tile_valid[t0 + k];
+      }
+    }
+    __syncthreads();
+    if (is_dict) {
+      ok = hybrid_decode_next(sm.idx, total, [&](uint32_t j, uint32_t v) { sm.tile_idx[j] = v; });
+      __syncthreads();
+      if (!ok) {
+        if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+        return;
+      }
+    }
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const bool valid = sm.tile_valid[i] != 0;
+      uint64_t v = 0;
+      if (valid) {
+        const uint32_t pos = sm.tile_pos[i];
+        if (is_dict) v = dict_lookup(sm.tile_idx[pos]);
+        else if (W == 1) {
+          const int64_t bit = val_cursor + pos;
+          v = (p[bit >> 3] >> (bit & 7)) & 1;
+        } else v = load_value<W>(p + (size_t)(val_cursor + pos) * W);
+      }
+      store_value<W>(co.data, row0 + base + i, v);
+      co.valid[row0 + base + i] = valid ? 1 : 0;
+    }
+    val_cursor += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kDecodeThreads) k_decode_pages(const PageDesc* __restrict__ pages,
+                                                                 const ColumnOut* __restrict__ cols,
+                                                                 uint32_t* col_has_nulls,
+                                                                 const int64_t* __restrict__ row_window,
+                                                                 uint32_t* d_error) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  DecodeShared& sm = *reinterpret_cast<DecodeShared*>(smem_raw);
+  const PageDesc pg = pages[blockIdx.x];
+  if (row_window) {
+    const int64_t lo = row_window[2 * pg.file_index], hi = row_window[2 * pg.file_index + 1];
+    if (pg.first_row + pg.num_values <= lo || pg.first_row >= hi) return;
+  }
+  const ColumnOut co = cols[pg.col];
+  switch (pg.phys_type) {
+    case pq::INT64:
+    case pq::DOUBLE: decode_page<8>(pg, co, col_has_nulls + pg.col, d_error, sm); break;
+    case pq::INT32:
+    case pq::FLOAT: decode_page<4>(pg, co, col_has_nulls + pg.col, d_error, sm); break;
+    case pq::BOOLEAN: decode_page<1>(pg, co, col_has_nulls + pg.col, d_error, sm); break;
+    default:
+      if (threadIdx.x == 0) set_error(d_error, DERR_UNSUPPORTED_TYPE, (uint32_t)pg.phys_type);
+  }
+}
+
+}  // namespace
+
+void launch_walk_pages(hs_ctx* ctx, const ChunkDesc* chunks, int n_chunks, int32_t* page_counts,
+                       const int64_t* page_offsets, PageDesc* pages, uint32_t* d_error, int mode) {
+  if (n_chunks == 0) return;
+  const int threads = 64;
+  k_walk_pages<<<(n_chunks + threads - 1) / threads, threads, 0, ctx->stream>>>(chunks, n_chunks, page_counts,
+                                                                                page_offsets, pages, d_error, mode);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_decode_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, const ColumnOut* cols,
+                         uint32_t* col_has_nulls, const int64_t* row_window, uint32_t* d_error) {
+  if (n_pages == 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HS_CUDA(cudaFuncSetAttribute(k_decode_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared)));
+    attr_set = true;
+  }
+  k_decode_pages<<<(unsigned)n_pages, kDecodeThreads, sizeof(DecodeShared), ctx->stream>>>(pages, cols, col_has_nulls,
+                                                                                           row_window, d_error);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace hs

@@ -1,0 +1,297 @@
+// radix_sort.cu -- K4: segmented stable LSD radix sort of (encoded key u64, row index u32) pairs.
+//
+// Replaces the per-bucket SortExec Spark's FileFormatWriter adds for BucketSpec(n, cols, cols)
+// (index/DataFrameWriterExtensions.scala:64; SURVEY.md section 3.1 HOT LOOP 2: UnsafeExternalRowSorter).  Each bucket is a
+// segment; tiles of 4096 pairs never straddle segments, so one launch per pass sorts all buckets at once.
+//
+// Per 8-bit digit pass:  k_sort_hist (tile digit histograms) -> k_seg_* (per-segment column scan giving every
+// (tile, digit) its global destination) -> k_sort_scatter (stable in-tile ranking with __match_any_sync, exchange
+// through shared memory so each digit's items leave the tile as one contiguous run).  Passes whose digit is constant
+// over the whole input (OR == AND on those bits) are skipped.
+#include "device_utils.cuh"
+#include "kernels.h"
+
+namespace hs {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kItems = kSortTile / kThreads;   // 16
+constexpr int kWarpRows = kSortTile / kWarps;  // 512
+constexpr int kChunkTiles = 128;
+
+struct SortChunk {
+  uint32_t seg;
+  uint32_t tile_begin, tile_end;
+};
+
+struct DigitShift {
+  int shift;
+  __device__ __forceinline__ uint32_t operator()(uint64_t key, uint32_t) const { return (uint32_t)(key >> shift) & 255u; }
+};
+struct DigitTable {
+  const uint8_t* table;
+  __device__ __forceinline__ uint32_t operator()(uint64_t, uint32_t val) const { return table[val]; }
+};
+
+template <typename Digit>
+__global__ void __launch_bounds__(kThreads) k_sort_hist(const SortTile* __restrict__ tiles,
+                                                         const uint64_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ vals, Digit digit,
+                                                         uint32_t* __restrict__ tile_hist) {
+  __shared__ uint32_t s_hist[256];
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const SortTile t = tiles[blockIdx.x];
+  for (uint32_t i = threadIdx.x; i < t.count; i += kThreads) {
+    const uint64_t pos = t.start + i;
+    atomicAdd(&s_hist[digit(keys[pos], vals[pos])], 1u);
+  }
+  __syncthreads();
+  tile_hist[(size_t)blockIdx.x * 256 + threadIdx.x] = s_hist[threadIdx.x];
+}
+
+// A: per chunk, per digit sums
+__global__ void __launch_bounds__(256) k_seg_chunk_sums(const SortChunk* __restrict__ chunks,
+                                                         const uint32_t* __restrict__ tile_hist,
+                                                         uint32_t* __restrict__ chunk_sums) {
+  const SortChunk c = chunks[blockIdx.x];
+  uint32_t s = 0;
+  for (uint32_t t = c.tile_begin; t < c.tile_end; t++) s += tile_hist[(size_t)t * 256 + threadIdx.x];
+  chunk_sums[(size_t)blockIdx.x * 256 + threadIdx.x] = s;
+}
+
+// B: one CTA per segment: prefix over the segment's chunks, then digit bases
+__global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restrict__ seg_chunk_begin,
+                                                   const uint64_t* __restrict__ seg_start,
+                                                   uint32_t* __restrict__ chunk_sums) {
+  __shared__ uint32_t warp_sums[40];
+  const uint32_t seg = blockIdx.x;
+  const uint32_t c0 = seg_chunk_begin[seg], c1 = seg_chunk_begin[seg + 1];
+  uint32_t tot = 0;
+  for (uint32_t c = c0; c < c1; c++) {
+    const uint32_t v = chunk_sums[(size_t)c * 256 + threadIdx.x];
+    chunk_sums[(size_t)c * 256 + threadIdx.x] = tot;
+    tot += v;
+  }
+  const uint32_t dbase = block_exclusive_scan(tot, warp_sums, nullptr) + (uint32_t)seg_start[seg];
+  for (uint32_t c = c0; c < c1; c++) chunk_sums[(size_t)c * 256 + threadIdx.x] += dbase;
+}
+
+// C: per chunk, turn tile histograms into destinations
+__global__ void __launch_bounds__(256) k_seg_apply(const SortChunk* __restrict__ chunks,
+                                                    uint32_t* __restrict__ tile_hist,
+                                                    const uint32_t* __restrict__ chunk_sums) {
+  const SortChunk c = chunks[blockIdx.x];
+  uint32_t run = chunk_sums[(size_t)blockIdx.x * 256 + threadIdx.x];
+  for (uint32_t t = c.tile_begin; t < c.tile_end; t++) {
+    const uint32_t v = tile_hist[(size_t)t * 256 + threadIdx.x];
+    tile_hist[(size_t)t * 256 + threadIdx.x] = run;
+    run += v;
+  }
+}
+
+struct ScatterShared {
+  uint64_t keys[kSortTile];
+  uint32_t vals[kSortTile];
+  uint16_t cnt[kWarps][256];
+  uint32_t bin_start[256];
+  uint32_t dst_base[256];
+  uint32_t warp_sums[40];
+};
+
+template <typename Digit>
+__global__ void __launch_bounds__(kThreads) k_sort_scatter(const SortTile* __restrict__ tiles,
+                                                            const uint64_t* __restrict__ keys,
+                                                            const uint32_t* __restrict__ vals, Digit digit,
+                                                            const uint32_t* __restrict__ tile_dst,
+                                                            uint64_t* __restrict__ out_keys,
+                                                            uint32_t* __restrict__ out_vals) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  ScatterShared& sm = *reinterpret_cast<ScatterShared*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1;
+  for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&sm.cnt[0][0])[i] = 0;
+  sm.dst_base[threadIdx.x] = tile_dst[(size_t)blockIdx.x * 256 + threadIdx.x];
+  __syncthreads();
+  const SortTile t = tiles[blockIdx.x];
+  uint64_t k[kItems];
+  uint32_t v[kItems];
+  uint16_t bin[kItems], rank[kItems];
+  bool act[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    const uint32_t i = warp * kWarpRows + j * 32 + lane;
+    act[j] = i < t.count;
+    k[j] = 0;
+    v[j] = 0;
+    bin[j] = 0;
+    if (act[j]) {
+      k[j] = keys[t.start + i];
+      v[j] = vals[t.start + i];
+      bin[j] = (uint16_t)digit(k[j], v[j]);
+    }
+  }
+  // stable rank of every item among the warp's earlier items with the same digit
+  uint16_t* cnt = sm.cnt[warp];
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    const unsigned amask = __ballot_sync(0xffffffffu, act[j]);
+    if (act[j]) {
+      const unsigned peers = __match_any_sync(amask, (unsigned)bin[j]);
+      const uint16_t pre = cnt[bin[j]];
+      rank[j] = (uint16_t)(pre + __popc(peers & lt));
+      __syncwarp(amask);
+      if ((peers & lt) == 0) cnt[bin[j]] = (uint16_t)(pre + __popc(peers));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: exclusive prefix over warps (in place) and the tile total
+  uint32_t total;
+  {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) {
+      const uint16_t c = sm.cnt[w][threadIdx.x];
+      sm.cnt[w][threadIdx.x] = (uint16_t)run;
+      run += c;
+    }
+    total = run;
+  }
+  const uint32_t start = block_exclusive_scan(total, sm.warp_sums, nullptr);
+  sm.bin_start[threadIdx.x] = start;
+  __syncthreads();
+  // exchange: digit-sorted order inside the tile
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    if (act[j]) {
+      const uint32_t pos = sm.bin_start[bin[j]] + sm.cnt[warp][bin[j]] + rank[j];
+      sm.keys[pos] = k[j];
+      sm.vals[pos] = v[j];
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < t.count; i += kThreads) {
+    const uint64_t key = sm.keys[i];
+    const uint32_t val = sm.vals[i];
+    const uint32_t d = digit(key, val);
+    const uint32_t dst = sm.dst_base[d] + (i - sm.bin_start[d]);
+    out_keys[dst] = key;
+    out_vals[dst] = val;
+  }
+}
+
+template <typename Digit>
+void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchunks, const uint32_t* seg_chunk_begin,
+              uint32_t* chunk_sums, const uint64_t* keys, const uint32_t* vals, uint64_t* out_keys, uint32_t* out_vals,
+              Digit digit) {
+  k_sort_hist<Digit><<<(unsigned)plan->ntiles, kThreads, 0, ctx->stream>>>(plan->tiles.get(), keys, vals, digit,
+                                                                          plan->tile_hist.get());
+  HS_LAUNCH_CHECK(ctx);
+  k_seg_chunk_sums<<<(unsigned)nchunks, 256, 0, ctx->stream>>>(chunks, plan->tile_hist.get(), chunk_sums);
+  HS_LAUNCH_CHECK(ctx);
+  k_seg_scan<<<(unsigned)plan->nseg, 256, 0, ctx->stream>>>(seg_chunk_begin, plan->seg_start.get(), chunk_sums);
+  HS_LAUNCH_CHECK(ctx);
+  k_seg_apply<<<(unsigned)nchunks, 256, 0, ctx->stream>>>(chunks, plan->tile_hist.get(), chunk_sums);
+  HS_LAUNCH_CHECK(ctx);
+  static bool attr_shift = false, attr_table = false;
+  bool& attr = std::is_same<Digit, DigitShift>::value ? attr_shift : attr_table;
+  if (!attr) {
+    HS_CUDA(cudaFuncSetAttribute(k_sort_scatter<Digit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(ScatterShared)));
+    attr = true;
+  }
+  k_sort_scatter<Digit><<<(unsigned)plan->ntiles, kThreads, sizeof(ScatterShared), ctx->stream>>>(
+      plan->tiles.get(), keys, vals, digit, plan->tile_hist.get(), out_keys, out_vals);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+struct ChunkPlan {
+  Buf<SortChunk> chunks;
+  Buf<uint32_t> seg_chunk_begin;
+  Buf<uint32_t> chunk_sums;
+  int64_t nchunks = 0;
+};
+
+// chunk lists are derived from the plan's host-side segment -> tile mapping
+ChunkPlan build_chunks(hs_ctx* ctx, const std::vector<uint32_t>& seg_tile_begin) {
+  ChunkPlan cp;
+  const int nseg = (int)seg_tile_begin.size() - 1;
+  std::vector<SortChunk> chunks;
+  std::vector<uint32_t> scb(nseg + 1);
+  for (int s = 0; s < nseg; s++) {
+    scb[s] = (uint32_t)chunks.size();
+    for (uint32_t t = seg_tile_begin[s]; t < seg_tile_begin[s + 1]; t += kChunkTiles)
+      chunks.push_back(SortChunk{(uint32_t)s, t, std::min<uint32_t>(t + kChunkTiles, seg_tile_begin[s + 1])});
+  }
+  scb[nseg] = (uint32_t)chunks.size();
+  cp.nchunks = (int64_t)chunks.size();
+  cp.chunks.alloc(ctx, std::max<size_t>(1, chunks.size()));
+  cp.seg_chunk_begin.alloc(ctx, scb.size());
+  cp.chunk_sums.alloc(ctx, std::max<size_t>(1, chunks.size()) * 256);
+  if (!chunks.empty())
+    HS_CUDA(cudaMemcpyAsync(cp.chunks.get(), chunks.data(), chunks.size() * sizeof(SortChunk), cudaMemcpyHostToDevice,
+                            ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(cp.seg_chunk_begin.get(), scb.data(), scb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  return cp;
+}
+
+}  // namespace
+
+void build_sort_plan(hs_ctx* ctx, const uint64_t* seg_offsets, int nseg, SortPlan* plan) {
+  std::vector<SortTile> tiles;
+  std::vector<uint32_t> stb(nseg + 1);
+  std::vector<uint64_t> sstart(nseg + 1);
+  for (int s = 0; s < nseg; s++) {
+    stb[s] = (uint32_t)tiles.size();
+    sstart[s] = seg_offsets[s];
+    const uint64_t b = seg_offsets[s], e = seg_offsets[s + 1];
+    for (uint64_t p = b; p < e; p += kSortTile)
+      tiles.push_back(SortTile{(uint32_t)s, (uint32_t)std::min<uint64_t>(kSortTile, e - p), p});
+  }
+  stb[nseg] = (uint32_t)tiles.size();
+  sstart[nseg] = seg_offsets[nseg];
+  if (seg_offsets[nseg] >= (1ull << 32)) fail(HS_EUNSUPPORTED, "more than 2^32-1 rows per GPU per call");
+  plan->n = (int64_t)seg_offsets[nseg];
+  plan->ntiles = (int64_t)tiles.size();
+  plan->nseg = nseg;
+  plan->tiles.alloc(ctx, std::max<size_t>(1, tiles.size()));
+  plan->seg_tile_begin.alloc(ctx, stb.size());
+  plan->seg_start.alloc(ctx, sstart.size());
+  plan->tile_hist.alloc(ctx, std::max<size_t>(1, tiles.size()) * 256);
+  if (!tiles.empty())
+    HS_CUDA(cudaMemcpyAsync(plan->tiles.get(), tiles.data(), tiles.size() * sizeof(SortTile), cudaMemcpyHostToDevice,
+                            ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(plan->seg_tile_begin.get(), stb.data(), stb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(plan->seg_start.get(), sstart.data(), sstart.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  plan->h_seg_tile_begin = stb;
+}
+
+void segmented_sort_pairs(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,
+                          uint32_t*& vals_alt, uint64_t bit_mask) {
+  if (plan->ntiles == 0) return;
+  ChunkPlan cp = build_chunks(ctx, plan->h_seg_tile_begin);
+  for (int pass = 0; pass < 8; pass++) {
+    if (((bit_mask >> (pass * 8)) & 0xff) == 0) continue;  // digit constant over the whole input
+    run_pass(ctx, plan, cp.chunks.get(), cp.nchunks, cp.seg_chunk_begin.get(), cp.chunk_sums.get(), keys, vals,
+             keys_alt, vals_alt, DigitShift{pass * 8});
+    std::swap(keys, keys_alt);
+    std::swap(vals, vals_alt);
+  }
+}
+
+void segmented_sort_pass_by_table(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,
+                                  uint32_t*& vals_alt, const uint8_t* digits) {
+  if (plan->ntiles == 0) return;
+  ChunkPlan cp = build_chunks(ctx, plan->h_seg_tile_begin);
+  run_pass(ctx, plan, cp.chunks.get(), cp.nchunks, cp.seg_chunk_begin.get(), cp.chunk_sums.get(), keys, vals, keys_alt,
+           vals_alt, DigitTable{digits});
+  std::swap(keys, keys_alt);
+  std::swap(vals, vals_alt);
+}
+
+}  // namespace hs

@@ -1,0 +1,228 @@
+/*
+ * hs_gpu.h -- C ABI of the B200-native covering-index engine (libhs_gpu.so).
+ *
+ * The reference (microsoft/hyperspace, Scala on the JVM) has no FFI boundary: its whole data path is three
+ * Spark calls.  This header is the seam a maintainer binds with JNI / ctypes; each entry
+ * point names the reference interface whose body it replaces.  Paths below are relative to
+ * src/main/scala/com/microsoft/hyperspace/ in the reference.
+ *
+ * Conventions: plain pointers and sizes only; strings are UTF-8, caller-owned, copied before return; every
+ * function returns 0 on success or a negative HS_E* code and writes a message into (err, errlen) when non-NULL.
+ * The library owns all device memory and every handle it returns until the matching *_free call.  There is no
+ * CPU fallback: without a CUDA device hs_init fails with HS_ENODEVICE and nothing else can be called.
+ * One hs_ctx drives one GPU on one CUDA stream; use one ctx per host thread / per rank.
+ */
+#ifndef HS_GPU_H
+#define HS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_ABI_VERSION 1
+
+/* error codes */
+#define HS_OK 0
+#define HS_EINVAL (-1)       /* bad argument / unknown column / unsupported configuration */
+#define HS_ENODEVICE (-2)    /* no CUDA device or CUDA runtime failure at init */
+#define HS_ECUDA (-3)        /* CUDA error during execution */
+#define HS_EFORMAT (-4)      /* malformed or unsupported Parquet input */
+#define HS_EIO (-5)          /* file system error */
+#define HS_EUNSUPPORTED (-6) /* valid input the GPU path does not handle yet (no CPU fallback exists) */
+#define HS_ENOMEM (-7)
+#define HS_ECOMM (-8)        /* NCCL / multi-GPU exchange failure */
+
+/* physical column types (Parquet physical type x Spark SQL type actually supported on the GPU path) */
+#define HS_TYPE_INT32 0  /* Spark int / date            */
+#define HS_TYPE_INT64 1  /* Spark long / timestamp(us)  */
+#define HS_TYPE_FLOAT 2
+#define HS_TYPE_DOUBLE 3
+#define HS_TYPE_BOOL 4
+#define HS_TYPE_STRING 5 /* BYTE_ARRAY; not yet supported on the GPU path -> HS_EUNSUPPORTED */
+
+typedef struct hs_ctx hs_ctx;
+typedef struct hs_index_result hs_index_result;
+typedef struct hs_batch hs_batch;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* ABI version of the loaded library (== HS_ABI_VERSION it was built with). */
+int hs_abi_version(void);
+/* Static description: compile arch, CUDA version, build flags. */
+const char* hs_build_info(void);
+
+/* Create a context on CUDA device `device_id`.  `cuda_stream` may be NULL (the library creates its own
+ * non-blocking stream) or a cudaStream_t owned by the caller (e.g. torch's current stream) on which every kernel
+ * and copy of this ctx is then issued.  Replaces: the Spark executor pool a Hyperspace action runs on
+ * (actions/Action.scala:84-105 runs op() on the driver thread; Spark schedules the tasks). */
+int hs_init(int device_id, void* cuda_stream, hs_ctx** out, char* err, size_t errlen);
+void hs_shutdown(hs_ctx* ctx);
+/* Return cached device/pinned buffers to the driver. */
+void hs_trim(hs_ctx* ctx);
+/* Page-locked host memory for file images handed to hs_create_index (a JNI direct ByteBuffer can wrap it); pageable
+ * memory works too but copies at a fraction of the PCIe rate. */
+void* hs_host_alloc(hs_ctx* ctx, size_t bytes);
+void hs_host_free(hs_ctx* ctx, void* p);
+
+/* Multi-GPU (one process per GPU).  Rank 0 calls hs_comm_unique_id and ships the 128 bytes to the other ranks
+ * out of band; every rank then calls hs_comm_init.  Replaces: Spark's shuffle service behind
+ * `indexData.repartition(numBuckets, indexedColumns)` (index/covering/CoveringIndex.scala:60). */
+int hs_comm_unique_id(void* out_id128, char* err, size_t errlen);
+int hs_comm_init(hs_ctx* ctx, int rank, int world_size, const void* id128, char* err, size_t errlen);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Write side: createIndex / refreshIndex(full|incremental) / optimizeIndex data path
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  const char* path;  /* read from the file system when data == NULL */
+  const void* data;  /* whole Parquet file image; host memory, or device memory when on_device != 0
+                        (device images must be 16-byte aligned) */
+  uint64_t size;     /* image size in bytes (ignored when data == NULL) */
+  int64_t file_id;   /* lineage id from FileIdTracker (index/IndexLogEntry.scala:627-703); -1 when lineage is off */
+  int32_t on_device;
+  int32_t reserved;
+} hs_source_file;
+
+#define HS_SAVE_OVERWRITE 0 /* create / refresh full / optimize  (covering/CoveringIndexTrait.scala:45-47) */
+#define HS_SAVE_APPEND 1    /* incremental refresh into an existing version dir (CoveringIndexTrait.scala:87-93) */
+
+#define HS_OUT_FILES 0  /* write <out_dir>/part-<bbbbb>-<uuid>_<bbbbb>.c000.parquet (the reference's effect) */
+#define HS_OUT_HOST 1   /* keep the bucket file images in pinned host memory owned by the result handle */
+#define HS_OUT_DEVICE 2 /* keep the bucket file images in device memory owned by the result handle */
+
+typedef struct {
+  const hs_source_file* files; /* this rank's share of the source files (all of them on one GPU) */
+  int32_t n_files;
+  const char* const* indexed_columns; /* resolved names, in IndexConfig order (CoveringIndex.scala:34) */
+  int32_t n_indexed;
+  const char* const* included_columns; /* CoveringIndex.scala:35 */
+  int32_t n_included;
+  int32_t num_buckets; /* spark.hyperspace.index.numBuckets, frozen in the log entry (CoveringIndex.scala:37) */
+  int32_t save_mode;   /* HS_SAVE_* */
+  int32_t output;      /* HS_OUT_* */
+  int32_t lineage;     /* != 0: append `_data_file_id` (int64) from hs_source_file.file_id (CoveringIndex.scala:152-186) */
+  const char* out_dir; /* ctx.indexDataPath = <index>/v__=<N> (actions/CreateActionBase.scala:32-37); HS_OUT_FILES only */
+  const char* job_uuid; /* the <uuid> of the part file names; NULL -> generated */
+  int64_t rows_per_page;      /* 0 -> 131072 */
+  int64_t rows_per_row_group; /* 0 -> 4194304 */
+  /* rows to drop: lineage ids whose rows must not reach the output (refreshIncremental's deleted files,
+   * CoveringIndexTrait.scala:78-94).  Requires a `_data_file_id` column in the source files. */
+  const int64_t* deleted_file_ids;
+  int32_t n_deleted_file_ids;
+  int32_t reserved;
+} hs_index_spec;
+
+typedef struct {
+  int64_t rows_in;       /* rows decoded on this rank */
+  int64_t rows_out;      /* rows written by this rank (after the exchange) */
+  int64_t bytes_in;      /* encoded source bytes consumed */
+  int64_t bytes_out;     /* encoded index bytes produced */
+  int64_t bytes_exchanged; /* bytes this rank sent through the all-to-all */
+  int32_t files_out;
+  int32_t gpu_launches;  /* kernels launched by this call */
+  float ms_total;        /* CUDA-event time of the whole call on the ctx stream */
+  float ms_h2d, ms_plan, ms_decode, ms_hash, ms_partition, ms_exchange, ms_sort, ms_gather, ms_encode, ms_d2h, ms_write;
+} hs_stats;
+
+/* Body of CoveringIndex.write(ctx, indexData, mode) (index/covering/CoveringIndex.scala:56-71): scan the source
+ * Parquet, project indexed ++ included columns, bucket = pmod(murmur3(keys, 42), num_buckets), sort each bucket
+ * ascending nulls-first on the indexed columns, and emit one Parquet file per non-empty bucket
+ * (index/DataFrameWriterExtensions.scala:50-68).  All-or-nothing: on failure nothing is left in out_dir. */
+int hs_create_index(hs_ctx* ctx, const hs_index_spec* spec, hs_index_result** out, hs_stats* stats, char* err,
+                    size_t errlen);
+
+int32_t hs_result_num_files(const hs_index_result* r);
+/* File i of the result: bucket id, file name (no directory), image pointer (host or device, NULL for
+ * HS_OUT_FILES), image size, row count. */
+int hs_result_file(const hs_index_result* r, int32_t i, int32_t* bucket, const char** name, const void** data,
+                   uint64_t* size, int64_t* rows);
+void hs_result_free(hs_index_result* r);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Read side: FilterIndexRule scan, JoinIndexRule bucket-aligned sort-merge join
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  const hs_source_file* files; /* index (or source) Parquet files */
+  int32_t n_files;
+  int32_t sorted_on_key;       /* != 0: every file is sorted ascending on key_column (index files) -> binary search;
+                                  0: full predicate scan (appended source files under Hybrid Scan) */
+  const char* key_column;      /* predicate column (first indexed column, covering/FilterIndexRule.scala:33-103) */
+  const char* const* projected_columns;
+  int32_t n_projected;
+  int32_t has_lo, has_hi;      /* inclusive bounds lo <= key <= hi on an integer key */
+  int64_t lo, hi;
+  const int64_t* deleted_file_ids; /* Hybrid Scan: NOT (_data_file_id IN ids) (covering/CoveringIndexRuleUtils.scala:244-253) */
+  int32_t n_deleted_file_ids;
+  int32_t reserved;
+} hs_scan_spec;
+
+/* Executes the scan FilterIndexRule.applyIndex substitutes for the source scan
+ * (index/covering/FilterIndexRule.scala:135-149; CoveringIndexRuleUtils.scala:98-130). */
+int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_stats* stats, char* err, size_t errlen);
+
+typedef struct {
+  const hs_source_file* left_files;  /* index files of the left side, any order; bucket id parsed from the name */
+  int32_t n_left;
+  const hs_source_file* right_files;
+  int32_t n_right;
+  const int32_t* left_buckets;       /* bucket id per left file  (BucketingUtils.getBucketId on the file name) */
+  const int32_t* right_buckets;
+  int32_t num_buckets;
+  int32_t reserved;
+  const char* left_key;              /* single integer join key on each side */
+  const char* right_key;
+  const char* const* left_columns;   /* projected from the left side */
+  int32_t n_left_columns;
+  const char* const* right_columns;
+  int32_t n_right_columns;
+} hs_join_spec;
+
+/* Inner equi-join bucket b of the left index with bucket b of the right index, no exchange -- what Spark plans
+ * after JoinIndexRule.applyIndex (index/covering/JoinIndexRule.scala:653-687; T/index/E2EHyperspaceRulesTest.scala:487-512).
+ * Buckets holding several files (after an incremental refresh) are merged first, as Spark's SortExec would. */
+int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_stats* stats, char* err, size_t errlen);
+
+int64_t hs_batch_num_rows(const hs_batch* b);
+int32_t hs_batch_num_columns(const hs_batch* b);
+/* Column i: name, HS_TYPE_*, host pointer to num_rows values, host pointer to one validity byte per row
+ * (NULL when the column has no nulls). */
+int hs_batch_column(const hs_batch* b, int32_t i, const char** name, int32_t* type, const void** data,
+                    const uint8_t** valid);
+void hs_batch_free(hs_batch* b);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Kernel-level entry points (host arrays in, host arrays out).  They exist so the parity tests can pin each
+ * kernel against the oracle in isolation; the JVM binding does not need them.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  int32_t type;         /* HS_TYPE_* */
+  int32_t reserved;
+  const void* data;     /* n values */
+  const uint8_t* valid; /* one byte per row or NULL */
+} hs_host_column;
+
+/* K2: bucket id per row (int32) and the num_buckets-bin histogram (int64) of Spark's HashPartitioning. */
+int hs_k_bucket_ids(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64_t nrows, int32_t num_buckets,
+                    int32_t* out_bucket, int64_t* out_hist, char* err, size_t errlen);
+/* K3+K4: permutation ordering rows by (bucket, keys ascending nulls-first); bucket_offsets has num_buckets+1 entries. */
+int hs_k_sort_perm(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64_t nrows, int32_t num_buckets,
+                   int64_t* out_perm, int64_t* out_bucket_offsets, char* err, size_t errlen);
+
+/* Synthetic table T of the benchmark: rows [first_row, first_row+nrows) of
+ * (k:int64, v1:int64, v2:float64, v3:int32, v4:float32)[:ncols], generated and Parquet-encoded on the GPU into
+ * n_files file images of row_groups_per_file row groups each (HS_OUT_HOST or HS_OUT_DEVICE). */
+int hs_synth_table(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, int32_t n_files,
+                   int32_t row_groups_per_file, int32_t output, hs_index_result** out, char* err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HS_GPU_H */
