@@ -194,6 +194,7 @@ void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const s
     }
     out->file_row_begin[f] = nrows;
     for (const pq::RowGroupMeta& rg : fm.row_groups) {
+      if (rg.num_rows == 0) continue;  // writers emit an empty row group for an empty table
       for (int c = 0; c < ncols; c++) {
         const pq::ColumnChunkMeta& cm = rg.columns[idx[c]];
         if (cm.codec != pq::UNCOMPRESSED)
