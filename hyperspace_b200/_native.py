@@ -82,7 +82,7 @@ class HostColumn(C.Structure):
 
 # every symbol include/hs_gpu.h declares; tests/test_abi.py checks the library exports all of them
 EXPORTED_SYMBOLS = [
-    "hs_abi_version", "hs_build_info", "hs_init", "hs_shutdown", "hs_trim", "hs_host_alloc", "hs_host_free",
+    "hs_abi_version", "hs_build_info", "hs_init", "hs_shutdown", "hs_trim", "hs_host_alloc", "hs_host_free", "hs_profile_enable", "hs_profile_report",
     "hs_comm_unique_id", "hs_comm_init", "hs_create_index", "hs_result_num_files", "hs_result_file", "hs_result_free",
     "hs_filter_scan", "hs_bucket_join", "hs_batch_num_rows", "hs_batch_num_columns", "hs_batch_column", "hs_batch_free",
     "hs_k_bucket_ids", "hs_k_sort_perm", "hs_synth_table",
@@ -113,6 +113,10 @@ def load_library() -> C.CDLL:
     L.hs_host_alloc.argtypes = [C.c_void_p, C.c_size_t]
     L.hs_host_free.restype = None
     L.hs_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.hs_profile_enable.restype = None
+    L.hs_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.hs_profile_report.restype = C.c_int
+    L.hs_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     L.hs_comm_unique_id.restype = C.c_int
     L.hs_comm_unique_id.argtypes = [C.c_void_p, *err]
     L.hs_comm_init.restype = C.c_int
@@ -299,6 +303,18 @@ class Context:
 
     def trim(self) -> None:
         load_library().hs_trim(self._h)
+
+    def profile_enable(self, on: bool = True) -> None:
+        load_library().hs_profile_enable(self._h, 1 if on else 0)
+
+    def profile_report(self) -> Dict[str, Dict[str, float]]:
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        rc = load_library().hs_profile_report(self._h, buf, len(buf))
+        if rc != HS_OK:
+            raise HyperspaceGpuError(rc, "hs_profile_report failed")
+        return json.loads(buf.value.decode())
 
     def host_alloc(self, nbytes: int) -> np.ndarray:
         """Pinned host buffer (owned by the context's pool) as a numpy uint8 view."""

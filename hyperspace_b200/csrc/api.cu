@@ -5,6 +5,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <map>
 
 #include "device_utils.cuh"
 #include "engine.h"
@@ -273,6 +274,53 @@ void hs_trim(hs_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->pool.trim();
+}
+
+void hs_profile_enable(hs_ctx* ctx, int on) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& k : ctx->kevents) {
+    ctx->event_pool.push_back(k.a);
+    ctx->event_pool.push_back(k.b);
+  }
+  ctx->kevents.clear();
+  ctx->profile = on != 0;
+}
+
+int hs_profile_report(hs_ctx* ctx, char* out, size_t outlen) {
+  if (!ctx || !out || !outlen) return HS_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  std::map<std::string, std::pair<int, double>> acc;
+  for (auto& k : ctx->kevents) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, k.a, k.b) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    auto& e = acc[k.name];
+    e.first++;
+    e.second += ms;
+  }
+  std::string s = "{";
+  bool first = true;
+  for (auto& kv : acc) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %d, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), kv.second.first,
+             kv.second.second);
+    s += buf;
+    first = false;
+  }
+  s += "}";
+  if (s.size() + 1 > outlen) return HS_ENOMEM;
+  memcpy(out, s.c_str(), s.size() + 1);
+  for (auto& k : ctx->kevents) {
+    ctx->event_pool.push_back(k.a);
+    ctx->event_pool.push_back(k.b);
+  }
+  ctx->kevents.clear();
+  return HS_OK;
 }
 
 void* hs_host_alloc(hs_ctx* ctx, size_t bytes) {

@@ -102,6 +102,7 @@ inline int grid_for(hs_ctx* ctx, int64_t n, int threads, int per_sm) {
 void launch_gather_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start,
                           const uint32_t* perm, const GatherColumn& col, const uint32_t* bucket_page_begin,
                           int64_t rows_per_page, uint8_t* arena) {
+  KernelScope _ks(ctx, "k_gather_encode");
   if (ntiles == 0) return;
   if (col.width == 8)
     k_gather_encode<8><<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, seg_start, perm, col, bucket_page_begin,
@@ -115,6 +116,7 @@ void launch_gather_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, co
 }
 
 void launch_gather_plain(hs_ctx* ctx, const void* src, const uint32_t* perm, int64_t n, int width, void* out) {
+  KernelScope _ks(ctx, "k_gather_plain");
   if (n == 0) return;
   const int grid = grid_for(ctx, n, 256, 16);
   switch (width) {
@@ -134,6 +136,7 @@ void launch_scatter_bytes(hs_ctx* ctx, const ByteCopy* copies, int64_t n, const 
 }
 
 void launch_synth_column(hs_ctx* ctx, int col, int64_t first_row, int64_t n, void* out) {
+  KernelScope _ks(ctx, "k_synth_column");
   if (n == 0) return;
   k_synth_column<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(col, first_row, n, out);
   HS_LAUNCH_CHECK(ctx);

@@ -236,6 +236,7 @@ inline int grid_for(hs_ctx* ctx, int64_t n, int threads, int per_sm) {
 
 void launch_bucket_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets,
                         uint16_t* bucket, uint32_t* tile_hist, unsigned long long* global_hist) {
+  KernelScope _ks(ctx, "k_bucket_hist");
   if (nrows == 0) return;
   const int64_t ntiles = ceil_div(nrows, kPartTile);
   const size_t smem = (size_t)kWarps * num_buckets * sizeof(uint16_t);
@@ -252,6 +253,7 @@ void launch_bucket_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t
 
 void launch_owner_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int world,
                        uint16_t* owner, uint32_t* tile_hist, unsigned long long* global_hist) {
+  KernelScope _ks(ctx, "k_bucket_hist");
   if (nrows == 0) return;
   const int64_t ntiles = ceil_div(nrows, kPartTile);
   const size_t smem = (size_t)kWarps * world * sizeof(uint16_t);
@@ -262,6 +264,7 @@ void launch_owner_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t 
 
 void launch_tile_offsets(hs_ctx* ctx, uint32_t* tile_hist, int64_t ntiles, int num_buckets,
                          const unsigned long long* global_hist, unsigned long long* bucket_offsets) {
+  KernelScope _ks(ctx, "k_tile_offsets");
   const int64_t nchunks = std::max<int64_t>(1, ceil_div(ntiles, kChunk));
   Buf<unsigned long long> chunk_sums(ctx, (size_t)nchunks * num_buckets);
   dim3 grid((num_buckets + 127) / 128, (unsigned)nchunks);
@@ -278,6 +281,7 @@ void launch_tile_offsets(hs_ctx* ctx, uint32_t* tile_hist, int64_t ntiles, int n
 
 void launch_partition_dest(hs_ctx* ctx, const uint16_t* bucket, int64_t nrows, int num_buckets,
                            const uint32_t* tile_offsets, uint32_t* dest) {
+  KernelScope _ks(ctx, "k_partition_dest");
   if (nrows == 0) return;
   const int64_t ntiles = ceil_div(nrows, kPartTile);
   const size_t smem = (size_t)kWarps * num_buckets * sizeof(uint16_t);
@@ -286,6 +290,7 @@ void launch_partition_dest(hs_ctx* ctx, const uint16_t* bucket, int64_t nrows, i
 }
 
 void launch_scatter_column(hs_ctx* ctx, const void* in, void* out, const uint32_t* dest, int64_t nrows, int width) {
+  KernelScope _ks(ctx, "k_scatter_column");
   if (nrows == 0) return;
   const int grid = grid_for(ctx, nrows, 256, 16);
   switch (width) {
@@ -299,6 +304,7 @@ void launch_scatter_column(hs_ctx* ctx, const void* in, void* out, const uint32_
 
 void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* src, int64_t nrows, uint64_t* out,
                         unsigned long long* or_and) {
+  KernelScope _ks(ctx, "k_encode_keys");
   if (nrows == 0) return;
   k_encode_keys<<<grid_for(ctx, nrows, 256, 16), 256, 0, ctx->stream>>>(in, type, type_width(type), src, nrows, out,
                                                                          or_and);

@@ -111,6 +111,14 @@ struct hs_ctx {
   int sm_count = 148;
   hs::BufferPool pool;
   int launches = 0;  // kernels launched by the current call (hs_stats.gpu_launches)
+  // per-kernel CUDA-event timing (hs_profile_enable): one (start, stop) event pair per profiled launch
+  bool profile = false;
+  struct KEvent {
+    const char* name;
+    cudaEvent_t a, b;
+  };
+  std::vector<KEvent> kevents;
+  std::vector<cudaEvent_t> event_pool;
   hs_comm_state* comm = nullptr;
   int rank = 0, world = 1;
 };
@@ -185,6 +193,32 @@ struct StageTimer {
     cudaEventSynchronize(b);
     cudaEventElapsedTime(&t, a, b);
     return t;
+  }
+};
+
+// RAII: brackets the kernel launches issued in its scope with CUDA events on the ctx stream when profiling is on.
+struct KernelScope {
+  hs_ctx* ctx;
+  size_t idx = (size_t)-1;
+  KernelScope(hs_ctx* c, const char* name) : ctx(c) {
+    if (!c->profile) return;
+    auto take = [&]() {
+      cudaEvent_t e;
+      if (!c->event_pool.empty()) {
+        e = c->event_pool.back();
+        c->event_pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    hs_ctx::KEvent ke{name, take(), take()};
+    cudaEventRecord(ke.a, c->stream);
+    idx = c->kevents.size();
+    c->kevents.push_back(ke);
+  }
+  ~KernelScope() {
+    if (idx != (size_t)-1) cudaEventRecord(ctx->kevents[idx].b, ctx->stream);
   }
 };
 

@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_pages(const PageDesc*
 
 void launch_walk_pages(hs_ctx* ctx, const ChunkDesc* chunks, int n_chunks, int32_t* page_counts,
                        const int64_t* page_offsets, PageDesc* pages, uint32_t* d_error, int mode) {
+  KernelScope _ks(ctx, "k_walk_pages");
   if (n_chunks == 0) return;
   const int threads = 64;
   k_walk_pages<<<(n_chunks + threads - 1) / threads, threads, 0, ctx->stream>>>(chunks, n_chunks, page_counts,
@@ -483,6 +484,7 @@ void launch_walk_pages(hs_ctx* ctx, const ChunkDesc* chunks, int n_chunks, int32
 
 void launch_decode_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, const ColumnOut* cols,
                          uint32_t* col_has_nulls, const int64_t* row_window, uint32_t* d_error) {
+  KernelScope _ks(ctx, "k_decode_pages");
   if (n_pages == 0) return;
   static bool attr_set = false;
   if (!attr_set) {

@@ -187,15 +187,20 @@ template <typename Digit>
 void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchunks, const uint32_t* seg_chunk_begin,
               uint32_t* chunk_sums, const uint64_t* keys, const uint32_t* vals, uint64_t* out_keys, uint32_t* out_vals,
               Digit digit) {
-  k_sort_hist<Digit><<<(unsigned)plan->ntiles, kThreads, 0, ctx->stream>>>(plan->tiles.get(), keys, vals, digit,
-                                                                          plan->tile_hist.get());
-  HS_LAUNCH_CHECK(ctx);
+  {
+    KernelScope _ks(ctx, "k_sort_hist");
+    k_sort_hist<Digit><<<(unsigned)plan->ntiles, kThreads, 0, ctx->stream>>>(plan->tiles.get(), keys, vals, digit,
+                                                                            plan->tile_hist.get());
+    HS_LAUNCH_CHECK(ctx);
+  }
+  KernelScope* _scan = new KernelScope(ctx, "k_seg_scan");
   k_seg_chunk_sums<<<(unsigned)nchunks, 256, 0, ctx->stream>>>(chunks, plan->tile_hist.get(), chunk_sums);
   HS_LAUNCH_CHECK(ctx);
   k_seg_scan<<<(unsigned)plan->nseg, 256, 0, ctx->stream>>>(seg_chunk_begin, plan->seg_start.get(), chunk_sums);
   HS_LAUNCH_CHECK(ctx);
   k_seg_apply<<<(unsigned)nchunks, 256, 0, ctx->stream>>>(chunks, plan->tile_hist.get(), chunk_sums);
   HS_LAUNCH_CHECK(ctx);
+  delete _scan;
   static bool attr_shift = false, attr_table = false;
   bool& attr = std::is_same<Digit, DigitShift>::value ? attr_shift : attr_table;
   if (!attr) {
@@ -203,6 +208,7 @@ void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchu
                                  (int)sizeof(ScatterShared)));
     attr = true;
   }
+  KernelScope _ks(ctx, "k_sort_scatter");
   k_sort_scatter<Digit><<<(unsigned)plan->ntiles, kThreads, sizeof(ScatterShared), ctx->stream>>>(
       plan->tiles.get(), keys, vals, digit, plan->tile_hist.get(), out_keys, out_vals);
   HS_LAUNCH_CHECK(ctx);

@@ -202,6 +202,7 @@ void launch_range_bounds(hs_ctx* ctx, const int64_t* keys, const uint64_t* seg_o
 
 void launch_join_count(hs_ctx* ctx, const int64_t* lkeys, const uint64_t* lseg, const int64_t* rkeys,
                        const uint64_t* rseg, int nseg, int64_t nl, uint32_t* counts, uint32_t* first_match) {
+  KernelScope _ks(ctx, "k_join_count");
   if (nl == 0) return;
   k_join_count<<<grid_for(ctx, nl, 256, 16), 256, 0, ctx->stream>>>(lkeys, lseg, rkeys, rseg, nseg, nl, counts,
                                                                      first_match);
@@ -210,6 +211,7 @@ void launch_join_count(hs_ctx* ctx, const int64_t* lkeys, const uint64_t* lseg, 
 
 void launch_join_emit(hs_ctx* ctx, const uint32_t* counts, const uint32_t* first_match, const uint64_t* out_offsets,
                       int64_t nl, uint32_t* out_li, uint32_t* out_ri) {
+  KernelScope _ks(ctx, "k_join_emit");
   if (nl == 0) return;
   k_join_emit<<<grid_for(ctx, nl, 256, 16), 256, 0, ctx->stream>>>(counts, first_match, out_offsets, nl, out_li, out_ri);
   HS_LAUNCH_CHECK(ctx);

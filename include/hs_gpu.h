@@ -64,6 +64,11 @@ int hs_init(int device_id, void* cuda_stream, hs_ctx** out, char* err, size_t er
 void hs_shutdown(hs_ctx* ctx);
 /* Return cached device/pinned buffers to the driver. */
 void hs_trim(hs_ctx* ctx);
+/* Per-kernel timing: when enabled, the hot kernels are bracketed with CUDA events on the ctx stream; hs_profile_report
+ * writes a JSON object {"kernel": {"launches": n, "ms": total}} covering the calls since the last report and resets
+ * it.  Used by bench.py for the roofline of the dominant kernel. */
+void hs_profile_enable(hs_ctx* ctx, int on);
+int hs_profile_report(hs_ctx* ctx, char* out_json, size_t outlen);
 /* Page-locked host memory for file images handed to hs_create_index (a JNI direct ByteBuffer can wrap it); pageable
  * memory works too but copies at a fraction of the PCIe rate. */
 void* hs_host_alloc(hs_ctx* ctx, size_t bytes);
