@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -219,6 +220,7 @@ class IndexResult:
 
     def __init__(self, ctx: "Context", handle: int, output: int):
         self._ctx, self._h, self.output = ctx, handle, output
+        ctx._results.add(self)  # a result must not outlive its context: Context.close() frees the stragglers
         L = load_library()
         self.files: List[ResultFile] = []
         for i in range(L.hs_result_num_files(handle)):
@@ -289,9 +291,12 @@ class Context:
         self._h = h.value
         self.device = device
         self.rank, self.world = 0, 1
+        self._results = weakref.WeakSet()
 
     def close(self) -> None:
         if self._h:
+            for r in list(self._results):
+                r.free()
             load_library().hs_shutdown(self._h)
             self._h = None
 

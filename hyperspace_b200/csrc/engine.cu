@@ -304,13 +304,19 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
   HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
-  const int64_t ntiles = ceil_div(nrows, kPartTile);
-  Buf<uint16_t> bucket(ctx, std::max<int64_t>(1, nrows));
+  const bool fused = fused_partition_supported(num_buckets);
+  const int64_t ntiles = ceil_div(nrows, fused ? kFusedTile : kPartTile);
+  Buf<uint16_t> bucket;
   Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * num_buckets);
   Buf<unsigned long long> ghist(ctx, num_buckets);
   out->d_bucket_offsets.alloc(ctx, num_buckets + 1);
   HS_CUDA(cudaMemsetAsync(ghist.get(), 0, sizeof(unsigned long long) * num_buckets, ctx->stream));
-  launch_bucket_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, bucket.get(), tile_hist.get(), ghist.get());
+  if (fused) {
+    launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), ghist.get());
+  } else {
+    bucket.alloc(ctx, std::max<int64_t>(1, nrows));
+    launch_bucket_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, bucket.get(), tile_hist.get(), ghist.get());
+  }
   launch_tile_offsets(ctx, tile_hist.get(), ntiles, num_buckets, ghist.get(),
                       (unsigned long long*)out->d_bucket_offsets.get());
   out->bucket_offsets.assign(num_buckets + 1, 0);
@@ -320,11 +326,10 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
 
   // ---- K3: stable partition -----------------------------------------------------------------------------------
   t_part.start();
-  Buf<uint32_t> dest(ctx, std::max<int64_t>(1, nrows));
-  launch_partition_dest(ctx, bucket.get(), nrows, num_buckets, tile_hist.get(), dest.get());
   out->part.nrows = nrows;
   out->part.cols.clear();
   out->part.cols.resize(ncols);
+  std::vector<PartColumn> h_pc;
   for (int c = 0; c < ncols; c++) {
     DevColumn& src = table.cols[c];
     DevColumn& dst = out->part.cols[c];
@@ -334,16 +339,28 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
     dst.schema = src.schema;
     dst.has_nulls = src.has_nulls;
     dst.data.alloc(ctx, (size_t)nrows * src.width + 16);
-    launch_scatter_column(ctx, src.data.get(), dst.data.get(), dest.get(), nrows, src.width);
+    h_pc.push_back(PartColumn{src.data.get(), dst.data.get(), src.width, 0});
     if (src.has_nulls) {
       dst.valid.alloc(ctx, (size_t)nrows + 16);
-      launch_scatter_column(ctx, src.valid.get(), dst.valid.get(), dest.get(), nrows, 1);
+      h_pc.push_back(PartColumn{src.valid.get(), dst.valid.get(), 1, 0});
     }
-    src.data.release();  // stream-ordered: the pool only re-issues it to work enqueued after the scatter
-    src.valid.release();
+  }
+  Buf<uint32_t> dest;
+  Buf<PartColumn> d_pc(ctx, h_pc.size());
+  if (fused) {
+    HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * h_pc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), d_pc.get(), (int)h_pc.size());
+  } else {
+    dest.alloc(ctx, std::max<int64_t>(1, nrows));
+    launch_partition_dest(ctx, bucket.get(), nrows, num_buckets, tile_hist.get(), dest.get());
+    for (const PartColumn& pc : h_pc) launch_scatter_column(ctx, pc.in, pc.out, dest.get(), nrows, pc.width);
   }
   t_part.stop();
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // bucket_offsets now valid on the host
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // h_pc is read by the async copy; bucket_offsets now valid on the host
+  for (int c = 0; c < ncols; c++) {
+    table.cols[c].data.release();
+    table.cols[c].valid.release();
+  }
 
   // ---- K4: segmented sort on the indexed columns, last column first ---------------------------------------------
   t_sort.start();
@@ -457,10 +474,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         for (int64_t p0 = r0; p0 < r1; p0 += P) {
           const int64_t np = std::min(P, r1 - p0);
           const size_t b = skeleton.size();
-          std::vector<uint8_t> defs;
-          pq::write_all_valid_def_levels(defs, np);
-          pq::write_data_page_header(skeleton, (int32_t)(defs.size() + (size_t)np * W), (int32_t)np, pq::ENC_PLAIN);
-          skeleton.insert(skeleton.end(), defs.begin(), defs.end());
+          pq::write_plain_page_prefix(skeleton, cursor, np, W);  // file images start 64-byte aligned in the arena
           emit(cursor, b);
           cursor += skeleton.size() - b;
           page_value_offset[c][page_counter + (p0 / P)] = cursor;

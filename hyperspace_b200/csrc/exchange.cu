@@ -95,16 +95,13 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
   HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
-  const int64_t ntiles = ceil_div(nrows, kPartTile);
-  Buf<uint16_t> owner(ctx, std::max<int64_t>(1, nrows));
+  const int64_t ntiles = ceil_div(nrows, kFusedTile);
   Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * world);
   Buf<unsigned long long> ghist(ctx, world);
   Buf<uint64_t> d_send_off(ctx, world + 1);
   HS_CUDA(cudaMemsetAsync(ghist.get(), 0, 8 * world, ctx->stream));
-  launch_owner_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, owner.get(), tile_hist.get(), ghist.get());
+  launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, tile_hist.get(), ghist.get());
   launch_tile_offsets(ctx, tile_hist.get(), ntiles, world, ghist.get(), (unsigned long long*)d_send_off.get());
-  Buf<uint32_t> dest(ctx, std::max<int64_t>(1, nrows));
-  launch_partition_dest(ctx, owner.get(), nrows, world, tile_hist.get(), dest.get());
   // ---- count matrix -----------------------------------------------------------------------------------------
   Buf<uint64_t> d_matrix(ctx, (size_t)world * world);  // row r = counts rank r sends to each destination
   HS_NCCL(nccl().AllGather(ghist.get(), d_matrix.get(), world, kNcclUint64, ctx->comm->comm, ctx->stream));
@@ -125,23 +122,30 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   HS_NCCL(nccl().AllGather(d_nulls.get(), d_nulls_all.get(), ncols, kNcclUint64, ctx->comm->comm, ctx->stream));
   HS_CUDA(cudaMemcpyAsync(h_nulls_all.data(), d_nulls_all.get(), 8 * (size_t)ncols * world, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  // ---- scatter into send buffers -----------------------------------------------------------------------------
+  // ---- partition into send buffers (rank-major, stable) ---------------------------------------------------------
   std::vector<Buf<uint8_t>> send_data(ncols), send_valid(ncols), recv_data(ncols), recv_valid(ncols);
   std::vector<bool> any_nulls(ncols, false);
+  std::vector<PartColumn> h_pc;
   for (int c = 0; c < ncols; c++) {
     for (int r = 0; r < world; r++) any_nulls[c] = any_nulls[c] || h_nulls_all[(size_t)r * ncols + c] != 0;
     DevColumn& col = table.cols[c];
     send_data[c].alloc(ctx, (size_t)nrows * col.width + 16);
-    launch_scatter_column(ctx, col.data.get(), send_data[c].get(), dest.get(), nrows, col.width);
     recv_data[c].alloc(ctx, (size_t)n_recv * col.width + 16);
+    h_pc.push_back(PartColumn{col.data.get(), send_data[c].get(), col.width, 0});
     if (any_nulls[c]) {
       send_valid[c].alloc(ctx, (size_t)nrows + 16);
-      if (col.valid) launch_scatter_column(ctx, col.valid.get(), send_valid[c].get(), dest.get(), nrows, 1);
-      else HS_CUDA(cudaMemsetAsync(send_valid[c].get(), 1, (size_t)nrows + 16, ctx->stream));
       recv_valid[c].alloc(ctx, (size_t)n_recv + 16);
+      if (col.valid) h_pc.push_back(PartColumn{col.valid.get(), send_valid[c].get(), 1, 0});
+      else HS_CUDA(cudaMemsetAsync(send_valid[c].get(), 1, (size_t)nrows + 16, ctx->stream));
     }
-    col.data.release();
-    col.valid.release();
+  }
+  Buf<PartColumn> d_pc(ctx, h_pc.size());
+  HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * h_pc.size(), cudaMemcpyHostToDevice, ctx->stream));
+  launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, tile_hist.get(), d_pc.get(), (int)h_pc.size());
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < ncols; c++) {
+    table.cols[c].data.release();
+    table.cols[c].valid.release();
   }
   t_part.stop();
   // ---- the all-to-all -----------------------------------------------------------------------------------------

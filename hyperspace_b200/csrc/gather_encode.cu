@@ -27,15 +27,19 @@ __global__ void __launch_bounds__(kThreads) k_gather_encode(const SortTile* __re
                                                              const uint32_t* __restrict__ perm, GatherColumn col,
                                                              const uint32_t* __restrict__ bucket_page_begin,
                                                              int64_t rows_per_page, uint8_t* __restrict__ arena) {
+  // tiles are kSortTile-aligned inside their bucket and rows_per_page is a multiple of kSortTile, so a tile lies inside
+  // one page: the destination is one base pointer per CTA plus i * W
   const SortTile t = tiles[blockIdx.x];
   const uint64_t lr0 = t.start - seg_start[t.seg];
-  const uint32_t page0 = bucket_page_begin[t.seg];
+  const uint64_t page = lr0 / (uint64_t)rows_per_page;
+  uint8_t* const base = arena + col.page_value_offset[bucket_page_begin[t.seg] + page] + (lr0 - page * (uint64_t)rows_per_page) * W;
+  // the host pads the definition-level block so that page bodies are 8-byte aligned whenever the page is large enough
+  const bool aligned = ((uintptr_t)base & (W - 1)) == 0;
   const uint32_t iters = (t.count + kThreads - 1) / kThreads;
   for (uint32_t it = 0; it < iters; it++) {
     const uint32_t i = it * kThreads + threadIdx.x;
     const bool active = i < t.count;
     uint64_t v = 0;
-    uint8_t* dst = nullptr;
     if (active) {
       const uint64_t p = t.start + i;
       if (col.sorted_keys) {
@@ -44,12 +48,15 @@ __global__ void __launch_bounds__(kThreads) k_gather_encode(const SortTile* __re
         const uint32_t src_row = perm[p];
         v = W == 8 ? ((const uint64_t*)col.src)[src_row] : ((const uint32_t*)col.src)[src_row];
       }
-      const uint64_t lr = lr0 + i;
-      const uint64_t page = lr / (uint64_t)rows_per_page;
-      const uint64_t in_page = lr - page * (uint64_t)rows_per_page;
-      dst = arena + col.page_value_offset[page0 + page] + in_page * W;
     }
-    warp_store_unaligned<W>(dst, v, active);
+    if (aligned) {
+      if (active) {
+        if (W == 8) reinterpret_cast<uint64_t*>(base)[i] = v;
+        else reinterpret_cast<uint32_t*>(base)[i] = (uint32_t)v;
+      }
+    } else {
+      warp_store_unaligned<W>(base + (size_t)i * W, v, active);
+    }
   }
 }
 

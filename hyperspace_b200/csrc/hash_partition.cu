@@ -318,3 +318,210 @@ void launch_iota_u32(hs_ctx* ctx, uint32_t* out, int64_t n) {
 }
 
 }  // namespace hs
+
+// =====================================================================================================================
+// Fused partition: one kernel hashes the keys, ranks the tile's rows stably by bucket and moves EVERY column through a
+// shared-memory exchange, so each bucket's rows leave the tile as one contiguous run per column (full-sector stores).
+// The unfused path above (bucket ids -> dest -> per-column scattered 8-byte stores) measured 613 GB/s on B200 at
+// 1 B rows / 200 buckets; scattered partial-sector writes are what HBM3e + L2 handle worst.
+// =====================================================================================================================
+namespace hs {
+namespace {
+
+constexpr int kFThreads = 512;
+constexpr int kFWarps = kFThreads / 32;
+constexpr int kFItems = kFusedTile / kFThreads;   // 16
+constexpr int kFWarpRows = kFusedTile / kFWarps;  // 512
+
+__global__ void __launch_bounds__(kFThreads) k_tile_hist(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
+                                                          int num_buckets, int owner_mod,
+                                                          uint32_t* __restrict__ tile_hist,
+                                                          unsigned long long* __restrict__ global_hist) {
+  extern __shared__ uint32_t s_hist[];  // nb
+  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
+  for (int i = threadIdx.x; i < nb; i += kFThreads) s_hist[i] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kFusedTile;
+#pragma unroll 4
+  for (int j = 0; j < kFItems; j++) {
+    const int64_t row = base + j * kFThreads + threadIdx.x;
+    if (row < nrows) {
+      int32_t b = row_bucket(keys, nkeys, row, num_buckets);
+      if (owner_mod > 0) b %= owner_mod;
+      atomicAdd(&s_hist[b], 1u);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nb; b += kFThreads) {
+    const uint32_t s = s_hist[b];
+    tile_hist[(size_t)blockIdx.x * nb + b] = s;
+    if (s) atomicAdd(&global_hist[b], (unsigned long long)s);
+  }
+}
+
+// dynamic shared memory layout: [exchange buffer kFusedTile * 8 B][pos_bin u16 kFusedTile][cnt u16 kFWarps*nb]
+// [bin_start u32 nb][dst_base u32 nb][warp_sums 40 u32]
+__global__ void __launch_bounds__(kFThreads) k_partition_rows(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
+                                                               int num_buckets, int owner_mod,
+                                                               const uint32_t* __restrict__ tile_dst,
+                                                               const PartColumn* __restrict__ cols, int ncols) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
+  uint64_t* xbuf = reinterpret_cast<uint64_t*>(smem);
+  uint16_t* pos_bin = reinterpret_cast<uint16_t*>(smem + (size_t)kFusedTile * 8);
+  uint16_t* cnt = pos_bin + kFusedTile;
+  uint32_t* bin_start = reinterpret_cast<uint32_t*>(cnt + (size_t)kFWarps * nb + ((kFWarps * nb) & 1));
+  uint32_t* dst_base = bin_start + nb;
+  uint32_t* warp_sums = dst_base + nb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1;
+  for (int i = threadIdx.x; i < kFWarps * nb; i += kFThreads) cnt[i] = 0;
+  for (int b = threadIdx.x; b < nb; b += kFThreads) dst_base[b] = tile_dst[(size_t)blockIdx.x * nb + b];
+  __syncthreads();
+  const int64_t tile_base = (int64_t)blockIdx.x * kFusedTile;
+  const int64_t wbase = tile_base + (int64_t)warp * kFWarpRows;
+  const uint32_t tile_count = (uint32_t)min((int64_t)kFusedTile, nrows - tile_base);
+  uint16_t bin[kFItems], pos[kFItems];
+  bool act[kFItems];
+#pragma unroll
+  for (int j = 0; j < kFItems; j++) {
+    const int64_t row = wbase + j * 32 + lane;
+    act[j] = row < nrows;
+    bin[j] = 0;
+    if (act[j]) {
+      int32_t b = row_bucket(keys, nkeys, row, num_buckets);
+      if (owner_mod > 0) b %= owner_mod;
+      bin[j] = (uint16_t)b;
+    }
+  }
+  // stable rank inside the warp's 512 consecutive rows
+  uint16_t* wcnt = cnt + (size_t)warp * nb;
+#pragma unroll
+  for (int j = 0; j < kFItems; j++) {
+    const unsigned amask = __ballot_sync(0xffffffffu, act[j]);
+    if (act[j]) {
+      const unsigned peers = __match_any_sync(amask, (unsigned)bin[j]);
+      const int leader = __ffs(peers) - 1;
+      uint32_t pre = 0;
+      if (lane == leader) {
+        pre = wcnt[bin[j]];
+        wcnt[bin[j]] = (uint16_t)(pre + __popc(peers));
+      }
+      pre = __shfl_sync(peers, pre, leader);
+      pos[j] = (uint16_t)(pre + __popc(peers & lt));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // per bin: exclusive prefix over warps (in place), tile total, then exclusive scan over bins
+  uint32_t carry = 0;
+  for (int b0 = 0; b0 < nb; b0 += kFThreads) {
+    const int b = b0 + threadIdx.x;
+    uint32_t total = 0;
+    if (b < nb) {
+#pragma unroll
+      for (int w = 0; w < kFWarps; w++) {
+        const uint16_t c = cnt[(size_t)w * nb + b];
+        cnt[(size_t)w * nb + b] = (uint16_t)total;
+        total += c;
+      }
+    }
+    uint32_t chunk_total = 0;
+    const uint32_t ex = block_exclusive_scan(total, warp_sums, &chunk_total);
+    if (b < nb) bin_start[b] = carry + ex;
+    carry += chunk_total;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kFItems; j++) {
+    if (act[j]) {
+      pos[j] = (uint16_t)(bin_start[bin[j]] + cnt[(size_t)warp * nb + bin[j]] + pos[j]);
+      pos_bin[pos[j]] = bin[j];
+    }
+  }
+  // ---- move every column through the exchange buffer -----------------------------------------------------------
+  for (int c = 0; c < ncols; c++) {
+    const PartColumn pc = cols[c];
+    __syncthreads();  // previous column's readers are done with xbuf (and pos_bin is complete)
+    if (pc.width == 8) {
+      const uint64_t* in = (const uint64_t*)pc.in;
+#pragma unroll
+      for (int j = 0; j < kFItems; j++)
+        if (act[j]) xbuf[pos[j]] = in[wbase + j * 32 + lane];
+    } else if (pc.width == 4) {
+      const uint32_t* in = (const uint32_t*)pc.in;
+      uint32_t* xb = reinterpret_cast<uint32_t*>(xbuf);
+#pragma unroll
+      for (int j = 0; j < kFItems; j++)
+        if (act[j]) xb[pos[j]] = in[wbase + j * 32 + lane];
+    } else {
+      const uint8_t* in = (const uint8_t*)pc.in;
+      uint8_t* xb = reinterpret_cast<uint8_t*>(xbuf);
+#pragma unroll
+      for (int j = 0; j < kFItems; j++)
+        if (act[j]) xb[pos[j]] = in[wbase + j * 32 + lane];
+    }
+    __syncthreads();
+    if (pc.width == 8) {
+      uint64_t* out = (uint64_t*)pc.out;
+      for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
+        const uint32_t b = pos_bin[i];
+        out[dst_base[b] + (i - bin_start[b])] = xbuf[i];
+      }
+    } else if (pc.width == 4) {
+      uint32_t* out = (uint32_t*)pc.out;
+      const uint32_t* xb = reinterpret_cast<const uint32_t*>(xbuf);
+      for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
+        const uint32_t b = pos_bin[i];
+        out[dst_base[b] + (i - bin_start[b])] = xb[i];
+      }
+    } else {
+      uint8_t* out = (uint8_t*)pc.out;
+      const uint8_t* xb = reinterpret_cast<const uint8_t*>(xbuf);
+      for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
+        const uint32_t b = pos_bin[i];
+        out[dst_base[b] + (i - bin_start[b])] = xb[i];
+      }
+    }
+  }
+}
+
+size_t fused_smem_bytes(int nb) {
+  size_t cnt_entries = (size_t)kFWarps * nb;
+  cnt_entries += cnt_entries & 1;
+  return (size_t)kFusedTile * 8 + (size_t)kFusedTile * 2 + cnt_entries * 2 + (size_t)nb * 4 * 2 + 40 * 4;
+}
+
+}  // namespace
+
+bool fused_partition_supported(int nbins) { return nbins <= kFusedMaxBins; }
+
+void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
+                      uint32_t* tile_hist, unsigned long long* global_hist) {
+  KernelScope _ks(ctx, "k_tile_hist");
+  if (nrows == 0) return;
+  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
+  const int64_t ntiles = ceil_div(nrows, kFusedTile);
+  k_tile_hist<<<(unsigned)ntiles, kFThreads, (size_t)nb * 4, ctx->stream>>>(d_keys, nkeys, nrows, num_buckets, owner_mod,
+                                                                            tile_hist, global_hist);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
+                           const uint32_t* tile_dst, const PartColumn* d_cols, int ncols) {
+  KernelScope _ks(ctx, "k_partition_rows");
+  if (nrows == 0) return;
+  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
+  const int64_t ntiles = ceil_div(nrows, kFusedTile);
+  static bool attr = false;
+  if (!attr) {
+    HS_CUDA(cudaFuncSetAttribute(k_partition_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fused_smem_bytes(kFusedMaxBins)));
+    attr = true;
+  }
+  k_partition_rows<<<(unsigned)ntiles, kFThreads, fused_smem_bytes(nb), ctx->stream>>>(d_keys, nkeys, nrows, num_buckets,
+                                                                                        owner_mod, tile_dst, d_cols, ncols);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace hs

@@ -79,6 +79,22 @@ void launch_partition_dest(hs_ctx* ctx, const uint16_t* bucket, int64_t nrows, i
                            const uint32_t* tile_offsets, uint32_t* dest);
 // out[dest[i]] = in[i]
 void launch_scatter_column(hs_ctx* ctx, const void* in, void* out, const uint32_t* dest, int64_t nrows, int width);
+// ---- fused partition (hash + stable rank + shared-memory exchange of every column in one kernel) ------------------
+constexpr int kFusedTile = 8192;     // rows per tile (512 threads x 16)
+constexpr int kFusedMaxBins = 1024;  // above this the per-warp counters no longer fit next to the exchange buffer
+struct PartColumn {
+  const void* in;
+  void* out;
+  int32_t width;  // 8, 4 or 1 (validity bytes travel as width-1 columns)
+  int32_t pad;
+};
+bool fused_partition_supported(int nbins);
+// tile histograms M[tile][bin] for kFusedTile-row tiles (+ global histogram); bin = bucket, or bucket % owner_mod
+void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
+                      uint32_t* tile_hist, unsigned long long* global_hist);
+// tile_dst = launch_tile_offsets(tile_hist); moves all columns into bin-major order, stable
+void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
+                           const uint32_t* tile_dst, const PartColumn* d_cols, int ncols);
 // out[i] = sort_encode(in[src ? src[i] : i])  (+ global OR / AND reduction into or_and[0], or_and[1])
 void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* src, int64_t nrows, uint64_t* out,
                         unsigned long long* or_and);
@@ -99,6 +115,7 @@ struct SortPlan {
   Buf<uint32_t> seg_tile_begin; // device, nseg+1: first tile of each segment
   Buf<uint64_t> seg_start;      // device, nseg+1: global start of each segment
   Buf<uint32_t> tile_hist;      // device, ntiles x 256
+  Buf<uint32_t> tile_dst;       // device, ntiles x 256: destination of every (tile, digit) for the current pass
   std::vector<uint32_t> h_seg_tile_begin;  // host mirror of seg_tile_begin
 };
 // seg_offsets: host array of nseg+1 global offsets

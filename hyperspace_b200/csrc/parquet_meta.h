@@ -255,6 +255,56 @@ inline void write_all_valid_def_levels(std::vector<uint8_t>& out, int64_t n) {
   out.insert(out.end(), tmp, tmp + len);
 }
 
+// Definition levels for `n` non-null values as several RLE runs of ones.  Splitting the single run (n ones) into extra
+// runs is a legal RLE/bit-packed hybrid encoding; each extra run of 1 value costs 2 bytes and each extra run of 64
+// values costs 3 bytes, which lets the writer choose the block length so that the values that follow start 8-byte
+// aligned in the file image (the GPU then writes page bodies with full-width aligned stores).
+inline void write_def_levels_runs(std::vector<uint8_t>& out, int64_t n, int small_runs, int medium_runs) {
+  std::vector<uint8_t> body;
+  auto run = [&](uint64_t count) {
+    uint64_t h = count << 1;
+    while (h >= 0x80) {
+      body.push_back((uint8_t)(h | 0x80));
+      h >>= 7;
+    }
+    body.push_back((uint8_t)h);
+    body.push_back(1);
+  };
+  run((uint64_t)(n - small_runs - 64 * (int64_t)medium_runs));
+  for (int i = 0; i < small_runs; i++) run(1);
+  for (int i = 0; i < medium_runs; i++) run(64);
+  uint32_t l32 = (uint32_t)body.size();
+  const uint8_t* lp = (const uint8_t*)&l32;
+  out.insert(out.end(), lp, lp + 4);
+  out.insert(out.end(), body.begin(), body.end());
+}
+
+// Appends [page header][definition levels] for a PLAIN v1 data page of `n` non-null W-byte values that starts at file
+// offset `page_offset`, choosing the run split so that the values start 8-byte aligned when n allows it.
+inline void write_plain_page_prefix(std::vector<uint8_t>& out, uint64_t page_offset, int64_t n, int W) {
+  for (int extra = 0; extra <= 24; extra++) {  // extra bytes over the single-run encoding
+    for (int medium = 0; 3 * medium <= extra; medium++) {
+      const int rest = extra - 3 * medium;
+      if (rest % 2) continue;
+      const int small = rest / 2;
+      if (n - small - 64 * (int64_t)medium < 1) continue;
+      std::vector<uint8_t> defs, hdr;
+      write_def_levels_runs(defs, n, small, medium);
+      write_data_page_header(hdr, (int32_t)(defs.size() + (size_t)n * W), (int32_t)n, ENC_PLAIN);
+      if ((page_offset + hdr.size() + defs.size()) % 8 == 0) {
+        out.insert(out.end(), hdr.begin(), hdr.end());
+        out.insert(out.end(), defs.begin(), defs.end());
+        return;
+      }
+    }
+  }
+  // tiny page: no aligned split exists; the GPU falls back to its unaligned store path
+  std::vector<uint8_t> defs;
+  write_all_valid_def_levels(defs, n);
+  write_data_page_header(out, (int32_t)(defs.size() + (size_t)n * W), (int32_t)n, ENC_PLAIN);
+  out.insert(out.end(), defs.begin(), defs.end());
+}
+
 struct OutChunk {
   int32_t type;
   int64_t num_values;

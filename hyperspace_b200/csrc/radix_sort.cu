@@ -15,11 +15,12 @@ namespace hs {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;                  // 512 x 8 items: <= 64 registers -> 2 CTAs (32 warps) per SM
 constexpr int kWarps = kThreads / 32;
-constexpr int kItems = kSortTile / kThreads;   // 16
-constexpr int kWarpRows = kSortTile / kWarps;  // 512
+constexpr int kItems = kSortTile / kThreads;   // 8
+constexpr int kWarpRows = kSortTile / kWarps;  // 256 consecutive pairs per warp
 constexpr int kChunkTiles = 128;
+constexpr int kHistThreads = 256;
 
 struct SortChunk {
   uint32_t seg;
@@ -36,7 +37,7 @@ struct DigitTable {
 };
 
 template <typename Digit>
-__global__ void __launch_bounds__(kThreads) k_sort_hist(const SortTile* __restrict__ tiles,
+__global__ void __launch_bounds__(kHistThreads) k_sort_hist(const SortTile* __restrict__ tiles,
                                                          const uint64_t* __restrict__ keys,
                                                          const uint32_t* __restrict__ vals, Digit digit,
                                                          uint32_t* __restrict__ tile_hist) {
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_hist(const SortTile* __restri
   s_hist[threadIdx.x] = 0;
   __syncthreads();
   const SortTile t = tiles[blockIdx.x];
-  for (uint32_t i = threadIdx.x; i < t.count; i += kThreads) {
+  for (uint32_t i = threadIdx.x; i < t.count; i += kHistThreads) {
     const uint64_t pos = t.start + i;
     atomicAdd(&s_hist[digit(keys[pos], vals[pos])], 1u);
   }
@@ -79,15 +80,29 @@ __global__ void __launch_bounds__(256) k_seg_scan(const uint32_t* __restrict__ s
   for (uint32_t c = c0; c < c1; c++) chunk_sums[(size_t)c * 256 + threadIdx.x] += dbase;
 }
 
-// C: per chunk, turn tile histograms into destinations
-__global__ void __launch_bounds__(256) k_seg_apply(const SortChunk* __restrict__ chunks,
-                                                    uint32_t* __restrict__ tile_hist,
-                                                    const uint32_t* __restrict__ chunk_sums) {
+// C: per chunk, turn tile histograms into destinations.  1024 threads = 4 groups x 256 digits; each group owns a
+// quarter of the chunk's tiles.  Input and output are distinct arrays so the loads can be issued ahead of the stores.
+__global__ void __launch_bounds__(1024) k_seg_apply(const SortChunk* __restrict__ chunks,
+                                                     const uint32_t* __restrict__ tile_hist,
+                                                     uint32_t* __restrict__ tile_dst,
+                                                     const uint32_t* __restrict__ chunk_sums) {
+  __shared__ uint32_t s_group[4][256];
   const SortChunk c = chunks[blockIdx.x];
-  uint32_t run = chunk_sums[(size_t)blockIdx.x * 256 + threadIdx.x];
-  for (uint32_t t = c.tile_begin; t < c.tile_end; t++) {
-    const uint32_t v = tile_hist[(size_t)t * 256 + threadIdx.x];
-    tile_hist[(size_t)t * 256 + threadIdx.x] = run;
+  const uint32_t d = threadIdx.x & 255, g = threadIdx.x >> 8;
+  const uint32_t n = c.tile_end - c.tile_begin;
+  const uint32_t per = (n + 3) / 4;
+  const uint32_t t0 = c.tile_begin + min(g * per, n), t1 = c.tile_begin + min((g + 1) * per, n);
+  uint32_t s = 0;
+#pragma unroll 8
+  for (uint32_t t = t0; t < t1; t++) s += tile_hist[(size_t)t * 256 + d];
+  s_group[g][d] = s;
+  __syncthreads();
+  uint32_t run = chunk_sums[(size_t)blockIdx.x * 256 + d];
+  for (uint32_t gg = 0; gg < g; gg++) run += s_group[gg][d];
+#pragma unroll 8
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t v = tile_hist[(size_t)t * 256 + d];
+    tile_dst[(size_t)t * 256 + d] = run;
     run += v;
   }
 }
@@ -113,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const SortTile* __res
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1;
   for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&sm.cnt[0][0])[i] = 0;
-  sm.dst_base[threadIdx.x] = tile_dst[(size_t)blockIdx.x * 256 + threadIdx.x];
+  if (threadIdx.x < 256) sm.dst_base[threadIdx.x] = tile_dst[(size_t)blockIdx.x * 256 + threadIdx.x];
   __syncthreads();
   const SortTile t = tiles[blockIdx.x];
   uint64_t k[kItems];
@@ -133,24 +148,29 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const SortTile* __res
       bin[j] = (uint16_t)digit(k[j], v[j]);
     }
   }
-  // stable rank of every item among the warp's earlier items with the same digit
+  // stable rank of every item among the warp's earlier items with the same digit: the lowest peer lane does the
+  // read-modify-write of the warp-private counter and broadcasts the old value (no intra-iteration hazard)
   uint16_t* cnt = sm.cnt[warp];
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
     const unsigned amask = __ballot_sync(0xffffffffu, act[j]);
     if (act[j]) {
       const unsigned peers = __match_any_sync(amask, (unsigned)bin[j]);
-      const uint16_t pre = cnt[bin[j]];
+      const int leader = __ffs(peers) - 1;
+      uint32_t pre = 0;
+      if (lane == leader) {
+        pre = cnt[bin[j]];
+        cnt[bin[j]] = (uint16_t)(pre + __popc(peers));
+      }
+      pre = __shfl_sync(peers, pre, leader);
       rank[j] = (uint16_t)(pre + __popc(peers & lt));
-      __syncwarp(amask);
-      if ((peers & lt) == 0) cnt[bin[j]] = (uint16_t)(pre + __popc(peers));
     }
-    __syncwarp();
+    __syncwarp();  // order this iteration's counter store before the next iteration's loads
   }
   __syncthreads();
   // per digit: exclusive prefix over warps (in place) and the tile total
-  uint32_t total;
-  {
+  uint32_t total = 0;
+  if (threadIdx.x < 256) {
     uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; w++) {
@@ -161,7 +181,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const SortTile* __res
     total = run;
   }
   const uint32_t start = block_exclusive_scan(total, sm.warp_sums, nullptr);
-  sm.bin_start[threadIdx.x] = start;
+  if (threadIdx.x < 256) sm.bin_start[threadIdx.x] = start;
   __syncthreads();
   // exchange: digit-sorted order inside the tile
 #pragma unroll
@@ -189,7 +209,7 @@ void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchu
               Digit digit) {
   {
     KernelScope _ks(ctx, "k_sort_hist");
-    k_sort_hist<Digit><<<(unsigned)plan->ntiles, kThreads, 0, ctx->stream>>>(plan->tiles.get(), keys, vals, digit,
+    k_sort_hist<Digit><<<(unsigned)plan->ntiles, kHistThreads, 0, ctx->stream>>>(plan->tiles.get(), keys, vals, digit,
                                                                             plan->tile_hist.get());
     HS_LAUNCH_CHECK(ctx);
   }
@@ -198,7 +218,7 @@ void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchu
   HS_LAUNCH_CHECK(ctx);
   k_seg_scan<<<(unsigned)plan->nseg, 256, 0, ctx->stream>>>(seg_chunk_begin, plan->seg_start.get(), chunk_sums);
   HS_LAUNCH_CHECK(ctx);
-  k_seg_apply<<<(unsigned)nchunks, 256, 0, ctx->stream>>>(chunks, plan->tile_hist.get(), chunk_sums);
+  k_seg_apply<<<(unsigned)nchunks, 1024, 0, ctx->stream>>>(chunks, plan->tile_hist.get(), plan->tile_dst.get(), chunk_sums);
   HS_LAUNCH_CHECK(ctx);
   delete _scan;
   static bool attr_shift = false, attr_table = false;
@@ -210,7 +230,7 @@ void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchu
   }
   KernelScope _ks(ctx, "k_sort_scatter");
   k_sort_scatter<Digit><<<(unsigned)plan->ntiles, kThreads, sizeof(ScatterShared), ctx->stream>>>(
-      plan->tiles.get(), keys, vals, digit, plan->tile_hist.get(), out_keys, out_vals);
+      plan->tiles.get(), keys, vals, digit, plan->tile_dst.get(), out_keys, out_vals);
   HS_LAUNCH_CHECK(ctx);
 }
 
@@ -268,6 +288,7 @@ void build_sort_plan(hs_ctx* ctx, const uint64_t* seg_offsets, int nseg, SortPla
   plan->seg_tile_begin.alloc(ctx, stb.size());
   plan->seg_start.alloc(ctx, sstart.size());
   plan->tile_hist.alloc(ctx, std::max<size_t>(1, tiles.size()) * 256);
+  plan->tile_dst.alloc(ctx, std::max<size_t>(1, tiles.size()) * 256);
   if (!tiles.empty())
     HS_CUDA(cudaMemcpyAsync(plan->tiles.get(), tiles.data(), tiles.size() * sizeof(SortTile), cudaMemcpyHostToDevice,
                             ctx->stream));
