@@ -176,6 +176,31 @@ __device__ __forceinline__ void warp_store_unaligned(uint8_t* dst, uint64_t v, b
   }
 }
 
+// ---- warp multi-split -------------------------------------------------------------------------------------------
+// Mask of the lanes in `amask` whose `v` equals this lane's, from NBITS ballots.  __match_any_sync does the same in one
+// instruction, but MATCH runs on the ADU pipe at roughly one lane per cycle: ncu showed the radix scatter kernel
+// ADU-bound at 73 % with it (profiles/r01_ncu_notes.md), while VOTE + LOP3 issue at full rate.
+__device__ __forceinline__ unsigned match_any_bits(unsigned amask, unsigned v, int nbits) {
+  unsigned peers = amask;
+  for (int b = 0; b < nbits; b++) {
+    const bool bit = (v >> b) & 1u;
+    const unsigned m = __ballot_sync(amask, bit);
+    peers &= bit ? m : ~m;
+  }
+  return peers;
+}
+template <int NBITS>
+__device__ __forceinline__ unsigned match_any_bits(unsigned amask, unsigned v) {
+  unsigned peers = amask;
+#pragma unroll
+  for (int b = 0; b < NBITS; b++) {
+    const bool bit = (v >> b) & 1u;
+    const unsigned m = __ballot_sync(amask, bit);
+    peers &= bit ? m : ~m;
+  }
+  return peers;
+}
+
 // ---- block-level exclusive scan of one uint32 per thread (blockDim.x <= 1024, multiple of 32) ------------------------
 // Returns the exclusive prefix; *total receives the block sum.  `warp_sums` is >= 32 words of shared memory.
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* warp_sums, uint32_t* total) {

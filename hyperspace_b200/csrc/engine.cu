@@ -10,6 +10,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <array>
 #include <random>
 
 #include "device_utils.cuh"
@@ -128,24 +129,37 @@ void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const s
   t_h2d.start();
   std::vector<Buf<uint8_t>> staging;  // pinned buffers for path-based files; kept until the copies have completed
   std::vector<std::vector<uint8_t>> dev_footers(n_files);
+  // device-resident images: fetch all 8-byte tails with one sync, then all footers with one more
+  std::vector<std::array<uint8_t, 8>> tails(n_files);
+  bool any_dev = false;
   for (int f = 0; f < n_files; f++) {
     const hs_source_file& sf = files[f];
-    const uint8_t* host = nullptr;
-    if (sf.data && sf.on_device) {
-      if (((uintptr_t)sf.data & 15) != 0) fail(HS_EINVAL, "%s: device images must be 16-byte aligned", imgs[f].what.c_str());
-      imgs[f].dev = (const uint8_t*)sf.data;
-      uint8_t tail[8];
-      HS_CUDA(cudaMemcpyAsync(tail, imgs[f].dev + sizes[f] - 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!(sf.data && sf.on_device)) continue;
+    if (((uintptr_t)sf.data & 15) != 0) fail(HS_EINVAL, "%s: device images must be 16-byte aligned", imgs[f].what.c_str());
+    imgs[f].dev = (const uint8_t*)sf.data;
+    HS_CUDA(cudaMemcpyAsync(tails[f].data(), imgs[f].dev + sizes[f] - 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    any_dev = true;
+  }
+  if (any_dev) {
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < n_files; f++) {
+      const hs_source_file& sf = files[f];
+      if (!(sf.data && sf.on_device)) continue;
       uint32_t flen;
-      memcpy(&flen, tail, 4);
-      if (memcmp(tail + 4, "PAR1", 4) != 0 || (uint64_t)flen + 12 > sizes[f])
+      memcpy(&flen, tails[f].data(), 4);
+      if (memcmp(tails[f].data() + 4, "PAR1", 4) != 0 || (uint64_t)flen + 12 > sizes[f])
         fail(HS_EFORMAT, "%s: not a Parquet file", imgs[f].what.c_str());
       dev_footers[f].resize(flen);
       HS_CUDA(cudaMemcpyAsync(dev_footers[f].data(), imgs[f].dev + sizes[f] - 8 - flen, flen, cudaMemcpyDeviceToHost,
                               ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
-      imgs[f].meta = pq::parse_footer_bytes(dev_footers[f].data(), flen, imgs[f].what.c_str());
+    }
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  for (int f = 0; f < n_files; f++) {
+    const hs_source_file& sf = files[f];
+    const uint8_t* host = nullptr;
+    if (sf.data && sf.on_device) {
+      imgs[f].meta = pq::parse_footer_bytes(dev_footers[f].data(), (uint32_t)dev_footers[f].size(), imgs[f].what.c_str());
     } else {
       if (sf.data) host = (const uint8_t*)sf.data;
       else {

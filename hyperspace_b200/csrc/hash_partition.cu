@@ -378,6 +378,8 @@ __global__ void __launch_bounds__(kFThreads) k_partition_rows(const KeyColumn* _
   for (int i = threadIdx.x; i < kFWarps * nb; i += kFThreads) cnt[i] = 0;
   for (int b = threadIdx.x; b < nb; b += kFThreads) dst_base[b] = tile_dst[(size_t)blockIdx.x * nb + b];
   __syncthreads();
+  int bin_bits = 1;
+  while ((1 << bin_bits) < nb) bin_bits++;
   const int64_t tile_base = (int64_t)blockIdx.x * kFusedTile;
   const int64_t wbase = tile_base + (int64_t)warp * kFWarpRows;
   const uint32_t tile_count = (uint32_t)min((int64_t)kFusedTile, nrows - tile_base);
@@ -400,14 +402,14 @@ __global__ void __launch_bounds__(kFThreads) k_partition_rows(const KeyColumn* _
   for (int j = 0; j < kFItems; j++) {
     const unsigned amask = __ballot_sync(0xffffffffu, act[j]);
     if (act[j]) {
-      const unsigned peers = __match_any_sync(amask, (unsigned)bin[j]);
+      const unsigned peers = match_any_bits(amask, (unsigned)bin[j], bin_bits);
       const int leader = __ffs(peers) - 1;
       uint32_t pre = 0;
       if (lane == leader) {
         pre = wcnt[bin[j]];
         wcnt[bin[j]] = (uint16_t)(pre + __popc(peers));
       }
-      pre = __shfl_sync(peers, pre, leader);
+      pre = __shfl_sync(amask, pre, leader);  // uniform mask: one shuffle for the whole warp
       pos[j] = (uint16_t)(pre + __popc(peers & lt));
     }
     __syncwarp();

@@ -308,17 +308,28 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
   bool has_def = def_p != nullptr;
   if (has_def) {
     if (threadIdx.x == 0) {
-      uint32_t h = 0;
-      int shift = 0;
+      // all-valid when the block is nothing but RLE runs of the value 1 that cover the page (writers emit one such run;
+      // this engine's own encoder emits a few, see write_plain_page_prefix)
       const uint8_t* q = def_p;
-      while (q < def_end) {
-        uint8_t b = *q++;
-        h |= (uint32_t)(b & 0x7f) << shift;
-        if (!(b & 0x80)) break;
-        shift += 7;
-        if (shift > 28) break;
+      uint32_t covered = 0;
+      bool all_ones = true;
+      for (int r = 0; r < 64 && covered < (uint32_t)n && all_ones; r++) {
+        uint32_t h = 0;
+        int shift = 0;
+        while (q < def_end) {
+          uint8_t b = *q++;
+          h |= (uint32_t)(b & 0x7f) << shift;
+          if (!(b & 0x80)) break;
+          shift += 7;
+          if (shift > 28) break;
+        }
+        if ((h & 1) || q >= def_end || !(*q & 1) || (h >> 1) == 0) all_ones = false;
+        else {
+          covered += h >> 1;
+          q++;
+        }
       }
-      sm.flag = (!(h & 1) && (h >> 1) >= (uint32_t)n && q < def_end && (*q & 1)) ? 1u : 0u;
+      sm.flag = (all_ones && covered >= (uint32_t)n) ? 1u : 0u;
     }
     __syncthreads();
     if (sm.flag) has_def = false;
@@ -348,10 +359,7 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
     }
     if (threadIdx.x == 0) hybrid_init(sm.idx.st, p, pend, idx_bw);
   }
-  if (has_def && threadIdx.x == 0) {
-    hybrid_init(sm.def.st, def_p, def_end, 1);
-    atomicOr(col_has_nulls, 1u);
-  }
+  if (has_def && threadIdx.x == 0) hybrid_init(sm.def.st, def_p, def_end, 1);
   __syncthreads();
   const int64_t row0 = pg.first_row;
   const uint32_t dict_count = (uint32_t)pg.dict_count;
@@ -411,6 +419,7 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
     for (int k = 0; k < kPer; k++) local += (t0 + k < cnt) ? sm.tile_valid[t0 + k] : 0;
     uint32_t total = 0;
     uint32_t pre = block_exclusive_scan(local, sm.warp_sums, &total);
+    if (threadIdx.x == 0 && total < cnt) atomicOr(col_has_nulls, 1u);  // an actual null, not just a level stream
 #pragma unroll
     for (int k = 0; k < kPer; k++) {
       if (t0 + k < cnt) {

@@ -4,6 +4,7 @@
 // covering/CoveringIndexTrait.scala:82-84 and CoveringIndexRuleUtils.scala:113-123 on the read side).
 #pragma once
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -282,25 +283,37 @@ inline void write_def_levels_runs(std::vector<uint8_t>& out, int64_t n, int smal
 // Appends [page header][definition levels] for a PLAIN v1 data page of `n` non-null W-byte values that starts at file
 // offset `page_offset`, choosing the run split so that the values start 8-byte aligned when n allows it.
 inline void write_plain_page_prefix(std::vector<uint8_t>& out, uint64_t page_offset, int64_t n, int W) {
-  for (int extra = 0; extra <= 24; extra++) {  // extra bytes over the single-run encoding
-    for (int medium = 0; 3 * medium <= extra; medium++) {
-      const int rest = extra - 3 * medium;
-      if (rest % 2) continue;
-      const int small = rest / 2;
-      if (n - small - 64 * (int64_t)medium < 1) continue;
-      std::vector<uint8_t> defs, hdr;
-      write_def_levels_runs(defs, n, small, medium);
-      write_data_page_header(hdr, (int32_t)(defs.size() + (size_t)n * W), (int32_t)n, ENC_PLAIN);
-      if ((page_offset + hdr.size() + defs.size()) % 8 == 0) {
-        out.insert(out.end(), hdr.begin(), hdr.end());
-        out.insert(out.end(), defs.begin(), defs.end());
-        return;
+  // the winning split depends only on (n, W, page_offset mod 8): memoised, since an index has ~40 k pages of a few shapes
+  struct Key {
+    int64_t n;
+    int w, mod;
+    bool operator<(const Key& o) const { return n != o.n ? n < o.n : (w != o.w ? w < o.w : mod < o.mod); }
+  };
+  static thread_local std::map<Key, std::pair<int, int>> memo;  // -> (small, medium), (-1,-1) = no aligned split
+  const Key key{n, W, (int)(page_offset % 8)};
+  auto it = memo.find(key);
+  if (it == memo.end()) {
+    std::pair<int, int> best{-1, -1};
+    for (int extra = 0; extra <= 24 && best.first < 0; extra++) {  // extra bytes over the single-run encoding
+      for (int medium = 0; 3 * medium <= extra; medium++) {
+        const int rest = extra - 3 * medium;
+        if (rest % 2) continue;
+        const int small = rest / 2;
+        if (n - small - 64 * (int64_t)medium < 1) continue;
+        std::vector<uint8_t> defs, hdr;
+        write_def_levels_runs(defs, n, small, medium);
+        write_data_page_header(hdr, (int32_t)(defs.size() + (size_t)n * W), (int32_t)n, ENC_PLAIN);
+        if ((page_offset + hdr.size() + defs.size()) % 8 == 0) {
+          best = {small, medium};
+          break;
+        }
       }
     }
+    it = memo.emplace(key, best).first;
   }
-  // tiny page: no aligned split exists; the GPU falls back to its unaligned store path
   std::vector<uint8_t> defs;
-  write_all_valid_def_levels(defs, n);
+  if (it->second.first >= 0) write_def_levels_runs(defs, n, it->second.first, it->second.second);
+  else write_all_valid_def_levels(defs, n);  // tiny page: the GPU falls back to its unaligned store path
   write_data_page_header(out, (int32_t)(defs.size() + (size_t)n * W), (int32_t)n, ENC_PLAIN);
   out.insert(out.end(), defs.begin(), defs.end());
 }

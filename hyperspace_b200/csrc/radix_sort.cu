@@ -155,14 +155,14 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const SortTile* __res
   for (int j = 0; j < kItems; j++) {
     const unsigned amask = __ballot_sync(0xffffffffu, act[j]);
     if (act[j]) {
-      const unsigned peers = __match_any_sync(amask, (unsigned)bin[j]);
+      const unsigned peers = match_any_bits<8>(amask, (unsigned)bin[j]);
       const int leader = __ffs(peers) - 1;
       uint32_t pre = 0;
       if (lane == leader) {
         pre = cnt[bin[j]];
         cnt[bin[j]] = (uint16_t)(pre + __popc(peers));
       }
-      pre = __shfl_sync(peers, pre, leader);
+      pre = __shfl_sync(amask, pre, leader);  // uniform mask: one shuffle for the whole warp
       rank[j] = (uint16_t)(pre + __popc(peers & lt));
     }
     __syncwarp();  // order this iteration's counter store before the next iteration's loads
