@@ -425,8 +425,6 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     const DevColumn& dc = table.cols[c];
     if (dc.width != 4 && dc.width != 8)
       fail(HS_EUNSUPPORTED, "column '%s': %d-byte values cannot be written by the GPU encoder yet", dc.name.c_str(), dc.width);
-    if (dc.has_nulls)
-      fail(HS_EUNSUPPORTED, "column '%s' contains nulls; the GPU encoder writes non-null columns only for now", dc.name.c_str());
   }
   std::vector<pq::SchemaColumn> schema(ncols);
   for (int c = 0; c < ncols; c++) {
@@ -441,6 +439,29 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     }
   }
   const std::string schema_json = pq::spark_schema_json(schema);
+
+  // nullable columns: per-tile non-null counts (tiles are kSortTile-aligned inside a segment and P is a multiple of
+  // kSortTile, so a tile never straddles a page)
+  const int64_t ntiles = req.plan->ntiles;
+  std::vector<std::vector<uint32_t>> tile_valid(ncols);
+  std::vector<std::vector<uint64_t>> tile_val_off(ncols), tile_def_off(ncols);
+  {
+    std::vector<Buf<uint32_t>> d_counts(ncols);
+    bool any = false;
+    for (int c = 0; c < ncols; c++) {
+      if (!table.cols[c].has_nulls) continue;
+      any = true;
+      d_counts[c].alloc(ctx, std::max<int64_t>(1, ntiles));
+      launch_tile_valid_counts(ctx, req.plan->tiles.get(), ntiles, req.d_perm, table.cols[c].valid.get(), d_counts[c].get());
+      tile_valid[c].resize(ntiles);
+      tile_val_off[c].assign(ntiles, 0);
+      tile_def_off[c].assign(ntiles, 0);
+      if (ntiles)
+        HS_CUDA(cudaMemcpyAsync(tile_valid[c].data(), d_counts[c].get(), sizeof(uint32_t) * ntiles, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (any) HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  const std::vector<uint32_t>& seg_tile_begin = req.plan->h_seg_tile_begin;
 
   std::vector<uint8_t> skeleton;
   std::vector<ByteCopy> copies;
@@ -488,11 +509,32 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         for (int64_t p0 = r0; p0 < r1; p0 += P) {
           const int64_t np = std::min(P, r1 - p0);
           const size_t b = skeleton.size();
-          pq::write_plain_page_prefix(skeleton, cursor, np, W);  // file images start 64-byte aligned in the arena
-          emit(cursor, b);
-          cursor += skeleton.size() - b;
-          page_value_offset[c][page_counter + (p0 / P)] = cursor;
-          cursor += (uint64_t)np * W;
+          if (!table.cols[c].has_nulls) {
+            pq::write_plain_page_prefix(skeleton, cursor, np, W);  // file images start 64-byte aligned in the arena
+            emit(cursor, b);
+            cursor += skeleton.size() - b;
+            page_value_offset[c][page_counter + (p0 / P)] = cursor;
+            cursor += (uint64_t)np * W;
+          } else {
+            // tiles of this page: [t0, t1) in the segment's tile list
+            const int64_t t0 = seg_tile_begin[s] + p0 / kSortTile, t1 = seg_tile_begin[s] + ceil_div(p0 + np, (int64_t)kSortTile);
+            int64_t non_null = 0;
+            for (int64_t t = t0; t < t1; t++) non_null += tile_valid[c][t];
+            pq::write_nullable_page_prefix(skeleton, np, non_null, W);
+            emit(cursor, b);
+            cursor += skeleton.size() - b;
+            const uint64_t def_bits = cursor;
+            cursor += (uint64_t)((np + 7) / 8);
+            page_value_offset[c][page_counter + (p0 / P)] = cursor;
+            uint64_t voff = cursor;
+            for (int64_t t = t0; t < t1; t++) {
+              tile_def_off[c][t] = def_bits + (uint64_t)(t - t0) * (kSortTile / 8);
+              tile_val_off[c][t] = voff;
+              voff += (uint64_t)tile_valid[c][t] * W;
+            }
+            cursor += (uint64_t)non_null * W;
+            ch.null_count += np - non_null;
+          }
         }
         ch.total_size = (int64_t)(cursor - chunk_begin);
         g.chunks.push_back(ch);
@@ -552,6 +594,16 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     gc.key_type = dc.type;
     gc.width = dc.width;
     gc.page_value_offset = d_pvo.get() + (size_t)c * page_counter;
+    if (dc.has_nulls) {
+      Buf<uint64_t> d_voff(ctx, std::max<int64_t>(1, ntiles)), d_doff(ctx, std::max<int64_t>(1, ntiles));
+      if (ntiles) {
+        HS_CUDA(cudaMemcpyAsync(d_voff.get(), tile_val_off[c].data(), 8 * ntiles, cudaMemcpyHostToDevice, ctx->stream));
+        HS_CUDA(cudaMemcpyAsync(d_doff.get(), tile_def_off[c].data(), 8 * ntiles, cudaMemcpyHostToDevice, ctx->stream));
+      }
+      launch_gather_encode_nullable(ctx, req.plan->tiles.get(), ntiles, req.d_perm, dc.data.get(), dc.valid.get(), dc.width,
+                                    d_voff.get(), d_doff.get(), out->arena.get());
+      continue;
+    }
     if (c == 0 && req.d_sorted_keys && (dc.type == HS_TYPE_INT32 || dc.type == HS_TYPE_INT64)) gc.sorted_keys = req.d_sorted_keys;
     launch_gather_encode(ctx, req.plan->tiles.get(), req.plan->ntiles, req.plan->seg_start.get(), req.d_perm, gc,
                          d_page_begin.get(), P, out->arena.get());

@@ -60,6 +60,74 @@ __global__ void __launch_bounds__(kThreads) k_gather_encode(const SortTile* __re
   }
 }
 
+// ---- nullable columns ---------------------------------------------------------------------------------------------
+// valid flags of the rows at the tile's sorted positions, counted (the host turns the per-tile counts into the page
+// layout: a page stores only its non-null values)
+__global__ void __launch_bounds__(kThreads) k_tile_valid_counts(const SortTile* __restrict__ tiles,
+                                                                 const uint32_t* __restrict__ perm,
+                                                                 const uint8_t* __restrict__ valid,
+                                                                 uint32_t* __restrict__ counts) {
+  __shared__ uint32_t s_total;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  const SortTile t = tiles[blockIdx.x];
+  uint32_t local = 0;
+  for (uint32_t i = threadIdx.x; i < t.count; i += kThreads) local += valid[perm[t.start + i]] ? 1u : 0u;
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_total, local);
+  __syncthreads();
+  if (threadIdx.x == 0) counts[blockIdx.x] = s_total;
+}
+
+// Per tile: definition levels as bits (one bit-packed hybrid run per page, written 32 levels per warp ballot) and the
+// non-null values compacted through shared memory into the page's dense value region.
+template <int W>
+__global__ void __launch_bounds__(kThreads) k_gather_encode_nullable(const SortTile* __restrict__ tiles,
+                                                                      const uint32_t* __restrict__ perm,
+                                                                      const void* __restrict__ src,
+                                                                      const uint8_t* __restrict__ valid,
+                                                                      const uint64_t* __restrict__ tile_value_offset,
+                                                                      const uint64_t* __restrict__ tile_def_offset,
+                                                                      uint8_t* __restrict__ arena) {
+  __shared__ uint64_t s_vals[kSortTile];
+  __shared__ uint32_t warp_sums[40];
+  const SortTile t = tiles[blockIdx.x];
+  uint8_t* const def_out = arena + tile_def_offset[blockIdx.x];
+  uint32_t base = 0;
+  const uint32_t iters = (t.count + kThreads - 1) / kThreads;
+  for (uint32_t it = 0; it < iters; it++) {
+    const uint32_t i = it * kThreads + threadIdx.x;
+    const bool active = i < t.count;
+    uint32_t flag = 0;
+    uint64_t v = 0;
+    if (active) {
+      const uint32_t row = perm[t.start + i];
+      flag = valid[row] ? 1u : 0u;
+      if (flag) v = W == 8 ? ((const uint64_t*)src)[row] : ((const uint32_t*)src)[row];
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, flag != 0);
+    if ((threadIdx.x & 31) == 0) {  // 32 levels = 4 bytes, LSB first; the last warp of a page may own fewer bytes
+      const uint32_t first = it * kThreads + (threadIdx.x & ~31u);
+      if (first < t.count) {
+        const uint32_t nbytes = min(4u, (t.count - first + 7) / 8);
+        for (uint32_t b = 0; b < nbytes; b++) def_out[first / 8 + b] = (uint8_t)(bits >> (8 * b));
+      }
+    }
+    uint32_t total = 0;
+    const uint32_t pos = block_exclusive_scan(flag, warp_sums, &total);
+    if (flag) s_vals[base + pos] = v;
+    base += total;
+  }
+  __syncthreads();
+  uint8_t* const val_out = arena + tile_value_offset[blockIdx.x];
+  const uint32_t viters = (base + kThreads - 1) / kThreads;
+  for (uint32_t it = 0; it < viters; it++) {
+    const uint32_t j = it * kThreads + threadIdx.x;
+    const bool active = j < base;
+    warp_store_unaligned<W>(val_out + (size_t)j * W, active ? s_vals[j] : 0, active);
+  }
+}
+
 // width-1 columns (BOOLEAN is bit-packed in PLAIN; handled by a byte-per-row staging column + k_pack_bits)
 template <typename T>
 __global__ void k_gather_plain(const T* __restrict__ src, const uint32_t* __restrict__ perm, int64_t n,
@@ -119,6 +187,30 @@ void launch_gather_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, co
                                                                         rows_per_page, arena);
   else
     fail(HS_EUNSUPPORTED, "gather_encode: column width %d", col.width);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_tile_valid_counts(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint32_t* perm,
+                              const uint8_t* valid, uint32_t* counts) {
+  KernelScope _ks(ctx, "k_tile_valid_counts");
+  if (ntiles == 0) return;
+  k_tile_valid_counts<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, perm, valid, counts);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_gather_encode_nullable(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint32_t* perm,
+                                   const void* src, const uint8_t* valid, int width, const uint64_t* tile_value_offset,
+                                   const uint64_t* tile_def_offset, uint8_t* arena) {
+  KernelScope _ks(ctx, "k_gather_encode_nullable");
+  if (ntiles == 0) return;
+  if (width == 8)
+    k_gather_encode_nullable<8><<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, perm, src, valid, tile_value_offset,
+                                                                                 tile_def_offset, arena);
+  else if (width == 4)
+    k_gather_encode_nullable<4><<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, perm, src, valid, tile_value_offset,
+                                                                                 tile_def_offset, arena);
+  else
+    fail(HS_EUNSUPPORTED, "gather_encode_nullable: column width %d", width);
   HS_LAUNCH_CHECK(ctx);
 }
 

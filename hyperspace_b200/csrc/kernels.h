@@ -141,6 +141,12 @@ struct GatherColumn {
 void launch_gather_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start,
                           const uint32_t* perm, const GatherColumn& col, const uint32_t* bucket_page_begin,
                           int64_t rows_per_page, uint8_t* arena);
+// nullable columns: per-tile non-null counts, then bit-packed definition levels + dense values per tile
+void launch_tile_valid_counts(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint32_t* perm,
+                              const uint8_t* valid, uint32_t* counts);
+void launch_gather_encode_nullable(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint32_t* perm,
+                                   const void* src, const uint8_t* valid, int width, const uint64_t* tile_value_offset,
+                                   const uint64_t* tile_def_offset, uint8_t* arena);
 // Plain gather: out[i] = src[perm[i]]
 void launch_gather_plain(hs_ctx* ctx, const void* src, const uint32_t* perm, int64_t n, int width, void* out);
 struct ByteCopy {

@@ -318,6 +318,26 @@ inline void write_plain_page_prefix(std::vector<uint8_t>& out, uint64_t page_off
   out.insert(out.end(), defs.begin(), defs.end());
 }
 
+// [page header][4-byte length][bit-packed run header] for a v1 data page of `n` rows whose definition levels are written as
+// ONE bit-packed run of ceil(n/8) groups (the bits themselves are written by the GPU right after this prefix) followed by
+// `non_null` dense PLAIN values.
+inline void write_nullable_page_prefix(std::vector<uint8_t>& out, int64_t n, int64_t non_null, int W) {
+  const uint64_t groups = (uint64_t)(n + 7) / 8;
+  uint8_t hv[10];
+  int hl = 0;
+  uint64_t h = (groups << 1) | 1;
+  while (h >= 0x80) {
+    hv[hl++] = (uint8_t)(h | 0x80);
+    h >>= 7;
+  }
+  hv[hl++] = (uint8_t)h;
+  const uint32_t def_len = (uint32_t)(hl + groups);
+  write_data_page_header(out, (int32_t)(4 + def_len + (size_t)non_null * W), (int32_t)n, ENC_PLAIN);
+  const uint8_t* lp = (const uint8_t*)&def_len;
+  out.insert(out.end(), lp, lp + 4);
+  out.insert(out.end(), hv, hv + hl);
+}
+
 struct OutChunk {
   int32_t type;
   int64_t num_values;

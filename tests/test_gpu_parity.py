@@ -285,6 +285,53 @@ def test_lineage_column(ctx, tmp_path):
     res2.free()
 
 
+def test_create_index_with_nulls(ctx, tmp_path):
+    """Nulls in the indexed column (hash unchanged -> bucket pmod(42, n); sorted first) and in included columns."""
+    from hyperspace_b200 import _native
+
+    rng = np.random.default_rng(31)
+    n = 70_000
+    k = rng.integers(-500, 500, size=n, dtype=np.int64)
+    kvalid = rng.random(n) > 0.05
+    v1 = rng.integers(0, 100, size=n, dtype=np.int32)
+    v1valid = rng.random(n) > 0.3
+    v2 = rng.standard_normal(n)
+    v2valid = rng.random(n) > 0.9          # mostly null
+    v3 = rng.standard_normal(n).astype(np.float32)
+    tbl = pa.table({"k": pa.array(k, mask=~kvalid), "v1": pa.array(v1, mask=~v1valid), "v2": pa.array(v2, mask=~v2valid),
+                    "v3": pa.array(v3)})
+    for variant, kw in (("plain", dict(use_dictionary=False)), ("dict", dict(use_dictionary=True, data_page_size=8192))):
+        p = str(tmp_path / f"n-{variant}.parquet")
+        pq.write_table(tbl, p, compression="NONE", row_group_size=25_000, **kw)
+        res, st = ctx.create_index([_native.FileImage(path=p)], ["k"], ["v1", "v2", "v3"], 16, output=_native.HS_OUT_HOST,
+                                   job_uuid="nn", rows_per_page=8192, rows_per_row_group=16384)
+        kz = np.where(kvalid, k, 0)
+        perm, offs, order = O.index_rows({"k": kz, "v1": v1, "v2": v2, "v3": v3}, ["k"], ["v1", "v2", "v3"], 16,
+                                         valids={"k": kvalid.astype(np.uint8)})
+        masks = {"k": kvalid, "v1": v1valid, "v2": v2valid, "v3": np.ones(n, bool)}
+        vals = {"k": k, "v1": v1, "v2": v2, "v3": v3}
+        total = 0
+        for i, f in enumerate(res.files):
+            t = _read_image(res.host_bytes(i))
+            lo, hi = int(offs[f.bucket]), int(offs[f.bucket + 1])
+            assert t.num_rows == hi - lo
+            for name in order:
+                arr = t.column(name).combine_chunks()
+                got_valid = np.asarray(arr.is_valid())
+                want_valid = masks[name][perm[lo:hi]]
+                assert np.array_equal(got_valid, want_valid), (variant, name, f.bucket)
+                got = np.asarray(arr.fill_null(0))
+                want = np.where(want_valid, vals[name][perm[lo:hi]], 0).astype(got.dtype)
+                assert np.array_equal(_bits(got), _bits(want)), (variant, name, f.bucket)
+            total += t.num_rows
+        assert total == n
+        # the GPU reads its own nullable files back: filter scan over the index == numpy
+        batch, _ = ctx.filter_scan(res.as_sources(), "k", ["k", "v1"], lo=-10, hi=10, sorted_on_key=False)
+        m = kvalid & (k >= -10) & (k <= 10)
+        assert batch.num_rows == int(m.sum())
+        res.free()
+
+
 def test_errors_are_loud(ctx, tmp_path):
     from hyperspace_b200 import _native
 
