@@ -357,9 +357,15 @@ int hs_create_index(hs_ctx* ctx, const hs_index_spec* spec, hs_index_result** ou
     load_sources(ctx, spec->files, spec->n_files, cols, &table, &st);
     if (spec->lineage) fill_lineage(ctx, table, spec->files, spec->n_files);
     if (spec->n_deleted_file_ids > 0) drop_deleted_rows(ctx, table, spec->deleted_file_ids, spec->n_deleted_file_ids);
-    if (ctx->world > 1) exchange_rows(ctx, table, spec->n_indexed, spec->num_buckets, &st);
     IndexedRows rows;
-    index_rows(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
+    if (p2p_exchange_supported(ctx, spec->num_buckets)) {
+      // partition + exchange fused over NVLink peer memory, then the local sort
+      exchange_partition_p2p(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
+      sort_partitioned_rows(ctx, spec->n_indexed, spec->num_buckets, &rows, &st);
+    } else {
+      if (ctx->world > 1) exchange_rows(ctx, table, spec->n_indexed, spec->num_buckets, &st);  // NCCL all-to-all
+      index_rows(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
+    }
 
     EncodeRequest req;
     req.table = &rows.part;

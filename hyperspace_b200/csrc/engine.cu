@@ -307,7 +307,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
     fail(HS_EUNSUPPORTED, "numBuckets = %d; the GPU path handles 1..%d buckets", num_buckets, kMaxBuckets);
   if (nkeys < 1 || nkeys > ncols) fail(HS_EINVAL, "bad number of indexed columns");
   if (nrows >= (1ll << 32)) fail(HS_EUNSUPPORTED, "more than 2^32-1 rows per GPU per call");
-  StageTimer t_hash(ctx), t_part(ctx), t_sort(ctx);
+  StageTimer t_hash(ctx), t_part(ctx);
 
   // ---- K2: bucket ids + histograms -----------------------------------------------------------------------------
   t_hash.start();
@@ -376,6 +376,14 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
     table.cols[c].valid.release();
   }
 
+  stats->ms_hash += t_hash.ms();
+  stats->ms_partition += t_part.ms();
+  sort_partitioned_rows(ctx, nkeys, num_buckets, out, stats);
+}
+
+void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats) {
+  const int64_t nrows = out->part.nrows;
+  StageTimer t_sort(ctx);
   // ---- K4: segmented sort on the indexed columns, last column first ---------------------------------------------
   t_sort.start();
   build_sort_plan(ctx, out->bucket_offsets.data(), num_buckets, &out->plan);
@@ -406,8 +414,6 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   out->sorted_perm = perm;
   t_sort.stop();
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  stats->ms_hash += t_hash.ms();
-  stats->ms_partition += t_part.ms();
   stats->ms_sort += t_sort.ms();
 }
 

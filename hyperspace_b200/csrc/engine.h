@@ -86,6 +86,12 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
 // the buckets it owns (owner(b) = b % world).  No-op when world == 1.
 void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_stats* stats);
 void comm_destroy(hs_ctx* ctx);
+// Fused alternative (NVLink peer memory): partitions by bucket and delivers every row to its final bucket-major position
+// on the owner GPU in one kernel; fills out->part / bucket_offsets so that sort_partitioned_rows can run next.
+bool p2p_exchange_supported(hs_ctx* ctx, int num_buckets);
+void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats);
+// K4 only: sorts out->part (already bucket-major, offsets in out->bucket_offsets) on the first nkeys columns.
+void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats);
 
 std::string make_uuid();
 

@@ -115,20 +115,24 @@ __global__ void k_chunk_sums(const uint32_t* __restrict__ tile_hist, int64_t nti
 }
 
 // one thread per bucket: bucket base (exclusive scan over buckets of the global histogram) + prefix over chunks
+// explicit_base != nullptr: the destination of bucket b starts at explicit_base[b] (positions in the owner GPU's
+// receive buffers, computed on the host from the all-gathered histograms) instead of the local exclusive scan
 __global__ void k_chunk_scan(unsigned long long* __restrict__ chunk_sums, int64_t nchunks, int nb,
                              const unsigned long long* __restrict__ global_hist,
-                             unsigned long long* __restrict__ bucket_offsets) {
+                             unsigned long long* __restrict__ bucket_offsets,
+                             const unsigned long long* __restrict__ explicit_base) {
   extern __shared__ unsigned long long s_base[];  // nb + 1
   if (threadIdx.x == 0) {
     unsigned long long run = 0;
     for (int b = 0; b < nb; b++) {
-      s_base[b] = run;
+      s_base[b] = explicit_base ? explicit_base[b] : run;
       run += global_hist[b];
     }
     s_base[nb] = run;
   }
   __syncthreads();
-  for (int b = threadIdx.x; b <= nb; b += blockDim.x) bucket_offsets[b] = s_base[b];
+  if (bucket_offsets)
+    for (int b = threadIdx.x; b <= nb; b += blockDim.x) bucket_offsets[b] = s_base[b];
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
     unsigned long long run = s_base[b];
     for (int64_t c = 0; c < nchunks; c++) {
@@ -263,7 +267,8 @@ void launch_owner_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t 
 }
 
 void launch_tile_offsets(hs_ctx* ctx, uint32_t* tile_hist, int64_t ntiles, int num_buckets,
-                         const unsigned long long* global_hist, unsigned long long* bucket_offsets) {
+                         const unsigned long long* global_hist, unsigned long long* bucket_offsets,
+                         const unsigned long long* explicit_base) {
   KernelScope _ks(ctx, "k_tile_offsets");
   const int64_t nchunks = std::max<int64_t>(1, ceil_div(ntiles, kChunk));
   Buf<unsigned long long> chunk_sums(ctx, (size_t)nchunks * num_buckets);
@@ -271,7 +276,7 @@ void launch_tile_offsets(hs_ctx* ctx, uint32_t* tile_hist, int64_t ntiles, int n
   k_chunk_sums<<<grid, 128, 0, ctx->stream>>>(tile_hist, ntiles, num_buckets, chunk_sums.get());
   HS_LAUNCH_CHECK(ctx);
   k_chunk_scan<<<1, 256, (num_buckets + 1) * sizeof(unsigned long long), ctx->stream>>>(
-      chunk_sums.get(), nchunks, num_buckets, global_hist, bucket_offsets);
+      chunk_sums.get(), nchunks, num_buckets, global_hist, bucket_offsets, explicit_base);
   HS_LAUNCH_CHECK(ctx);
   k_chunk_apply<<<grid, 128, 0, ctx->stream>>>(tile_hist, ntiles, num_buckets, chunk_sums.get());
   HS_LAUNCH_CHECK(ctx);
@@ -364,7 +369,8 @@ __global__ void __launch_bounds__(kFThreads) k_tile_hist(const KeyColumn* __rest
 __global__ void __launch_bounds__(kFThreads) k_partition_rows(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
                                                                int num_buckets, int owner_mod,
                                                                const uint32_t* __restrict__ tile_dst,
-                                                               const PartColumn* __restrict__ cols, int ncols) {
+                                                               const PartColumn* __restrict__ cols, int ncols,
+                                                               void* const* __restrict__ peer_out, int out_world) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int nb = owner_mod > 0 ? owner_mod : num_buckets;
   uint64_t* xbuf = reinterpret_cast<uint64_t*>(smem);
@@ -464,24 +470,27 @@ __global__ void __launch_bounds__(kFThreads) k_partition_rows(const KeyColumn* _
         if (act[j]) xb[pos[j]] = in[wbase + j * 32 + lane];
     }
     __syncthreads();
+    // peer_out != nullptr: bucket b lives on GPU (b % out_world); its column c buffer is peer_out[c * out_world + owner]
+    // (a peer-mapped pointer: these stores go straight over NVLink into the owner's memory)
+    void* const* pout = peer_out ? peer_out + (size_t)c * out_world : nullptr;
     if (pc.width == 8) {
-      uint64_t* out = (uint64_t*)pc.out;
       for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
         const uint32_t b = pos_bin[i];
+        uint64_t* out = (uint64_t*)(pout ? pout[b % out_world] : pc.out);
         out[dst_base[b] + (i - bin_start[b])] = xbuf[i];
       }
     } else if (pc.width == 4) {
-      uint32_t* out = (uint32_t*)pc.out;
       const uint32_t* xb = reinterpret_cast<const uint32_t*>(xbuf);
       for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
         const uint32_t b = pos_bin[i];
+        uint32_t* out = (uint32_t*)(pout ? pout[b % out_world] : pc.out);
         out[dst_base[b] + (i - bin_start[b])] = xb[i];
       }
     } else {
-      uint8_t* out = (uint8_t*)pc.out;
       const uint8_t* xb = reinterpret_cast<const uint8_t*>(xbuf);
       for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
         const uint32_t b = pos_bin[i];
+        uint8_t* out = (uint8_t*)(pout ? pout[b % out_world] : pc.out);
         out[dst_base[b] + (i - bin_start[b])] = xb[i];
       }
     }
@@ -510,7 +519,8 @@ void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t n
 }
 
 void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
-                           const uint32_t* tile_dst, const PartColumn* d_cols, int ncols) {
+                           const uint32_t* tile_dst, const PartColumn* d_cols, int ncols, void* const* d_peer_out,
+                           int out_world) {
   KernelScope _ks(ctx, "k_partition_rows");
   if (nrows == 0) return;
   const int nb = owner_mod > 0 ? owner_mod : num_buckets;
@@ -522,7 +532,8 @@ void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int6
     attr = true;
   }
   k_partition_rows<<<(unsigned)ntiles, kFThreads, fused_smem_bytes(nb), ctx->stream>>>(d_keys, nkeys, nrows, num_buckets,
-                                                                                        owner_mod, tile_dst, d_cols, ncols);
+                                                                                        owner_mod, tile_dst, d_cols, ncols,
+                                                                                        d_peer_out, out_world);
   HS_LAUNCH_CHECK(ctx);
 }
 

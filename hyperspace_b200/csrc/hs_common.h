@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -79,13 +80,22 @@ class BufferPool {
     (it->second.pinned ? free_pinned_ : free_dev_).emplace(it->second.bytes, p);
     live_.erase(it);
   }
+  // Buffers whose IPC handle was given to a peer process stay allocated until the pool dies (a peer may hold a mapping).
+  void mark_exported(void* p) { exported_.insert(p); }
   void trim() {
-    for (auto& kv : free_dev_) cudaFree(kv.second);
+    for (auto it = free_dev_.begin(); it != free_dev_.end();) {
+      if (exported_.count(it->second)) {
+        ++it;
+        continue;
+      }
+      cudaFree(it->second);
+      it = free_dev_.erase(it);
+    }
     for (auto& kv : free_pinned_) cudaFreeHost(kv.second);
-    free_dev_.clear();
     free_pinned_.clear();
   }
   ~BufferPool() {
+    exported_.clear();
     trim();
     for (auto& kv : live_) kv.second.pinned ? cudaFreeHost(kv.first) : cudaFree(kv.first);
   }
@@ -97,6 +107,7 @@ class BufferPool {
   };
   std::multimap<size_t, void*> free_dev_, free_pinned_;
   std::map<void*, Live> live_;
+  std::set<void*> exported_;
 };
 
 }  // namespace hs

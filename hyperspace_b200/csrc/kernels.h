@@ -72,8 +72,10 @@ void launch_bucket_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t
 void launch_owner_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int world,
                        uint16_t* owner, uint32_t* tile_hist, unsigned long long* global_hist);
 // in-place: tile_hist[t][b] <- bucket_base[b] + sum_{t'<t} tile_hist[t'][b]   (bucket_base = exclusive scan of global hist)
+// explicit_base (optional, device, nb entries): start of every bucket's destination instead of the local scan
 void launch_tile_offsets(hs_ctx* ctx, uint32_t* tile_hist, int64_t ntiles, int num_buckets,
-                         const unsigned long long* global_hist, unsigned long long* bucket_offsets /* nb+1 */);
+                         const unsigned long long* global_hist, unsigned long long* bucket_offsets /* nb+1 or null */,
+                         const unsigned long long* explicit_base = nullptr);
 // dest[row] = stable position of the row in bucket-major order
 void launch_partition_dest(hs_ctx* ctx, const uint16_t* bucket, int64_t nrows, int num_buckets,
                            const uint32_t* tile_offsets, uint32_t* dest);
@@ -93,8 +95,10 @@ bool fused_partition_supported(int nbins);
 void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
                       uint32_t* tile_hist, unsigned long long* global_hist);
 // tile_dst = launch_tile_offsets(tile_hist); moves all columns into bin-major order, stable
+// d_peer_out (optional): [ncols][out_world] peer-mapped output pointers; bucket b is written to GPU b % out_world
 void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
-                           const uint32_t* tile_dst, const PartColumn* d_cols, int ncols);
+                           const uint32_t* tile_dst, const PartColumn* d_cols, int ncols, void* const* d_peer_out = nullptr,
+                           int out_world = 1);
 // out[i] = sort_encode(in[src ? src[i] : i])  (+ global OR / AND reduction into or_and[0], or_and[1])
 void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* src, int64_t nrows, uint64_t* out,
                         unsigned long long* or_and);
