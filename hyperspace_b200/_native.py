@@ -255,29 +255,47 @@ class IndexResult:
 
 
 class Batch:
-    """Host copy of an hs_batch (columns as numpy arrays)."""
+    """An hs_batch: result columns in pinned host memory, exposed as zero-copy numpy views.  The views are valid until
+    ``free()`` (or garbage collection of the Batch); copy them if they must outlive it."""
 
-    def __init__(self, handle: int):
+    def __init__(self, handle: int, ctx: "Context" = None):
         L = load_library()
+        self._h = handle
+        if ctx is not None:
+            ctx._results.add(self)
         self.num_rows = L.hs_batch_num_rows(handle)
         self.columns: List[Tuple[str, np.ndarray, Optional[np.ndarray]]] = []
+        n = self.num_rows
         for i in range(L.hs_batch_num_columns(handle)):
             nm, ty, d, v = C.c_char_p(), C.c_int32(), C.c_void_p(), C.c_void_p()
             L.hs_batch_column(handle, i, C.byref(nm), C.byref(ty), C.byref(d), C.byref(v))
             dt = np.dtype(_NP_OF_TYPE[ty.value])
-            n = self.num_rows
-            data = np.frombuffer(C.string_at(d.value, n * dt.itemsize), dtype=dt).copy() if n else np.empty(0, dt)
+            if n:
+                data = np.ctypeslib.as_array((C.c_uint8 * (n * dt.itemsize)).from_address(d.value)).view(dt)
+            else:
+                data = np.empty(0, dt)
             valid = None
             if v.value:
-                valid = np.frombuffer(C.string_at(v.value, n), dtype=np.uint8).copy() if n else np.empty(0, np.uint8)
+                valid = np.ctypeslib.as_array((C.c_uint8 * n).from_address(v.value)) if n else np.empty(0, np.uint8)
             self.columns.append((nm.value.decode(), data, valid))
-        L.hs_batch_free(handle)
 
     def column(self, name: str) -> np.ndarray:
         for n, d, _ in self.columns:
             if n == name:
                 return d
         raise KeyError(name)
+
+    def free(self) -> None:
+        if self._h:
+            self.columns = []
+            load_library().hs_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Context:
@@ -395,7 +413,7 @@ class Context:
         res, st = C.c_void_p(), Stats()
         err = C.create_string_buffer(1024)
         _check(L.hs_filter_scan(self._h, C.byref(spec), C.byref(res), C.byref(st), err, len(err)), err)
-        return Batch(res.value), st.as_dict()
+        return Batch(res.value, self), st.as_dict()
 
     def bucket_join(self, left: Sequence[FileImage], left_buckets: Sequence[int], right: Sequence[FileImage],
                     right_buckets: Sequence[int], num_buckets: int, left_key: str, right_key: str,
@@ -415,7 +433,7 @@ class Context:
         res, st = C.c_void_p(), Stats()
         err = C.create_string_buffer(1024)
         _check(L.hs_bucket_join(self._h, C.byref(spec), C.byref(res), C.byref(st), err, len(err)), err)
-        return Batch(res.value), st.as_dict()
+        return Batch(res.value, self), st.as_dict()
 
     # ---- kernel-level entry points ----------------------------------------------------------------------------------
     @staticmethod

@@ -497,20 +497,33 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
         lineage_col = (int)(it - cols.begin());
       }
     }
+    const bool try_sorted = spec->sorted_on_key && spec->n_deleted_file_ids == 0;
+    SourceSet src;
+    open_sources(ctx, spec->files, spec->n_files, &src, &st);
     Table t;
-    load_sources(ctx, spec->files, spec->n_files, cols, &t, &st);
+    if (try_sorted) {
+      // phase 1: only the key column; the other columns are decoded after the binary search, restricted to the pages
+      // that hold qualifying rows
+      decode_sources(ctx, src, {cols[0]}, nullptr, &t, &st);
+    } else {
+      decode_sources(ctx, src, cols, nullptr, &t, &st);
+    }
     if (t.cols[0].type != HS_TYPE_INT64 && t.cols[0].type != HS_TYPE_INT32)
       fail(HS_EUNSUPPORTED, "filter scan: key column must be int32/int64");
     const int64_t n = t.nrows;
-    // widen an int32 key to int64 for the comparison kernels
-    Buf<int64_t> k64;
     const int64_t* d_keys = (const int64_t*)t.cols[0].data.get();
     StageTimer t_scan(ctx);
     t_scan.start();
     if (t.cols[0].type == HS_TYPE_INT32) fail(HS_EUNSUPPORTED, "filter scan on int32 keys not wired yet");
     Buf<uint32_t> idx;
     int64_t n_out = 0;
-    const bool sorted = spec->sorted_on_key && !t.cols[0].has_nulls && spec->n_deleted_file_ids == 0;
+    bool sorted = try_sorted && !t.cols[0].has_nulls;
+    if (try_sorted && !sorted) {  // nulls in the key: fall back to the predicate scan over all columns
+      Table full;
+      decode_sources(ctx, src, cols, nullptr, &full, &st);
+      t = std::move(full);
+      d_keys = (const int64_t*)t.cols[0].data.get();
+    }
     if (sorted) {
       // K7: two binary searches per file
       const int nseg = spec->n_files;
@@ -525,6 +538,14 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
       HS_CUDA(cudaStreamSynchronize(ctx->stream));
       std::vector<uint64_t> oo(nseg + 1, 0);
       for (int f = 0; f < nseg; f++) oo[f + 1] = oo[f] + (uint64_t)(bounds[2 * f + 1] - bounds[2 * f]);
+      if (cols.size() > 1) {  // phase 2: decode the other columns, only the pages inside each file's [first, last)
+        std::vector<std::pair<int64_t, int64_t>> windows(nseg);
+        for (int f = 0; f < nseg; f++) windows[f] = {bounds[2 * f], bounds[2 * f + 1]};
+        std::vector<std::string> rest(cols.begin() + 1, cols.end());
+        Table others;
+        decode_sources(ctx, src, rest, &windows, &others, &st);
+        for (auto& c : others.cols) t.cols.push_back(std::move(c));
+      }
       n_out = (int64_t)oo[nseg];
       Buf<uint64_t> d_oo(ctx, nseg + 1);
       HS_CUDA(cudaMemcpyAsync(d_oo.get(), oo.data(), 8 * (nseg + 1), cudaMemcpyHostToDevice, ctx->stream));

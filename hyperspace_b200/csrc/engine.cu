@@ -97,10 +97,26 @@ void read_whole_file(const char* path, uint8_t* dst, uint64_t size) {
 
 }  // namespace
 
+struct SourceSet::Impl {
+  std::vector<FileImage> imgs;
+  Buf<uint8_t> d_images;
+};
+SourceSet::SourceSet() : impl(new Impl()) {}
+SourceSet::~SourceSet() { delete impl; }
+
 void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const std::vector<std::string>& columns,
                   Table* out, hs_stats* stats) {
-  StageTimer t_h2d(ctx), t_plan(ctx), t_dec(ctx);
-  std::vector<FileImage> imgs(n_files);
+  SourceSet src;
+  open_sources(ctx, files, n_files, &src, stats);
+  decode_sources(ctx, src, columns, nullptr, out, stats);
+}
+
+void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceSet* set, hs_stats* stats) {
+  StageTimer t_h2d(ctx);
+  set->n_files = n_files;
+  std::vector<FileImage>& imgs = set->impl->imgs;
+  Buf<uint8_t>& d_images = set->impl->d_images;
+  imgs.assign(n_files, FileImage());
   // ---- sizes + device arena for host-supplied images --------------------------------------------------------
   std::vector<uint64_t> sizes(n_files), dev_off(n_files, 0);
   uint64_t arena_bytes = 0;
@@ -123,7 +139,6 @@ void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const s
       arena_bytes += round_up(sizes[f], 16) + 16;
     }
   }
-  Buf<uint8_t> d_images;
   if (arena_bytes) d_images.alloc(ctx, arena_bytes);
   // ---- H2D + footers -----------------------------------------------------------------------------------------
   t_h2d.start();
@@ -174,7 +189,15 @@ void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const s
     stats->bytes_in += (int64_t)sizes[f];
   }
   t_h2d.stop();
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // pinned staging buffers and caller memory are free to go
+  stats->ms_h2d += t_h2d.ms();
+}
 
+void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>& columns,
+                    const std::vector<std::pair<int64_t, int64_t>>* file_windows, Table* out, hs_stats* stats) {
+  StageTimer t_plan(ctx), t_dec(ctx);
+  const int n_files = set.n_files;
+  std::vector<FileImage>& imgs = set.impl->imgs;
   // ---- resolve columns, build chunk descriptors -----------------------------------------------------------------
   t_plan.start();
   const int ncols = (int)columns.size();
@@ -253,7 +276,6 @@ void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const s
   t_plan.stop();
   if (n_chunks == 0 || nrows == 0) {
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
-    stats->ms_h2d += t_h2d.ms();
     return;
   }
   // ---- page walk -----------------------------------------------------------------------------------------
@@ -280,7 +302,20 @@ void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const s
   HS_CUDA(cudaMemcpyAsync(d_offsets.get(), offsets.data(), sizeof(int64_t) * n_chunks, cudaMemcpyHostToDevice, ctx->stream));
   launch_walk_pages(ctx, d_chunks.get(), n_chunks, d_counts.get(), d_offsets.get(), d_pages.get(), d_flags.get(), 1);
   // ---- decode -----------------------------------------------------------------------------------------
-  launch_decode_pages(ctx, d_pages.get(), n_pages, d_cols.get(), d_flags.get() + 1, nullptr, d_flags.get());
+  // optional per-file row windows (file-relative -> global): pages that do not intersect their file's window are skipped
+  Buf<int64_t> d_window;
+  if (file_windows) {
+    std::vector<int64_t> w(2 * (size_t)n_files);
+    for (int f = 0; f < n_files; f++) {
+      w[2 * f] = out->file_row_begin[f] + (*file_windows)[f].first;
+      w[2 * f + 1] = out->file_row_begin[f] + (*file_windows)[f].second;
+    }
+    d_window.alloc(ctx, w.size());
+    HS_CUDA(cudaMemcpyAsync(d_window.get(), w.data(), 8 * w.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  launch_decode_pages(ctx, d_pages.get(), n_pages, d_cols.get(), d_flags.get() + 1, file_windows ? d_window.get() : nullptr,
+                      d_flags.get());
   std::vector<uint32_t> flags(1 + ncols);
   HS_CUDA(cudaMemcpyAsync(flags.data(), d_flags.get(), sizeof(uint32_t) * (1 + ncols), cudaMemcpyDeviceToHost, ctx->stream));
   t_dec.stop();
@@ -293,7 +328,6 @@ void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const s
     fail(ecode, "Parquet decode failed: %s (detail %u)", decode_error_text(code), detail);
   }
   for (int c = 0; c < ncols; c++) out->cols[c].has_nulls = flags[1 + c] != 0;
-  stats->ms_h2d += t_h2d.ms();
   stats->ms_plan += t_plan.ms();
   stats->ms_decode += t_dec.ms();
 }

@@ -58,6 +58,21 @@ struct LoadOptions {
 // host, page walk + decode on the GPU).
 void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const std::vector<std::string>& columns,
                   Table* out, hs_stats* stats);
+// The same in two steps, so that a query can decode the key column first and then only the pages of the other columns
+// that intersect the qualifying row range of each file.
+struct SourceSet {
+  struct Impl;
+  Impl* impl;
+  int n_files = 0;
+  SourceSet();
+  ~SourceSet();
+  SourceSet(const SourceSet&) = delete;
+  SourceSet& operator=(const SourceSet&) = delete;
+};
+void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceSet* set, hs_stats* stats);
+// file_windows (optional): per file, the half-open range of file-relative rows that must be decoded
+void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>& columns,
+                    const std::vector<std::pair<int64_t, int64_t>>* file_windows, Table* out, hs_stats* stats);
 
 // K2-K4 on a decoded table whose first nkeys columns are the indexed columns.
 void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats);

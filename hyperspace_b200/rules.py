@@ -187,7 +187,9 @@ class ScanExec:
         lo, hi = self._bounds(key)
         batch, _ = self.session.gpu.filter_scan(files, key, out_cols, lo=lo, hi=hi, sorted_on_key=sorted_on_key,
                                                 deleted_file_ids=list(deleted_ids))
-        return {n: d for n, d, _ in batch.columns}
+        out = {n: d.copy() for n, d, _ in batch.columns}
+        batch.free()
+        return out
 
     def execute(self) -> Dict[str, np.ndarray]:
         out_cols = self.lin.output
@@ -261,7 +263,8 @@ class BucketJoinExec:
         out: Dict[str, np.ndarray] = {}
         for i, (n, d, _) in enumerate(batch.columns):
             name = n if n not in out else f"{n}_right"
-            out[name] = d
+            out[name] = d.copy()
+        batch.free()
         return out
 
 
