@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--plain", action="store_true", help="PLAIN-only source and index files (no dictionary encoding)")
     return ap.parse_args()
 
 
@@ -127,7 +128,7 @@ def cpu_create_index(sample_rows: int, nthreads: int, workdir: str):
     for f in range(n_files):
         p = os.path.join(src_dir, f"part-{f:05d}.parquet")
         if not os.path.exists(p):
-            pq.write_table(pa.table(O.synthetic_table(f * per, per, 5)), p, compression="NONE", use_dictionary=False)
+            pq.write_table(pa.table(O.synthetic_table(f * per, per, 5)), p, compression="NONE", use_dictionary=["v1", "v3", "v4"])
         paths.append(p)
     out_dir = os.path.join(workdir, "idx")
     t0 = time.perf_counter()
@@ -145,7 +146,8 @@ def cpu_create_index(sample_rows: int, nthreads: int, workdir: str):
             return
         idx = perm[lo:hi]
         part = pa.table({name: cols[name][idx] for name in order})
-        pq.write_table(part, os.path.join(out_dir, O.bucket_file_name(b, "cpu")), compression="NONE", use_dictionary=False)
+        pq.write_table(part, os.path.join(out_dir, O.bucket_file_name(b, "cpu")), compression="NONE",
+                       use_dictionary=["v1", "v3", "v4"])
 
     with ThreadPoolExecutor(max_workers=nthreads) as ex:
         list(ex.map(write_bucket, range(NUM_BUCKETS)))
@@ -185,8 +187,9 @@ def workload_config(args, sample_rows=None):
     cfg = {"workload": "createIndex: 1B rows x (k:int64 indexed; v1:int64, v2:float64, v3:int32, v4:float32 included), "
                        "200 buckets, 256 source Parquet files" if args.rows == 1_000_000_000 else
                        f"createIndex: {args.rows} rows x 5 columns of T, 200 buckets, {args.files} source Parquet files",
-           "rows": args.rows, "source_files": args.files, "num_buckets": NUM_BUCKETS, "source_encoding": "PLAIN, UNCOMPRESSED",
-           "index_encoding": "PLAIN, UNCOMPRESSED", "l2": "inputs (>= 32 B/row x rows) far exceed the 126 MB L2; no flush needed"}
+           "rows": args.rows, "source_files": args.files, "num_buckets": NUM_BUCKETS, "source_encoding": "PLAIN, UNCOMPRESSED" if args.plain else
+           "PLAIN_DICTIONARY (v1, v3, v4) + PLAIN (k, v2), UNCOMPRESSED -- what parquet-mr / pyarrow write by default",
+           "index_encoding": "PLAIN, UNCOMPRESSED" if args.plain else "PLAIN_DICTIONARY (v1, v3, v4) + PLAIN (k, v2), UNCOMPRESSED", "l2": "inputs (>= 32 B/row x rows) far exceed the 126 MB L2; no flush needed"}
     if sample_rows:
         cfg["cpu_sample_rows"] = sample_rows
     return cfg
@@ -247,12 +250,14 @@ def run_ours(args):
         return float(t.item())
 
     # ---- inputs resident in HBM -----------------------------------------------------------------------------------
-    src = ctx.synth_table(first_row, my_rows, 5, n_files=my_files, row_groups_per_file=4, output=N.HS_OUT_DEVICE)
+    src = ctx.synth_table(first_row, my_rows, 5, n_files=my_files, row_groups_per_file=4, output=N.HS_OUT_DEVICE,
+                          dictionary=not args.plain)
     sources = src.as_sources()
     src_bytes = sum(f.size for f in src.files)
 
     def step_device():
-        res, st = ctx.create_index(sources, INDEXED, INCLUDED, NUM_BUCKETS, output=N.HS_OUT_DEVICE, job_uuid="bench")
+        res, st = ctx.create_index(sources, INDEXED, INCLUDED, NUM_BUCKETS, output=N.HS_OUT_DEVICE, job_uuid="bench",
+                                   dictionary=not args.plain)
         res.free()
         return st
 
@@ -312,11 +317,13 @@ def run_ours(args):
         # host memory (outside the timed region)
         src.free()
         ctx.trim()
-        hsrc = ctx.synth_table(first_row, my_rows, 5, n_files=my_files, row_groups_per_file=4, output=N.HS_OUT_HOST)
+        hsrc = ctx.synth_table(first_row, my_rows, 5, n_files=my_files, row_groups_per_file=4, output=N.HS_OUT_HOST,
+                               dictionary=not args.plain)
         host_in = hsrc.as_sources()
 
         def step_host():
-            res, st = ctx.create_index(host_in, INDEXED, INCLUDED, NUM_BUCKETS, output=N.HS_OUT_HOST, job_uuid="bench")
+            res, st = ctx.create_index(host_in, INDEXED, INCLUDED, NUM_BUCKETS, output=N.HS_OUT_HOST, job_uuid="bench",
+                                       dictionary=not args.plain)
             out_bytes = sum(f.size for f in res.files)
             # read the result on the host: first and last byte of every file image (the images are complete Parquet files)
             chk = 0

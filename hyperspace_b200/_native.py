@@ -46,7 +46,7 @@ class IndexSpec(C.Structure):
                 ("num_buckets", C.c_int32), ("save_mode", C.c_int32), ("output", C.c_int32), ("lineage", C.c_int32),
                 ("out_dir", C.c_char_p), ("job_uuid", C.c_char_p),
                 ("rows_per_page", C.c_int64), ("rows_per_row_group", C.c_int64),
-                ("deleted_file_ids", C.POINTER(C.c_int64)), ("n_deleted_file_ids", C.c_int32), ("reserved", C.c_int32)]
+                ("deleted_file_ids", C.POINTER(C.c_int64)), ("n_deleted_file_ids", C.c_int32), ("disable_dictionary", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -149,7 +149,7 @@ def load_library() -> C.CDLL:
     L.hs_k_sort_perm.restype = C.c_int
     L.hs_k_sort_perm.argtypes = [C.c_void_p, C.POINTER(HostColumn), C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, *err]
     L.hs_synth_table.restype = C.c_int
-    L.hs_synth_table.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+    L.hs_synth_table.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.POINTER(C.c_void_p), *err]
     if L.hs_abi_version() != 1:
         raise HyperspaceGpuError(HS_EINVAL, f"ABI version mismatch: library {L.hs_abi_version()}, binding 1")
@@ -367,7 +367,8 @@ class Context:
     def create_index(self, files: Sequence[FileImage], indexed: Sequence[str], included: Sequence[str], num_buckets: int,
                      out_dir: Optional[str] = None, output: int = HS_OUT_FILES, job_uuid: Optional[str] = None,
                      save_mode: int = HS_SAVE_OVERWRITE, lineage: bool = False, deleted_file_ids: Sequence[int] = (),
-                     rows_per_page: int = 0, rows_per_row_group: int = 0) -> Tuple[IndexResult, Dict[str, float]]:
+                     rows_per_page: int = 0, rows_per_row_group: int = 0, dictionary: bool = True
+                     ) -> Tuple[IndexResult, Dict[str, float]]:
         L = load_library()
         src, keep = _source_array(files)
         ic, nc = _cstr_array(indexed), _cstr_array(included)
@@ -381,18 +382,19 @@ class Context:
         spec.rows_per_page, spec.rows_per_row_group = rows_per_page, rows_per_row_group
         dl = (C.c_int64 * max(1, len(deleted_file_ids)))(*deleted_file_ids)
         spec.deleted_file_ids, spec.n_deleted_file_ids = dl, len(deleted_file_ids)
+        spec.disable_dictionary = 0 if dictionary else 1
         res, st = C.c_void_p(), Stats()
         err = C.create_string_buffer(1024)
         _check(L.hs_create_index(self._h, C.byref(spec), C.byref(res), C.byref(st), err, len(err)), err)
         return IndexResult(self, res.value, output), st.as_dict()
 
     def synth_table(self, first_row: int, nrows: int, ncols: int = 5, n_files: int = 1, row_groups_per_file: int = 1,
-                    output: int = HS_OUT_HOST) -> IndexResult:
+                    output: int = HS_OUT_HOST, dictionary: bool = True) -> IndexResult:
         L = load_library()
         res = C.c_void_p()
         err = C.create_string_buffer(1024)
-        _check(L.hs_synth_table(self._h, first_row, nrows, ncols, n_files, row_groups_per_file, output, C.byref(res), err,
-                                len(err)), err)
+        _check(L.hs_synth_table(self._h, first_row, nrows, ncols, n_files, row_groups_per_file, 1 if dictionary else 0, output,
+                                C.byref(res), err, len(err)), err)
         return IndexResult(self, res.value, output)
 
     # ---- read side ----------------------------------------------------------------------------------

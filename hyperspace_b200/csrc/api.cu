@@ -375,6 +375,7 @@ int hs_create_index(hs_ctx* ctx, const hs_index_spec* spec, hs_index_result** ou
     req.seg_offsets = rows.bucket_offsets;
     req.rows_per_page = spec->rows_per_page;
     req.rows_per_row_group = spec->rows_per_row_group;
+    req.use_dictionary = spec->disable_dictionary == 0;
     const std::string uuid = spec->job_uuid ? spec->job_uuid : make_uuid();
     req.seg_names.resize(spec->num_buckets);
     for (int b = 0; b < spec->num_buckets; b++) {
@@ -823,7 +824,8 @@ int hs_k_sort_perm(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64
 }
 
 int hs_synth_table(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, int32_t n_files,
-                   int32_t row_groups_per_file, int32_t output, hs_index_result** out, char* err, size_t errlen) {
+                   int32_t row_groups_per_file, int32_t dictionary, int32_t output, hs_index_result** out, char* err,
+                   size_t errlen) {
   if (!ctx || !out) return HS_EINVAL;
   *out = nullptr;
   std::unique_ptr<hs_index_result> res(new hs_index_result());
@@ -862,6 +864,7 @@ int hs_synth_table(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols,
     req.plan = &plan;
     req.seg_offsets = seg;
     req.rows_per_page = P;
+    req.use_dictionary = dictionary != 0;
     req.rows_per_row_group = std::max<int64_t>(P, (int64_t)round_up((size_t)ceil_div(per_file, row_groups_per_file), (size_t)P));
     req.seg_names.resize(n_files);
     for (int f = 0; f < n_files; f++) {

@@ -503,6 +503,79 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
   }
   const std::vector<uint32_t>& seg_tile_begin = req.plan->h_seg_tile_begin;
 
+  // ---- dictionary analysis: distinct values of every non-null column, capped at kMaxDictEntries ---------------------
+  struct ColDict {
+    bool use = false;
+    uint32_t bw = 0, ndict = 0, empty_index = 0;
+    Buf<unsigned long long> keys;
+    Buf<uint32_t> slot_index;
+    size_t skel_off = 0, skel_len = 0;  // [dictionary page header][PLAIN values] inside the skeleton
+    std::vector<uint64_t> values;       // sorted dictionary (raw bits)
+  };
+  std::vector<ColDict> dicts(ncols);
+  const int64_t total_rows = table.nrows;
+  if (req.use_dictionary && total_rows > 0) {
+    Buf<uint32_t> d_state(ctx, 4);
+    for (int c = 0; c < ncols; c++) {
+      const DevColumn& dc = table.cols[c];
+      if (dc.has_nulls) continue;
+      ColDict& cd = dicts[c];
+      cd.keys.alloc(ctx, kDictCapacity);
+      HS_CUDA(cudaMemsetAsync(cd.keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
+      HS_CUDA(cudaMemsetAsync(d_state.get(), 0, 16, ctx->stream));
+      uint32_t st[4] = {0, 0, 0, 0};
+      // a 1 M-row sample first: high-cardinality columns (keys, measures) overflow here and cost almost nothing
+      const int64_t sample = std::min<int64_t>(total_rows, 1 << 20);
+      launch_dict_build(ctx, dc.data.get(), dc.width, 0, sample, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state.get());
+      HS_CUDA(cudaMemcpyAsync(st, d_state.get(), 16, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (!st[1] && sample < total_rows) {
+        launch_dict_build(ctx, dc.data.get(), dc.width, sample, total_rows, cd.keys.get(), kDictCapacity, kMaxDictEntries,
+                          d_state.get());
+        HS_CUDA(cudaMemcpyAsync(st, d_state.get(), 16, cudaMemcpyDeviceToHost, ctx->stream));
+        HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
+      if (st[1]) {
+        cd.keys.release();
+        continue;
+      }
+      std::vector<unsigned long long> h_keys(kDictCapacity);
+      HS_CUDA(cudaMemcpyAsync(h_keys.data(), cd.keys.get(), sizeof(unsigned long long) * kDictCapacity, cudaMemcpyDeviceToHost,
+                              ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (unsigned long long v : h_keys)
+        if (v != ~0ull) cd.values.push_back(v);
+      if (st[2]) cd.values.push_back(~0ull);
+      const int type = dc.type;
+      std::sort(cd.values.begin(), cd.values.end(), [type](uint64_t a, uint64_t b) { return sort_encode(type, a) < sort_encode(type, b); });
+      cd.ndict = (uint32_t)cd.values.size();
+      cd.bw = 1;
+      while ((1u << cd.bw) < cd.ndict) cd.bw++;
+      const double plain_bytes = (double)total_rows * dc.width;
+      const double dict_bytes = (double)total_rows * cd.bw / 8.0 + (double)cd.ndict * dc.width * std::max(1, nseg);
+      if (cd.ndict == 0 || cd.ndict > kMaxDictEntries || dict_bytes > 0.9 * plain_bytes) {
+        cd.keys.release();
+        continue;
+      }
+      std::vector<uint32_t> slot(kDictCapacity, 0);
+      {
+        std::vector<std::pair<uint64_t, uint32_t>> by_value(cd.ndict);
+        for (uint32_t i = 0; i < cd.ndict; i++) by_value[i] = {cd.values[i], i};
+        std::sort(by_value.begin(), by_value.end());
+        for (uint32_t s = 0; s < kDictCapacity; s++) {
+          if (h_keys[s] == ~0ull) continue;
+          auto it = std::lower_bound(by_value.begin(), by_value.end(), std::pair<uint64_t, uint32_t>((uint64_t)h_keys[s], 0u));
+          slot[s] = it->second;
+        }
+        if (st[2]) cd.empty_index = std::lower_bound(by_value.begin(), by_value.end(), std::pair<uint64_t, uint32_t>(~(uint64_t)0, 0u))->second;
+      }
+      cd.slot_index.alloc(ctx, kDictCapacity);
+      HS_CUDA(cudaMemcpyAsync(cd.slot_index.get(), slot.data(), 4 * kDictCapacity, cudaMemcpyHostToDevice, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      cd.use = true;
+    }
+  }
+
   std::vector<uint8_t> skeleton;
   std::vector<ByteCopy> copies;
   std::vector<uint32_t> seg_page_begin(nseg + 1, 0);
@@ -512,6 +585,18 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
   auto emit = [&](uint64_t dst, size_t skel_begin) {
     copies.push_back(ByteCopy{dst, (uint32_t)skel_begin, (uint32_t)(skeleton.size() - skel_begin)});
   };
+  for (int c = 0; c < ncols; c++) {
+    ColDict& cd = dicts[c];
+    if (!cd.use) continue;
+    const int W = table.cols[c].width;
+    cd.skel_off = skeleton.size();
+    pq::write_dict_page_header(skeleton, (int32_t)(cd.ndict * W), (int32_t)cd.ndict);
+    for (uint64_t v : cd.values) {
+      const uint8_t* vp = (const uint8_t*)&v;
+      skeleton.insert(skeleton.end(), vp, vp + W);
+    }
+    cd.skel_len = skeleton.size() - cd.skel_off;
+  }
   out->files.clear();
   for (int s = 0; s < nseg; s++) {
     seg_page_begin[s] = page_counter;
@@ -546,10 +631,23 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         ch.null_count = 0;
         ch.value_width = W;
         const uint64_t chunk_begin = cursor;
+        if (dicts[c].use) {  // every chunk of the column carries the same (global) dictionary page
+          ch.has_dictionary = true;
+          ch.dictionary_page_offset = (int64_t)(cursor - file_off);
+          copies.push_back(ByteCopy{cursor, (uint32_t)dicts[c].skel_off, (uint32_t)dicts[c].skel_len});
+          cursor += dicts[c].skel_len;
+          ch.data_page_offset = (int64_t)(cursor - file_off);
+        }
         for (int64_t p0 = r0; p0 < r1; p0 += P) {
           const int64_t np = std::min(P, r1 - p0);
           const size_t b = skeleton.size();
-          if (!table.cols[c].has_nulls) {
+          if (dicts[c].use) {
+            pq::write_dict_data_page_prefix(skeleton, np, dicts[c].bw);
+            emit(cursor, b);
+            cursor += skeleton.size() - b;
+            page_value_offset[c][page_counter + (p0 / P)] = cursor;
+            cursor += (uint64_t)((np + 7) / 8) * dicts[c].bw;
+          } else if (!table.cols[c].has_nulls) {
             pq::write_plain_page_prefix(skeleton, cursor, np, W);  // file images start 64-byte aligned in the arena
             emit(cursor, b);
             cursor += skeleton.size() - b;
@@ -634,6 +732,12 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     gc.key_type = dc.type;
     gc.width = dc.width;
     gc.page_value_offset = d_pvo.get() + (size_t)c * page_counter;
+    if (dicts[c].use) {
+      launch_dict_encode(ctx, req.plan->tiles.get(), ntiles, req.plan->seg_start.get(), req.d_perm, dc.data.get(), dc.width,
+                         dicts[c].keys.get(), dicts[c].slot_index.get(), kDictCapacity, dicts[c].empty_index, dicts[c].bw,
+                         d_pvo.get() + (size_t)c * page_counter, d_page_begin.get(), P, out->arena.get());
+      continue;
+    }
     if (dc.has_nulls) {
       Buf<uint64_t> d_voff(ctx, std::max<int64_t>(1, ntiles)), d_doff(ctx, std::max<int64_t>(1, ntiles));
       if (ntiles) {

@@ -89,6 +89,7 @@ struct EncodeRequest {
   int64_t rows_per_page = 0;
   int64_t rows_per_row_group = 0;
   std::vector<int64_t> seg_rows_per_row_group;  // optional per-segment override
+  bool use_dictionary = true;                   // dictionary-encode columns whose distinct values fit (like parquet-mr)
 };
 struct EncodedFiles {
   Buf<uint8_t> arena;       // device

@@ -338,6 +338,27 @@ inline void write_nullable_page_prefix(std::vector<uint8_t>& out, int64_t n, int
   out.insert(out.end(), hv, hv + hl);
 }
 
+// [page header][all-valid definition levels][bit width byte][bit-packed run header] of a PLAIN_DICTIONARY v1 data page of
+// `n` non-null values whose indices are written as ONE bit-packed run of ceil(n/8) groups of `bw` bits (the packed bytes
+// follow this prefix).
+inline void write_dict_data_page_prefix(std::vector<uint8_t>& out, int64_t n, uint32_t bw) {
+  std::vector<uint8_t> defs;
+  write_all_valid_def_levels(defs, n);
+  const uint64_t groups = (uint64_t)(n + 7) / 8;
+  uint8_t hv[10];
+  int hl = 0;
+  uint64_t h = (groups << 1) | 1;
+  while (h >= 0x80) {
+    hv[hl++] = (uint8_t)(h | 0x80);
+    h >>= 7;
+  }
+  hv[hl++] = (uint8_t)h;
+  write_data_page_header(out, (int32_t)(defs.size() + 1 + hl + groups * bw), (int32_t)n, ENC_PLAIN_DICTIONARY);
+  out.insert(out.end(), defs.begin(), defs.end());
+  out.push_back((uint8_t)bw);
+  out.insert(out.end(), hv, hv + hl);
+}
+
 struct OutChunk {
   int32_t type;
   int64_t num_values;

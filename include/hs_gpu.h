@@ -120,7 +120,8 @@ typedef struct {
    * CoveringIndexTrait.scala:78-94).  Requires a `_data_file_id` column in the source files. */
   const int64_t* deleted_file_ids;
   int32_t n_deleted_file_ids;
-  int32_t reserved;
+  int32_t disable_dictionary; /* 0 (default): dictionary-encode columns whose distinct values fit a dictionary page, as
+                                 parquet-mr does; != 0: PLAIN only */
 } hs_index_spec;
 
 typedef struct {
@@ -223,9 +224,11 @@ int hs_k_sort_perm(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64
 
 /* Synthetic table T of the benchmark: rows [first_row, first_row+nrows) of
  * (k:int64, v1:int64, v2:float64, v3:int32, v4:float32)[:ncols], generated and Parquet-encoded on the GPU into
- * n_files file images of row_groups_per_file row groups each (HS_OUT_HOST or HS_OUT_DEVICE). */
+ * n_files file images of row_groups_per_file row groups each (HS_OUT_HOST or HS_OUT_DEVICE).  dictionary != 0: low-cardinality
+ * columns (v1, v3, v4) are PLAIN_DICTIONARY-encoded like a parquet-mr / pyarrow writer would; 0: PLAIN only. */
 int hs_synth_table(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, int32_t n_files,
-                   int32_t row_groups_per_file, int32_t output, hs_index_result** out, char* err, size_t errlen);
+                   int32_t row_groups_per_file, int32_t dictionary, int32_t output, hs_index_result** out, char* err,
+                   size_t errlen);
 
 #ifdef __cplusplus
 }

@@ -264,6 +264,42 @@ def test_create_index_is_deterministic_and_device_resident_inputs_work(ctx):
         r.free()
 
 
+def test_dictionary_encoding_applied_and_optional(ctx):
+    """Low-cardinality columns are PLAIN_DICTIONARY-encoded (as parquet-mr does); high-cardinality ones stay PLAIN."""
+    from hyperspace_b200 import _native
+
+    n = 150_000
+    cols = O.synthetic_table(0, n, 5)
+    src = ctx.synth_table(0, n, 5, n_files=2, row_groups_per_file=2, output=_native.HS_OUT_HOST, dictionary=True)
+    md = pq.ParquetFile(pa.BufferReader(src.host_bytes(0))).metadata
+    enc = {md.schema.column(i).name: md.row_group(0).column(i) for i in range(5)}
+    assert enc["v1"].has_dictionary_page and enc["v3"].has_dictionary_page and enc["v4"].has_dictionary_page
+    assert not enc["k"].has_dictionary_page and not enc["v2"].has_dictionary_page
+    assert enc["v1"].total_compressed_size < enc["k"].total_compressed_size // 4   # 10 bits vs 64 bits per value
+    got = pa.concat_tables([_read_image(src.host_bytes(i)) for i in range(2)])
+    for name, arr in cols.items():
+        assert np.array_equal(_bits(got.column(name).to_numpy()), _bits(arr)), name
+    plain = ctx.synth_table(0, n, 5, n_files=2, row_groups_per_file=2, output=_native.HS_OUT_HOST, dictionary=False)
+    assert sum(f.size for f in src.files) < 0.7 * sum(f.size for f in plain.files)
+    for dictionary in (True, False):
+        res, st = ctx.create_index(src.as_sources(), ["k"], ["v1", "v2", "v3", "v4"], 20, output=_native.HS_OUT_HOST, job_uuid="dd",
+                                   dictionary=dictionary)
+        _check_index(res, cols, ["k"], ["v1", "v2", "v3", "v4"], 20, "dd")
+        m = pq.ParquetFile(pa.BufferReader(res.host_bytes(0))).metadata.row_group(0)
+        assert m.column(1).has_dictionary_page == dictionary and not m.column(0).has_dictionary_page
+        res.free()
+    # values equal to the hash set's empty marker (all ones) and a single-value column
+    sink = io.BytesIO()
+    odd = {"k": np.arange(5000, dtype=np.int64), "a": np.where(np.arange(5000) % 3 == 0, -1, 7).astype(np.int64),
+           "b": np.full(5000, 3, dtype=np.int32)}
+    pq.write_table(pa.table(odd), sink, compression="NONE")
+    res, _ = ctx.create_index([_native.FileImage(data=sink.getvalue())], ["k"], ["a", "b"], 4, output=_native.HS_OUT_HOST, job_uuid="o")
+    _check_index(res, odd, ["k"], ["a", "b"], 4, "o")
+    res.free()
+    src.free()
+    plain.free()
+
+
 def test_lineage_column(ctx, tmp_path):
     from hyperspace_b200 import _native
 
