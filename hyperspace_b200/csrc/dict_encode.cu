@@ -43,15 +43,19 @@ __global__ void __launch_bounds__(kThreads) k_dict_build(const void* __restrict_
       continue;
     }
     uint32_t h = dict_hash(v) & mask;
-    for (;;) {
+    // Successful inserts are reserved through state[0] BEFORE the CAS, so at most max_distinct slots of the
+    // 4 x max_distinct table are ever occupied and probing always terminates.
+    for (uint32_t probes = 0; probes <= mask; probes++) {
       const unsigned long long cur = keys[h];
       if (cur == v) break;
       if (cur == kEmpty) {
-        const unsigned long long old = atomicCAS(&keys[h], kEmpty, (unsigned long long)v);
-        if (old == kEmpty) {
-          if (atomicAdd(&state[0], 1u) + 1 > max_distinct) state[1] = 1;
-          break;
+        if (atomicAdd(&state[0], 1u) >= max_distinct) {
+          state[1] = 1;
+          return;
         }
+        const unsigned long long old = atomicCAS(&keys[h], kEmpty, (unsigned long long)v);
+        if (old == kEmpty) break;          // inserted
+        atomicSub(&state[0], 1u);          // lost the race for this slot: give the reservation back
         if (old == v) break;
       }
       h = (h + 1) & mask;
@@ -80,7 +84,8 @@ __global__ void __launch_bounds__(kThreads) k_dict_encode(const SortTile* __rest
     uint32_t idx = empty_index;
     if (v != kEmpty) {
       uint32_t h = dict_hash(v) & mask;
-      while (keys[h] != v) h = (h + 1) & mask;  // present by construction
+      uint32_t probes = 0;
+      while (keys[h] != v && probes++ <= mask) h = (h + 1) & mask;  // present by construction; bounded regardless
       idx = slot_index[h];
     }
     const uint32_t bit = i * bw;
