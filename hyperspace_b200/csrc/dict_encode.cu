@@ -17,14 +17,8 @@ namespace {
 constexpr unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ uint32_t dict_hash(uint64_t v) {
-  v ^= v >> 33;
-  v *= 0xff51afd7ed558ccdull;
-  v ^= v >> 33;
-  v *= 0xc4ceb9fe1a85ec53ull;
-  v ^= v >> 33;
-  return (uint32_t)v;
-}
+// Fibonacci hashing: one 64-bit multiply; the top bits of the product depend on every input bit
+__device__ __forceinline__ uint32_t dict_hash(uint64_t v) { return (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> 32); }
 
 __device__ __forceinline__ uint64_t load_raw_value(const void* src, int width, int64_t i) {
   return width == 8 ? ((const uint64_t*)src)[i] : (uint64_t)((const uint32_t*)src)[i];
@@ -35,72 +29,127 @@ __global__ void __launch_bounds__(kThreads) k_dict_build(const void* __restrict_
                                                           unsigned long long* __restrict__ keys, uint32_t mask,
                                                           uint32_t max_distinct, uint32_t* __restrict__ state) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
-    if (*(volatile uint32_t*)&state[1]) return;
-    const uint64_t v = load_raw_value(src, width, i);
-    if (v == kEmpty) {
-      state[2] = 1;
-      continue;
-    }
-    uint32_t h = dict_hash(v) & mask;
-    // Successful inserts are reserved through state[0] BEFORE the CAS, so at most max_distinct slots of the
-    // 4 x max_distinct table are ever occupied and probing always terminates.
-    for (uint32_t probes = 0; probes <= mask; probes++) {
-      const unsigned long long cur = keys[h];
-      if (cur == v) break;
-      if (cur == kEmpty) {
-        if (atomicAdd(&state[0], 1u) >= max_distinct) {
-          state[1] = 1;
-          return;
-        }
-        const unsigned long long old = atomicCAS(&keys[h], kEmpty, (unsigned long long)v);
-        if (old == kEmpty) break;          // inserted
-        atomicSub(&state[0], 1u);          // lost the race for this slot: give the reservation back
-        if (old == v) break;
+  uint32_t it = 0;
+  for (int64_t i0 = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end; i0 += 2 * stride, it++) {
+    // the overflow flag lives in one L2 line: polling it for every element serialises the whole grid on that line
+    // (measured: 31 ms for 3 columns x 1 B rows), so look only every 32 iterations
+    if ((it & 31) == 0 && *(volatile uint32_t*)&state[1]) return;
+    const int64_t i1 = i0 + stride;
+    uint64_t vals[2];
+    vals[0] = load_raw_value(src, width, i0);
+    vals[1] = i1 < end ? load_raw_value(src, width, i1) : vals[0];  // two independent loads in flight
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const uint64_t v = vals[u];
+      if (v == kEmpty) {
+        state[2] = 1;
+        continue;
       }
-      h = (h + 1) & mask;
+      uint32_t h = dict_hash(v) & mask;
+      // A thread inserts only while the distinct count is still below max_distinct; threads that passed that check
+      // concurrently can overshoot by at most two inserts each, and the launcher caps the grid so that
+      // max_distinct + 2 * #threads stays below the table capacity: the table never fills, probing terminates.
+      for (uint32_t probes = 0; probes <= mask; probes++) {
+        const unsigned long long cur = keys[h];
+        if (cur == v) break;
+        if (cur == kEmpty) {
+          if (*(volatile uint32_t*)&state[0] >= max_distinct) {
+            state[1] = 1;
+            return;
+          }
+          const unsigned long long old = atomicCAS(&keys[h], kEmpty, (unsigned long long)v);
+          if (old == kEmpty) {
+            atomicAdd(&state[0], 1u);
+            break;
+          }
+          if (old == v) break;
+        }
+        h = (h + 1) & mask;
+      }
     }
   }
 }
 
-template <int W>
-__global__ void __launch_bounds__(kThreads) k_dict_encode(const SortTile* __restrict__ tiles,
-                                                           const uint64_t* __restrict__ seg_start,
-                                                           const uint32_t* __restrict__ perm, const void* __restrict__ src,
-                                                           const unsigned long long* __restrict__ keys,
-                                                           const uint32_t* __restrict__ slot_index, uint32_t mask,
-                                                           uint32_t empty_index, uint32_t bw,
-                                                           const uint64_t* __restrict__ page_value_offset,
-                                                           const uint32_t* __restrict__ bucket_page_begin,
-                                                           int64_t rows_per_page, uint8_t* __restrict__ arena) {
-  __shared__ uint32_t s_bits[kSortTile * 16 / 32 + 1];  // up to 16 bits per index
-  const SortTile t = tiles[blockIdx.x];
-  const uint32_t words = (kSortTile * bw + 31) / 32 + 1;
-  for (uint32_t w = threadIdx.x; w < words; w += kThreads) s_bits[w] = 0;
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < t.count; i += kThreads) {
-    const uint32_t row = perm[t.start + i];
-    const uint64_t v = W == 8 ? ((const uint64_t*)src)[row] : (uint64_t)((const uint32_t*)src)[row];
-    uint32_t idx = empty_index;
-    if (v != kEmpty) {
-      uint32_t h = dict_hash(v) & mask;
-      uint32_t probes = 0;
-      while (keys[h] != v && probes++ <= mask) h = (h + 1) & mask;  // present by construction; bounded regardless
-      idx = slot_index[h];
+// Streaming map value -> dictionary index (u16) in partitioned row order.  Coalesced reads, no payload gathers, so the few
+// hot lines of the hash table stay in L1; the gather + bit-pack pass below then moves 2-byte indices instead of values.
+__global__ void __launch_bounds__(kThreads) k_dict_map(const void* __restrict__ src, int width, int64_t n,
+                                                        const unsigned long long* __restrict__ keys,
+                                                        const uint32_t* __restrict__ slot_index, uint32_t mask,
+                                                        uint32_t empty_index, uint16_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    uint64_t vals[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {  // four independent streaming loads in flight per thread
+      const int64_t i = i0 + u * stride;
+      vals[u] = i < n ? load_raw_value(src, width, i) : kEmpty;
     }
-    const uint32_t bit = i * bw;
-    const uint32_t sh = bit & 31;
-    atomicOr(&s_bits[bit >> 5], idx << sh);
-    if (sh + bw > 32) atomicOr(&s_bits[(bit >> 5) + 1], idx >> (32 - sh));
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n) break;
+      const uint64_t v = vals[u];
+      uint32_t ix = empty_index;
+      if (v != kEmpty) {
+        uint32_t h = dict_hash(v) & mask;
+        uint32_t probes = 0;
+        while (keys[h] != v && probes++ <= mask) h = (h + 1) & mask;  // present by construction; bounded regardless
+        ix = slot_index[h];
+      }
+      out[i] = (uint16_t)ix;
+    }
+  }
+}
+
+// One thread = one bit-packing group of 8 values (bw bytes, byte aligned in the page): gathers eight 2-byte indices through
+// the sort permutation, packs them in a 128-bit register pair, stages the tile in shared memory and copies it out coalesced.
+__global__ void __launch_bounds__(kThreads) k_dict_pack(const SortTile* __restrict__ tiles,
+                                                         const uint64_t* __restrict__ seg_start,
+                                                         const uint32_t* __restrict__ perm,
+                                                         const uint16_t* __restrict__ idx16, uint32_t bw,
+                                                         const uint64_t* __restrict__ page_value_offset,
+                                                         const uint32_t* __restrict__ bucket_page_begin,
+                                                         int64_t rows_per_page, uint8_t* __restrict__ arena) {
+  __shared__ __align__(16) uint8_t s_bytes[kSortTile / 8 * 16];  // up to 16 bytes per group
+  const SortTile t = tiles[blockIdx.x];
+  const uint32_t ngroups = (t.count + 7) / 8;
+  for (uint32_t g = threadIdx.x; g < ngroups; g += kThreads) {
+    uint32_t ix[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t i = g * 8 + j;
+      ix[j] = i < t.count ? idx16[perm[t.start + i]] : 0u;  // padding indices of the last group are zero
+    }
+    unsigned long long lo = 0, hi = 0;  // 8 x bw <= 128 bits, LSB first
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t bit = j * bw;
+      if (bit < 64) {
+        lo |= (unsigned long long)ix[j] << bit;
+        if (bit + bw > 64) hi |= (unsigned long long)ix[j] >> (64 - bit);
+      } else {
+        hi |= (unsigned long long)ix[j] << (bit - 64);
+      }
+    }
+    uint8_t* dst = s_bytes + (size_t)g * bw;
+    for (uint32_t b = 0; b < bw; b++) dst[b] = (uint8_t)(b < 8 ? (lo >> (8 * b)) : (hi >> (8 * (b - 8))));
   }
   __syncthreads();
   const uint64_t lr0 = t.start - seg_start[t.seg];
   const uint64_t page = lr0 / (uint64_t)rows_per_page;
   const uint64_t in_page = lr0 - page * (uint64_t)rows_per_page;
   uint8_t* const out = arena + page_value_offset[bucket_page_begin[t.seg] + page] + in_page * bw / 8;
-  const uint32_t nbytes = ((t.count + 7) / 8) * bw;  // whole groups of 8 values; the padding indices are zero
-  const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_bits);
-  for (uint32_t b = threadIdx.x; b < nbytes; b += kThreads) out[b] = sb[b];
+  const uint32_t nbytes = ngroups * bw;
+  // coalesced copy: 4-byte words once the destination is aligned (page offsets are arbitrary)
+  const uint32_t head = min(nbytes, (uint32_t)((4 - ((uintptr_t)out & 3)) & 3));
+  for (uint32_t b = threadIdx.x; b < head; b += kThreads) out[b] = s_bytes[b];
+  const uint32_t nwords = (nbytes - head) / 4;
+  uint32_t* out32 = reinterpret_cast<uint32_t*>(out + head);
+  for (uint32_t w = threadIdx.x; w < nwords; w += kThreads) {
+    const uint8_t* p = s_bytes + head + 4 * w;
+    out32[w] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+  }
+  for (uint32_t b = head + 4 * nwords + threadIdx.x; b < nbytes; b += kThreads) out[b] = s_bytes[b];
 }
 
 inline int grid_for(hs_ctx* ctx, int64_t n, int threads, int per_sm) {
@@ -115,25 +164,28 @@ void launch_dict_build(hs_ctx* ctx, const void* src, int width, int64_t begin, i
                        uint32_t capacity, uint32_t max_distinct, uint32_t* state) {
   KernelScope _ks(ctx, "k_dict_build");
   if (end <= begin) return;
-  k_dict_build<<<grid_for(ctx, end - begin, kThreads, 16), kThreads, 0, ctx->stream>>>(src, width, begin, end, keys,
-                                                                                       capacity - 1, max_distinct, state);
+  // grid * 256 threads * 2 values + max_distinct < capacity: see the capacity argument in k_dict_build
+  int grid = grid_for(ctx, end - begin, kThreads * 2, 6);
+  while ((uint64_t)grid * kThreads * 2 + max_distinct >= capacity && grid > 1) grid /= 2;
+  k_dict_build<<<grid, kThreads, 0, ctx->stream>>>(src, width, begin, end, keys, capacity - 1, max_distinct, state);
   HS_LAUNCH_CHECK(ctx);
 }
 
 void launch_dict_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,
-                        const void* src, int width, const unsigned long long* keys, const uint32_t* slot_index,
-                        uint32_t capacity, uint32_t empty_index, uint32_t bw, const uint64_t* page_value_offset,
-                        const uint32_t* bucket_page_begin, int64_t rows_per_page, uint8_t* arena) {
-  KernelScope _ks(ctx, "k_dict_encode");
+                        const void* src, int width, int64_t nrows, const unsigned long long* keys, const uint32_t* slot_index,
+                        uint32_t capacity, uint32_t empty_index, uint32_t bw, uint16_t* idx16_scratch,
+                        const uint64_t* page_value_offset, const uint32_t* bucket_page_begin, int64_t rows_per_page,
+                        uint8_t* arena) {
   if (ntiles == 0) return;
-  if (width == 8)
-    k_dict_encode<8><<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, seg_start, perm, src, keys, slot_index, capacity - 1,
-                                                                      empty_index, bw, page_value_offset, bucket_page_begin,
-                                                                      rows_per_page, arena);
-  else
-    k_dict_encode<4><<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, seg_start, perm, src, keys, slot_index, capacity - 1,
-                                                                      empty_index, bw, page_value_offset, bucket_page_begin,
-                                                                      rows_per_page, arena);
+  {
+    KernelScope _ks(ctx, "k_dict_map");
+    k_dict_map<<<grid_for(ctx, nrows, kThreads, 16), kThreads, 0, ctx->stream>>>(src, width, nrows, keys, slot_index, capacity - 1,
+                                                                                  empty_index, idx16_scratch);
+    HS_LAUNCH_CHECK(ctx);
+  }
+  KernelScope _ks(ctx, "k_dict_pack");
+  k_dict_pack<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, seg_start, perm, idx16_scratch, bw, page_value_offset,
+                                                              bucket_page_begin, rows_per_page, arena);
   HS_LAUNCH_CHECK(ctx);
 }
 

@@ -509,6 +509,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     uint32_t bw = 0, ndict = 0, empty_index = 0;
     Buf<unsigned long long> keys;
     Buf<uint32_t> slot_index;
+    Buf<unsigned long long> d_values;   // sorted dictionary on the device
     size_t skel_off = 0, skel_len = 0;  // [dictionary page header][PLAIN values] inside the skeleton
     std::vector<uint64_t> values;       // sorted dictionary (raw bits)
   };
@@ -524,8 +525,8 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       HS_CUDA(cudaMemsetAsync(cd.keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
       HS_CUDA(cudaMemsetAsync(d_state.get(), 0, 16, ctx->stream));
       uint32_t st[4] = {0, 0, 0, 0};
-      // a 1 M-row sample first: high-cardinality columns (keys, measures) overflow here and cost almost nothing
-      const int64_t sample = std::min<int64_t>(total_rows, 1 << 20);
+      // a 256 K-row sample first: high-cardinality columns (keys, measures) overflow here and cost almost nothing
+      const int64_t sample = std::min<int64_t>(total_rows, 1 << 18);
       launch_dict_build(ctx, dc.data.get(), dc.width, 0, sample, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state.get());
       HS_CUDA(cudaMemcpyAsync(st, d_state.get(), 16, cudaMemcpyDeviceToHost, ctx->stream));
       HS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -571,6 +572,8 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       }
       cd.slot_index.alloc(ctx, kDictCapacity);
       HS_CUDA(cudaMemcpyAsync(cd.slot_index.get(), slot.data(), 4 * kDictCapacity, cudaMemcpyHostToDevice, ctx->stream));
+      cd.d_values.alloc(ctx, cd.ndict);
+      HS_CUDA(cudaMemcpyAsync(cd.d_values.get(), cd.values.data(), 8 * (size_t)cd.ndict, cudaMemcpyHostToDevice, ctx->stream));
       HS_CUDA(cudaStreamSynchronize(ctx->stream));
       cd.use = true;
     }
@@ -733,9 +736,11 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     gc.width = dc.width;
     gc.page_value_offset = d_pvo.get() + (size_t)c * page_counter;
     if (dicts[c].use) {
+      Buf<uint16_t> idx16(ctx, std::max<int64_t>(1, table.nrows));
       launch_dict_encode(ctx, req.plan->tiles.get(), ntiles, req.plan->seg_start.get(), req.d_perm, dc.data.get(), dc.width,
-                         dicts[c].keys.get(), dicts[c].slot_index.get(), kDictCapacity, dicts[c].empty_index, dicts[c].bw,
-                         d_pvo.get() + (size_t)c * page_counter, d_page_begin.get(), P, out->arena.get());
+                         table.nrows, dicts[c].keys.get(), dicts[c].slot_index.get(), kDictCapacity, dicts[c].empty_index,
+                         dicts[c].bw, idx16.get(), d_pvo.get() + (size_t)c * page_counter, d_page_begin.get(), P,
+                         out->arena.get());
       continue;
     }
     if (dc.has_nulls) {

@@ -153,16 +153,18 @@ void launch_gather_encode_nullable(hs_ctx* ctx, const SortTile* tiles, int64_t n
                                    const uint64_t* tile_def_offset, uint8_t* arena);
 // ---- dictionary encoding (dict_encode.cu) -------------------------------------------------------------------------
 constexpr uint32_t kMaxDictEntries = 65536;          // bit width <= 16
-constexpr uint32_t kDictCapacity = 4 * kMaxDictEntries;  // open-addressing slots (power of two)
+constexpr uint32_t kDictCapacity = 8 * kMaxDictEntries;  // open-addressing slots (power of two)
 // inserts the distinct raw values of src[begin, end) into the hash set `keys` (capacity slots preset to all-ones);
 // state[0] = distinct count, state[1] = 1 when more than max_distinct values were seen, state[2] = the all-ones value occurs
 void launch_dict_build(hs_ctx* ctx, const void* src, int width, int64_t begin, int64_t end, unsigned long long* keys,
                        uint32_t capacity, uint32_t max_distinct, uint32_t* state);
-// per tile: index = slot_index[slot of src[perm[p]]], bit-packed with `bw` bits into the page body
+// two passes: (1) streaming map of every value of src[0, nrows) to its dictionary index (u16 scratch, partitioned order);
+// (2) per tile, gather the indices through perm and bit-pack them with `bw` bits into the page body
 void launch_dict_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,
-                        const void* src, int width, const unsigned long long* keys, const uint32_t* slot_index,
-                        uint32_t capacity, uint32_t empty_index, uint32_t bw, const uint64_t* page_value_offset,
-                        const uint32_t* bucket_page_begin, int64_t rows_per_page, uint8_t* arena);
+                        const void* src, int width, int64_t nrows, const unsigned long long* keys, const uint32_t* slot_index,
+                        uint32_t capacity, uint32_t empty_index, uint32_t bw, uint16_t* idx16_scratch,
+                        const uint64_t* page_value_offset, const uint32_t* bucket_page_begin, int64_t rows_per_page,
+                        uint8_t* arena);
 // Plain gather: out[i] = src[perm[i]]
 void launch_gather_plain(hs_ctx* ctx, const void* src, const uint32_t* perm, int64_t n, int width, void* out);
 struct ByteCopy {
