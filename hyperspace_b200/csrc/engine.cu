@@ -440,7 +440,29 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
     HS_CUDA(cudaMemcpyAsync(or_and, d_or_and.get(), sizeof or_and, cudaMemcpyDeviceToHost, ctx->stream));
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
     const uint64_t varying = nrows ? (or_and[0] ^ or_and[1]) : 0;
-    segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying);
+    // Keys with more than four varying bytes: LSD passes over the top four varying bytes only, then fix up the (rare,
+    // short) runs of rows that agree on those bytes.  Falls back to full passes when a run is long (low-entropy high bytes).
+    int nbytes = 0, fourth_from_top = 0;
+    for (int b = 7, seen = 0; b >= 0; b--)
+      if ((varying >> (8 * b)) & 0xff) {
+        nbytes++;
+        if (++seen == 4) fourth_from_top = b;
+      }
+    static const bool full_sort_only = getenv("HS_FULL_SORT") != nullptr;
+    if (nbytes > 4 && !full_sort_only) {
+      const uint64_t high_mask = ~0ull << (8 * fourth_from_top);
+      const uint64_t low_mask = ~high_mask;
+      segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying & high_mask);
+      Buf<uint32_t> d_flag(ctx, 1);
+      HS_CUDA(cudaMemsetAsync(d_flag.get(), 0, 4, ctx->stream));
+      launch_fix_runs(ctx, &out->plan, keys, perm, high_mask, low_mask, 64, d_flag.get());
+      uint32_t flag = 0;
+      HS_CUDA(cudaMemcpyAsync(&flag, d_flag.get(), 4, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (flag) segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying);
+    } else {
+      segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying);
+    }
     if (kc.has_nulls)  // nulls first: one more stable pass on the validity byte (0 = null)
       segmented_sort_pass_by_table(ctx, &out->plan, keys, keys_alt, perm, perm_alt, kc.valid.get());
   }

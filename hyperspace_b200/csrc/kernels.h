@@ -128,6 +128,10 @@ void build_sort_plan(hs_ctx* ctx, const uint64_t* seg_offsets, int nseg, SortPla
 // are all constant are skipped).  Result is left in (keys, vals); (keys_alt, vals_alt) are scratch of the same size.
 void segmented_sort_pairs(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,
                           uint32_t*& vals_alt, uint64_t bit_mask);
+// After sorting on the bits of high_mask: stable insertion sort of every run of equal (key & high_mask) on (key & low_mask);
+// *d_flag is set when a run is longer than max_run (the caller then runs the remaining passes instead).
+void launch_fix_runs(hs_ctx* ctx, SortPlan* plan, uint64_t* keys, uint32_t* vals, uint64_t high_mask, uint64_t low_mask,
+                     uint32_t max_run, uint32_t* d_flag);
 // One extra stable pass on an external 8-bit digit: digit = digits[vals[i]]  (null flags for nullable 64-bit keys)
 void segmented_sort_pass_by_table(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,
                                   uint32_t*& vals_alt, const uint8_t* digits);

@@ -203,6 +203,46 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const SortTile* __res
   }
 }
 
+// ---- tie-run fix-up ---------------------------------------------------------------------------------------------
+// After the stable LSD passes over the HIGH bytes of the key, rows are ordered by (key & high_mask) and rows that share
+// those bits still sit in their original relative order.  For high-entropy keys such runs are rare and tiny, so instead
+// of four more full passes over the data the head of every run insertion-sorts it (stably) on (key & low_mask).  A run
+// longer than max_run raises `flag`; the caller then falls back to full LSD passes, which is still correct because equal
+// full keys are in original order both inside untouched runs and inside insertion-sorted ones.
+__global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ tiles, const uint64_t* __restrict__ seg_start,
+                                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                   uint64_t high_mask, uint64_t low_mask, uint32_t max_run,
+                                                   uint32_t* __restrict__ flag) {
+  const SortTile t = tiles[blockIdx.x];
+  const uint64_t segb = seg_start[t.seg], sege = seg_start[t.seg + 1];
+  for (uint32_t i = threadIdx.x; i < t.count; i += blockDim.x) {
+    const uint64_t p = t.start + i;
+    const uint64_t kh = keys[p] & high_mask;
+    if (p > segb && (keys[p - 1] & high_mask) == kh) continue;  // not the head of a run
+    uint64_t q = p + 1;
+    while (q < sege && q - p <= max_run && (keys[q] & high_mask) == kh) q++;
+    const uint32_t len = (uint32_t)(q - p);
+    if (len == 1) continue;
+    if (len > max_run) {
+      *flag = 1;
+      continue;
+    }
+    for (uint32_t a = 1; a < len; a++) {  // stable insertion sort on the low bits
+      const uint64_t ka = keys[p + a];
+      const uint32_t va = vals[p + a];
+      const uint64_t la = ka & low_mask;
+      uint32_t b = a;
+      while (b > 0 && (keys[p + b - 1] & low_mask) > la) {
+        keys[p + b] = keys[p + b - 1];
+        vals[p + b] = vals[p + b - 1];
+        b--;
+      }
+      keys[p + b] = ka;
+      vals[p + b] = va;
+    }
+  }
+}
+
 template <typename Digit>
 void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchunks, const uint32_t* seg_chunk_begin,
               uint32_t* chunk_sums, const uint64_t* keys, const uint32_t* vals, uint64_t* out_keys, uint32_t* out_vals,
@@ -309,6 +349,15 @@ void segmented_sort_pairs(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t
     std::swap(keys, keys_alt);
     std::swap(vals, vals_alt);
   }
+}
+
+void launch_fix_runs(hs_ctx* ctx, SortPlan* plan, uint64_t* keys, uint32_t* vals, uint64_t high_mask, uint64_t low_mask,
+                     uint32_t max_run, uint32_t* d_flag) {
+  KernelScope _ks(ctx, "k_fix_runs");
+  if (plan->ntiles == 0) return;
+  k_fix_runs<<<(unsigned)plan->ntiles, 256, 0, ctx->stream>>>(plan->tiles.get(), plan->seg_start.get(), keys, vals, high_mask,
+                                                              low_mask, max_run, d_flag);
+  HS_LAUNCH_CHECK(ctx);
 }
 
 void segmented_sort_pass_by_table(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,

@@ -87,6 +87,24 @@ def test_sort_perm_matches_oracle_exactly(ctx, n, nb, lo, hi):
     assert np.array_equal(perm, want_perm)  # stable: ties keep source order, like the oracle
 
 
+def test_sort_tie_run_fixup_and_fallback(ctx):
+    """Keys with > 4 varying bytes are sorted on their top four varying bytes and short tie runs are fixed up in place;
+    long runs (low-entropy high bytes) must fall back to full passes.  Both must equal the oracle's stable order."""
+    rng = np.random.default_rng(77)
+    n = 300_000
+    hi = rng.integers(0, 1 << 16, size=n, dtype=np.int64) << 44      # 65536 distinct values in the top bytes
+    lo = rng.integers(0, 5, size=n, dtype=np.int64) << 8             # few distinct low parts -> ties on the full key too
+    for keys in (hi | lo,                                             # short runs: fix-up path
+                 (rng.integers(0, 3, size=n, dtype=np.int64) << 60) | rng.integers(0, 1 << 30, size=n, dtype=np.int64),  # long runs
+                 -(hi | lo)):                                         # negative keys
+        for nb in (1, 8):
+            perm, offs = ctx.k_sort_perm([keys], nb)
+            b = O.bucket_ids([keys], nb)
+            want_perm, want_offs = O.sort_perm([keys], nb, b)
+            assert np.array_equal(offs, want_offs)
+            assert np.array_equal(perm, want_perm)
+
+
 def test_sort_perm_other_key_types(ctx):
     rng = np.random.default_rng(5)
     n = 100_000
