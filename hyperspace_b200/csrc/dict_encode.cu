@@ -70,6 +70,33 @@ __global__ void __launch_bounds__(kThreads) k_dict_build(const void* __restrict_
   }
 }
 
+// distinct values out of the hash set (order arbitrary; the host sorts the small list)
+__global__ void k_dict_collect(const unsigned long long* __restrict__ keys, uint32_t capacity,
+                               unsigned long long* __restrict__ out, uint32_t* __restrict__ counter) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= capacity) return;
+  const unsigned long long v = keys[s];
+  if (v != kEmpty) out[atomicAdd(counter, 1u)] = v;
+}
+
+// slot -> rank of its key in the sorted dictionary (binary search on the order-preserving encoding)
+__global__ void k_dict_slot_index(const unsigned long long* __restrict__ keys, uint32_t capacity,
+                                  const unsigned long long* __restrict__ sorted_values, uint32_t ndict, int type,
+                                  uint32_t* __restrict__ slot_index) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= capacity) return;
+  const unsigned long long v = keys[s];
+  if (v == kEmpty) return;
+  const uint64_t e = sort_encode(type, v);
+  uint32_t lo = 0, hi = ndict;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (sort_encode(type, sorted_values[mid]) < e) lo = mid + 1;
+    else hi = mid;
+  }
+  slot_index[s] = lo;
+}
+
 // Streaming map value -> dictionary index (u16) in partitioned row order.  Coalesced reads, no payload gathers, so the few
 // hot lines of the hash table stay in L1; the gather + bit-pack pass below then moves 2-byte indices instead of values.
 __global__ void __launch_bounds__(kThreads) k_dict_map(const void* __restrict__ src, int width, int64_t n,
@@ -168,6 +195,18 @@ void launch_dict_build(hs_ctx* ctx, const void* src, int width, int64_t begin, i
   int grid = grid_for(ctx, end - begin, kThreads * 2, 6);
   while ((uint64_t)grid * kThreads * 2 + max_distinct >= capacity && grid > 1) grid /= 2;
   k_dict_build<<<grid, kThreads, 0, ctx->stream>>>(src, width, begin, end, keys, capacity - 1, max_distinct, state);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity, unsigned long long* out,
+                         uint32_t* counter) {
+  k_dict_collect<<<(capacity + 255) / 256, 256, 0, ctx->stream>>>(keys, capacity, out, counter);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_dict_slot_index(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity,
+                            const unsigned long long* sorted_values, uint32_t ndict, int type, uint32_t* slot_index) {
+  k_dict_slot_index<<<(capacity + 255) / 256, 256, 0, ctx->stream>>>(keys, capacity, sorted_values, ndict, type, slot_index);
   HS_LAUNCH_CHECK(ctx);
 }
 

@@ -162,6 +162,11 @@ constexpr uint32_t kDictCapacity = 8 * kMaxDictEntries;  // open-addressing slot
 // state[0] = distinct count, state[1] = 1 when more than max_distinct values were seen, state[2] = the all-ones value occurs
 void launch_dict_build(hs_ctx* ctx, const void* src, int width, int64_t begin, int64_t end, unsigned long long* keys,
                        uint32_t capacity, uint32_t max_distinct, uint32_t* state);
+// compacts the distinct values out of the hash set (counter must be zeroed); then slot -> rank in the sorted dictionary
+void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity, unsigned long long* out,
+                         uint32_t* counter);
+void launch_dict_slot_index(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity,
+                            const unsigned long long* sorted_values, uint32_t ndict, int type, uint32_t* slot_index);
 // two passes: (1) streaming map of every value of src[0, nrows) to its dictionary index (u16 scratch, partitioned order);
 // (2) per tile, gather the indices through perm and bit-pack them with `bw` bits into the page body
 void launch_dict_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,

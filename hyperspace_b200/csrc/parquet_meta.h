@@ -311,11 +311,18 @@ inline void write_plain_page_prefix(std::vector<uint8_t>& out, uint64_t page_off
     }
     it = memo.emplace(key, best).first;
   }
-  std::vector<uint8_t> defs;
-  if (it->second.first >= 0) write_def_levels_runs(defs, n, it->second.first, it->second.second);
-  else write_all_valid_def_levels(defs, n);  // tiny page: the GPU falls back to its unaligned store path
-  write_data_page_header(out, (int32_t)(defs.size() + (size_t)n * W), (int32_t)n, ENC_PLAIN);
-  out.insert(out.end(), defs.begin(), defs.end());
+  // the serialised prefix itself is cached too: an index has tens of thousands of identical full pages
+  static thread_local std::map<Key, std::vector<uint8_t>> bytes_memo;
+  auto bt = bytes_memo.find(key);
+  if (bt == bytes_memo.end()) {
+    std::vector<uint8_t> pre, defs;
+    if (it->second.first >= 0) write_def_levels_runs(defs, n, it->second.first, it->second.second);
+    else write_all_valid_def_levels(defs, n);  // tiny page: the GPU falls back to its unaligned store path
+    write_data_page_header(pre, (int32_t)(defs.size() + (size_t)n * W), (int32_t)n, ENC_PLAIN);
+    pre.insert(pre.end(), defs.begin(), defs.end());
+    bt = bytes_memo.emplace(key, std::move(pre)).first;
+  }
+  out.insert(out.end(), bt->second.begin(), bt->second.end());
 }
 
 // [page header][4-byte length][bit-packed run header] for a v1 data page of `n` rows whose definition levels are written as
@@ -341,7 +348,14 @@ inline void write_nullable_page_prefix(std::vector<uint8_t>& out, int64_t n, int
 // [page header][all-valid definition levels][bit width byte][bit-packed run header] of a PLAIN_DICTIONARY v1 data page of
 // `n` non-null values whose indices are written as ONE bit-packed run of ceil(n/8) groups of `bw` bits (the packed bytes
 // follow this prefix).
-inline void write_dict_data_page_prefix(std::vector<uint8_t>& out, int64_t n, uint32_t bw) {
+inline void write_dict_data_page_prefix(std::vector<uint8_t>& real_out, int64_t n, uint32_t bw) {
+  static thread_local std::map<std::pair<int64_t, uint32_t>, std::vector<uint8_t>> memo;
+  auto it = memo.find({n, bw});
+  if (it != memo.end()) {
+    real_out.insert(real_out.end(), it->second.begin(), it->second.end());
+    return;
+  }
+  std::vector<uint8_t> out;
   std::vector<uint8_t> defs;
   write_all_valid_def_levels(defs, n);
   const uint64_t groups = (uint64_t)(n + 7) / 8;
@@ -357,6 +371,8 @@ inline void write_dict_data_page_prefix(std::vector<uint8_t>& out, int64_t n, ui
   out.insert(out.end(), defs.begin(), defs.end());
   out.push_back((uint8_t)bw);
   out.insert(out.end(), hv, hv + hl);
+  real_out.insert(real_out.end(), out.begin(), out.end());
+  memo.emplace(std::make_pair(n, bw), std::move(out));
 }
 
 struct OutChunk {
