@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <random>
 
 #include "device_utils.cuh"
@@ -451,14 +452,20 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
     const uint64_t varying = nrows ? (or_and[0] ^ or_and[1]) : 0;
     // Keys with more than four varying bytes: LSD passes over the top four varying bytes only, then fix up the (rare,
     // short) runs of rows that agree on those bytes.  Falls back to full passes when a run is long (low-entropy high bytes).
+    // How many high bytes: enough that a bucket's rows spread over more prefixes than it has rows (expected rows per
+    // prefix <= 0.5 for uniformly spread keys), at least 2.  5 M-row buckets -> 3 bytes, 125 M-row buckets -> 4.
+    uint64_t max_bucket = 1;
+    for (int b = 0; b < num_buckets; b++) max_bucket = std::max<uint64_t>(max_bucket, out->bucket_offsets[b + 1] - out->bucket_offsets[b]);
+    int want_bytes = 2;
+    while (want_bytes < 8 && (double)max_bucket / std::pow(256.0, want_bytes) > 0.5) want_bytes++;
     int nbytes = 0, fourth_from_top = 0;
     for (int b = 7, seen = 0; b >= 0; b--)
       if ((varying >> (8 * b)) & 0xff) {
         nbytes++;
-        if (++seen == 4) fourth_from_top = b;
+        if (++seen == want_bytes) fourth_from_top = b;
       }
     static const bool full_sort_only = getenv("HS_FULL_SORT") != nullptr;
-    if (nbytes > 4 && !full_sort_only) {
+    if (nbytes > want_bytes && !full_sort_only) {
       const uint64_t high_mask = ~0ull << (8 * fourth_from_top);
       const uint64_t low_mask = ~high_mask;
       segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying & high_mask);
@@ -759,14 +766,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     gc.key_type = dc.type;
     gc.width = dc.width;
     gc.page_value_offset = d_pvo.get() + (size_t)c * page_counter;
-    if (dicts[c].use) {
-      Buf<uint16_t> idx16(ctx, std::max<int64_t>(1, table.nrows));
-      launch_dict_encode(ctx, req.plan->tiles.get(), ntiles, req.plan->seg_start.get(), req.d_perm, dc.data.get(), dc.width,
-                         table.nrows, dicts[c].keys.get(), dicts[c].slot_index.get(), kDictCapacity, dicts[c].empty_index,
-                         dicts[c].bw, idx16.get(), d_pvo.get() + (size_t)c * page_counter, d_page_begin.get(), P,
-                         out->arena.get());
-      continue;
-    }
+    if (dicts[c].use) continue;  // handled below, all dictionary columns together
     if (dc.has_nulls) {
       Buf<uint64_t> d_voff(ctx, std::max<int64_t>(1, ntiles)), d_doff(ctx, std::max<int64_t>(1, ntiles));
       if (ntiles) {
@@ -780,6 +780,32 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     if (c == 0 && req.d_sorted_keys && (dc.type == HS_TYPE_INT32 || dc.type == HS_TYPE_INT64)) gc.sorted_keys = req.d_sorted_keys;
     launch_gather_encode(ctx, req.plan->tiles.get(), req.plan->ntiles, req.plan->seg_start.get(), req.d_perm, gc,
                          d_page_begin.get(), P, out->arena.get());
+  }
+  {  // dictionary columns, up to 8 per launch pair
+    std::vector<int> dcols;
+    for (int c = 0; c < ncols; c++)
+      if (dicts[c].use) dcols.push_back(c);
+    for (size_t b0 = 0; b0 < dcols.size(); b0 += 8) {
+      DictMapArgs ma;
+      DictPackArgs pa;
+      memset(&ma, 0, sizeof ma);
+      memset(&pa, 0, sizeof pa);
+      const int nd = (int)std::min<size_t>(8, dcols.size() - b0);
+      ma.ncols = pa.ncols = nd;
+      for (int j = 0; j < nd; j++) {
+        const int c = dcols[b0 + j];
+        ma.src[j] = table.cols[c].data.get();
+        ma.width[j] = table.cols[c].width;
+        ma.keys[j] = dicts[c].keys.get();
+        ma.slot_index[j] = dicts[c].slot_index.get();
+        ma.empty_index[j] = dicts[c].empty_index;
+        pa.page_value_offset[j] = d_pvo.get() + (size_t)c * page_counter;
+        pa.bw[j] = dicts[c].bw;
+      }
+      Buf<uint16_t> rec(ctx, (size_t)std::max<int64_t>(1, table.nrows) * (nd <= 4 ? 4 : 8));
+      launch_dict_encode_all(ctx, req.plan->tiles.get(), ntiles, req.plan->seg_start.get(), req.d_perm, ma, pa, table.nrows,
+                             kDictCapacity, rec.get(), d_page_begin.get(), P, out->arena.get());
+    }
   }
   t_enc.stop();
   HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host plan vectors are about to go out of scope

@@ -174,6 +174,24 @@ void launch_dict_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, cons
                         uint32_t capacity, uint32_t empty_index, uint32_t bw, uint16_t* idx16_scratch,
                         const uint64_t* page_value_offset, const uint32_t* bucket_page_begin, int64_t rows_per_page,
                         uint8_t* arena);
+// all dictionary columns of a table in one map + one pack launch (up to 8 columns per call)
+struct DictMapArgs {
+  const void* src[8];
+  const unsigned long long* keys[8];
+  const uint32_t* slot_index[8];
+  uint32_t empty_index[8];
+  int32_t width[8];
+  int32_t ncols;
+};
+struct DictPackArgs {
+  const uint64_t* page_value_offset[8];
+  uint32_t bw[8];
+  int32_t ncols;
+};
+// rec_scratch: nrows records of 4 (ncols <= 4) or 8 uint16 indices
+void launch_dict_encode_all(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,
+                            const DictMapArgs& map_args, const DictPackArgs& pack_args, int64_t nrows, uint32_t capacity,
+                            uint16_t* rec_scratch, const uint32_t* bucket_page_begin, int64_t rows_per_page, uint8_t* arena);
 // Plain gather: out[i] = src[perm[i]]
 void launch_gather_plain(hs_ctx* ctx, const void* src, const uint32_t* perm, int64_t n, int width, void* out);
 struct ByteCopy {
