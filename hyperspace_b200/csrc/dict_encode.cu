@@ -82,13 +82,17 @@ __global__ void k_dict_collect(const unsigned long long* __restrict__ keys, uint
 }
 
 // slot -> rank of its key in the sorted dictionary (binary search on the order-preserving encoding)
+// ... stored next to the key in one 16-byte entry, so that a look-up costs ONE 32-byte sector request
 __global__ void k_dict_slot_index(const unsigned long long* __restrict__ keys, uint32_t capacity,
                                   const unsigned long long* __restrict__ sorted_values, uint32_t ndict, int type,
-                                  uint32_t* __restrict__ slot_index) {
+                                  uint4* __restrict__ entries) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= capacity) return;
   const unsigned long long v = keys[s];
-  if (v == kEmpty) return;
+  if (v == kEmpty) {
+    entries[s] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+    return;
+  }
   const uint64_t e = sort_encode(type, v);
   uint32_t lo = 0, hi = ndict;
   while (lo < hi) {
@@ -96,89 +100,7 @@ __global__ void k_dict_slot_index(const unsigned long long* __restrict__ keys, u
     if (sort_encode(type, sorted_values[mid]) < e) lo = mid + 1;
     else hi = mid;
   }
-  slot_index[s] = lo;
-}
-
-// Streaming map value -> dictionary index (u16) in partitioned row order.  Coalesced reads, no payload gathers, so the few
-// hot lines of the hash table stay in L1; the gather + bit-pack pass below then moves 2-byte indices instead of values.
-__global__ void __launch_bounds__(kThreads) k_dict_map(const void* __restrict__ src, int width, int64_t n,
-                                                        const unsigned long long* __restrict__ keys,
-                                                        const uint32_t* __restrict__ slot_index, uint32_t mask,
-                                                        uint32_t empty_index, uint16_t* __restrict__ out) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
-    uint64_t vals[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {  // four independent streaming loads in flight per thread
-      const int64_t i = i0 + u * stride;
-      vals[u] = i < n ? load_raw_value(src, width, i) : kEmpty;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int64_t i = i0 + u * stride;
-      if (i >= n) break;
-      const uint64_t v = vals[u];
-      uint32_t ix = empty_index;
-      if (v != kEmpty) {
-        uint32_t h = dict_hash(v) & mask;
-        uint32_t probes = 0;
-        while (keys[h] != v && probes++ <= mask) h = (h + 1) & mask;  // present by construction; bounded regardless
-        ix = slot_index[h];
-      }
-      out[i] = (uint16_t)ix;
-    }
-  }
-}
-
-// One thread = one bit-packing group of 8 values (bw bytes, byte aligned in the page): gathers eight 2-byte indices through
-// the sort permutation, packs them in a 128-bit register pair, stages the tile in shared memory and copies it out coalesced.
-__global__ void __launch_bounds__(kThreads) k_dict_pack(const SortTile* __restrict__ tiles,
-                                                         const uint64_t* __restrict__ seg_start,
-                                                         const uint32_t* __restrict__ perm,
-                                                         const uint16_t* __restrict__ idx16, uint32_t bw,
-                                                         const uint64_t* __restrict__ page_value_offset,
-                                                         const uint32_t* __restrict__ bucket_page_begin,
-                                                         int64_t rows_per_page, uint8_t* __restrict__ arena) {
-  __shared__ __align__(16) uint8_t s_bytes[kSortTile / 8 * 16];  // up to 16 bytes per group
-  const SortTile t = tiles[blockIdx.x];
-  const uint32_t ngroups = (t.count + 7) / 8;
-  for (uint32_t g = threadIdx.x; g < ngroups; g += kThreads) {
-    uint32_t ix[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t i = g * 8 + j;
-      ix[j] = i < t.count ? idx16[perm[t.start + i]] : 0u;  // padding indices of the last group are zero
-    }
-    unsigned long long lo = 0, hi = 0;  // 8 x bw <= 128 bits, LSB first
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t bit = j * bw;
-      if (bit < 64) {
-        lo |= (unsigned long long)ix[j] << bit;
-        if (bit + bw > 64) hi |= (unsigned long long)ix[j] >> (64 - bit);
-      } else {
-        hi |= (unsigned long long)ix[j] << (bit - 64);
-      }
-    }
-    uint8_t* dst = s_bytes + (size_t)g * bw;
-    for (uint32_t b = 0; b < bw; b++) dst[b] = (uint8_t)(b < 8 ? (lo >> (8 * b)) : (hi >> (8 * (b - 8))));
-  }
-  __syncthreads();
-  const uint64_t lr0 = t.start - seg_start[t.seg];
-  const uint64_t page = lr0 / (uint64_t)rows_per_page;
-  const uint64_t in_page = lr0 - page * (uint64_t)rows_per_page;
-  uint8_t* const out = arena + page_value_offset[bucket_page_begin[t.seg] + page] + in_page * bw / 8;
-  const uint32_t nbytes = ngroups * bw;
-  // coalesced copy: 4-byte words once the destination is aligned (page offsets are arbitrary)
-  const uint32_t head = min(nbytes, (uint32_t)((4 - ((uintptr_t)out & 3)) & 3));
-  for (uint32_t b = threadIdx.x; b < head; b += kThreads) out[b] = s_bytes[b];
-  const uint32_t nwords = (nbytes - head) / 4;
-  uint32_t* out32 = reinterpret_cast<uint32_t*>(out + head);
-  for (uint32_t w = threadIdx.x; w < nwords; w += kThreads) {
-    const uint8_t* p = s_bytes + head + 4 * w;
-    out32[w] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-  }
-  for (uint32_t b = head + 4 * nwords + threadIdx.x; b < nbytes; b += kThreads) out[b] = s_bytes[b];
+  entries[s] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), lo, 0u);
 }
 
 // ---- all dictionary columns at once ---------------------------------------------------------------------------------
@@ -200,9 +122,15 @@ __global__ void __launch_bounds__(kThreads) k_dict_map_all(DictMapArgs a, int64_
         x = a.empty_index[c];
         if (v[c] != kEmpty) {
           uint32_t h = dict_hash(v[c]) & mask;
+          const uint4* tab = reinterpret_cast<const uint4*>(a.entries[c]);
+          const uint32_t vlo = (uint32_t)v[c], vhi = (uint32_t)(v[c] >> 32);
+          uint4 e = tab[h];
           uint32_t probes = 0;
-          while (a.keys[c][h] != v[c] && probes++ <= mask) h = (h + 1) & mask;
-          x = a.slot_index[c][h];
+          while ((e.x != vlo || e.y != vhi) && probes++ <= mask) {  // present by construction; bounded regardless
+            h = (h + 1) & mask;
+            e = tab[h];
+          }
+          x = e.z;
         }
       }
       ix[c] = (uint16_t)x;
@@ -323,26 +251,8 @@ void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t c
 }
 
 void launch_dict_slot_index(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity,
-                            const unsigned long long* sorted_values, uint32_t ndict, int type, uint32_t* slot_index) {
-  k_dict_slot_index<<<(capacity + 255) / 256, 256, 0, ctx->stream>>>(keys, capacity, sorted_values, ndict, type, slot_index);
-  HS_LAUNCH_CHECK(ctx);
-}
-
-void launch_dict_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,
-                        const void* src, int width, int64_t nrows, const unsigned long long* keys, const uint32_t* slot_index,
-                        uint32_t capacity, uint32_t empty_index, uint32_t bw, uint16_t* idx16_scratch,
-                        const uint64_t* page_value_offset, const uint32_t* bucket_page_begin, int64_t rows_per_page,
-                        uint8_t* arena) {
-  if (ntiles == 0) return;
-  {
-    KernelScope _ks(ctx, "k_dict_map");
-    k_dict_map<<<grid_for(ctx, nrows, kThreads, 16), kThreads, 0, ctx->stream>>>(src, width, nrows, keys, slot_index, capacity - 1,
-                                                                                  empty_index, idx16_scratch);
-    HS_LAUNCH_CHECK(ctx);
-  }
-  KernelScope _ks(ctx, "k_dict_pack");
-  k_dict_pack<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, seg_start, perm, idx16_scratch, bw, page_value_offset,
-                                                              bucket_page_begin, rows_per_page, arena);
+                            const unsigned long long* sorted_values, uint32_t ndict, int type, void* entries) {
+  k_dict_slot_index<<<(capacity + 255) / 256, 256, 0, ctx->stream>>>(keys, capacity, sorted_values, ndict, type, (uint4*)entries);
   HS_LAUNCH_CHECK(ctx);
 }
 

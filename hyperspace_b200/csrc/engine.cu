@@ -546,7 +546,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     bool use = false;
     uint32_t bw = 0, ndict = 0, empty_index = 0;
     Buf<unsigned long long> keys;
-    Buf<uint32_t> slot_index;
+    Buf<uint8_t> entries;               // capacity x 16 bytes {key, dictionary index}
     Buf<unsigned long long> d_values;   // sorted dictionary on the device
     size_t skel_off = 0, skel_len = 0;  // [dictionary page header][PLAIN values] inside the skeleton
     std::vector<uint64_t> values;       // sorted dictionary (raw bits)
@@ -603,8 +603,8 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         cd.empty_index = (uint32_t)(std::find(cd.values.begin(), cd.values.end(), ~(uint64_t)0) - cd.values.begin());
       cd.d_values.alloc(ctx, cd.ndict);
       HS_CUDA(cudaMemcpyAsync(cd.d_values.get(), cd.values.data(), 8 * (size_t)cd.ndict, cudaMemcpyHostToDevice, ctx->stream));
-      cd.slot_index.alloc(ctx, kDictCapacity);
-      launch_dict_slot_index(ctx, cd.keys.get(), kDictCapacity, cd.d_values.get(), cd.ndict, type, cd.slot_index.get());
+      cd.entries.alloc(ctx, (size_t)kDictCapacity * 16);
+      launch_dict_slot_index(ctx, cd.keys.get(), kDictCapacity, cd.d_values.get(), cd.ndict, type, cd.entries.get());
       HS_CUDA(cudaStreamSynchronize(ctx->stream));
       cd.use = true;
     }
@@ -796,8 +796,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         const int c = dcols[b0 + j];
         ma.src[j] = table.cols[c].data.get();
         ma.width[j] = table.cols[c].width;
-        ma.keys[j] = dicts[c].keys.get();
-        ma.slot_index[j] = dicts[c].slot_index.get();
+        ma.entries[j] = dicts[c].entries.get();
         ma.empty_index[j] = dicts[c].empty_index;
         pa.page_value_offset[j] = d_pvo.get() + (size_t)c * page_counter;
         pa.bw[j] = dicts[c].bw;

@@ -165,20 +165,13 @@ void launch_dict_build(hs_ctx* ctx, const void* src, int width, int64_t begin, i
 // compacts the distinct values out of the hash set (counter must be zeroed); then slot -> rank in the sorted dictionary
 void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity, unsigned long long* out,
                          uint32_t* counter);
+// entries: capacity x 16 bytes {key lo, key hi, dictionary index, 0}
 void launch_dict_slot_index(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity,
-                            const unsigned long long* sorted_values, uint32_t ndict, int type, uint32_t* slot_index);
-// two passes: (1) streaming map of every value of src[0, nrows) to its dictionary index (u16 scratch, partitioned order);
-// (2) per tile, gather the indices through perm and bit-pack them with `bw` bits into the page body
-void launch_dict_encode(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,
-                        const void* src, int width, int64_t nrows, const unsigned long long* keys, const uint32_t* slot_index,
-                        uint32_t capacity, uint32_t empty_index, uint32_t bw, uint16_t* idx16_scratch,
-                        const uint64_t* page_value_offset, const uint32_t* bucket_page_begin, int64_t rows_per_page,
-                        uint8_t* arena);
+                            const unsigned long long* sorted_values, uint32_t ndict, int type, void* entries);
 // all dictionary columns of a table in one map + one pack launch (up to 8 columns per call)
 struct DictMapArgs {
   const void* src[8];
-  const unsigned long long* keys[8];
-  const uint32_t* slot_index[8];
+  const void* entries[8];  // 16-byte {key, index} hash-table entries
   uint32_t empty_index[8];
   int32_t width[8];
   int32_t ncols;

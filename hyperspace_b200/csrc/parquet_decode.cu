@@ -387,6 +387,33 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
         for (int i = threadIdx.x; i < n; i += blockDim.x) store_value<W>(co.data, row0 + i, load_value<W>(p + (size_t)i * W));
       }
     } else {
+      // Fast path: the whole index stream is ONE bit-packed run (what this engine's encoder writes, and what parquet-mr /
+      // pyarrow write for pages without long repeats): every index sits at a fixed bit offset, so all threads extract
+      // in parallel with no run table and no barriers.
+      if (threadIdx.x == 0) {
+        uint32_t h = 0;
+        int shift = 0;
+        const uint8_t* q = p;
+        while (q < pend) {
+          const uint8_t b = *q++;
+          h |= (uint32_t)(b & 0x7f) << shift;
+          if (!(b & 0x80)) break;
+          shift += 7;
+          if (shift > 28) break;
+        }
+        const uint64_t groups = h >> 1;
+        const bool single = (h & 1) && groups * 8 >= (uint64_t)n && q + groups * idx_bw <= pend;
+        sm.flag = single ? (uint32_t)(q - p) : 0u;
+      }
+      __syncthreads();
+      const uint32_t hdr_len = sm.flag;
+      if (hdr_len) {
+        const uint8_t* run = p + hdr_len;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+          store_value<W>(co.data, row0 + i, dict_lookup(extract_bits(run, (uint64_t)i, idx_bw)));
+        return;
+      }
       for (int base = 0; base < n; base += kTileRows) {
         const uint32_t cnt = (uint32_t)min(kTileRows, n - base);
         bool ok = hybrid_decode_next(sm.idx, cnt, [&](uint32_t i, uint32_t v) {

@@ -210,3 +210,30 @@ def test_hybrid_scan_with_deleted_source_file(env):
     assert "deletedIds=[5]" in q.explain()
     cur = np.concatenate([_table(i * 5_000, 5_000)["k"] for i in range(5)])
     assert len(q.collect()["k"]) == int((cur <= 100).sum())  # HybridScanSuite.scala:378-441 checkAnswer
+
+
+def test_hybrid_scan_join_with_appended_files(env):
+    """JoinIndexRule under Hybrid Scan: appended source files are bucketed on the fly and merged per bucket with the index
+    (BucketUnion, S/index/covering/CoveringIndexRuleUtils.scala:256-284; T/index/HybridScanSuite.scala)."""
+    from hyperspace_b200.index_config import IndexConfig
+
+    s, hs, tmp = env
+    for i in range(5):
+        _write(tmp / "l", f"f{i}.parquet", _table(i * 4_000, 4_000))
+    R = _table(50_000, 15_000)
+    _write(tmp / "r", "a.parquet", {"k": R["k"], "w": R["v1"]})
+    hs.createIndex(s.read.parquet(str(tmp / "l")), IndexConfig("lidx", ["k"], ["v1"]))
+    hs.createIndex(s.read.parquet(str(tmp / "r")), IndexConfig("ridx", ["k"], ["w"]))
+    _write(tmp / "l", "f5.parquet", _table(20_000, 3_000))  # appended after the index was built: 3/23 of the bytes < 0.3
+    s.enableHyperspace()
+    dl, dr = s.read.parquet(str(tmp / "l")), s.read.parquet(str(tmp / "r"))
+    j = dl.join(dr, on="k").select("v1", "w")
+    assert "Name: lidx" not in j.explain()  # stale signature: the left index is not used without Hybrid Scan
+    s.conf.set("spark.hyperspace.index.hybridscan.enabled", True)
+    plan = j.explain()
+    assert "Name: lidx" in plan and "Name: ridx" in plan
+    got = j.collect()
+    s.disableHyperspace()
+    base = j.collect()
+    assert len(got["v1"]) == len(base["v1"]) > 0
+    assert np.array_equal(_rows(got, ["v1", "w"]), _rows(base, ["v1", "w"]))
