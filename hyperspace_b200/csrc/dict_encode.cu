@@ -72,6 +72,42 @@ __global__ void __launch_bounds__(kThreads) k_dict_build(const void* __restrict_
   }
 }
 
+// Hash set filled from the dictionary pages of the source chunks (one CTA per data page; pages of one chunk insert the same
+// few values again, which costs nothing).  Used when every page of a column was dictionary-encoded.
+__global__ void __launch_bounds__(kThreads) k_dict_build_from_pages(const PageDesc* __restrict__ pages, int col, int width,
+                                                                     unsigned long long* __restrict__ keys, uint32_t mask,
+                                                                     uint32_t max_distinct, uint32_t* __restrict__ state) {
+  const PageDesc pg = pages[blockIdx.x];
+  if (pg.col != col || pg.dict == nullptr) return;
+  for (int i = threadIdx.x; i < pg.dict_count; i += kThreads) {
+    if (*(volatile uint32_t*)&state[1]) return;
+    const uint8_t* p = pg.dict + (size_t)i * width;
+    const uint64_t v = width == 8 ? load_le64_unaligned(p) : (uint64_t)load_le32_unaligned(p);
+    if (v == kEmpty) {
+      state[2] = 1;
+      continue;
+    }
+    uint32_t h = dict_hash(v) & mask;
+    for (uint32_t probes = 0; probes <= mask; probes++) {
+      const unsigned long long cur = keys[h];
+      if (cur == v) break;
+      if (cur == kEmpty) {
+        if (*(volatile uint32_t*)&state[0] >= max_distinct) {
+          state[1] = 1;
+          return;
+        }
+        const unsigned long long old = atomicCAS(&keys[h], kEmpty, (unsigned long long)v);
+        if (old == kEmpty) {
+          atomicAdd(&state[0], 1u);
+          break;
+        }
+        if (old == v) break;
+      }
+      h = (h + 1) & mask;
+    }
+  }
+}
+
 // distinct values out of the hash set (order arbitrary; the host sorts the small list)
 __global__ void k_dict_collect(const unsigned long long* __restrict__ keys, uint32_t capacity,
                                unsigned long long* __restrict__ out, uint32_t* __restrict__ counter) {
@@ -242,6 +278,20 @@ void launch_dict_build(hs_ctx* ctx, const void* src, int width, int64_t begin, i
   while ((uint64_t)grid * kThreads * 2 + max_distinct >= capacity && grid > 1) grid /= 2;
   k_dict_build<<<grid, kThreads, 0, ctx->stream>>>(src, width, begin, end, keys, capacity - 1, max_distinct, state);
   HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_dict_build_from_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, int col, int width,
+                                  unsigned long long* keys, uint32_t capacity, uint32_t max_distinct, uint32_t* state) {
+  KernelScope _ks(ctx, "k_dict_build_from_pages");
+  if (n_pages == 0) return;
+  // one CTA per page, 256 threads: at most n_pages * 256 concurrent inserts; the table has capacity - max_distinct spare
+  // slots and a dictionary page rarely has more than a few thousand entries, but keep the bound explicit:
+  const int64_t max_ctas = (capacity - max_distinct) / kThreads - 1;
+  for (int64_t p0 = 0; p0 < n_pages; p0 += max_ctas) {
+    const unsigned grid = (unsigned)std::min<int64_t>(max_ctas, n_pages - p0);
+    k_dict_build_from_pages<<<grid, kThreads, 0, ctx->stream>>>(pages + p0, col, width, keys, capacity - 1, max_distinct, state);
+    HS_LAUNCH_CHECK(ctx);
+  }
 }
 
 void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity, unsigned long long* out,

@@ -337,7 +337,33 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
                           : HS_EFORMAT;
     fail(ecode, "Parquet decode failed: %s (detail %u)", decode_error_text(code), detail);
   }
-  for (int c = 0; c < ncols; c++) out->cols[c].has_nulls = flags[1 + c] != 0;
+  for (int c = 0; c < ncols; c++) out->cols[c].has_nulls = (flags[1 + c] & 1u) != 0;
+  // columns whose every page was dictionary-encoded: the union of the chunk dictionaries becomes the encoder's hash set
+  if (!file_windows && ctx->world == 1) {
+    std::vector<int> cand;
+    Buf<uint32_t> d_states(ctx, 4 * (size_t)std::max(1, ncols));
+    HS_CUDA(cudaMemsetAsync(d_states.get(), 0, 16 * (size_t)std::max(1, ncols), ctx->stream));
+    for (int c = 0; c < ncols; c++) {
+      DevColumn& dc = out->cols[c];
+      if ((flags[1 + c] & 2u) || (dc.width != 4 && dc.width != 8)) continue;
+      dc.dict_keys.alloc(ctx, kDictCapacity);
+      HS_CUDA(cudaMemsetAsync(dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
+      launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, c, dc.width, dc.dict_keys.get(), kDictCapacity, kMaxDictEntries,
+                                   d_states.get() + 4 * c);
+      cand.push_back(c);
+    }
+    if (!cand.empty()) {
+      std::vector<uint32_t> h_states(4 * (size_t)ncols);
+      HS_CUDA(cudaMemcpyAsync(h_states.data(), d_states.get(), 16 * (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (int c : cand) {
+        DevColumn& dc = out->cols[c];
+        memcpy(dc.dict_state, &h_states[4 * c], 16);
+        dc.dict_ready = dc.dict_state[1] == 0;
+        if (!dc.dict_ready) dc.dict_keys.release();
+      }
+    }
+  }
   stats->ms_plan += t_plan.ms();
   stats->ms_decode += t_dec.ms();
 }
@@ -396,6 +422,9 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
     dst.width = src.width;
     dst.schema = src.schema;
     dst.has_nulls = src.has_nulls;
+    dst.dict_keys = std::move(src.dict_keys);
+    memcpy(dst.dict_state, src.dict_state, sizeof dst.dict_state);
+    dst.dict_ready = src.dict_ready;
     dst.data.alloc(ctx, (size_t)nrows * src.width + 16);
     h_pc.push_back(PartColumn{src.data.get(), dst.data.get(), src.width, 0});
     if (src.has_nulls) {
@@ -545,7 +574,8 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
   struct ColDict {
     bool use = false;
     uint32_t bw = 0, ndict = 0, empty_index = 0;
-    Buf<unsigned long long> keys;
+    Buf<unsigned long long> keys;       // owned when the set was built here
+    const unsigned long long* keys_ptr = nullptr;  // the hash set in use (own or the column's ready-made one)
     Buf<uint8_t> entries;               // capacity x 16 bytes {key, dictionary index}
     Buf<unsigned long long> d_values;   // sorted dictionary on the device
     size_t skel_off = 0, skel_len = 0;  // [dictionary page header][PLAIN values] inside the skeleton
@@ -559,21 +589,41 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       const DevColumn& dc = table.cols[c];
       if (dc.has_nulls) continue;
       ColDict& cd = dicts[c];
-      cd.keys.alloc(ctx, kDictCapacity);
-      HS_CUDA(cudaMemsetAsync(cd.keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
-      HS_CUDA(cudaMemsetAsync(d_state.get(), 0, 16, ctx->stream));
       uint32_t st[4] = {0, 0, 0, 0};
-      // a 256 K-row sample first: high-cardinality columns (keys, measures) overflow here and cost almost nothing
-      const int64_t sample = std::min<int64_t>(total_rows, 1 << 18);
-      launch_dict_build(ctx, dc.data.get(), dc.width, 0, sample, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state.get());
+      const bool ready = dc.dict_ready && dc.dict_keys;
+      if (ready) {
+        cd.keys_ptr = dc.dict_keys.get();
+        memcpy(st, dc.dict_state, 16);
+      } else {
+        cd.keys.alloc(ctx, kDictCapacity);
+        cd.keys_ptr = cd.keys.get();
+        HS_CUDA(cudaMemsetAsync(cd.keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
+      }
+      HS_CUDA(cudaMemsetAsync(d_state.get(), 0, 16, ctx->stream));
+      if (!ready) {
+      // staged sampling: 16 K rows that are (nearly) all distinct mark a key-like column at once; a 256 K-row sample then
+      // lets the remaining high-cardinality columns overflow cheaply (the overflow path serialises on one counter)
+      const int64_t mini = std::min<int64_t>(total_rows, 1 << 14);
+      launch_dict_build(ctx, dc.data.get(), dc.width, 0, mini, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state.get());
       HS_CUDA(cudaMemcpyAsync(st, d_state.get(), 16, cudaMemcpyDeviceToHost, ctx->stream));
       HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (total_rows > (1 << 20) && st[0] + st[2] > 0.95 * mini) {
+        cd.keys.release();
+        continue;
+      }
+      const int64_t sample = std::min<int64_t>(total_rows, 1 << 18);
+      if (sample > mini) {
+        launch_dict_build(ctx, dc.data.get(), dc.width, mini, sample, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state.get());
+        HS_CUDA(cudaMemcpyAsync(st, d_state.get(), 16, cudaMemcpyDeviceToHost, ctx->stream));
+        HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
       if (!st[1] && sample < total_rows) {
         launch_dict_build(ctx, dc.data.get(), dc.width, sample, total_rows, cd.keys.get(), kDictCapacity, kMaxDictEntries,
                           d_state.get());
         HS_CUDA(cudaMemcpyAsync(st, d_state.get(), 16, cudaMemcpyDeviceToHost, ctx->stream));
         HS_CUDA(cudaStreamSynchronize(ctx->stream));
       }
+      }  // !ready
       if (st[1]) {
         cd.keys.release();
         continue;
@@ -582,7 +632,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       const uint32_t ntab = st[0];
       Buf<unsigned long long> d_list(ctx, std::max<uint32_t>(1, ntab) + 1);
       HS_CUDA(cudaMemsetAsync(d_state.get() + 3, 0, 4, ctx->stream));
-      launch_dict_collect(ctx, cd.keys.get(), kDictCapacity, d_list.get(), d_state.get() + 3);
+      launch_dict_collect(ctx, cd.keys_ptr, kDictCapacity, d_list.get(), d_state.get() + 3);
       cd.values.resize(ntab);
       if (ntab)
         HS_CUDA(cudaMemcpyAsync(cd.values.data(), d_list.get(), 8 * (size_t)ntab, cudaMemcpyDeviceToHost, ctx->stream));
@@ -604,7 +654,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       cd.d_values.alloc(ctx, cd.ndict);
       HS_CUDA(cudaMemcpyAsync(cd.d_values.get(), cd.values.data(), 8 * (size_t)cd.ndict, cudaMemcpyHostToDevice, ctx->stream));
       cd.entries.alloc(ctx, (size_t)kDictCapacity * 16);
-      launch_dict_slot_index(ctx, cd.keys.get(), kDictCapacity, cd.d_values.get(), cd.ndict, type, cd.entries.get());
+      launch_dict_slot_index(ctx, cd.keys_ptr, kDictCapacity, cd.d_values.get(), cd.ndict, type, cd.entries.get());
       HS_CUDA(cudaStreamSynchronize(ctx->stream));
       cd.use = true;
     }

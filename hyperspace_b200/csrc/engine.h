@@ -19,6 +19,11 @@ struct DevColumn {
   Buf<uint8_t> data;          // nrows * width
   Buf<uint8_t> valid;         // nrows bytes, only for optional columns
   bool has_nulls = false;
+  // Optional superset of the column's distinct values as a ready-made hash set (built from the source chunks' dictionary
+  // pages when every page was dictionary-encoded); lets the encoder skip its full-column distinct scan.
+  Buf<unsigned long long> dict_keys;
+  uint32_t dict_state[4] = {0, 0, 0, 0};
+  bool dict_ready = false;
 };
 
 struct Table {

@@ -162,6 +162,9 @@ constexpr uint32_t kDictCapacity = 8 * kMaxDictEntries;  // open-addressing slot
 // state[0] = distinct count, state[1] = 1 when more than max_distinct values were seen, state[2] = the all-ones value occurs
 void launch_dict_build(hs_ctx* ctx, const void* src, int width, int64_t begin, int64_t end, unsigned long long* keys,
                        uint32_t capacity, uint32_t max_distinct, uint32_t* state);
+// same hash set, filled from the dictionary pages of the decoded source chunks of projected column `col`
+void launch_dict_build_from_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, int col, int width,
+                                  unsigned long long* keys, uint32_t capacity, uint32_t max_distinct, uint32_t* state);
 // compacts the distinct values out of the hash set (counter must be zeroed); then slot -> rank in the sorted dictionary
 void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity, unsigned long long* out,
                          uint32_t* counter);

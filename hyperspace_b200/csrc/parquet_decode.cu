@@ -284,6 +284,9 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
     if (threadIdx.x == 0) set_error(d_error, DERR_UNSUPPORTED_ENCODING, (uint32_t)pg.encoding);
     return;
   }
+  // bit 1 of the column's flag word: a page that is NOT dictionary-encoded was seen (when it stays clear, the union of the
+  // chunk dictionaries is a superset of the column's distinct values and the encoder can skip its full-column scan)
+  if (!is_dict && threadIdx.x == 0) atomicOr(col_has_nulls, 2u);
   // ---- definition levels -----------------------------------------------------------------------------------
   const uint8_t* def_p = nullptr;
   const uint8_t* def_end = nullptr;
