@@ -301,8 +301,19 @@ def run_ours(args):
         avg_ms = ss["ms"] / max(1, ss["launches"])
         rows_after_exchange = total_rows / world  # rows each rank sorts (uniform hash)
         achieved = SORT_SCATTER_BYTES_PER_ROW * rows_after_exchange / (avg_ms / 1e3) / 1e9
+        # DRAM traffic of the kernel from the committed ncu capture (bytes per row are size-independent for this kernel:
+        # every pair is read once and written once), scaled to the rows of one launch here
+        traffic, traffic_note = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["k_sort_scatter"]
+            per_row = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["rows_per_launch"]
+            traffic = per_row * rows_after_exchange
+            traffic_note = (f"dram__bytes_read+write.sum = {per_row:.2f} B/row measured by ncu --set full at "
+                            f"{tr['rows_per_launch']} rows/launch (profiles/r01_ncu_traffic.json), scaled to this launch size")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "k_sort_scatter", "achieved": achieved, "peak": peak, "peak_source": peak_src,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                     "algorithmic_bytes_per_launch": SORT_SCATTER_BYTES_PER_ROW * rows_after_exchange,
                     "avg_launch_ms": avg_ms, "launches_timed": ss["launches"],
                     "whole_path": {"achieved": ALGO_BYTES_PER_ROW * value / world / 1e9, "unit": "GB/s",
