@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <map>
 #include <random>
 
 #include "device_utils.cuh"
@@ -66,10 +67,11 @@ const char* decode_error_text(uint32_t code) {
     case DERR_BAD_HEADER: return "malformed page header";
     case DERR_UNSUPPORTED_ENCODING: return "unsupported page encoding (PLAIN and PLAIN_/RLE_DICTIONARY are handled)";
     case DERR_VALUE_COUNT: return "page value counts do not add up to the column chunk's num_values";
-    case DERR_COMPRESSED: return "compressed page (only UNCOMPRESSED is handled on the GPU path)";
+    case DERR_COMPRESSED: return "page sizes disagree in an UNCOMPRESSED chunk";
     case DERR_OVERRUN: return "page data shorter than its header claims";
     case DERR_DICT_INDEX: return "dictionary index out of range or missing dictionary page";
     case DERR_UNSUPPORTED_TYPE: return "unsupported physical type";
+    case DERR_SNAPPY: return "corrupt snappy stream";
   }
   return "unknown decode error";
 }
@@ -215,6 +217,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   out->cols.resize(ncols);
   out->file_row_begin.assign(n_files + 1, 0);
   std::vector<ChunkDesc> chunks;
+  bool any_compressed = false;
   std::vector<bool> col_optional(ncols, false);
   int64_t nrows = 0;
   for (int f = 0; f < n_files; f++) {
@@ -244,9 +247,10 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       if (rg.num_rows == 0) continue;  // writers emit an empty row group for an empty table
       for (int c = 0; c < ncols; c++) {
         const pq::ColumnChunkMeta& cm = rg.columns[idx[c]];
-        if (cm.codec != pq::UNCOMPRESSED)
-          fail(HS_EUNSUPPORTED, "%s: column '%s' uses compression codec %d; the GPU path reads UNCOMPRESSED pages only", what,
+        if (cm.codec != pq::UNCOMPRESSED && cm.codec != pq::SNAPPY)
+          fail(HS_EUNSUPPORTED, "%s: column '%s' uses compression codec %d; the GPU path reads UNCOMPRESSED and SNAPPY pages", what,
                columns[c].c_str(), cm.codec);
+        any_compressed = any_compressed || cm.codec != pq::UNCOMPRESSED;
         if (cm.num_values != rg.num_rows)
           fail(HS_EFORMAT, "%s: column '%s' has %lld values for %lld rows", what, columns[c].c_str(), (long long)cm.num_values,
                (long long)rg.num_rows);
@@ -262,6 +266,8 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
         cd.phys_type = fm.columns[idx[c]].type;
         cd.max_def = fm.columns[idx[c]].repetition == pq::OPTIONAL ? 1 : 0;
         cd.file_index = f;
+        cd.codec = cm.codec;
+        cd.pad = 0;
         chunks.push_back(cd);
       }
       nrows += rg.num_rows;
@@ -311,6 +317,56 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   Buf<PageDesc> d_pages(ctx, std::max<int64_t>(1, n_pages));
   HS_CUDA(cudaMemcpyAsync(d_offsets.get(), offsets.data(), sizeof(int64_t) * n_chunks, cudaMemcpyHostToDevice, ctx->stream));
   launch_walk_pages(ctx, d_chunks.get(), n_chunks, d_counts.get(), d_offsets.get(), d_pages.get(), d_flags.get(), 1);
+  // ---- snappy: decompress the compressed page bodies (and dictionary pages) into a scratch buffer, repoint the pages ----
+  Buf<uint8_t> d_scratch;
+  if (any_compressed && n_pages > 0) {
+    std::vector<PageDesc> h_pages((size_t)n_pages);
+    HS_CUDA(cudaMemcpyAsync(h_pages.data(), d_pages.get(), sizeof(PageDesc) * (size_t)n_pages, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<SnappyBlob> blobs;
+    std::map<const uint8_t*, uint64_t> dict_off;  // stored dictionary page -> scratch offset of its decompressed copy
+    uint64_t cursor = 0;
+    for (PageDesc& pg : h_pages) {
+      if (pg.codec == pq::UNCOMPRESSED) continue;
+      if (pg.dict) {  // the dictionary page of a compressed chunk is compressed too
+        auto it = dict_off.find(pg.dict);
+        if (it == dict_off.end()) {
+          it = dict_off.emplace(pg.dict, cursor).first;
+          blobs.push_back(SnappyBlob{pg.dict, cursor, (uint32_t)pg.dict_size, (uint32_t)pg.dict_uncompressed_size, 0u, 1u});
+          cursor += round_up((size_t)pg.dict_uncompressed_size, 16) + 16;
+        }
+        pg.dict = (const uint8_t*)(uintptr_t)(it->second + 1);  // patched to a pointer below (offset + 1 marks "relocated")
+        pg.dict_size = -1;
+      }
+      if (pg.is_compressed || pg.size != pg.uncompressed_size) {
+        const uint32_t prefix = pg.page_type == pq::DATA_PAGE_V2 ? (uint32_t)(pg.rep_bytes + std::max(0, pg.def_bytes)) : 0u;
+        if (prefix > (uint32_t)pg.size || prefix > (uint32_t)pg.uncompressed_size)
+          fail(HS_EFORMAT, "compressed page has level bytes beyond its size");
+        blobs.push_back(SnappyBlob{pg.data, cursor, (uint32_t)pg.size, (uint32_t)pg.uncompressed_size, prefix,
+                                   (uint32_t)(pg.is_compressed ? 1 : 0)});
+        pg.data = (const uint8_t*)(uintptr_t)(cursor + 1);
+        pg.size = -pg.uncompressed_size;  // negative: data is a scratch offset (+1)
+        cursor += round_up((size_t)pg.uncompressed_size, 16) + 16;
+      }
+    }
+    d_scratch.alloc(ctx, std::max<uint64_t>(cursor, 16));
+    for (PageDesc& pg : h_pages) {
+      if (pg.codec == pq::UNCOMPRESSED) continue;
+      if (pg.dict_size == -1) {
+        pg.dict = d_scratch.get() + ((uintptr_t)pg.dict - 1);
+        pg.dict_size = pg.dict_uncompressed_size;
+      }
+      if (pg.size < 0) {
+        pg.data = d_scratch.get() + ((uintptr_t)pg.data - 1);
+        pg.size = pg.uncompressed_size;
+      }
+    }
+    Buf<SnappyBlob> d_blobs(ctx, std::max<size_t>(1, blobs.size()));
+    HS_CUDA(cudaMemcpyAsync(d_blobs.get(), blobs.data(), sizeof(SnappyBlob) * blobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaMemcpyAsync(d_pages.get(), h_pages.data(), sizeof(PageDesc) * (size_t)n_pages, cudaMemcpyHostToDevice, ctx->stream));
+    launch_snappy_decompress(ctx, d_blobs.get(), (int64_t)blobs.size(), d_scratch.get(), d_flags.get());
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  }
   // ---- decode -----------------------------------------------------------------------------------------
   // optional per-file row windows (file-relative -> global): pages that do not intersect their file's window are skipped
   Buf<int64_t> d_window;

@@ -14,6 +14,8 @@ struct ChunkDesc {          // one per (file, row group, projected column)
   int32_t phys_type;        // pq::PhysType
   int32_t max_def;          // 0 (required) or 1 (optional)
   int32_t file_index;
+  int32_t codec;            // pq::Codec of the chunk (UNCOMPRESSED or SNAPPY)
+  int32_t pad;
 };
 
 struct PageDesc {           // one per data page
@@ -29,6 +31,11 @@ struct PageDesc {           // one per data page
   int32_t rep_bytes;        // v2
   int32_t col, phys_type, max_def;
   int32_t file_index;
+  int32_t uncompressed_size;  // body bytes after decompression (== size for stored pages)
+  // compressed chunks only: the chunk's dictionary page as stored, and whether this page / the dictionary is compressed
+  int32_t dict_size, dict_uncompressed_size;
+  int32_t is_compressed;      // this page's values are snappy-compressed
+  int32_t codec;
   int32_t pad;
 };
 
@@ -42,8 +49,19 @@ struct ColumnOut {          // decoded column destination
 // device error word: 0 = ok, else (code << 24 | detail)
 enum DecodeError : uint32_t {
   DERR_NONE = 0, DERR_BAD_HEADER = 1, DERR_UNSUPPORTED_ENCODING = 2, DERR_VALUE_COUNT = 3, DERR_COMPRESSED = 4,
-  DERR_OVERRUN = 5, DERR_DICT_INDEX = 6, DERR_UNSUPPORTED_TYPE = 7
+  DERR_OVERRUN = 5, DERR_DICT_INDEX = 6, DERR_UNSUPPORTED_TYPE = 7, DERR_SNAPPY = 8
 };
+
+// ---- snappy (snappy.cu) ---------------------------------------------------------------------------------------------
+struct SnappyBlob {
+  const uint8_t* src;   // stored bytes (device)
+  uint64_t dst_off;     // offset of the decompressed bytes in the scratch buffer
+  uint32_t src_len;
+  uint32_t dst_len;     // prefix + decompressed length
+  uint32_t prefix;      // leading bytes copied verbatim (v2 level bytes)
+  uint32_t compressed;  // 0: copy, 1: snappy
+};
+void launch_snappy_decompress(hs_ctx* ctx, const SnappyBlob* blobs, int64_t n, uint8_t* scratch, uint32_t* d_error);
 
 // Walks the page headers of every chunk.  mode 0: page_counts[chunk] = number of data pages.
 // mode 1: fills pages[page_offsets[chunk] ...].

@@ -83,7 +83,7 @@ __global__ void k_walk_pages(const ChunkDesc* __restrict__ chunks, int n_chunks,
   const ChunkDesc ch = chunks[c];
   thrift::Reader r(ch.data, ch.data + ch.size);
   const uint8_t* dict = nullptr;
-  int32_t dict_count = 0;
+  int32_t dict_count = 0, dict_size = 0, dict_usize = 0;
   int64_t values_seen = 0;
   int32_t n_pages = 0;
   int64_t out = mode ? page_offsets[c] : 0;
@@ -97,6 +97,9 @@ __global__ void k_walk_pages(const ChunkDesc* __restrict__ chunks, int n_chunks,
     if (h.type == pq::DICTIONARY_PAGE) {
       dict = body;
       dict_count = h.num_values;
+      dict_size = h.compressed_size;
+      dict_usize = h.uncompressed_size;
+      if (ch.codec == pq::UNCOMPRESSED && h.compressed_size != h.uncompressed_size) set_error(d_error, DERR_COMPRESSED, (uint32_t)c);
     } else if (h.type == pq::DATA_PAGE || h.type == pq::DATA_PAGE_V2) {
       if (mode) {
         PageDesc pd;
@@ -114,10 +117,16 @@ __global__ void k_walk_pages(const ChunkDesc* __restrict__ chunks, int n_chunks,
         pd.phys_type = ch.phys_type;
         pd.max_def = ch.max_def;
         pd.file_index = ch.file_index;
+        pd.uncompressed_size = h.uncompressed_size;
+        pd.dict_size = dict_size;
+        pd.dict_uncompressed_size = dict_usize;
+        pd.codec = ch.codec;
+        // v1 pages of a compressed chunk are always compressed; v2 pages say so in their header
+        pd.is_compressed = ch.codec != pq::UNCOMPRESSED && (h.type == pq::DATA_PAGE || h.is_compressed) ? 1 : 0;
         pd.pad = 0;
         pages[out + n_pages] = pd;
       }
-      if (h.compressed_size != h.uncompressed_size) set_error(d_error, DERR_COMPRESSED, (uint32_t)c);
+      if (ch.codec == pq::UNCOMPRESSED && h.compressed_size != h.uncompressed_size) set_error(d_error, DERR_COMPRESSED, (uint32_t)c);
       values_seen += h.num_values;
       n_pages++;
     }  // index pages and unknown page types are skipped

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 def _write(dirpath, name, cols):
     os.makedirs(dirpath, exist_ok=True)
-    pq.write_table(pa.table(cols), os.path.join(dirpath, name), compression="NONE")
+    pq.write_table(pa.table(cols), os.path.join(dirpath, name), compression="snappy")  # Spark's default codec
 
 
 def _table(first, n):

@@ -167,7 +167,7 @@ def _write_sources(tmp_path, cols, n_files, **kw):
     for f in range(n_files):
         part = {k: v[f * per:(f + 1) * per] for k, v in cols.items()}
         p = str(tmp_path / f"src-{f}.parquet")
-        pq.write_table(pa.table(part), p, compression="NONE", **kw)
+        pq.write_table(pa.table(part), p, **{"compression": "NONE", **kw})
         paths.append(p)
     return paths
 
@@ -191,7 +191,8 @@ def _check_index(res, cols, indexed, included, nb, job_uuid):
     assert seen == nonempty  # one file per non-empty bucket, none for empty ones
 
 
-@pytest.mark.parametrize("variant", ["plain_v1", "dict_v1", "dict_v2", "plain_v2_small_pages"])
+@pytest.mark.parametrize("variant", ["plain_v1", "dict_v1", "dict_v2", "plain_v2_small_pages", "snappy_v1", "snappy_dict_v2",
+                                     "snappy_small_pages"])
 def test_create_index_matches_oracle(ctx, tmp_path, variant):
     from hyperspace_b200 import _native
 
@@ -202,6 +203,10 @@ def test_create_index_matches_oracle(ctx, tmp_path, variant):
         "dict_v1": dict(use_dictionary=True, data_page_version="1.0"),
         "dict_v2": dict(use_dictionary=True, data_page_version="2.0", row_group_size=30_000),
         "plain_v2_small_pages": dict(use_dictionary=False, data_page_version="2.0", data_page_size=4096, row_group_size=50_000),
+        # Spark's default codec: snappy pages (v1: whole page compressed; v2: levels stored, values compressed)
+        "snappy_v1": dict(use_dictionary=False, data_page_version="1.0", compression="snappy"),
+        "snappy_dict_v2": dict(use_dictionary=True, data_page_version="2.0", compression="snappy", row_group_size=30_000),
+        "snappy_small_pages": dict(use_dictionary=["v1", "v3"], data_page_version="1.0", compression="snappy", data_page_size=2048),
     }[variant]
     paths = _write_sources(tmp_path, cols, 3, **kw)
     files = [_native.FileImage(path=p) for p in paths]
@@ -354,9 +359,10 @@ def test_create_index_with_nulls(ctx, tmp_path):
     v3 = rng.standard_normal(n).astype(np.float32)
     tbl = pa.table({"k": pa.array(k, mask=~kvalid), "v1": pa.array(v1, mask=~v1valid), "v2": pa.array(v2, mask=~v2valid),
                     "v3": pa.array(v3)})
-    for variant, kw in (("plain", dict(use_dictionary=False)), ("dict", dict(use_dictionary=True, data_page_size=8192))):
+    for variant, kw in (("plain", dict(use_dictionary=False)), ("dict", dict(use_dictionary=True, data_page_size=8192)),
+                        ("snappy", dict(use_dictionary=True, compression="snappy", data_page_version="2.0"))):
         p = str(tmp_path / f"n-{variant}.parquet")
-        pq.write_table(tbl, p, compression="NONE", row_group_size=25_000, **kw)
+        pq.write_table(tbl, p, **{"compression": "NONE", "row_group_size": 25_000, **kw})
         res, st = ctx.create_index([_native.FileImage(path=p)], ["k"], ["v1", "v2", "v3"], 16, output=_native.HS_OUT_HOST,
                                    job_uuid="nn", rows_per_page=8192, rows_per_row_group=16384)
         kz = np.where(kvalid, k, 0)
@@ -391,7 +397,7 @@ def test_errors_are_loud(ctx, tmp_path):
 
     cols = O.synthetic_table(0, 1000, 2)
     p = str(tmp_path / "s.parquet")
-    pq.write_table(pa.table(cols), p, compression="snappy")
+    pq.write_table(pa.table(cols), p, compression="zstd")
     with pytest.raises(_native.HyperspaceGpuError) as e:
         ctx.create_index([_native.FileImage(path=p)], ["k"], ["v1"], 4, output=_native.HS_OUT_HOST)
     assert e.value.code == _native.HS_EUNSUPPORTED
