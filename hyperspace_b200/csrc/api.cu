@@ -454,6 +454,24 @@ static void batch_from_gather(hs_ctx* ctx, const Table& t, const std::vector<int
   b->nrows = n_out;
 }
 
+// int32 keys are widened once so that the comparison kernels (range bounds, predicate mask, join probes) stay int64-only
+__global__ void k_widen_i32(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
+}
+
+static const int64_t* widened_key(hs_ctx* ctx, const DevColumn& c, int64_t n, Buf<int64_t>* hold) {
+  if (c.type == HS_TYPE_INT64) return (const int64_t*)c.data.get();
+  if (c.type != HS_TYPE_INT32) fail(HS_EUNSUPPORTED, "key column '%s' must be int32 or int64 on the read side", c.name.c_str());
+  hold->alloc(ctx, std::max<int64_t>(1, n));
+  if (n) {
+    k_widen_i32<<<(int)std::min<int64_t>(ceil_div(n, 256), ctx->sm_count * 16), 256, 0, ctx->stream>>>((const int32_t*)c.data.get(), n,
+                                                                                                      hold->get());
+    HS_LAUNCH_CHECK(ctx);
+  }
+  return hold->get();
+}
+
 __global__ void k_ranges_to_indices(const int64_t* __restrict__ bounds, const uint64_t* __restrict__ seg_offsets,
                                     const uint64_t* __restrict__ out_offsets, int nseg, uint32_t* __restrict__ out_idx) {
   // one CTA per segment
@@ -512,10 +530,10 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
     if (t.cols[0].type != HS_TYPE_INT64 && t.cols[0].type != HS_TYPE_INT32)
       fail(HS_EUNSUPPORTED, "filter scan: key column must be int32/int64");
     const int64_t n = t.nrows;
-    const int64_t* d_keys = (const int64_t*)t.cols[0].data.get();
+    Buf<int64_t> k64;
+    const int64_t* d_keys = widened_key(ctx, t.cols[0], n, &k64);
     StageTimer t_scan(ctx);
     t_scan.start();
-    if (t.cols[0].type == HS_TYPE_INT32) fail(HS_EUNSUPPORTED, "filter scan on int32 keys not wired yet");
     Buf<uint32_t> idx;
     int64_t n_out = 0;
     bool sorted = try_sorted && !t.cols[0].has_nulls;
@@ -523,7 +541,7 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
       Table full;
       decode_sources(ctx, src, cols, nullptr, &full, &st);
       t = std::move(full);
-      d_keys = (const int64_t*)t.cols[0].data.get();
+      d_keys = widened_key(ctx, t.cols[0], n, &k64);
     }
     if (sorted) {
       // K7: two binary searches per file
@@ -596,7 +614,8 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
 // through K2-K4 again, which is what Spark's SortExec does for multi-file buckets.
 static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_files, const int32_t* buckets, int nb,
                               const std::vector<std::string>& cols, Table* t, IndexedRows* rows, hs_stats* st,
-                              std::vector<uint64_t>* seg, const int64_t** d_keys, const uint32_t** d_perm, Buf<uint32_t>* iota) {
+                              std::vector<uint64_t>* seg, const int64_t** d_keys, const uint32_t** d_perm, Buf<uint32_t>* iota,
+                              Buf<int64_t>* k64) {
   // reorder files by bucket so the decoded table is bucket-major
   std::vector<int> order(n_files);
   for (int i = 0; i < n_files; i++) order[i] = i;
@@ -609,7 +628,8 @@ static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_fi
     per_bucket[buckets[order[i]]]++;
   }
   load_sources(ctx, sorted_files.data(), n_files, cols, t, st);
-  if (t->cols[0].type != HS_TYPE_INT64) fail(HS_EUNSUPPORTED, "bucket join: key column must be int64");
+  if (t->cols[0].type != HS_TYPE_INT64 && t->cols[0].type != HS_TYPE_INT32)
+    fail(HS_EUNSUPPORTED, "bucket join: key column must be int32 or int64");
   if (t->cols[0].has_nulls) fail(HS_EUNSUPPORTED, "bucket join: null join keys are not handled yet");
   const bool single = std::all_of(per_bucket.begin(), per_bucket.end(), [](int c) { return c <= 1; });
   if (single) {
@@ -620,7 +640,7 @@ static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_fi
       if (per_bucket[b]) fi++;
     }
     (*seg)[nb] = (uint64_t)t->nrows;
-    *d_keys = (const int64_t*)t->cols[0].data.get();
+    *d_keys = widened_key(ctx, t->cols[0], t->nrows, k64);
     iota->alloc(ctx, std::max<int64_t>(1, t->nrows));
     launch_iota_u32(ctx, iota->get(), t->nrows);
     *d_perm = iota->get();
@@ -628,8 +648,10 @@ static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_fi
     index_rows(ctx, *t, 1, nb, rows, st);
     *seg = rows->bucket_offsets;
     // materialise the sorted key column
-    Buf<uint8_t> sk(ctx, (size_t)std::max<int64_t>(1, rows->part.nrows) * 8);
-    launch_gather_plain(ctx, rows->part.cols[0].data.get(), rows->sorted_perm, rows->part.nrows, 8, sk.get());
+    const int kw = rows->part.cols[0].width;
+    const int ktype = rows->part.cols[0].type;
+    Buf<uint8_t> sk(ctx, (size_t)std::max<int64_t>(1, rows->part.nrows) * kw);
+    launch_gather_plain(ctx, rows->part.cols[0].data.get(), rows->sorted_perm, rows->part.nrows, kw, sk.get());
     rows->keys_alt.release();
     t->cols.clear();
     t->cols = std::move(rows->part.cols);
@@ -637,11 +659,11 @@ static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_fi
     // keep the sorted keys in a column appended at the end
     DevColumn kc;
     kc.name = "__sorted_key";
-    kc.type = HS_TYPE_INT64;
-    kc.width = 8;
+    kc.type = ktype;
+    kc.width = kw;
     kc.data = std::move(sk);
     t->cols.push_back(std::move(kc));
-    *d_keys = (const int64_t*)t->cols.back().data.get();
+    *d_keys = widened_key(ctx, t->cols.back(), t->nrows, k64);
     *d_perm = rows->sorted_perm;
   }
 }
@@ -684,8 +706,12 @@ int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_sta
     const int64_t *lkeys = nullptr, *rkeys = nullptr;
     const uint32_t *lperm = nullptr, *rperm = nullptr;
     Buf<uint32_t> liota, riota;
-    prepare_join_side(ctx, spec->left_files, spec->n_left, spec->left_buckets, nb, lcols, &lt, &lrows, &st, &lseg, &lkeys, &lperm, &liota);
-    prepare_join_side(ctx, spec->right_files, spec->n_right, spec->right_buckets, nb, rcols, &rt, &rrows, &st, &rseg, &rkeys, &rperm, &riota);
+    Buf<int64_t> lk64, rk64;
+    prepare_join_side(ctx, spec->left_files, spec->n_left, spec->left_buckets, nb, lcols, &lt, &lrows, &st, &lseg, &lkeys, &lperm, &liota, &lk64);
+    prepare_join_side(ctx, spec->right_files, spec->n_right, spec->right_buckets, nb, rcols, &rt, &rrows, &st, &rseg, &rkeys, &rperm, &riota, &rk64);
+    // hashInt and hashLong put equal values into different buckets: both sides must have been bucketed on the same type
+    // (JoinIndexRule only pairs indexes whose indexed columns have the same data type)
+    if (lt.cols[0].type != rt.cols[0].type) fail(HS_EUNSUPPORTED, "bucket join: key columns have different types");
     const int64_t nl = lt.nrows, nr = rt.nrows;
     if (nr >= (1ll << 32) || nl >= (1ll << 32)) fail(HS_EUNSUPPORTED, "join side larger than 2^32-1 rows");
     StageTimer t_join(ctx);

@@ -716,6 +716,9 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     }
   }
 
+  const bool stats_on_key = req.d_sorted_keys != nullptr && !table.cols[0].has_nulls &&
+                            (table.cols[0].type == HS_TYPE_INT32 || table.cols[0].type == HS_TYPE_INT64);
+  std::vector<StatPatch> stat_patches;
   std::vector<uint8_t> skeleton;
   std::vector<ByteCopy> copies;
   std::vector<uint32_t> seg_page_begin(nseg + 1, 0);
@@ -770,6 +773,9 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         ch.data_page_offset = (int64_t)(cursor - file_off);
         ch.null_count = 0;
         ch.value_width = W;
+        // the indexed column is sorted inside a bucket: min / max of a row group are its first / last key (filled in on the
+        // GPU after the sort); this is what lets a Spark reader prune row groups on the key
+        ch.has_minmax = stats_on_key && c == 0;
         const uint64_t chunk_begin = cursor;
         if (dicts[c].use) {  // every chunk of the column carries the same (global) dictionary page
           ch.has_dictionary = true;
@@ -822,7 +828,22 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     }
     {
       const size_t b = skeleton.size();
-      std::vector<uint8_t> footer = pq::write_footer(schema, rgs, n, schema_json);
+      std::vector<pq::StatSlot> slots;
+      std::vector<uint8_t> footer = pq::write_footer(schema, rgs, n, schema_json, &slots);
+      for (const pq::StatSlot& sl : slots) {
+        StatPatch sp;
+        int64_t row0 = 0;
+        for (int g = 0; g < sl.row_group; g++) row0 += rgs[g].num_rows;
+        sp.first_pos = req.seg_offsets[s] + (uint64_t)row0;
+        sp.last_pos = sp.first_pos + (uint64_t)rgs[sl.row_group].num_rows - 1;
+        for (int j = 0; j < 2; j++) {
+          sp.min_off[j] = cursor + sl.min_off[j];
+          sp.max_off[j] = cursor + sl.max_off[j];
+        }
+        sp.width = sl.width;
+        sp.pad = 0;
+        stat_patches.push_back(sp);
+      }
       skeleton.insert(skeleton.end(), footer.begin(), footer.end());
       uint32_t flen = (uint32_t)footer.size();
       const uint8_t* lp = (const uint8_t*)&flen;
@@ -886,6 +907,11 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     if (c == 0 && req.d_sorted_keys && (dc.type == HS_TYPE_INT32 || dc.type == HS_TYPE_INT64)) gc.sorted_keys = req.d_sorted_keys;
     launch_gather_encode(ctx, req.plan->tiles.get(), req.plan->ntiles, req.plan->seg_start.get(), req.d_perm, gc,
                          d_page_begin.get(), P, out->arena.get());
+  }
+  if (!stat_patches.empty()) {
+    Buf<StatPatch> d_sp(ctx, stat_patches.size());
+    HS_CUDA(cudaMemcpyAsync(d_sp.get(), stat_patches.data(), sizeof(StatPatch) * stat_patches.size(), cudaMemcpyHostToDevice, ctx->stream));
+    launch_patch_key_stats(ctx, d_sp.get(), (int64_t)stat_patches.size(), req.d_sorted_keys, table.cols[0].type, out->arena.get());
   }
   {  // dictionary columns, up to 8 per launch pair
     std::vector<int> dcols;

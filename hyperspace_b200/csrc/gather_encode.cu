@@ -145,6 +145,24 @@ __global__ void k_scatter_bytes(const ByteCopy* __restrict__ copies, int64_t n, 
   for (uint32_t i = lane; i < c.len; i += 32) arena[c.dst + i] = skeleton[c.src + i];
 }
 
+// min / max statistics of the (sorted) indexed column: first and last key of every row group, written over the
+// placeholders the host left in the footer
+__global__ void k_patch_key_stats(const StatPatch* __restrict__ patches, int64_t n, const uint64_t* __restrict__ sorted_keys,
+                                  int key_type, uint8_t* __restrict__ arena) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const StatPatch p = patches[i];
+  const uint64_t vmin = sort_decode_int(key_type, sorted_keys[p.first_pos]);
+  const uint64_t vmax = sort_decode_int(key_type, sorted_keys[p.last_pos]);
+  for (int b = 0; b < p.width; b++) {
+    const uint8_t lo = (uint8_t)(vmin >> (8 * b)), hi = (uint8_t)(vmax >> (8 * b));
+    arena[p.min_off[0] + b] = lo;
+    arena[p.min_off[1] + b] = lo;
+    arena[p.max_off[0] + b] = hi;
+    arena[p.max_off[1] + b] = hi;
+  }
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t seed, uint64_t i) {
   uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -231,6 +249,13 @@ void launch_scatter_bytes(hs_ctx* ctx, const ByteCopy* copies, int64_t n, const 
   if (n == 0) return;
   const int64_t threads = n * 32;
   k_scatter_bytes<<<(unsigned)ceil_div(threads, 256), 256, 0, ctx->stream>>>(copies, n, skeleton, arena);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_patch_key_stats(hs_ctx* ctx, const StatPatch* patches, int64_t n, const uint64_t* sorted_keys, int key_type,
+                            uint8_t* arena) {
+  if (n == 0) return;
+  k_patch_key_stats<<<(unsigned)ceil_div(n, 128), 128, 0, ctx->stream>>>(patches, n, sorted_keys, key_type, arena);
   HS_LAUNCH_CHECK(ctx);
 }
 

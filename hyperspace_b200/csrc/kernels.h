@@ -208,6 +208,13 @@ void launch_dict_encode_all(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, 
                             uint16_t* rec_scratch, const uint32_t* bucket_page_begin, int64_t rows_per_page, uint8_t* arena);
 // Plain gather: out[i] = src[perm[i]]
 void launch_gather_plain(hs_ctx* ctx, const void* src, const uint32_t* perm, int64_t n, int width, void* out);
+struct StatPatch {        // min/max of the sorted key column of one row group
+  uint64_t first_pos, last_pos;  // sorted positions of the row group's first and last row
+  uint64_t min_off[2], max_off[2];  // arena offsets of the footer placeholders
+  int32_t width, pad;
+};
+void launch_patch_key_stats(hs_ctx* ctx, const StatPatch* patches, int64_t n, const uint64_t* sorted_keys, int key_type,
+                            uint8_t* arena);
 struct ByteCopy {
   uint64_t dst;  // arena offset
   uint32_t src;  // offset into the skeleton byte stream

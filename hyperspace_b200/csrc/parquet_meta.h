@@ -384,7 +384,7 @@ struct OutChunk {
   bool has_dictionary = false;
   int64_t null_count = -1;
   bool has_minmax = false;
-  uint8_t min_le[8], max_le[8];  // little-endian plain-encoded min/max (fixed-width types)
+  uint8_t min_le[8] = {0}, max_le[8] = {0};  // little-endian plain-encoded min/max (fixed-width types)
   int32_t value_width = 0;
 };
 
@@ -395,10 +395,17 @@ struct OutRowGroup {
   std::vector<OutChunk> chunks;
 };
 
+// Where the min / max statistics of a chunk sit inside the serialised footer (deprecated max/min + max_value/min_value).
+struct StatSlot {
+  int32_t row_group, column, width;
+  size_t max_off[2], min_off[2];
+};
+
 // Serialises FileMetaData.  `spark_schema_json` is stored under org.apache.spark.sql.parquet.row.metadata exactly as
 // Spark's ParquetWriteSupport does, so Spark reads the index with the same StructType it was built from.
 inline std::vector<uint8_t> write_footer(const std::vector<SchemaColumn>& cols, const std::vector<OutRowGroup>& rgs,
-                                         int64_t num_rows, const std::string& spark_schema_json) {
+                                         int64_t num_rows, const std::string& spark_schema_json,
+                                         std::vector<StatSlot>* stat_slots = nullptr) {
   thrift::Writer w;
   w.struct_begin();
   w.f_i32(1, 1);  // version
@@ -420,7 +427,8 @@ inline std::vector<uint8_t> write_footer(const std::vector<SchemaColumn>& cols, 
   }
   w.f_i64(3, num_rows);
   w.f_list_begin(4, thrift::T_STRUCT, (uint32_t)rgs.size());
-  for (auto& g : rgs) {
+  for (size_t gi = 0; gi < rgs.size(); gi++) {
+    auto& g = rgs[gi];
     w.struct_begin();
     w.f_list_begin(1, thrift::T_STRUCT, (uint32_t)g.chunks.size());
     for (size_t ci = 0; ci < g.chunks.size(); ci++) {
@@ -449,14 +457,19 @@ inline std::vector<uint8_t> write_footer(const std::vector<SchemaColumn>& cols, 
       if (ch.has_dictionary) w.f_i64(11, ch.dictionary_page_offset);
       if (ch.null_count >= 0 || ch.has_minmax) {
         w.f_struct_begin(12);
+        StatSlot slot;
+        slot.row_group = (int32_t)gi;
+        slot.column = (int32_t)ci;
+        slot.width = ch.value_width;
         if (ch.has_minmax) {
-          w.f_binary(1, ch.max_le, ch.value_width);
-          w.f_binary(2, ch.min_le, ch.value_width);
+          slot.max_off[0] = w.f_binary(1, ch.max_le, ch.value_width);
+          slot.min_off[0] = w.f_binary(2, ch.min_le, ch.value_width);
         }
         if (ch.null_count >= 0) w.f_i64(3, ch.null_count);
         if (ch.has_minmax) {
-          w.f_binary(5, ch.max_le, ch.value_width);
-          w.f_binary(6, ch.min_le, ch.value_width);
+          slot.max_off[1] = w.f_binary(5, ch.max_le, ch.value_width);
+          slot.min_off[1] = w.f_binary(6, ch.min_le, ch.value_width);
+          if (stat_slots) stat_slots->push_back(slot);
         }
         w.struct_end();
       }

@@ -189,11 +189,14 @@ class Writer {
     varint(s.size());
     buf.insert(buf.end(), s.begin(), s.end());
   }
-  void f_binary(int16_t fid, const void* d, size_t n) {
+  // returns the offset of the payload inside buf (so fixed-width values can be patched in later)
+  size_t f_binary(int16_t fid, const void* d, size_t n) {
     field(fid, T_BINARY);
     varint(n);
     const uint8_t* b = (const uint8_t*)d;
+    const size_t off = buf.size();
     buf.insert(buf.end(), b, b + n);
+    return off;
   }
   void f_struct_begin(int16_t fid) {
     field(fid, T_STRUCT);

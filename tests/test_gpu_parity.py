@@ -512,3 +512,79 @@ def test_bucket_join_with_multi_file_buckets(ctx):
     assert got == want
     for x in (a, b2, r):
         x.free()
+
+
+def test_read_side_with_int32_keys(ctx):
+    """IntegerType keys (hashInt buckets): filter scan and bucket join widen the key on the GPU."""
+    rng = np.random.default_rng(31)
+    nl, nr, nb = 50_000, 30_000, 12
+    L = {"k": rng.integers(-20_000, 20_000, size=nl, dtype=np.int32), "v1": np.arange(nl, dtype=np.int64)}
+    R = {"k": rng.integers(-20_000, 20_000, size=nr, dtype=np.int32), "v2": np.arange(nr, dtype=np.float64)}
+    li = _index_in_memory(ctx, L, ["k"], ["v1"], nb, "L")
+    ri = _index_in_memory(ctx, R, ["k"], ["v2"], nb, "R")
+    for lo, hi in ((-50, 50), (None, -19_900), (7, 7)):
+        for sorted_on_key in (True, False):
+            batch, _ = ctx.filter_scan(li.as_sources(), "k", ["k", "v1"], lo=lo, hi=hi, sorted_on_key=sorted_on_key)
+            m = np.ones(nl, bool)
+            if lo is not None:
+                m &= L["k"] >= lo
+            if hi is not None:
+                m &= L["k"] <= hi
+            assert batch.column("k").dtype == np.int32
+            got = np.rec.fromarrays([batch.column("k"), batch.column("v1")])
+            assert np.array_equal(np.sort(got), np.sort(np.rec.fromarrays([L["k"][m], L["v1"][m]])))
+    batch, _ = ctx.bucket_join(li.as_sources(), [f.bucket for f in li.files], ri.as_sources(), [f.bucket for f in ri.files],
+                               nb, "k", "k", ["k", "v1"], ["v2"])
+    want = []
+    lperm, loffs, _ = O.index_rows(L, ["k"], ["v1"], nb)
+    rperm, roffs, _ = O.index_rows(R, ["k"], ["v2"], nb)
+    for b in range(nb):
+        lp, rp = lperm[loffs[b]:loffs[b + 1]], rperm[roffs[b]:roffs[b + 1]]
+        a, c = O.merge_join(L["k"][lp].astype(np.int64), R["k"][rp].astype(np.int64))
+        want.append(np.rec.fromarrays([L["k"][lp][a], L["v1"][lp][a], _bits(R["v2"][rp][c])]))
+    want = np.concatenate(want)
+    got = np.rec.fromarrays([batch.column("k"), batch.column("v1"), _bits(batch.column("v2"))])
+    assert np.array_equal(got, want)
+    # a long-keyed index is bucketed with hashLong: pairing it with an int-keyed one must be refused
+    R64 = {"k": R["k"].astype(np.int64), "v2": R["v2"]}
+    r64 = _index_in_memory(ctx, R64, ["k"], ["v2"], nb, "R64")
+    with pytest.raises(Exception, match="different types"):
+        ctx.bucket_join(li.as_sources(), [f.bucket for f in li.files], r64.as_sources(), [f.bucket for f in r64.files],
+                        nb, "k", "k", ["v1"], ["v2"])
+    for x in (li, ri, r64):
+        x.free()
+
+
+def test_key_statistics_in_index_files(ctx):
+    """Every row group of an index file carries min / max of the (sorted) indexed column, so a Parquet reader can prune."""
+    rng = np.random.default_rng(37)
+    n = 60_000
+    for dtype in (np.int64, np.int32):
+        cols = {"k": rng.integers(-1_000_000, 1_000_000, size=n).astype(dtype), "v": rng.integers(0, 9, size=n, dtype=np.int64)}
+        from hyperspace_b200 import _native
+
+        sink = io.BytesIO()
+        pq.write_table(pa.table(cols), sink, compression="NONE")
+        res, _ = ctx.create_index([_native.FileImage(data=sink.getvalue())], ["k"], ["v"], 5, output=_native.HS_OUT_HOST,
+                                  job_uuid="s", rows_per_row_group=2_000, rows_per_page=500)
+        seen = 0
+        for i in range(len(res.files)):
+            image = res.host_bytes(i)
+            pf = pq.ParquetFile(io.BytesIO(image))
+            assert pf.metadata.num_row_groups > 1
+            tbl = pf.read()
+            r0 = 0
+            for g in range(pf.metadata.num_row_groups):
+                rg = pf.metadata.row_group(g)
+                st = rg.column(0).statistics
+                assert st is not None and st.has_min_max and st.null_count == 0
+                k = tbl.column("k").to_numpy()[r0:r0 + rg.num_rows]
+                assert st.min == k.min() == k[0] and st.max == k.max() == k[-1]
+                r0 += rg.num_rows
+                seen += rg.num_rows
+            # the statistics drive row-group pruning in any Parquet reader
+            probe = int(tbl.column("k")[len(tbl) // 2].as_py())
+            hit = pq.read_table(io.BytesIO(image), filters=[("k", "==", probe)])
+            assert len(hit) == int((tbl.column("k").to_numpy() == probe).sum())
+        assert seen == n
+        res.free()
