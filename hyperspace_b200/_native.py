@@ -14,7 +14,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhs_gpu.so")
+# HS_GPU_LIB: load another build of the same library (kernel A/B experiments); there is still no CPU fallback
+LIB_PATH = os.environ.get("HS_GPU_LIB") or os.path.join(_HERE, "lib", "libhs_gpu.so")
 
 HS_OK, HS_EINVAL, HS_ENODEVICE, HS_ECUDA, HS_EFORMAT, HS_EIO, HS_EUNSUPPORTED, HS_ENOMEM, HS_ECOMM = 0, -1, -2, -3, -4, -5, -6, -7, -8
 HS_TYPE_INT32, HS_TYPE_INT64, HS_TYPE_FLOAT, HS_TYPE_DOUBLE, HS_TYPE_BOOL, HS_TYPE_STRING = range(6)

@@ -194,9 +194,37 @@ __device__ __forceinline__ unsigned match_any_bits(unsigned amask, unsigned v) {
   unsigned peers = amask;
 #pragma unroll
   for (int b = 0; b < NBITS; b++) {
-    const bool bit = (v >> b) & 1u;
+    const bool bit = (v & (1u << b)) != 0;  // one LOP3 with predicate output
     const unsigned m = __ballot_sync(amask, bit);
-    peers &= bit ? m : ~m;
+    peers &= m ^ (bit ? 0u : ~0u);          // SEL + one three-input LOP3
+  }
+  return peers;
+}
+
+// Full-warp variant (every lane takes part, no branch around it): bit test, ballot and the select of m / ~m are spelled
+// out in PTX so that each bit costs LOP3.P + VOTE + SEL + LOP3.
+template <int NBITS>
+__device__ __forceinline__ unsigned match_any_full(unsigned v) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < NBITS; b++) {
+    unsigned m, x;
+#ifdef HS_ASM_NOVOLATILE
+    asm(
+#else
+    asm volatile(
+#endif
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+        "selp.b32 %1, 0, 0xffffffff, p;\n\t"
+        "}"
+        : "=r"(m), "=r"(x)
+        : "r"(v), "r"(1u << b));
+    peers &= m ^ x;
   }
   return peers;
 }

@@ -451,8 +451,14 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   Buf<unsigned long long> ghist(ctx, num_buckets);
   out->d_bucket_offsets.alloc(ctx, num_buckets + 1);
   HS_CUDA(cudaMemsetAsync(ghist.get(), 0, sizeof(unsigned long long) * num_buckets, ctx->stream));
+  Buf<unsigned long long> d_key_bits(ctx, 2);
   if (fused) {
-    launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), ghist.get());
+    const unsigned long long init[2] = {0ull, ~0ull};
+    HS_CUDA(cudaMemcpyAsync(d_key_bits.get(), init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), ghist.get(), d_key_bits.get(),
+                     single_key_type_of(h_keys.data(), nkeys));
+    HS_CUDA(cudaMemcpyAsync(out->key_or_and, d_key_bits.get(), sizeof out->key_or_and, cudaMemcpyDeviceToHost, ctx->stream));
+    out->have_key_bits = true;  // valid after the stream synchronisation below
   } else {
     bucket.alloc(ctx, std::max<int64_t>(1, nrows));
     launch_bucket_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, bucket.get(), tile_hist.get(), ghist.get());
@@ -492,7 +498,8 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   Buf<PartColumn> d_pc(ctx, h_pc.size());
   if (fused) {
     HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * h_pc.size(), cudaMemcpyHostToDevice, ctx->stream));
-    launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), d_pc.get(), (int)h_pc.size());
+    launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), d_pc.get(), (int)h_pc.size(),
+                          nullptr, 1, single_key_type_of(h_keys.data(), nkeys));
   } else {
     dest.alloc(ctx, std::max<int64_t>(1, nrows));
     launch_partition_dest(ctx, bucket.get(), nrows, num_buckets, tile_hist.get(), dest.get());
@@ -524,16 +531,25 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
   uint64_t* keys_alt = out->keys_alt.get();
   uint32_t* perm = out->perm.get();
   uint32_t* perm_alt = out->perm_alt.get();
-  launch_iota_u32(ctx, perm, nrows);
   Buf<unsigned long long> d_or_and(ctx, 2);
   for (int k = nkeys - 1; k >= 0; k--) {
     DevColumn& kc = out->part.cols[k];
-    const unsigned long long init[2] = {0ull, ~0ull};
-    HS_CUDA(cudaMemcpyAsync(d_or_and.get(), init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
-    launch_encode_keys(ctx, kc.data.get(), kc.type, k == nkeys - 1 ? nullptr : perm, nrows, keys, d_or_and.get());
+    // The first column sorted (the last indexed column) starts from rows in partition order: its first radix pass reads
+    // the raw column and encodes on the fly, so neither the identity permutation nor the encoded keys are written out
+    // beforehand; only the OR / AND of the encoded keys is needed to pick the passes.
+    const bool from_raw = k == nkeys - 1 && kc.type >= HS_TYPE_INT32 && kc.type <= HS_TYPE_DOUBLE;
+    if (k == nkeys - 1 && !from_raw) launch_iota_u32(ctx, perm, nrows);
     unsigned long long or_and[2] = {0, 0};
-    HS_CUDA(cudaMemcpyAsync(or_and, d_or_and.get(), sizeof or_and, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (from_raw && out->have_key_bits) {  // the partition's histogram pass has them already
+      or_and[0] = out->key_or_and[0];
+      or_and[1] = out->key_or_and[1];
+    } else {
+      const unsigned long long init[2] = {0ull, ~0ull};
+      HS_CUDA(cudaMemcpyAsync(d_or_and.get(), init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+      launch_encode_keys(ctx, kc.data.get(), kc.type, from_raw ? nullptr : perm, nrows, from_raw ? nullptr : keys, d_or_and.get());
+      HS_CUDA(cudaMemcpyAsync(or_and, d_or_and.get(), sizeof or_and, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     const uint64_t varying = nrows ? (or_and[0] ^ or_and[1]) : 0;
     // Keys with more than four varying bytes: LSD passes over the top four varying bytes only, then fix up the (rare,
     // short) runs of rows that agree on those bytes.  Falls back to full passes when a run is long (low-entropy high bytes).
@@ -550,10 +566,17 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
         if (++seen == want_bytes) fourth_from_top = b;
       }
     static const bool full_sort_only = getenv("HS_FULL_SORT") != nullptr;
+    const RawKeyColumn raw{kc.data.get(), kc.type, kc.width};
+    const RawKeyColumn* first_src = from_raw ? &raw : nullptr;
+    if (from_raw && (varying == 0 || nrows == 0)) {  // nothing to sort on: materialise the pairs as they stand
+      launch_iota_u32(ctx, perm, nrows);
+      launch_encode_keys(ctx, kc.data.get(), kc.type, nullptr, nrows, keys, d_or_and.get());
+      first_src = nullptr;
+    }
     if (nbytes > want_bytes && !full_sort_only) {
       const uint64_t high_mask = ~0ull << (8 * fourth_from_top);
       const uint64_t low_mask = ~high_mask;
-      segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying & high_mask);
+      segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying & high_mask, first_src);
       Buf<uint32_t> d_flag(ctx, 1);
       HS_CUDA(cudaMemsetAsync(d_flag.get(), 0, 4, ctx->stream));
       launch_fix_runs(ctx, &out->plan, keys, perm, high_mask, low_mask, 64, d_flag.get());
@@ -562,7 +585,7 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
       HS_CUDA(cudaStreamSynchronize(ctx->stream));
       if (flag) segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying);
     } else {
-      segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying);
+      segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying, first_src);
     }
     if (kc.has_nulls)  // nulls first: one more stable pass on the validity byte (0 = null)
       segmented_sort_pass_by_table(ctx, &out->plan, keys, keys_alt, perm, perm_alt, kc.valid.get());

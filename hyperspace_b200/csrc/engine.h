@@ -40,6 +40,9 @@ struct IndexedRows {
   SortPlan plan;
   Buf<uint64_t> keys, keys_alt;       // sorted encoded first-key column (keys) + scratch
   Buf<uint32_t> perm, perm_alt;       // perm[p] = partitioned row at sorted position p
+  // OR / AND of the sort-encoded last indexed column, when the partition's histogram pass already computed them
+  bool have_key_bits = false;
+  unsigned long long key_or_and[2] = {0, ~0ull};
   uint64_t* sorted_keys = nullptr;    // points into keys or keys_alt
   uint32_t* sorted_perm = nullptr;
 };

@@ -105,7 +105,8 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   Buf<unsigned long long> ghist(ctx, world);
   Buf<uint64_t> d_send_off(ctx, world + 1);
   HS_CUDA(cudaMemsetAsync(ghist.get(), 0, 8 * world, ctx->stream));
-  launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, tile_hist.get(), ghist.get());
+  launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, tile_hist.get(), ghist.get(), nullptr,
+                   single_key_type_of(h_keys.data(), nkeys));
   launch_tile_offsets(ctx, tile_hist.get(), ntiles, world, ghist.get(), (unsigned long long*)d_send_off.get());
   // ---- count matrix -----------------------------------------------------------------------------------------
   Buf<uint64_t> d_matrix(ctx, (size_t)world * world);  // row r = counts rank r sends to each destination
@@ -146,7 +147,8 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   }
   Buf<PartColumn> d_pc(ctx, h_pc.size());
   HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * h_pc.size(), cudaMemcpyHostToDevice, ctx->stream));
-  launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, tile_hist.get(), d_pc.get(), (int)h_pc.size());
+  launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, tile_hist.get(), d_pc.get(), (int)h_pc.size(),
+                        nullptr, 1, single_key_type_of(h_keys.data(), nkeys));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data.release();
@@ -307,7 +309,8 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   std::vector<unsigned long long> h_mine(msg, 0), h_all((size_t)msg * world);
   for (int c = 0; c < ncols; c++) h_mine[nb + c] = table.cols[c].has_nulls ? 1 : 0;
   HS_CUDA(cudaMemcpyAsync(d_mine.get(), h_mine.data(), 8 * msg, cudaMemcpyHostToDevice, ctx->stream));
-  launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_mine.get());
+  launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_mine.get(), nullptr,
+                   single_key_type_of(h_keys.data(), nkeys));
   HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), msg, kNcclUint64, ctx->comm->comm, ctx->stream));
   HS_CUDA(cudaMemcpyAsync(h_all.data(), d_all.get(), 8 * (size_t)msg * world, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -405,7 +408,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   HS_CUDA(cudaMemcpyAsync(d_peer.get(), h_peer.data(), sizeof(void*) * nmoved * world, cudaMemcpyHostToDevice, ctx->stream));
   launch_tile_offsets(ctx, tile_hist.get(), ntiles, nb, d_mine.get(), nullptr, d_base.get());
   launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_pc.get(), nmoved,
-                        (void* const*)d_peer.get(), world);
+                        (void* const*)d_peer.get(), world, single_key_type_of(h_keys.data(), nkeys));
   // closing barrier: nobody reads its receive buffers before every peer's kernel has completed
   HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), 1, kNcclUint64, ctx->comm->comm, ctx->stream));
   t_x.stop();

@@ -210,7 +210,7 @@ __global__ void k_encode_keys(const void* __restrict__ in, int type, int width, 
     const int64_t r = src ? (int64_t)src[i] : i;
     uint64_t raw = width == 8 ? ((const uint64_t*)in)[r] : width == 4 ? ((const uint32_t*)in)[r] : ((const uint8_t*)in)[r];
     uint64_t e = sort_encode(type, raw);
-    out[i] = e;
+    if (out) out[i] = e;  // out == nullptr: only the OR / AND of the encoded keys is wanted
     vor |= e;
     vand &= e;
   }
@@ -338,22 +338,98 @@ constexpr int kFWarps = kFThreads / 32;
 constexpr int kFItems = kFusedTile / kFThreads;   // 16
 constexpr int kFWarpRows = kFusedTile / kFWarps;  // 512
 
+// pmod(hash, n) and bucket % world without an integer division per row: Lemire's fastmod (M = 2^64 / n + 1; exact for
+// 32-bit operands).  The signed Murmur3 value is shifted into unsigned range first and the shift is taken out again
+// modulo n:  pmod(h, n) = ((h + 2^31) mod n - (2^31 mod n)) mod+ n.
+struct ModConst {
+  uint64_t M;
+  uint32_t n;
+  uint32_t bias;  // 2^31 mod n
+};
+__host__ ModConst make_mod_const(uint32_t n) {
+  ModConst m;
+  m.M = ~0ull / n + 1;  // wraps to 0 for n == 1, which still yields x mod 1 == 0
+  m.n = n;
+  m.bias = (uint32_t)((1ull << 31) % n);
+  return m;
+}
+__device__ __forceinline__ uint32_t fast_mod(uint32_t x, const ModConst& m) { return (uint32_t)__umul64hi(m.M * x, m.n); }
+__device__ __forceinline__ uint32_t fast_pmod(uint32_t h, const ModConst& m) {
+  const uint32_t r = fast_mod(h ^ 0x80000000u, m);
+  return r >= m.bias ? r - m.bias : r + m.n - m.bias;
+}
+
+// last_encoded (optional): receives the sort encoding of the LAST key column's value (0 for a null)
+__device__ __forceinline__ uint32_t row_hash(const KeyColumn* keys, int nkeys, int64_t row, uint64_t* last_encoded = nullptr) {
+  uint32_t h = 42;
+  if (last_encoded) *last_encoded = 0;
+  for (int k = 0; k < nkeys; k++) {
+    const KeyColumn kc = keys[k];
+    if (kc.valid && !kc.valid[row]) continue;  // null leaves the hash unchanged
+    const uint64_t raw = load_raw(kc, row);
+    if (last_encoded && k == nkeys - 1) *last_encoded = sort_encode(kc.type, raw);
+    h = mm3_hash_value(kc.type, raw, h);
+  }
+  return h;
+}
+
+// KT >= 0: exactly one indexed column, of HS_TYPE KT and without nulls -- its descriptor is read once per thread and the
+// hash is straight-line code, so a thread's key loads issue back to back.  KT < 0: any number / type of key columns.
+template <int KT>
+struct RowHasher {
+  const KeyColumn* keys;
+  int nkeys;
+  const void* k0;
+  __device__ __forceinline__ RowHasher(const KeyColumn* k, int n) : keys(k), nkeys(n), k0(KT >= 0 ? k[0].data : nullptr) {}
+  __device__ __forceinline__ uint32_t operator()(int64_t row, uint64_t* last_encoded = nullptr) const {
+    if (KT >= 0) {
+      const uint64_t raw = (KT == HS_TYPE_INT64 || KT == HS_TYPE_DOUBLE) ? ((const uint64_t*)k0)[row]
+                                                                         : (uint64_t)((const uint32_t*)k0)[row];
+      if (last_encoded) *last_encoded = sort_encode(KT, raw);
+      return mm3_hash_value(KT, raw, 42u);
+    }
+    return row_hash(keys, nkeys, row, last_encoded);
+  }
+};
+
+template <int KT>
 __global__ void __launch_bounds__(kFThreads) k_tile_hist(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
-                                                          int num_buckets, int owner_mod,
+                                                          ModConst bucket_mod, ModConst owner_mod, int use_owner,
                                                           uint32_t* __restrict__ tile_hist,
-                                                          unsigned long long* __restrict__ global_hist) {
+                                                          unsigned long long* __restrict__ global_hist,
+                                                          unsigned long long* __restrict__ key_or_and) {
   extern __shared__ uint32_t s_hist[];  // nb
-  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
+  const int nb = use_owner ? (int)owner_mod.n : (int)bucket_mod.n;
   for (int i = threadIdx.x; i < nb; i += kFThreads) s_hist[i] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * kFusedTile;
+  const RowHasher<KT> hasher(keys, nkeys);
+  uint64_t vor = 0, vand = ~0ull;
 #pragma unroll 4
   for (int j = 0; j < kFItems; j++) {
     const int64_t row = base + j * kFThreads + threadIdx.x;
     if (row < nrows) {
-      int32_t b = row_bucket(keys, nkeys, row, num_buckets);
-      if (owner_mod > 0) b %= owner_mod;
+      uint64_t e;
+      uint32_t b = fast_pmod(hasher(row, &e), bucket_mod);
+      if (use_owner) b = fast_mod(b, owner_mod);
       atomicAdd(&s_hist[b], 1u);
+      vor |= e;
+      vand &= e;
+    }
+  }
+  if (key_or_and) {  // which bits of the last indexed column vary: picks the radix passes of the sort that follows
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      vor |= __shfl_xor_sync(0xffffffffu, (unsigned long long)vor, o);
+      vand &= __shfl_xor_sync(0xffffffffu, (unsigned long long)vand, o);
+    }
+    // the two accumulators saturate after a few tiles: look first, and only touch them when this warp adds information
+    // (millions of atomics on two addresses would serialise in L2)
+    if ((threadIdx.x & 31) == 0) {
+      const unsigned long long cur_or = *(volatile unsigned long long*)&key_or_and[0];
+      const unsigned long long cur_and = *(volatile unsigned long long*)&key_or_and[1];
+      if ((vor | cur_or) != cur_or) atomicOr(&key_or_and[0], (unsigned long long)vor);
+      if ((vand & cur_and) != cur_and) atomicAnd(&key_or_and[1], (unsigned long long)vand);
     }
   }
   __syncthreads();
@@ -365,133 +441,159 @@ __global__ void __launch_bounds__(kFThreads) k_tile_hist(const KeyColumn* __rest
 }
 
 // dynamic shared memory layout: [exchange buffer kFusedTile * 8 B][pos_bin u16 kFusedTile][cnt u16 kFWarps*nb]
-// [bin_start u32 nb][dst_base u32 nb][warp_sums 40 u32]
+// [out_adj u32 nb][bin_owner u32 nb][warp_sums 40 u32]
+//
+// All warp collectives run with the full mask and outside any branch: slots past the end of the last tile carry the
+// last bin and, being the last slots of the tile, rank behind every real row of that bin; they are never written out.
+template <int BITS, int KT>
 __global__ void __launch_bounds__(kFThreads) k_partition_rows(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
-                                                               int num_buckets, int owner_mod,
+                                                               ModConst bucket_mod, ModConst owner_mod, int use_owner,
                                                                const uint32_t* __restrict__ tile_dst,
                                                                const PartColumn* __restrict__ cols, int ncols,
                                                                void* const* __restrict__ peer_out, int out_world) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
+  const int nb = use_owner ? (int)owner_mod.n : (int)bucket_mod.n;
   uint64_t* xbuf = reinterpret_cast<uint64_t*>(smem);
   uint16_t* pos_bin = reinterpret_cast<uint16_t*>(smem + (size_t)kFusedTile * 8);
   uint16_t* cnt = pos_bin + kFusedTile;
-  uint32_t* bin_start = reinterpret_cast<uint32_t*>(cnt + (size_t)kFWarps * nb + ((kFWarps * nb) & 1));
-  uint32_t* dst_base = bin_start + nb;
-  uint32_t* warp_sums = dst_base + nb;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* out_adj = reinterpret_cast<uint32_t*>(cnt + (size_t)kFWarps * nb + ((kFWarps * nb) & 1));
+  uint32_t* bin_owner = out_adj + nb;
+  uint32_t* warp_sums = bin_owner + nb;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1;
   for (int i = threadIdx.x; i < kFWarps * nb; i += kFThreads) cnt[i] = 0;
-  for (int b = threadIdx.x; b < nb; b += kFThreads) dst_base[b] = tile_dst[(size_t)blockIdx.x * nb + b];
-  __syncthreads();
-  int bin_bits = 1;
-  while ((1 << bin_bits) < nb) bin_bits++;
   const int64_t tile_base = (int64_t)blockIdx.x * kFusedTile;
-  const int64_t wbase = tile_base + (int64_t)warp * kFWarpRows;
+  const uint32_t first = warp * kFWarpRows + lane;  // tile-relative row of this thread's item 0
+  const int64_t wbase = tile_base + first;
   const uint32_t tile_count = (uint32_t)min((int64_t)kFusedTile, nrows - tile_base);
-  uint16_t bin[kFItems], pos[kFItems];
-  bool act[kFItems];
+  uint32_t bin[kFItems];  // bin id in the low half; the in-warp rank joins it in the high half; finally the position
+  const RowHasher<KT> hasher(keys, nkeys);
 #pragma unroll
   for (int j = 0; j < kFItems; j++) {
-    const int64_t row = wbase + j * 32 + lane;
-    act[j] = row < nrows;
-    bin[j] = 0;
-    if (act[j]) {
-      int32_t b = row_bucket(keys, nkeys, row, num_buckets);
-      if (owner_mod > 0) b %= owner_mod;
-      bin[j] = (uint16_t)b;
+    bin[j] = (uint32_t)nb - 1;
+    if (first + j * 32 < tile_count) {
+#ifdef HS_PART_OLDMOD
+      uint32_t b = (uint32_t)spark_pmod(hasher(wbase + j * 32), (int32_t)bucket_mod.n);
+      if (use_owner) b %= owner_mod.n;
+#else
+      uint32_t b = fast_pmod(hasher(wbase + j * 32), bucket_mod);
+      if (use_owner) b = fast_mod(b, owner_mod);
+#endif
+      bin[j] = b;
     }
   }
+  __syncthreads();
   // stable rank inside the warp's 512 consecutive rows
   uint16_t* wcnt = cnt + (size_t)warp * nb;
 #pragma unroll
   for (int j = 0; j < kFItems; j++) {
-    const unsigned amask = __ballot_sync(0xffffffffu, act[j]);
-    if (act[j]) {
-      const unsigned peers = match_any_bits(amask, (unsigned)bin[j], bin_bits);
-      const int leader = __ffs(peers) - 1;
-      uint32_t pre = 0;
-      if (lane == leader) {
-        pre = wcnt[bin[j]];
-        wcnt[bin[j]] = (uint16_t)(pre + __popc(peers));
-      }
-      pre = __shfl_sync(amask, pre, leader);  // uniform mask: one shuffle for the whole warp
-      pos[j] = (uint16_t)(pre + __popc(peers & lt));
+#ifdef HS_PART_ASM
+    const unsigned peers = match_any_full<BITS>(bin[j]);
+#else
+    const unsigned peers = match_any_bits<BITS>(0xffffffffu, bin[j]);
+#endif
+    const uint32_t before = __popc(peers & lt);
+#ifdef HS_PART_LEADER
+    uint32_t pre = 0;
+    const int leader = __ffs(peers) - 1;
+    if (before == 0) {
+      pre = wcnt[bin[j]];
+      wcnt[bin[j]] = (uint16_t)(pre + __popc(peers));
     }
+    pre = __shfl_sync(0xffffffffu, pre, leader);
     __syncwarp();
+#else
+    const uint32_t pre = wcnt[bin[j]];  // every peer reads the same counter (broadcast)
+    __syncwarp();
+    if (before == 0) wcnt[bin[j]] = (uint16_t)(pre + __popc(peers));
+    __syncwarp();
+#endif
+    bin[j] |= (pre + before) << 16;
   }
   __syncthreads();
-  // per bin: exclusive prefix over warps (in place), tile total, then exclusive scan over bins
+  // per bin: exclusive prefix over warps and bins -> first in-tile position of every (warp, bin)
   uint32_t carry = 0;
   for (int b0 = 0; b0 < nb; b0 += kFThreads) {
     const int b = b0 + threadIdx.x;
     uint32_t total = 0;
     if (b < nb) {
 #pragma unroll
-      for (int w = 0; w < kFWarps; w++) {
-        const uint16_t c = cnt[(size_t)w * nb + b];
-        cnt[(size_t)w * nb + b] = (uint16_t)total;
-        total += c;
-      }
+      for (int w = 0; w < kFWarps; w++) total += cnt[(size_t)w * nb + b];
     }
     uint32_t chunk_total = 0;
     const uint32_t ex = block_exclusive_scan(total, warp_sums, &chunk_total);
-    if (b < nb) bin_start[b] = carry + ex;
+    if (b < nb) {
+      uint32_t run = carry + ex;
+      out_adj[b] = tile_dst[(size_t)blockIdx.x * nb + b] - run;
+      bin_owner[b] = out_world > 1 ? (uint32_t)b % (uint32_t)out_world : 0u;
+#pragma unroll
+      for (int w = 0; w < kFWarps; w++) {
+        const uint16_t c = cnt[(size_t)w * nb + b];
+        cnt[(size_t)w * nb + b] = (uint16_t)run;
+        run += c;
+      }
+    }
     carry += chunk_total;
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < kFItems; j++) {
-    if (act[j]) {
-      pos[j] = (uint16_t)(bin_start[bin[j]] + cnt[(size_t)warp * nb + bin[j]] + pos[j]);
-      pos_bin[pos[j]] = bin[j];
-    }
+    const uint32_t b = bin[j] & 0xffffu;
+    bin[j] = wcnt[b] + (bin[j] >> 16);
+    pos_bin[bin[j]] = (uint16_t)b;
   }
+  const uint32_t(&pos)[kFItems] = bin;
   // ---- move every column through the exchange buffer -----------------------------------------------------------
   for (int c = 0; c < ncols; c++) {
     const PartColumn pc = cols[c];
     __syncthreads();  // previous column's readers are done with xbuf (and pos_bin is complete)
     if (pc.width == 8) {
-      const uint64_t* in = (const uint64_t*)pc.in;
+      const uint64_t* in = (const uint64_t*)pc.in + wbase;
 #pragma unroll
       for (int j = 0; j < kFItems; j++)
-        if (act[j]) xbuf[pos[j]] = in[wbase + j * 32 + lane];
+        if (first + j * 32 < tile_count) xbuf[pos[j]] = in[j * 32];
     } else if (pc.width == 4) {
-      const uint32_t* in = (const uint32_t*)pc.in;
+      const uint32_t* in = (const uint32_t*)pc.in + wbase;
       uint32_t* xb = reinterpret_cast<uint32_t*>(xbuf);
 #pragma unroll
       for (int j = 0; j < kFItems; j++)
-        if (act[j]) xb[pos[j]] = in[wbase + j * 32 + lane];
+        if (first + j * 32 < tile_count) xb[pos[j]] = in[j * 32];
     } else {
-      const uint8_t* in = (const uint8_t*)pc.in;
+      const uint8_t* in = (const uint8_t*)pc.in + wbase;
       uint8_t* xb = reinterpret_cast<uint8_t*>(xbuf);
 #pragma unroll
       for (int j = 0; j < kFItems; j++)
-        if (act[j]) xb[pos[j]] = in[wbase + j * 32 + lane];
+        if (first + j * 32 < tile_count) xb[pos[j]] = in[j * 32];
     }
     __syncthreads();
     // peer_out != nullptr: bucket b lives on GPU (b % out_world); its column c buffer is peer_out[c * out_world + owner]
     // (a peer-mapped pointer: these stores go straight over NVLink into the owner's memory)
     void* const* pout = peer_out ? peer_out + (size_t)c * out_world : nullptr;
     if (pc.width == 8) {
+#ifndef HS_PART_NOUNROLL
+#pragma unroll 4
+#endif
       for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
         const uint32_t b = pos_bin[i];
-        uint64_t* out = (uint64_t*)(pout ? pout[b % out_world] : pc.out);
-        out[dst_base[b] + (i - bin_start[b])] = xbuf[i];
+        uint64_t* out = (uint64_t*)(pout ? pout[bin_owner[b]] : pc.out);
+        out[out_adj[b] + i] = xbuf[i];
       }
     } else if (pc.width == 4) {
       const uint32_t* xb = reinterpret_cast<const uint32_t*>(xbuf);
+#ifndef HS_PART_NOUNROLL
+#pragma unroll 4
+#endif
       for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
         const uint32_t b = pos_bin[i];
-        uint32_t* out = (uint32_t*)(pout ? pout[b % out_world] : pc.out);
-        out[dst_base[b] + (i - bin_start[b])] = xb[i];
+        uint32_t* out = (uint32_t*)(pout ? pout[bin_owner[b]] : pc.out);
+        out[out_adj[b] + i] = xb[i];
       }
     } else {
       const uint8_t* xb = reinterpret_cast<const uint8_t*>(xbuf);
       for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
         const uint32_t b = pos_bin[i];
-        uint8_t* out = (uint8_t*)(pout ? pout[b % out_world] : pc.out);
-        out[dst_base[b] + (i - bin_start[b])] = xb[i];
+        uint8_t* out = (uint8_t*)(pout ? pout[bin_owner[b]] : pc.out);
+        out[out_adj[b] + i] = xb[i];
       }
     }
   }
@@ -508,33 +610,73 @@ size_t fused_smem_bytes(int nb) {
 bool fused_partition_supported(int nbins) { return nbins <= kFusedMaxBins; }
 
 void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
-                      uint32_t* tile_hist, unsigned long long* global_hist) {
+                      uint32_t* tile_hist, unsigned long long* global_hist, unsigned long long* key_or_and,
+                      int single_key_type) {
   KernelScope _ks(ctx, "k_tile_hist");
   if (nrows == 0) return;
   const int nb = owner_mod > 0 ? owner_mod : num_buckets;
   const int64_t ntiles = ceil_div(nrows, kFusedTile);
-  k_tile_hist<<<(unsigned)ntiles, kFThreads, (size_t)nb * 4, ctx->stream>>>(d_keys, nkeys, nrows, num_buckets, owner_mod,
-                                                                            tile_hist, global_hist);
+  const ModConst bm = make_mod_const((uint32_t)num_buckets), om = make_mod_const((uint32_t)std::max(owner_mod, 1));
+  const int uo = owner_mod > 0 ? 1 : 0;
+#define HS_HIST(KT)                                                                                                      \
+  k_tile_hist<KT><<<(unsigned)ntiles, kFThreads, (size_t)nb * 4, ctx->stream>>>(d_keys, nkeys, nrows, bm, om, uo, tile_hist, \
+                                                                                global_hist, key_or_and)
+  switch (single_key_type) {
+    case HS_TYPE_INT32: HS_HIST(HS_TYPE_INT32); break;
+    case HS_TYPE_INT64: HS_HIST(HS_TYPE_INT64); break;
+    default: HS_HIST(-1); break;
+  }
+#undef HS_HIST
   HS_LAUNCH_CHECK(ctx);
+}
+
+template <int BITS, int KT>
+static void launch_partition_rows_t(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets,
+                                    int owner_mod, const uint32_t* tile_dst, const PartColumn* d_cols, int ncols,
+                                    void* const* d_peer_out, int out_world) {
+  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
+  const int64_t ntiles = ceil_div(nrows, kFusedTile);
+  static bool attr = false;  // one per instantiation
+  if (!attr) {
+    HS_CUDA(cudaFuncSetAttribute(k_partition_rows<BITS, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fused_smem_bytes(kFusedMaxBins)));
+    attr = true;
+  }
+  k_partition_rows<BITS, KT><<<(unsigned)ntiles, kFThreads, fused_smem_bytes(nb), ctx->stream>>>(
+      d_keys, nkeys, nrows, make_mod_const((uint32_t)num_buckets), make_mod_const((uint32_t)std::max(owner_mod, 1)),
+      owner_mod > 0 ? 1 : 0, tile_dst, d_cols, ncols, d_peer_out, out_world);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+template <int BITS>
+static void launch_partition_rows_bits(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets,
+                                       int owner_mod, const uint32_t* tile_dst, const PartColumn* d_cols, int ncols,
+                                       void* const* d_peer_out, int out_world, int single_key_type) {
+  switch (single_key_type) {
+    case HS_TYPE_INT32:
+      launch_partition_rows_t<BITS, HS_TYPE_INT32>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world);
+      break;
+    case HS_TYPE_INT64:
+      launch_partition_rows_t<BITS, HS_TYPE_INT64>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world);
+      break;
+    default:
+      launch_partition_rows_t<BITS, -1>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world);
+  }
 }
 
 void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
                            const uint32_t* tile_dst, const PartColumn* d_cols, int ncols, void* const* d_peer_out,
-                           int out_world) {
+                           int out_world, int single_key_type) {
   KernelScope _ks(ctx, "k_partition_rows");
   if (nrows == 0) return;
   const int nb = owner_mod > 0 ? owner_mod : num_buckets;
-  const int64_t ntiles = ceil_div(nrows, kFusedTile);
-  static bool attr = false;
-  if (!attr) {
-    HS_CUDA(cudaFuncSetAttribute(k_partition_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)fused_smem_bytes(kFusedMaxBins)));
-    attr = true;
-  }
-  k_partition_rows<<<(unsigned)ntiles, kFThreads, fused_smem_bytes(nb), ctx->stream>>>(d_keys, nkeys, nrows, num_buckets,
-                                                                                        owner_mod, tile_dst, d_cols, ncols,
-                                                                                        d_peer_out, out_world);
-  HS_LAUNCH_CHECK(ctx);
+  // the ranking votes once per bin-id bit: 4, 8 or 10 (kFusedMaxBins = 1024)
+  if (nb <= 16)
+    launch_partition_rows_bits<4>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type);
+  else if (nb <= 256)
+    launch_partition_rows_bits<8>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type);
+  else
+    launch_partition_rows_bits<10>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type);
 }
 
 }  // namespace hs

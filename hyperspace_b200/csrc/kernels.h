@@ -100,7 +100,10 @@ void launch_partition_dest(hs_ctx* ctx, const uint16_t* bucket, int64_t nrows, i
 // out[dest[i]] = in[i]
 void launch_scatter_column(hs_ctx* ctx, const void* in, void* out, const uint32_t* dest, int64_t nrows, int width);
 // ---- fused partition (hash + stable rank + shared-memory exchange of every column in one kernel) ------------------
-constexpr int kFusedTile = 8192;     // rows per tile (512 threads x 16)
+#ifndef HS_FUSED_TILE
+#define HS_FUSED_TILE 8192
+#endif
+constexpr int kFusedTile = HS_FUSED_TILE;     // rows per tile (512 threads x 16)
 constexpr int kFusedMaxBins = 1024;  // above this the per-warp counters no longer fit next to the exchange buffer
 struct PartColumn {
   const void* in;
@@ -109,14 +112,21 @@ struct PartColumn {
   int32_t pad;
 };
 bool fused_partition_supported(int nbins);
+// key_or_and (optional, {0, ~0} on entry): accumulates OR / AND of the sort-encoded values of the last key column
 // tile histograms M[tile][bin] for kFusedTile-row tiles (+ global histogram); bin = bucket, or bucket % owner_mod
 void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
-                      uint32_t* tile_hist, unsigned long long* global_hist);
+                      uint32_t* tile_hist, unsigned long long* global_hist,
+                      unsigned long long* key_or_and = nullptr, int single_key_type = -1);
+// single_key_type: HS_TYPE_INT32 / HS_TYPE_INT64 when there is exactly one key column, of that type and without nulls
+// (selects a kernel with the hash inlined for it); -1 otherwise.  See single_key_type_of().
+inline int single_key_type_of(const KeyColumn* h_keys, int nkeys) {
+  return nkeys == 1 && h_keys[0].valid == nullptr && (h_keys[0].type == 0 || h_keys[0].type == 1) ? h_keys[0].type : -1;
+}
 // tile_dst = launch_tile_offsets(tile_hist); moves all columns into bin-major order, stable
 // d_peer_out (optional): [ncols][out_world] peer-mapped output pointers; bucket b is written to GPU b % out_world
 void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
                            const uint32_t* tile_dst, const PartColumn* d_cols, int ncols, void* const* d_peer_out = nullptr,
-                           int out_world = 1);
+                           int out_world = 1, int single_key_type = -1);
 // out[i] = sort_encode(in[src ? src[i] : i])  (+ global OR / AND reduction into or_and[0], or_and[1])
 void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* src, int64_t nrows, uint64_t* out,
                         unsigned long long* or_and);
@@ -144,8 +154,15 @@ struct SortPlan {
 void build_sort_plan(hs_ctx* ctx, const uint64_t* seg_offsets, int nseg, SortPlan* plan);
 // Stable LSD radix sort of (key, val) pairs within each segment on the key bits set in `bit_mask` (bytes whose bits
 // are all constant are skipped).  Result is left in (keys, vals); (keys_alt, vals_alt) are scratch of the same size.
+// first_pass_source (optional): the pairs have not been materialised yet -- the first pass that runs reads the raw key
+// column (position p holds the value of row p) and uses p itself as the row index.  bit_mask must then select at least
+// one byte.
+struct RawKeyColumn {
+  const void* data;
+  int type, width;
+};
 void segmented_sort_pairs(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,
-                          uint32_t*& vals_alt, uint64_t bit_mask);
+                          uint32_t*& vals_alt, uint64_t bit_mask, const RawKeyColumn* first_pass_source = nullptr);
 // After sorting on the bits of high_mask: stable insertion sort of every run of equal (key & high_mask) on (key & low_mask);
 // *d_flag is set when a run is longer than max_run (the caller then runs the remaining passes instead).
 void launch_fix_runs(hs_ctx* ctx, SortPlan* plan, uint64_t* keys, uint32_t* vals, uint64_t high_mask, uint64_t low_mask,

@@ -36,18 +36,40 @@ struct DigitTable {
   __device__ __forceinline__ uint32_t operator()(uint64_t, uint32_t val) const { return table[val]; }
 };
 
-template <typename Digit>
-__global__ void __launch_bounds__(kHistThreads) k_sort_hist(const SortTile* __restrict__ tiles,
-                                                         const uint64_t* __restrict__ keys,
-                                                         const uint32_t* __restrict__ vals, Digit digit,
+// Where a pass reads its (key, row) pairs from: the ping-pong arrays, or -- for the first pass over a freshly partitioned
+// key column -- the raw column itself, encoded on the fly with the row's own position as its value (so the encoded-key
+// and iota arrays are never materialised).
+struct SrcPairs {
+  const uint64_t* __restrict__ keys;
+  const uint32_t* __restrict__ vals;
+  __device__ __forceinline__ void load(uint64_t p, uint64_t& k, uint32_t& v) const {
+    k = keys[p];
+    v = vals[p];
+  }
+};
+template <int TYPE>  // HS_TYPE_*: a compile-time type keeps the loads of a thread's items back to back
+struct SrcRaw {
+  const void* __restrict__ raw;
+  __device__ __forceinline__ void load(uint64_t p, uint64_t& k, uint32_t& v) const {
+    const uint64_t r = (TYPE == HS_TYPE_INT64 || TYPE == HS_TYPE_DOUBLE) ? ((const uint64_t*)raw)[p]
+                                                                          : (uint64_t)((const uint32_t*)raw)[p];
+    k = sort_encode(TYPE, r);
+    v = (uint32_t)p;
+  }
+};
+
+template <typename Src, typename Digit>
+__global__ void __launch_bounds__(kHistThreads) k_sort_hist(const SortTile* __restrict__ tiles, Src src, Digit digit,
                                                          uint32_t* __restrict__ tile_hist) {
   __shared__ uint32_t s_hist[256];
   s_hist[threadIdx.x] = 0;
   __syncthreads();
   const SortTile t = tiles[blockIdx.x];
   for (uint32_t i = threadIdx.x; i < t.count; i += kHistThreads) {
-    const uint64_t pos = t.start + i;
-    atomicAdd(&s_hist[digit(keys[pos], vals[pos])], 1u);
+    uint64_t k;
+    uint32_t v;
+    src.load(t.start + i, k, v);
+    atomicAdd(&s_hist[digit(k, v)], 1u);
   }
   __syncthreads();
   tile_hist[(size_t)blockIdx.x * 256 + threadIdx.x] = s_hist[threadIdx.x];
@@ -110,96 +132,99 @@ __global__ void __launch_bounds__(1024) k_seg_apply(const SortChunk* __restrict_
 struct ScatterShared {
   uint64_t keys[kSortTile];
   uint32_t vals[kSortTile];
-  uint16_t cnt[kWarps][256];
-  uint32_t bin_start[256];
-  uint32_t dst_base[256];
+  uint16_t cnt[kWarps][256];   // ranking: per-warp digit counts; afterwards: first in-tile position of (warp, digit)
+  uint32_t out_adj[256];       // global destination of a digit's run minus its first in-tile position
   uint32_t warp_sums[40];
 };
 
-template <typename Digit>
-__global__ void __launch_bounds__(kThreads) k_sort_scatter(const SortTile* __restrict__ tiles,
-                                                            const uint64_t* __restrict__ keys,
-                                                            const uint32_t* __restrict__ vals, Digit digit,
-                                                            const uint32_t* __restrict__ tile_dst,
-                                                            uint64_t* __restrict__ out_keys,
-                                                            uint32_t* __restrict__ out_vals) {
+// All warp-collectives below run with the full mask and outside any branch: slots past the end of a partial tile carry
+// digit 255 and, being the last slots of the tile, rank behind every real item of that digit, so they never disturb a
+// real item's position and are simply not written out.
+template <typename Src, typename Digit>
+__global__ void __launch_bounds__(kThreads, 2) k_sort_scatter(const SortTile* __restrict__ tiles, Src src, Digit digit,
+                                                               const uint32_t* __restrict__ tile_dst,
+                                                               uint64_t* __restrict__ out_keys,
+                                                               uint32_t* __restrict__ out_vals) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   ScatterShared& sm = *reinterpret_cast<ScatterShared*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1;
-  for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&sm.cnt[0][0])[i] = 0;
-  if (threadIdx.x < 256) sm.dst_base[threadIdx.x] = tile_dst[(size_t)blockIdx.x * 256 + threadIdx.x];
-  __syncthreads();
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(&sm.cnt[0][0]);
+#pragma unroll
+    for (int i = 0; i < kWarps * 256 / 2 / kThreads; i++) z[threadIdx.x + i * kThreads] = 0;
+  }
   const SortTile t = tiles[blockIdx.x];
+  uint32_t dst0 = 0;
+  if (threadIdx.x < 256) dst0 = tile_dst[(size_t)blockIdx.x * 256 + threadIdx.x];
+  const uint32_t first = warp * kWarpRows + lane;
+  const uint64_t p0 = t.start + first;
   uint64_t k[kItems];
   uint32_t v[kItems];
-  uint16_t bin[kItems], rank[kItems];
-  bool act[kItems];
+  uint32_t bin[kItems];
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
-    const uint32_t i = warp * kWarpRows + j * 32 + lane;
-    act[j] = i < t.count;
-    k[j] = 0;
+    const bool a = first + j * 32 < t.count;
+    k[j] = ~0ull;
     v[j] = 0;
-    bin[j] = 0;
-    if (act[j]) {
-      k[j] = keys[t.start + i];
-      v[j] = vals[t.start + i];
-      bin[j] = (uint16_t)digit(k[j], v[j]);
-    }
-  }
-  // stable rank of every item among the warp's earlier items with the same digit: the lowest peer lane does the
-  // read-modify-write of the warp-private counter and broadcasts the old value (no intra-iteration hazard)
-  uint16_t* cnt = sm.cnt[warp];
-#pragma unroll
-  for (int j = 0; j < kItems; j++) {
-    const unsigned amask = __ballot_sync(0xffffffffu, act[j]);
-    if (act[j]) {
-      const unsigned peers = match_any_bits<8>(amask, (unsigned)bin[j]);
-      const int leader = __ffs(peers) - 1;
-      uint32_t pre = 0;
-      if (lane == leader) {
-        pre = cnt[bin[j]];
-        cnt[bin[j]] = (uint16_t)(pre + __popc(peers));
-      }
-      pre = __shfl_sync(amask, pre, leader);  // uniform mask: one shuffle for the whole warp
-      rank[j] = (uint16_t)(pre + __popc(peers & lt));
-    }
-    __syncwarp();  // order this iteration's counter store before the next iteration's loads
+    if (a) src.load(p0 + j * 32, k[j], v[j]);
+    bin[j] = a ? digit(k[j], v[j]) : 255u;
   }
   __syncthreads();
-  // per digit: exclusive prefix over warps (in place) and the tile total
+  // stable rank of every item among the warp's earlier items with the same digit
+  uint16_t* cnt = sm.cnt[warp];
+  uint32_t rank[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+#ifdef HS_SCATTER_NOASM
+    const unsigned peers = match_any_bits<8>(0xffffffffu, bin[j]);
+#else
+    const unsigned peers = match_any_full<8>(bin[j]);
+#endif
+    const uint32_t before = __popc(peers & lt);
+    const uint32_t pre = cnt[bin[j]];   // every peer reads the same counter (broadcast)
+    __syncwarp();
+    if (before == 0) cnt[bin[j]] = (uint16_t)(pre + __popc(peers));
+    __syncwarp();
+    rank[j] = pre + before;
+  }
+  __syncthreads();
+  // per digit: exclusive prefix over warps and digits -> first in-tile position of every (warp, digit)
   uint32_t total = 0;
   if (threadIdx.x < 256) {
-    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) total += sm.cnt[w][threadIdx.x];
+  }
+  const uint32_t start = block_exclusive_scan(total, sm.warp_sums, nullptr);
+  if (threadIdx.x < 256) {
+    uint32_t run = start;
 #pragma unroll
     for (int w = 0; w < kWarps; w++) {
       const uint16_t c = sm.cnt[w][threadIdx.x];
       sm.cnt[w][threadIdx.x] = (uint16_t)run;
       run += c;
     }
-    total = run;
+    sm.out_adj[threadIdx.x] = dst0 - start;
   }
-  const uint32_t start = block_exclusive_scan(total, sm.warp_sums, nullptr);
-  if (threadIdx.x < 256) sm.bin_start[threadIdx.x] = start;
   __syncthreads();
   // exchange: digit-sorted order inside the tile
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
-    if (act[j]) {
-      const uint32_t pos = sm.bin_start[bin[j]] + sm.cnt[warp][bin[j]] + rank[j];
-      sm.keys[pos] = k[j];
-      sm.vals[pos] = v[j];
-    }
+    const uint32_t pos = cnt[bin[j]] + rank[j];
+    sm.keys[pos] = k[j];
+    sm.vals[pos] = v[j];
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < t.count; i += kThreads) {
-    const uint64_t key = sm.keys[i];
-    const uint32_t val = sm.vals[i];
-    const uint32_t d = digit(key, val);
-    const uint32_t dst = sm.dst_base[d] + (i - sm.bin_start[d]);
-    out_keys[dst] = key;
-    out_vals[dst] = val;
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    const uint32_t i = threadIdx.x + j * kThreads;
+    if (i < t.count) {
+      const uint64_t key = sm.keys[i];
+      const uint32_t val = sm.vals[i];
+      const uint32_t dst = sm.out_adj[digit(key, val)] + i;
+      out_keys[dst] = key;
+      out_vals[dst] = val;
+    }
   }
 }
 
@@ -209,20 +234,46 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const SortTile* __res
 // of four more full passes over the data the head of every run insertion-sorts it (stably) on (key & low_mask).  A run
 // longer than max_run raises `flag`; the caller then falls back to full LSD passes, which is still correct because equal
 // full keys are in original order both inside untouched runs and inside insertion-sorted ones.
+//
+// Two phases per tile so that the divergent part runs with full warps: (1) every thread tests its rows for "head of a
+// run of two or more" -- a straight-line compare against both neighbours -- and the heads are compacted into a list in
+// shared memory; (2) the threads walk that list, one run each.  With 24 sorted bits and 5 M-row buckets about a quarter
+// of the rows head such a run; testing and sorting in the same loop left three quarters of every warp idle.
 __global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ tiles, const uint64_t* __restrict__ seg_start,
                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                    uint64_t high_mask, uint64_t low_mask, uint32_t max_run,
                                                    uint32_t* __restrict__ flag) {
+  __shared__ uint16_t s_heads[kSortTile / 2 + 32];
+  __shared__ uint32_t s_n;
   const SortTile t = tiles[blockIdx.x];
   const uint64_t segb = seg_start[t.seg], sege = seg_start[t.seg + 1];
-  for (uint32_t i = threadIdx.x; i < t.count; i += blockDim.x) {
-    const uint64_t p = t.start + i;
+  const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (uint32_t i0 = 0; i0 < t.count; i0 += 256) {  // uniform trip count: the ballot below needs whole warps
+    const uint32_t i = i0 + threadIdx.x;
+    bool head = false;
+    if (i < t.count) {
+      const uint64_t p = t.start + i;
+      const uint64_t kh = keys[p] & high_mask;
+      head = (p == segb || (keys[p - 1] & high_mask) != kh) && p + 1 < sege && (keys[p + 1] & high_mask) == kh;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, head);
+    if (m) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&s_n, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (head) s_heads[base + __popc(m & lt)] = (uint16_t)i;
+    }
+  }
+  __syncthreads();
+  const uint32_t nheads = s_n;
+  for (uint32_t e = threadIdx.x; e < nheads; e += 256) {
+    const uint64_t p = t.start + s_heads[e];
     const uint64_t kh = keys[p] & high_mask;
-    if (p > segb && (keys[p - 1] & high_mask) == kh) continue;  // not the head of a run
-    uint64_t q = p + 1;
+    uint64_t q = p + 2;  // p + 1 is known to belong to the run
     while (q < sege && q - p <= max_run && (keys[q] & high_mask) == kh) q++;
     const uint32_t len = (uint32_t)(q - p);
-    if (len == 1) continue;
     if (len > max_run) {
       *flag = 1;
       continue;
@@ -237,20 +288,21 @@ __global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ t
         vals[p + b] = vals[p + b - 1];
         b--;
       }
-      keys[p + b] = ka;
-      vals[p + b] = va;
+      if (b != a) {
+        keys[p + b] = ka;
+        vals[p + b] = va;
+      }
     }
   }
 }
 
-template <typename Digit>
+template <typename Src, typename Digit>
 void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchunks, const uint32_t* seg_chunk_begin,
-              uint32_t* chunk_sums, const uint64_t* keys, const uint32_t* vals, uint64_t* out_keys, uint32_t* out_vals,
-              Digit digit) {
+              uint32_t* chunk_sums, Src src, uint64_t* out_keys, uint32_t* out_vals, Digit digit) {
   {
     KernelScope _ks(ctx, "k_sort_hist");
-    k_sort_hist<Digit><<<(unsigned)plan->ntiles, kHistThreads, 0, ctx->stream>>>(plan->tiles.get(), keys, vals, digit,
-                                                                            plan->tile_hist.get());
+    k_sort_hist<Src, Digit><<<(unsigned)plan->ntiles, kHistThreads, 0, ctx->stream>>>(plan->tiles.get(), src, digit,
+                                                                                 plan->tile_hist.get());
     HS_LAUNCH_CHECK(ctx);
   }
   KernelScope* _scan = new KernelScope(ctx, "k_seg_scan");
@@ -261,16 +313,15 @@ void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchu
   k_seg_apply<<<(unsigned)nchunks, 1024, 0, ctx->stream>>>(chunks, plan->tile_hist.get(), plan->tile_dst.get(), chunk_sums);
   HS_LAUNCH_CHECK(ctx);
   delete _scan;
-  static bool attr_shift = false, attr_table = false;
-  bool& attr = std::is_same<Digit, DigitShift>::value ? attr_shift : attr_table;
+  static bool attr = false;  // one per (Src, Digit) instantiation
   if (!attr) {
-    HS_CUDA(cudaFuncSetAttribute(k_sort_scatter<Digit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HS_CUDA(cudaFuncSetAttribute(k_sort_scatter<Src, Digit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(ScatterShared)));
     attr = true;
   }
   KernelScope _ks(ctx, "k_sort_scatter");
-  k_sort_scatter<Digit><<<(unsigned)plan->ntiles, kThreads, sizeof(ScatterShared), ctx->stream>>>(
-      plan->tiles.get(), keys, vals, digit, plan->tile_dst.get(), out_keys, out_vals);
+  k_sort_scatter<Src, Digit><<<(unsigned)plan->ntiles, kThreads, sizeof(ScatterShared), ctx->stream>>>(
+      plan->tiles.get(), src, digit, plan->tile_dst.get(), out_keys, out_vals);
   HS_LAUNCH_CHECK(ctx);
 }
 
@@ -339,16 +390,35 @@ void build_sort_plan(hs_ctx* ctx, const uint64_t* seg_offsets, int nseg, SortPla
 }
 
 void segmented_sort_pairs(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,
-                          uint32_t*& vals_alt, uint64_t bit_mask) {
+                          uint32_t*& vals_alt, uint64_t bit_mask, const RawKeyColumn* first_pass_source) {
   if (plan->ntiles == 0) return;
   ChunkPlan cp = build_chunks(ctx, plan->h_seg_tile_begin);
+  bool first = first_pass_source != nullptr;
   for (int pass = 0; pass < 8; pass++) {
     if (((bit_mask >> (pass * 8)) & 0xff) == 0) continue;  // digit constant over the whole input
-    run_pass(ctx, plan, cp.chunks.get(), cp.nchunks, cp.seg_chunk_begin.get(), cp.chunk_sums.get(), keys, vals,
-             keys_alt, vals_alt, DigitShift{pass * 8});
+    if (first) {
+      const void* raw = first_pass_source->data;
+      const DigitShift digit{pass * 8};
+#define HS_RAW_PASS(T)                                                                                                   \
+  run_pass(ctx, plan, cp.chunks.get(), cp.nchunks, cp.seg_chunk_begin.get(), cp.chunk_sums.get(), SrcRaw<T>{raw}, keys_alt, \
+           vals_alt, digit)
+      switch (first_pass_source->type) {
+        case HS_TYPE_INT32: HS_RAW_PASS(HS_TYPE_INT32); break;
+        case HS_TYPE_INT64: HS_RAW_PASS(HS_TYPE_INT64); break;
+        case HS_TYPE_FLOAT: HS_RAW_PASS(HS_TYPE_FLOAT); break;
+        case HS_TYPE_DOUBLE: HS_RAW_PASS(HS_TYPE_DOUBLE); break;
+        default: fail(HS_EUNSUPPORTED, "sort: key type %d", first_pass_source->type);
+      }
+#undef HS_RAW_PASS
+      first = false;
+    } else {
+      run_pass(ctx, plan, cp.chunks.get(), cp.nchunks, cp.seg_chunk_begin.get(), cp.chunk_sums.get(), SrcPairs{keys, vals},
+               keys_alt, vals_alt, DigitShift{pass * 8});
+    }
     std::swap(keys, keys_alt);
     std::swap(vals, vals_alt);
   }
+  if (first) fail(HS_EINVAL, "segmented_sort_pairs: raw first-pass source given but no pass ran");
 }
 
 void launch_fix_runs(hs_ctx* ctx, SortPlan* plan, uint64_t* keys, uint32_t* vals, uint64_t high_mask, uint64_t low_mask,
@@ -364,8 +434,8 @@ void segmented_sort_pass_by_table(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, 
                                   uint32_t*& vals_alt, const uint8_t* digits) {
   if (plan->ntiles == 0) return;
   ChunkPlan cp = build_chunks(ctx, plan->h_seg_tile_begin);
-  run_pass(ctx, plan, cp.chunks.get(), cp.nchunks, cp.seg_chunk_begin.get(), cp.chunk_sums.get(), keys, vals, keys_alt,
-           vals_alt, DigitTable{digits});
+  run_pass(ctx, plan, cp.chunks.get(), cp.nchunks, cp.seg_chunk_begin.get(), cp.chunk_sums.get(), SrcPairs{keys, vals},
+           keys_alt, vals_alt, DigitTable{digits});
   std::swap(keys, keys_alt);
   std::swap(vals, vals_alt);
 }
