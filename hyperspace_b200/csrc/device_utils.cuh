@@ -93,6 +93,10 @@ HS_HD uint64_t sort_encode(int type, uint64_t raw) {
   return raw;
 }
 
+// Fibonacci hashing of a dictionary value's raw bits: one 64-bit multiply; the top bits of the product depend on every
+// input bit.  Shared by the device hash sets / look-up tables and the host code that builds the compact look-up table.
+HS_HD uint32_t dict_hash_u64(uint64_t v) { return (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> 32); }
+
 HS_HD int type_width(int type) {
   switch (type) {
     case 0: case 2: return 4;

@@ -18,7 +18,7 @@ constexpr unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;
 constexpr int kThreads = 256;
 
 // Fibonacci hashing: one 64-bit multiply; the top bits of the product depend on every input bit
-__device__ __forceinline__ uint32_t dict_hash(uint64_t v) { return (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> 32); }
+__device__ __forceinline__ uint32_t dict_hash(uint64_t v) { return dict_hash_u64(v); }
 
 // Column values are read exactly once: streaming (evict-first) loads keep them from evicting the few hot lines of the
 // hash table out of L1 (with default caching the look-ups went to L2: ~6 sector requests per row, L2-request bound).
@@ -144,7 +144,7 @@ __global__ void k_dict_slot_index(const unsigned long long* __restrict__ keys, u
 // that k_dict_pack_all fetches all of a row's indices with a single 32-byte L2 sector request instead of one request per
 // column (the single-column pack kernel was L2-sector-bound: lts__throughput 66 %, DRAM 14 %).
 template <int SLOTS>
-__global__ void __launch_bounds__(kThreads) k_dict_map_all(DictMapArgs a, int64_t n, uint32_t mask, uint16_t* __restrict__ rec) {
+__global__ void __launch_bounds__(kThreads) k_dict_map_all(DictMapArgs a, int64_t n, uint16_t* __restrict__ rec) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint64_t v[SLOTS];
@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(kThreads) k_dict_map_all(DictMapArgs a, int64_
       if (c < a.ncols) {
         x = a.empty_index[c];
         if (v[c] != kEmpty) {
+          const uint32_t mask = a.mask[c];
           uint32_t h = dict_hash(v[c]) & mask;
           const uint4* tab = reinterpret_cast<const uint4*>(a.entries[c]);
           const uint32_t vlo = (uint32_t)v[c], vhi = (uint32_t)(v[c] >> 32);
@@ -314,8 +315,8 @@ void launch_dict_encode_all(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, 
   {
     KernelScope _ks(ctx, "k_dict_map");
     const int grid = grid_for(ctx, nrows, kThreads, 16);
-    if (slots == 4) k_dict_map_all<4><<<grid, kThreads, 0, ctx->stream>>>(map_args, nrows, capacity - 1, rec_scratch);
-    else k_dict_map_all<8><<<grid, kThreads, 0, ctx->stream>>>(map_args, nrows, capacity - 1, rec_scratch);
+    if (slots == 4) k_dict_map_all<4><<<grid, kThreads, 0, ctx->stream>>>(map_args, nrows, rec_scratch);
+    else k_dict_map_all<8><<<grid, kThreads, 0, ctx->stream>>>(map_args, nrows, rec_scratch);
     HS_LAUNCH_CHECK(ctx);
   }
   KernelScope _ks(ctx, "k_dict_pack");

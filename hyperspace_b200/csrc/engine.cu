@@ -349,7 +349,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
         cursor += round_up((size_t)pg.uncompressed_size, 16) + 16;
       }
     }
-    d_scratch.alloc(ctx, std::max<uint64_t>(cursor, 16));
+    d_scratch.alloc(ctx, std::max<uint64_t>(cursor, 16) + 16);  // decoders may read one aligned word past a page
     for (PageDesc& pg : h_pages) {
       if (pg.codec == pq::UNCOMPRESSED) continue;
       if (pg.dict_size == -1) {
@@ -652,7 +652,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
   // ---- dictionary analysis: distinct values of every non-null column, capped at kMaxDictEntries ---------------------
   struct ColDict {
     bool use = false;
-    uint32_t bw = 0, ndict = 0, empty_index = 0;
+    uint32_t bw = 0, ndict = 0, empty_index = 0, mask = 0;
     Buf<unsigned long long> keys;       // owned when the set was built here
     const unsigned long long* keys_ptr = nullptr;  // the hash set in use (own or the column's ready-made one)
     Buf<uint8_t> entries;               // capacity x 16 bytes {key, dictionary index}
@@ -732,9 +732,26 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         cd.empty_index = (uint32_t)(std::find(cd.values.begin(), cd.values.end(), ~(uint64_t)0) - cd.values.begin());
       cd.d_values.alloc(ctx, cd.ndict);
       HS_CUDA(cudaMemcpyAsync(cd.d_values.get(), cd.values.data(), 8 * (size_t)cd.ndict, cudaMemcpyHostToDevice, ctx->stream));
-      cd.entries.alloc(ctx, (size_t)kDictCapacity * 16);
-      launch_dict_slot_index(ctx, cd.keys_ptr, kDictCapacity, cd.d_values.get(), cd.ndict, type, cd.entries.get());
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      // value -> dictionary index look-up table for the encoder, built here on the host (<= 65536 inserts): open
+      // addressing sized to the dictionary (load <= 0.5) rather than to the 4 MB distinct-value set, so that the tables of
+      // all dictionary columns stay resident in L1 while k_dict_map streams the rows through them
+      uint32_t cap = 256;
+      while (cap < 2 * cd.ndict) cap <<= 1;
+      cd.mask = cap - 1;
+      std::vector<uint32_t> tab((size_t)cap * 4, 0u);
+      for (uint32_t s2 = 0; s2 < cap; s2++) tab[(size_t)s2 * 4] = tab[(size_t)s2 * 4 + 1] = 0xffffffffu;  // empty = ~0 key
+      for (uint32_t i = 0; i < cd.ndict; i++) {
+        const uint64_t v = cd.values[i];
+        if (v == ~0ull) continue;  // the empty marker itself is mapped through empty_index
+        uint32_t h = dict_hash_u64(v) & cd.mask;
+        while (tab[(size_t)h * 4] != 0xffffffffu || tab[(size_t)h * 4 + 1] != 0xffffffffu) h = (h + 1) & cd.mask;
+        tab[(size_t)h * 4] = (uint32_t)v;
+        tab[(size_t)h * 4 + 1] = (uint32_t)(v >> 32);
+        tab[(size_t)h * 4 + 2] = i;
+      }
+      cd.entries.alloc(ctx, (size_t)cap * 16);
+      HS_CUDA(cudaMemcpyAsync(cd.entries.get(), tab.data(), (size_t)cap * 16, cudaMemcpyHostToDevice, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));  // tab goes out of scope
       cd.use = true;
     }
   }
@@ -952,6 +969,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         ma.src[j] = table.cols[c].data.get();
         ma.width[j] = table.cols[c].width;
         ma.entries[j] = dicts[c].entries.get();
+        ma.mask[j] = dicts[c].mask;
         ma.empty_index[j] = dicts[c].empty_index;
         pa.page_value_offset[j] = d_pvo.get() + (size_t)c * page_counter;
         pa.bw[j] = dicts[c].bw;

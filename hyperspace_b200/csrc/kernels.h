@@ -209,7 +209,8 @@ void launch_dict_slot_index(hs_ctx* ctx, const unsigned long long* keys, uint32_
 // all dictionary columns of a table in one map + one pack launch (up to 8 columns per call)
 struct DictMapArgs {
   const void* src[8];
-  const void* entries[8];  // 16-byte {key, index} hash-table entries
+  const void* entries[8];  // 16-byte {key, index} hash-table entries (open addressing, linear probing, dict_hash_u64)
+  uint32_t mask[8];        // table capacity - 1 (a power of two sized to the dictionary, so that the table stays in L1)
   uint32_t empty_index[8];
   int32_t width[8];
   int32_t ncols;

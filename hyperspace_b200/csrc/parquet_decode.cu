@@ -395,8 +395,35 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
           if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
           return;
         }
-#pragma unroll 4
-        for (int i = threadIdx.x; i < n; i += blockDim.x) store_value<W>(co.data, row0 + i, load_value<W>(p + (size_t)i * W));
+        // A straight copy.  Both variants keep a thread's loads free of branches so that eight of them are in flight
+        // at once: naturally aligned bodies (this engine's own files) take plain vector loads; any other alignment
+        // assembles each value from the two aligned words around it (the second word of the page's last value may
+        // lie past the page but never past the file: a footer and the magic follow every page).
+        if (W == 8) {
+          uint64_t* dst = (uint64_t*)co.data + row0;
+          if (((uintptr_t)p & 7) == 0) {
+            const uint64_t* src = (const uint64_t*)p;
+#pragma unroll 8
+            for (int i = threadIdx.x; i < n; i += kDecodeThreads) dst[i] = __ldg(src + i);
+          } else {
+            const uint64_t* w = (const uint64_t*)((uintptr_t)p & ~(uintptr_t)7);
+            const unsigned sh = (unsigned)((uintptr_t)p & 7) * 8;
+#pragma unroll 8
+            for (int i = threadIdx.x; i < n; i += kDecodeThreads) dst[i] = (__ldg(w + i) >> sh) | (__ldg(w + i + 1) << (64 - sh));
+          }
+        } else {
+          uint32_t* dst = (uint32_t*)co.data + row0;
+          if (((uintptr_t)p & 3) == 0) {
+            const uint32_t* src = (const uint32_t*)p;
+#pragma unroll 8
+            for (int i = threadIdx.x; i < n; i += kDecodeThreads) dst[i] = __ldg(src + i);
+          } else {
+            const uint32_t* w = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+            const unsigned sh = (unsigned)((uintptr_t)p & 3) * 8;
+#pragma unroll 8
+            for (int i = threadIdx.x; i < n; i += kDecodeThreads) dst[i] = __funnelshift_r(__ldg(w + i), __ldg(w + i + 1), sh);
+          }
+        }
       }
     } else {
       // Fast path: the whole index stream is ONE bit-packed run (what this engine's encoder writes, and what parquet-mr /
@@ -421,8 +448,8 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
       const uint32_t hdr_len = sm.flag;
       if (hdr_len) {
         const uint8_t* run = p + hdr_len;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
+#pragma unroll 8
+        for (int i = threadIdx.x; i < n; i += kDecodeThreads)
           store_value<W>(co.data, row0 + i, dict_lookup(extract_bits(run, (uint64_t)i, idx_bw)));
         return;
       }
