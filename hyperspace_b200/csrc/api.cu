@@ -354,7 +354,17 @@ int hs_create_index(hs_ctx* ctx, const hs_index_spec* spec, hs_index_result** ou
       for (size_t j = i + 1; j < cols.size(); j++)
         if (cols[i] == cols[j]) fail(HS_EINVAL, "duplicate column '%s' in index config", cols[i].c_str());
     Table table;
-    load_sources(ctx, spec->files, spec->n_files, cols, &table, &st);
+    // Included columns whose source pages are all dictionary-encoded travel through the build as 16-bit dictionary codes
+    // (late materialisation).  Only where nothing between decode and encode needs their values: one GPU, the fused
+    // partition, no rows to drop.  HS_NO_CARRY=1 switches it off (A/B measurements).
+    const bool no_carry = getenv("HS_NO_CARRY") != nullptr;
+    CarryOptions carry;
+    if (ctx->world == 1 && !spec->disable_dictionary && spec->n_deleted_file_ids == 0 && !no_carry &&
+        fused_partition_supported(spec->num_buckets)) {
+      carry.first_col = spec->n_indexed;
+      carry.num_segments = spec->num_buckets;
+    }
+    load_sources(ctx, spec->files, spec->n_files, cols, &table, &st, &carry);
     if (spec->lineage) fill_lineage(ctx, table, spec->files, spec->n_files);
     if (spec->n_deleted_file_ids > 0) drop_deleted_rows(ctx, table, spec->deleted_file_ids, spec->n_deleted_file_ids);
     IndexedRows rows;

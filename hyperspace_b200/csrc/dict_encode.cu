@@ -307,10 +307,32 @@ void launch_dict_slot_index(hs_ctx* ctx, const unsigned long long* keys, uint32_
   HS_LAUNCH_CHECK(ctx);
 }
 
+void launch_dict_pack(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,
+                      const DictPackArgs& pack_args, int slots, const uint16_t* rec, const uint32_t* bucket_page_begin,
+                      int64_t rows_per_page, uint8_t* arena) {
+  KernelScope _ks(ctx, "k_dict_pack");
+  if (ntiles == 0) return;
+  const size_t smem = (size_t)pack_args.ncols * (kSortTile / 8 * 16);
+  static bool attr = false;
+  if (!attr) {
+    HS_CUDA(cudaFuncSetAttribute(k_dict_pack_all<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (kSortTile / 8 * 16)));
+    HS_CUDA(cudaFuncSetAttribute(k_dict_pack_all<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (kSortTile / 8 * 16)));
+    attr = true;
+  }
+  if (slots == 4)
+    k_dict_pack_all<4><<<(unsigned)ntiles, kThreads, smem, ctx->stream>>>(tiles, seg_start, perm, rec, pack_args,
+                                                                         bucket_page_begin, rows_per_page, arena);
+  else
+    k_dict_pack_all<8><<<(unsigned)ntiles, kThreads, smem, ctx->stream>>>(tiles, seg_start, perm, rec, pack_args,
+                                                                         bucket_page_begin, rows_per_page, arena);
+  HS_LAUNCH_CHECK(ctx);
+}
+
 void launch_dict_encode_all(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,
                             const DictMapArgs& map_args, const DictPackArgs& pack_args, int64_t nrows, uint32_t capacity,
                             uint16_t* rec_scratch, const uint32_t* bucket_page_begin, int64_t rows_per_page, uint8_t* arena) {
   if (ntiles == 0) return;
+  (void)capacity;
   const int slots = map_args.ncols <= 4 ? 4 : 8;
   {
     KernelScope _ks(ctx, "k_dict_map");
@@ -319,21 +341,7 @@ void launch_dict_encode_all(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, 
     else k_dict_map_all<8><<<grid, kThreads, 0, ctx->stream>>>(map_args, nrows, rec_scratch);
     HS_LAUNCH_CHECK(ctx);
   }
-  KernelScope _ks(ctx, "k_dict_pack");
-  const size_t smem = (size_t)map_args.ncols * (kSortTile / 8 * 16);
-  static bool attr = false;
-  if (!attr) {
-    HS_CUDA(cudaFuncSetAttribute(k_dict_pack_all<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (kSortTile / 8 * 16)));
-    HS_CUDA(cudaFuncSetAttribute(k_dict_pack_all<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (kSortTile / 8 * 16)));
-    attr = true;
-  }
-  if (slots == 4)
-    k_dict_pack_all<4><<<(unsigned)ntiles, kThreads, smem, ctx->stream>>>(tiles, seg_start, perm, rec_scratch, pack_args,
-                                                                         bucket_page_begin, rows_per_page, arena);
-  else
-    k_dict_pack_all<8><<<(unsigned)ntiles, kThreads, smem, ctx->stream>>>(tiles, seg_start, perm, rec_scratch, pack_args,
-                                                                         bucket_page_begin, rows_per_page, arena);
-  HS_LAUNCH_CHECK(ctx);
+  launch_dict_pack(ctx, tiles, ntiles, seg_start, perm, pack_args, slots, rec_scratch, bucket_page_begin, rows_per_page, arena);
 }
 
 }  // namespace hs

@@ -108,10 +108,71 @@ SourceSet::SourceSet() : impl(new Impl()) {}
 SourceSet::~SourceSet() { delete impl; }
 
 void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const std::vector<std::string>& columns,
-                  Table* out, hs_stats* stats) {
+                  Table* out, hs_stats* stats, const CarryOptions* carry) {
   SourceSet src;
   open_sources(ctx, files, n_files, &src, stats);
-  decode_sources(ctx, src, columns, nullptr, out, stats);
+  decode_sources(ctx, src, columns, nullptr, out, stats, carry);
+}
+
+// ---- dictionary helpers shared by the decoder (late-materialised columns) and the page encoder -------------------------
+
+// The distinct values of a device hash set (state[0] of them, plus the empty marker when state[2] is set), sorted in the
+// column's order.  Synchronises the stream.
+static std::vector<uint64_t> sorted_dictionary(hs_ctx* ctx, const unsigned long long* keys, const uint32_t* state, int type) {
+  const uint32_t ntab = state[0];
+  Buf<unsigned long long> d_list(ctx, std::max<uint32_t>(1, ntab) + 1);
+  Buf<uint32_t> d_counter(ctx, 1);
+  HS_CUDA(cudaMemsetAsync(d_counter.get(), 0, 4, ctx->stream));
+  launch_dict_collect(ctx, keys, kDictCapacity, d_list.get(), d_counter.get());
+  std::vector<uint64_t> values(ntab);
+  if (ntab) HS_CUDA(cudaMemcpyAsync(values.data(), d_list.get(), 8 * (size_t)ntab, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (state[2]) values.push_back(~0ull);
+  std::sort(values.begin(), values.end(), [type](uint64_t a, uint64_t b) { return sort_encode(type, a) < sort_encode(type, b); });
+  return values;
+}
+
+// parquet-mr's choice, restated: dictionary-encode when the bit-packed codes plus one dictionary page per output file are
+// clearly smaller than the PLAIN values
+static bool dictionary_pays_off(uint32_t ndict, uint32_t bw, int width, int64_t total_rows, int nseg) {
+  const double plain_bytes = (double)total_rows * width;
+  const double dict_bytes = (double)total_rows * bw / 8.0 + (double)ndict * width * std::max(1, nseg);
+  return ndict > 0 && ndict <= kMaxDictEntries && dict_bytes <= 0.9 * plain_bytes;
+}
+
+static uint32_t bits_for(uint32_t ndict) {
+  uint32_t bw = 1;
+  while ((1u << bw) < ndict) bw++;
+  return bw;
+}
+
+// value -> code look-up table (open addressing, linear probing, 16-byte {key lo, key hi, code, 0} entries), built on the
+// host (<= 65536 inserts) and sized to the dictionary (load <= 0.5) so that it stays resident in L1 while rows stream
+// through it.  The empty marker ~0 cannot be stored: *empty_index receives its code instead.  Synchronises the stream.
+static void upload_lookup_table(hs_ctx* ctx, const std::vector<uint64_t>& values, Buf<uint8_t>* entries, uint32_t* mask,
+                                uint32_t* empty_index) {
+  const uint32_t ndict = (uint32_t)values.size();
+  uint32_t cap = 256;
+  while (cap < 2 * ndict) cap <<= 1;
+  *mask = cap - 1;
+  *empty_index = 0;
+  std::vector<uint32_t> tab((size_t)cap * 4, 0u);
+  for (uint32_t s2 = 0; s2 < cap; s2++) tab[(size_t)s2 * 4] = tab[(size_t)s2 * 4 + 1] = 0xffffffffu;
+  for (uint32_t i = 0; i < ndict; i++) {
+    const uint64_t v = values[i];
+    if (v == ~0ull) {
+      *empty_index = i;
+      continue;
+    }
+    uint32_t h = dict_hash_u64(v) & *mask;
+    while (tab[(size_t)h * 4] != 0xffffffffu || tab[(size_t)h * 4 + 1] != 0xffffffffu) h = (h + 1) & *mask;
+    tab[(size_t)h * 4] = (uint32_t)v;
+    tab[(size_t)h * 4 + 1] = (uint32_t)(v >> 32);
+    tab[(size_t)h * 4 + 2] = i;
+  }
+  entries->alloc(ctx, (size_t)cap * 16);
+  HS_CUDA(cudaMemcpyAsync(entries->get(), tab.data(), (size_t)cap * 16, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // tab goes out of scope
 }
 
 void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceSet* set, hs_stats* stats) {
@@ -206,7 +267,8 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
 }
 
 void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>& columns,
-                    const std::vector<std::pair<int64_t, int64_t>>* file_windows, Table* out, hs_stats* stats) {
+                    const std::vector<std::pair<int64_t, int64_t>>* file_windows, Table* out, hs_stats* stats,
+                    const CarryOptions* carry) {
   StageTimer t_plan(ctx), t_dec(ctx);
   const int n_files = set.n_files;
   std::vector<FileImage>& imgs = set.impl->imgs;
@@ -279,18 +341,24 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   stats->rows_in += nrows;
 
   std::vector<ColumnOut> h_cols(ncols);
-  for (int c = 0; c < ncols; c++) {
-    DevColumn& dc = out->cols[c];
-    dc.data.alloc(ctx, (size_t)nrows * dc.width + 16);
-    if (col_optional[c]) {
-      dc.valid.alloc(ctx, (size_t)nrows + 16);
-      HS_CUDA(cudaMemsetAsync(dc.valid.get(), 1, (size_t)nrows + 16, ctx->stream));
+  std::vector<Buf<uint8_t>> carry_tables(ncols);  // look-up tables of the late-materialised columns (decode only)
+  // destinations are allocated once the late-materialised columns are known (they get 2-byte codes, not values)
+  auto alloc_destinations = [&]() {
+    for (int c = 0; c < ncols; c++) {
+      DevColumn& dc = out->cols[c];
+      if (dc.carried) continue;
+      dc.data.alloc(ctx, (size_t)nrows * dc.width + 16);
+      if (col_optional[c]) {
+        dc.valid.alloc(ctx, (size_t)nrows + 16);
+        HS_CUDA(cudaMemsetAsync(dc.valid.get(), 1, (size_t)nrows + 16, ctx->stream));
+      }
+      h_cols[c] = ColumnOut{dc.data.get(), col_optional[c] ? dc.valid.get() : nullptr, dc.width, dc.type, nullptr, 0u, 0u, 0, 0};
     }
-    h_cols[c] = ColumnOut{dc.data.get(), col_optional[c] ? dc.valid.get() : nullptr, dc.width, dc.type};
-  }
+  };
   const int n_chunks = (int)chunks.size();
   t_plan.stop();
   if (n_chunks == 0 || nrows == 0) {
+    alloc_destinations();
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
     return;
   }
@@ -302,7 +370,6 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   Buf<uint32_t> d_flags(ctx, 1 + ncols);  // [0] error word, [1..] per-column has-nulls
   Buf<ColumnOut> d_cols(ctx, ncols);
   HS_CUDA(cudaMemcpyAsync(d_chunks.get(), chunks.data(), sizeof(ChunkDesc) * n_chunks, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(d_cols.get(), h_cols.data(), sizeof(ColumnOut) * ncols, cudaMemcpyHostToDevice, ctx->stream));
   HS_CUDA(cudaMemsetAsync(d_flags.get(), 0, sizeof(uint32_t) * (1 + ncols), ctx->stream));
   launch_walk_pages(ctx, d_chunks.get(), n_chunks, d_counts.get(), nullptr, nullptr, d_flags.get(), 0);
   std::vector<int32_t> counts(n_chunks);
@@ -367,6 +434,55 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
     launch_snappy_decompress(ctx, d_blobs.get(), (int64_t)blobs.size(), d_scratch.get(), d_flags.get());
     HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
   }
+  // ---- late-materialised dictionary columns --------------------------------------------------------------------------
+  // A candidate column whose every page is dictionary-encoded and free of nulls, and whose chunk dictionaries unite to a
+  // dictionary that pays off, is decoded to 16-bit codes of that dictionary: its values are never written to HBM, the
+  // partition moves 2 bytes per row instead of 4 or 8, and the page encoder finds its codes ready-made.
+  if (carry && carry->first_col >= 0 && !file_windows && ctx->world == 1 && n_pages > 0) {
+    Buf<uint32_t> d_class(ctx, ncols);
+    HS_CUDA(cudaMemsetAsync(d_class.get(), 0, 4 * (size_t)ncols, ctx->stream));
+    launch_classify_pages(ctx, d_pages.get(), n_pages, d_class.get());
+    std::vector<uint32_t> cls(ncols);
+    HS_CUDA(cudaMemcpyAsync(cls.data(), d_class.get(), 4 * (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> cand;
+    for (int c = carry->first_col; c < ncols && (int)cand.size() < kMaxCarried; c++)
+      if (cls[c] == 0 && (out->cols[c].width == 4 || out->cols[c].width == 8)) cand.push_back(c);
+    if (!cand.empty()) {
+      Buf<uint32_t> d_states(ctx, 4 * (size_t)ncols);
+      HS_CUDA(cudaMemsetAsync(d_states.get(), 0, 16 * (size_t)ncols, ctx->stream));
+      for (int c : cand) {
+        DevColumn& dc = out->cols[c];
+        dc.dict_keys.alloc(ctx, kDictCapacity);
+        HS_CUDA(cudaMemsetAsync(dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
+        launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, c, dc.width, dc.dict_keys.get(), kDictCapacity, kMaxDictEntries,
+                                     d_states.get() + 4 * c);
+      }
+      std::vector<uint32_t> h_states(4 * (size_t)ncols);
+      HS_CUDA(cudaMemcpyAsync(h_states.data(), d_states.get(), 16 * (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (int c : cand) {
+        DevColumn& dc = out->cols[c];
+        const uint32_t* st = &h_states[4 * (size_t)c];
+        if (st[1] == 0) {  // the union fits a dictionary page
+          std::vector<uint64_t> values = sorted_dictionary(ctx, dc.dict_keys.get(), st, dc.type);
+          const uint32_t bw = bits_for((uint32_t)values.size());
+          if (dictionary_pays_off((uint32_t)values.size(), bw, dc.width, nrows, carry->num_segments)) {
+            uint32_t mask = 0, empty_index = 0;
+            upload_lookup_table(ctx, values, &carry_tables[c], &mask, &empty_index);
+            dc.carried = true;
+            dc.dict_values = std::move(values);
+            dc.dict_bw = bw;
+            dc.codes.alloc(ctx, (size_t)nrows + 16);
+            h_cols[c] = ColumnOut{dc.codes.get(), nullptr, dc.width, dc.type, carry_tables[c].get(), mask, empty_index, 1, 0};
+          }
+        }
+        dc.dict_keys.release();
+      }
+    }
+  }
+  alloc_destinations();
+  HS_CUDA(cudaMemcpyAsync(d_cols.get(), h_cols.data(), sizeof(ColumnOut) * ncols, cudaMemcpyHostToDevice, ctx->stream));
   // ---- decode -----------------------------------------------------------------------------------------
   // optional per-file row windows (file-relative -> global): pages that do not intersect their file's window are skipped
   Buf<int64_t> d_window;
@@ -401,7 +517,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
     HS_CUDA(cudaMemsetAsync(d_states.get(), 0, 16 * (size_t)std::max(1, ncols), ctx->stream));
     for (int c = 0; c < ncols; c++) {
       DevColumn& dc = out->cols[c];
-      if ((flags[1 + c] & 2u) || (dc.width != 4 && dc.width != 8)) continue;
+      if (dc.carried || (flags[1 + c] & 2u) || (dc.width != 4 && dc.width != 8)) continue;
       dc.dict_keys.alloc(ctx, kDictCapacity);
       HS_CUDA(cudaMemsetAsync(dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
       launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, c, dc.width, dc.dict_keys.get(), kDictCapacity, kMaxDictEntries,
@@ -476,6 +592,8 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   out->part.cols.clear();
   out->part.cols.resize(ncols);
   std::vector<PartColumn> h_pc;
+  CodePackRound pack;
+  memset(&pack, 0, sizeof pack);
   for (int c = 0; c < ncols; c++) {
     DevColumn& src = table.cols[c];
     DevColumn& dst = out->part.cols[c];
@@ -487,6 +605,15 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
     dst.dict_keys = std::move(src.dict_keys);
     memcpy(dst.dict_state, src.dict_state, sizeof dst.dict_state);
     dst.dict_ready = src.dict_ready;
+    if (src.carried) {  // travels as a 16-bit code inside the row's code record
+      if (!fused || c < nkeys || pack.n >= kMaxCarried) fail(HS_EINVAL, "column '%s' cannot be late-materialised here", src.name.c_str());
+      dst.carried = true;
+      dst.dict_values = std::move(src.dict_values);
+      dst.dict_bw = src.dict_bw;
+      dst.carry_slot = pack.n;
+      pack.src[pack.n++] = src.codes.get();
+      continue;
+    }
     dst.data.alloc(ctx, (size_t)nrows * src.width + 16);
     h_pc.push_back(PartColumn{src.data.get(), dst.data.get(), src.width, 0});
     if (src.has_nulls) {
@@ -498,8 +625,12 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   Buf<PartColumn> d_pc(ctx, h_pc.size());
   if (fused) {
     HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * h_pc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (pack.n > 0) {
+      out->part.rec.alloc(ctx, (size_t)nrows * 8 + 16);
+      pack.out = out->part.rec.get();
+    }
     launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), d_pc.get(), (int)h_pc.size(),
-                          nullptr, 1, single_key_type_of(h_keys.data(), nkeys));
+                          nullptr, 1, single_key_type_of(h_keys.data(), nkeys), &pack);
   } else {
     dest.alloc(ctx, std::max<int64_t>(1, nrows));
     launch_partition_dest(ctx, bucket.get(), nrows, num_buckets, tile_hist.get(), dest.get());
@@ -510,6 +641,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data.release();
     table.cols[c].valid.release();
+    table.cols[c].codes.release();
   }
 
   stats->ms_hash += t_hash.ms();
@@ -655,18 +787,29 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     uint32_t bw = 0, ndict = 0, empty_index = 0, mask = 0;
     Buf<unsigned long long> keys;       // owned when the set was built here
     const unsigned long long* keys_ptr = nullptr;  // the hash set in use (own or the column's ready-made one)
-    Buf<uint8_t> entries;               // capacity x 16 bytes {key, dictionary index}
-    Buf<unsigned long long> d_values;   // sorted dictionary on the device
+    Buf<uint8_t> entries;               // value -> code look-up table, 16-byte entries (upload_lookup_table)
     size_t skel_off = 0, skel_len = 0;  // [dictionary page header][PLAIN values] inside the skeleton
     std::vector<uint64_t> values;       // sorted dictionary (raw bits)
   };
   std::vector<ColDict> dicts(ncols);
   const int64_t total_rows = table.nrows;
+  std::vector<int> carried_cols(kMaxCarried, -1);  // by record slot
+  for (int c = 0; c < ncols; c++) {
+    const DevColumn& dc = table.cols[c];
+    if (!dc.carried) continue;  // late-materialised: the dictionary and the codes were fixed when the sources were decoded
+    if (dc.carry_slot < 0 || dc.carry_slot >= kMaxCarried || !table.rec) fail(HS_EINVAL, "column '%s': code record missing", dc.name.c_str());
+    ColDict& cd = dicts[c];
+    cd.values = dc.dict_values;
+    cd.ndict = (uint32_t)cd.values.size();
+    cd.bw = dc.dict_bw;
+    cd.use = true;
+    carried_cols[dc.carry_slot] = c;
+  }
   if (req.use_dictionary && total_rows > 0) {
     Buf<uint32_t> d_state(ctx, 4);
     for (int c = 0; c < ncols; c++) {
       const DevColumn& dc = table.cols[c];
-      if (dc.has_nulls) continue;
+      if (dc.has_nulls || dc.carried) continue;
       ColDict& cd = dicts[c];
       uint32_t st[4] = {0, 0, 0, 0};
       const bool ready = dc.dict_ready && dc.dict_keys;
@@ -707,51 +850,15 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         cd.keys.release();
         continue;
       }
-      // distinct values: compacted on the device, sorted on the host (<= 65536 of them), ranks written back by a kernel
-      const uint32_t ntab = st[0];
-      Buf<unsigned long long> d_list(ctx, std::max<uint32_t>(1, ntab) + 1);
-      HS_CUDA(cudaMemsetAsync(d_state.get() + 3, 0, 4, ctx->stream));
-      launch_dict_collect(ctx, cd.keys_ptr, kDictCapacity, d_list.get(), d_state.get() + 3);
-      cd.values.resize(ntab);
-      if (ntab)
-        HS_CUDA(cudaMemcpyAsync(cd.values.data(), d_list.get(), 8 * (size_t)ntab, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (st[2]) cd.values.push_back(~0ull);
-      const int type = dc.type;
-      std::sort(cd.values.begin(), cd.values.end(), [type](uint64_t a, uint64_t b) { return sort_encode(type, a) < sort_encode(type, b); });
+      // distinct values: compacted on the device, sorted on the host (<= 65536 of them)
+      cd.values = sorted_dictionary(ctx, cd.keys_ptr, st, dc.type);
       cd.ndict = (uint32_t)cd.values.size();
-      cd.bw = 1;
-      while ((1u << cd.bw) < cd.ndict) cd.bw++;
-      const double plain_bytes = (double)total_rows * dc.width;
-      const double dict_bytes = (double)total_rows * cd.bw / 8.0 + (double)cd.ndict * dc.width * std::max(1, nseg);
-      if (cd.ndict == 0 || cd.ndict > kMaxDictEntries || dict_bytes > 0.9 * plain_bytes) {
+      cd.bw = bits_for(cd.ndict);
+      if (!dictionary_pays_off(cd.ndict, cd.bw, dc.width, total_rows, nseg)) {
         cd.keys.release();
         continue;
       }
-      if (st[2])
-        cd.empty_index = (uint32_t)(std::find(cd.values.begin(), cd.values.end(), ~(uint64_t)0) - cd.values.begin());
-      cd.d_values.alloc(ctx, cd.ndict);
-      HS_CUDA(cudaMemcpyAsync(cd.d_values.get(), cd.values.data(), 8 * (size_t)cd.ndict, cudaMemcpyHostToDevice, ctx->stream));
-      // value -> dictionary index look-up table for the encoder, built here on the host (<= 65536 inserts): open
-      // addressing sized to the dictionary (load <= 0.5) rather than to the 4 MB distinct-value set, so that the tables of
-      // all dictionary columns stay resident in L1 while k_dict_map streams the rows through them
-      uint32_t cap = 256;
-      while (cap < 2 * cd.ndict) cap <<= 1;
-      cd.mask = cap - 1;
-      std::vector<uint32_t> tab((size_t)cap * 4, 0u);
-      for (uint32_t s2 = 0; s2 < cap; s2++) tab[(size_t)s2 * 4] = tab[(size_t)s2 * 4 + 1] = 0xffffffffu;  // empty = ~0 key
-      for (uint32_t i = 0; i < cd.ndict; i++) {
-        const uint64_t v = cd.values[i];
-        if (v == ~0ull) continue;  // the empty marker itself is mapped through empty_index
-        uint32_t h = dict_hash_u64(v) & cd.mask;
-        while (tab[(size_t)h * 4] != 0xffffffffu || tab[(size_t)h * 4 + 1] != 0xffffffffu) h = (h + 1) & cd.mask;
-        tab[(size_t)h * 4] = (uint32_t)v;
-        tab[(size_t)h * 4 + 1] = (uint32_t)(v >> 32);
-        tab[(size_t)h * 4 + 2] = i;
-      }
-      cd.entries.alloc(ctx, (size_t)cap * 16);
-      HS_CUDA(cudaMemcpyAsync(cd.entries.get(), tab.data(), (size_t)cap * 16, cudaMemcpyHostToDevice, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));  // tab goes out of scope
+      upload_lookup_table(ctx, cd.values, &cd.entries, &cd.mask, &cd.empty_index);
       cd.use = true;
     }
   }
@@ -956,7 +1063,19 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
   {  // dictionary columns, up to 8 per launch pair
     std::vector<int> dcols;
     for (int c = 0; c < ncols; c++)
-      if (dicts[c].use) dcols.push_back(c);
+      if (dicts[c].use && !table.cols[c].carried) dcols.push_back(c);
+    if (carried_cols[0] >= 0) {  // codes are already in the partitioned records: bit-pack only
+      DictPackArgs pa;
+      memset(&pa, 0, sizeof pa);
+      for (int slot = 0; slot < kMaxCarried && carried_cols[slot] >= 0; slot++) {
+        const int c = carried_cols[slot];
+        pa.page_value_offset[slot] = d_pvo.get() + (size_t)c * page_counter;
+        pa.bw[slot] = dicts[c].bw;
+        pa.ncols = slot + 1;
+      }
+      launch_dict_pack(ctx, req.plan->tiles.get(), ntiles, req.plan->seg_start.get(), req.d_perm, pa, 4,
+                       (const uint16_t*)table.rec.get(), d_page_begin.get(), P, out->arena.get());
+    }
     for (size_t b0 = 0; b0 < dcols.size(); b0 += 8) {
       DictMapArgs ma;
       DictPackArgs pa;

@@ -24,12 +24,30 @@ struct DevColumn {
   Buf<unsigned long long> dict_keys;
   uint32_t dict_state[4] = {0, 0, 0, 0};
   bool dict_ready = false;
+  // Late-materialised dictionary column (index builds on one GPU): every source page was dictionary-encoded and free of
+  // nulls, so the column travels as 16-bit codes of one column-wide sorted dictionary and its values are never written
+  // to HBM.  `data` stays empty.  Before the partition `codes` holds one code per row; the partition packs the codes of
+  // all carried columns of a row into one 8-byte record (Table::rec, slot `carry_slot`) that the page encoder bit-packs.
+  bool carried = false;
+  Buf<uint16_t> codes;
+  std::vector<uint64_t> dict_values;  // sorted dictionary, raw value bits; code = position
+  uint32_t dict_bw = 0;               // bits per code
+  int carry_slot = -1;
 };
+
+constexpr int kMaxCarried = 4;  // codes per record
 
 struct Table {
   int64_t nrows = 0;
   std::vector<DevColumn> cols;
   std::vector<int64_t> file_row_begin;  // nfiles+1: row range of every source file
+  Buf<uint8_t> rec;                     // nrows x 4 uint16 codes of the carried columns (after the partition)
+};
+
+// Which columns may be late-materialised while decoding (nullptr / first_col < 0: none).
+struct CarryOptions {
+  int first_col = -1;   // columns [first_col, ncols) are candidates (the indexed columns never are)
+  int num_segments = 1; // output files: every one repeats the dictionary page, which enters the size criterion
 };
 
 // Rows in bucket-major, key-sorted order (result of K2-K4).
@@ -65,7 +83,7 @@ struct LoadOptions {
 // Loads the projected columns of the source files into HBM (H2D of the file images when needed, footer parse on the
 // host, page walk + decode on the GPU).
 void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const std::vector<std::string>& columns,
-                  Table* out, hs_stats* stats);
+                  Table* out, hs_stats* stats, const CarryOptions* carry = nullptr);
 // The same in two steps, so that a query can decode the key column first and then only the pages of the other columns
 // that intersect the qualifying row range of each file.
 struct SourceSet {
@@ -80,7 +98,8 @@ struct SourceSet {
 void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceSet* set, hs_stats* stats);
 // file_windows (optional): per file, the half-open range of file-relative rows that must be decoded
 void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>& columns,
-                    const std::vector<std::pair<int64_t, int64_t>>* file_windows, Table* out, hs_stats* stats);
+                    const std::vector<std::pair<int64_t, int64_t>>* file_windows, Table* out, hs_stats* stats,
+                    const CarryOptions* carry = nullptr);
 
 // K2-K4 on a decoded table whose first nkeys columns are the indexed columns.
 void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats);

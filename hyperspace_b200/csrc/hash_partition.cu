@@ -446,11 +446,12 @@ __global__ void __launch_bounds__(kFThreads) k_tile_hist(const KeyColumn* __rest
 // All warp collectives run with the full mask and outside any branch: slots past the end of the last tile carry the
 // last bin and, being the last slots of the tile, rank behind every real row of that bin; they are never written out.
 template <int BITS, int KT>
-__global__ void __launch_bounds__(kFThreads) k_partition_rows(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
+__global__ void __launch_bounds__(kFThreads, 2) k_partition_rows(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
                                                                ModConst bucket_mod, ModConst owner_mod, int use_owner,
                                                                const uint32_t* __restrict__ tile_dst,
                                                                const PartColumn* __restrict__ cols, int ncols,
-                                                               void* const* __restrict__ peer_out, int out_world) {
+                                                               void* const* __restrict__ peer_out, int out_world,
+                                                               CodePackRound pack) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int nb = use_owner ? (int)owner_mod.n : (int)bucket_mod.n;
   uint64_t* xbuf = reinterpret_cast<uint64_t*>(smem);
@@ -597,6 +598,25 @@ __global__ void __launch_bounds__(kFThreads) k_partition_rows(const KeyColumn* _
       }
     }
   }
+  // ---- the 16-bit code columns of a row leave as one 8-byte record ---------------------------------------------------
+  if (pack.n > 0) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kFItems; j++) {
+      if (first + j * 32 < tile_count) {
+        const int64_t row = wbase + j * 32;
+        uint32_t lo = pack.src[0][row], hi = 0;
+        if (pack.n > 1) lo |= (uint32_t)pack.src[1][row] << 16;
+        if (pack.n > 2) hi = pack.src[2][row];
+        if (pack.n > 3) hi |= (uint32_t)pack.src[3][row] << 16;
+        xbuf[pos[j]] = (uint64_t)lo | ((uint64_t)hi << 32);
+      }
+    }
+    __syncthreads();
+    uint64_t* out = (uint64_t*)pack.out;
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) out[out_adj[pos_bin[i]] + i] = xbuf[i];
+  }
 }
 
 size_t fused_smem_bytes(int nb) {
@@ -633,7 +653,7 @@ void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t n
 template <int BITS, int KT>
 static void launch_partition_rows_t(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets,
                                     int owner_mod, const uint32_t* tile_dst, const PartColumn* d_cols, int ncols,
-                                    void* const* d_peer_out, int out_world) {
+                                    void* const* d_peer_out, int out_world, const CodePackRound& pack) {
   const int nb = owner_mod > 0 ? owner_mod : num_buckets;
   const int64_t ntiles = ceil_div(nrows, kFusedTile);
   static bool attr = false;  // one per instantiation
@@ -644,39 +664,44 @@ static void launch_partition_rows_t(hs_ctx* ctx, const KeyColumn* d_keys, int nk
   }
   k_partition_rows<BITS, KT><<<(unsigned)ntiles, kFThreads, fused_smem_bytes(nb), ctx->stream>>>(
       d_keys, nkeys, nrows, make_mod_const((uint32_t)num_buckets), make_mod_const((uint32_t)std::max(owner_mod, 1)),
-      owner_mod > 0 ? 1 : 0, tile_dst, d_cols, ncols, d_peer_out, out_world);
+      owner_mod > 0 ? 1 : 0, tile_dst, d_cols, ncols, d_peer_out, out_world, pack);
   HS_LAUNCH_CHECK(ctx);
 }
 
 template <int BITS>
 static void launch_partition_rows_bits(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets,
                                        int owner_mod, const uint32_t* tile_dst, const PartColumn* d_cols, int ncols,
-                                       void* const* d_peer_out, int out_world, int single_key_type) {
+                                       void* const* d_peer_out, int out_world, int single_key_type,
+                                       const CodePackRound& pack) {
   switch (single_key_type) {
     case HS_TYPE_INT32:
-      launch_partition_rows_t<BITS, HS_TYPE_INT32>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world);
+      launch_partition_rows_t<BITS, HS_TYPE_INT32>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, pack);
       break;
     case HS_TYPE_INT64:
-      launch_partition_rows_t<BITS, HS_TYPE_INT64>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world);
+      launch_partition_rows_t<BITS, HS_TYPE_INT64>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, pack);
       break;
     default:
-      launch_partition_rows_t<BITS, -1>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world);
+      launch_partition_rows_t<BITS, -1>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, pack);
   }
 }
 
 void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
                            const uint32_t* tile_dst, const PartColumn* d_cols, int ncols, void* const* d_peer_out,
-                           int out_world, int single_key_type) {
+                           int out_world, int single_key_type, const CodePackRound* pack_round) {
   KernelScope _ks(ctx, "k_partition_rows");
   if (nrows == 0) return;
+  CodePackRound pack;
+  memset(&pack, 0, sizeof pack);
+  if (pack_round) pack = *pack_round;
+  if (pack.n > 0 && d_peer_out) fail(HS_EINVAL, "code records cannot be routed to peer GPUs");
   const int nb = owner_mod > 0 ? owner_mod : num_buckets;
   // the ranking votes once per bin-id bit: 4, 8 or 10 (kFusedMaxBins = 1024)
   if (nb <= 16)
-    launch_partition_rows_bits<4>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type);
+    launch_partition_rows_bits<4>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type, pack);
   else if (nb <= 256)
-    launch_partition_rows_bits<8>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type);
+    launch_partition_rows_bits<8>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type, pack);
   else
-    launch_partition_rows_bits<10>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type);
+    launch_partition_rows_bits<10>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type, pack);
 }
 
 }  // namespace hs

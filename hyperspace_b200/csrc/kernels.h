@@ -40,11 +40,23 @@ struct PageDesc {           // one per data page
 };
 
 struct ColumnOut {          // decoded column destination
-  void* data;               // num_rows values of `width` bytes (row order)
+  void* data;               // num_rows values of `width` bytes (row order); carry != 0: one uint16 code per row
   uint8_t* valid;           // one byte per row (pre-set to 1) or nullptr for required columns
   int32_t width;
   int32_t type;             // HS_TYPE_*
+  // Late-materialised dictionary column (carry != 0): every page of the column is dictionary-encoded and free of nulls, and
+  // the union of the chunk dictionaries is already final.  The decoder then translates each chunk-local index into the
+  // code of the value in that global dictionary (look-up table `carry_entries`, see DictMapArgs) and never writes values.
+  const void* carry_entries;
+  uint32_t carry_mask;
+  uint32_t carry_empty_index;  // code of the value 0xFFFF...F, which the look-up table cannot hold
+  int32_t carry;
+  int32_t pad;
 };
+
+// Per-column OR over the column's data pages (k_classify_pages), read before decoding to pick late-materialised columns
+enum : uint32_t { PAGECLASS_NOT_DICT = 1u, PAGECLASS_MAYBE_NULLS = 2u };
+void launch_classify_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, uint32_t* col_flags);
 
 // device error word: 0 = ok, else (code << 24 | detail)
 enum DecodeError : uint32_t {
@@ -124,9 +136,17 @@ inline int single_key_type_of(const KeyColumn* h_keys, int nkeys) {
 }
 // tile_dst = launch_tile_offsets(tile_hist); moves all columns into bin-major order, stable
 // d_peer_out (optional): [ncols][out_world] peer-mapped output pointers; bucket b is written to GPU b % out_world
+// pack (optional, single GPU only): one more round that reads up to four 16-bit code columns and writes them as ONE
+// 8-byte record per row (slot s in bits [16 s, 16 s + 16)) -- the layout k_dict_pack_all gathers from
+struct CodePackRound {
+  const uint16_t* src[4];
+  void* out;   // nrows x 8 bytes
+  int32_t n;   // code columns in use (0: no such round)
+  int32_t pad;
+};
 void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
                            const uint32_t* tile_dst, const PartColumn* d_cols, int ncols, void* const* d_peer_out = nullptr,
-                           int out_world = 1, int single_key_type = -1);
+                           int out_world = 1, int single_key_type = -1, const CodePackRound* pack = nullptr);
 // out[i] = sort_encode(in[src ? src[i] : i])  (+ global OR / AND reduction into or_and[0], or_and[1])
 void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* src, int64_t nrows, uint64_t* out,
                         unsigned long long* or_and);
@@ -221,6 +241,10 @@ struct DictPackArgs {
   int32_t ncols;
 };
 // rec_scratch: nrows records of 4 (ncols <= 4) or 8 uint16 indices
+// bit-packs the codes of already mapped records (4 or 8 uint16 slots per row) into the dictionary-encoded data pages
+void launch_dict_pack(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,
+                      const DictPackArgs& pack_args, int slots, const uint16_t* rec, const uint32_t* bucket_page_begin,
+                      int64_t rows_per_page, uint8_t* arena);
 void launch_dict_encode_all(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint64_t* seg_start, const uint32_t* perm,
                             const DictMapArgs& map_args, const DictPackArgs& pack_args, int64_t nrows, uint32_t capacity,
                             uint16_t* rec_scratch, const uint32_t* bucket_page_begin, int64_t rows_per_page, uint8_t* arena);

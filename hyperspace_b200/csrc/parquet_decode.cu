@@ -257,6 +257,84 @@ __device__ bool hybrid_decode_next(HybridShared& hs, uint32_t count, Sink sink) 
   return true;
 }
 
+// all-valid when the definition-level block is nothing but RLE runs of the value 1 that cover the page (writers emit one
+// such run; this engine's own encoder emits a few, see write_plain_page_prefix)
+__device__ bool def_levels_all_valid(const uint8_t* def_p, const uint8_t* def_end, uint32_t n) {
+  const uint8_t* q = def_p;
+  uint32_t covered = 0;
+  bool all_ones = true;
+  for (int r = 0; r < 64 && covered < n && all_ones; r++) {
+    uint32_t h = 0;
+    int shift = 0;
+    while (q < def_end) {
+      uint8_t b = *q++;
+      h |= (uint32_t)(b & 0x7f) << shift;
+      if (!(b & 0x80)) break;
+      shift += 7;
+      if (shift > 28) break;
+    }
+    if ((h & 1) || q >= def_end || !(*q & 1) || (h >> 1) == 0) all_ones = false;
+    else {
+      covered += h >> 1;
+      q++;
+    }
+  }
+  return all_ones && covered >= n;
+}
+
+// where the definition levels of a page sit; returns false when the page is malformed
+__device__ __forceinline__ bool locate_def_levels(const PageDesc& pg, const uint8_t*& p, const uint8_t*& def_p,
+                                                  const uint8_t*& def_end) {
+  const uint8_t* pend = pg.data + pg.size;
+  def_p = def_end = nullptr;
+  if (pg.page_type == pq::DATA_PAGE_V2) {
+    p += pg.rep_bytes;
+    if (pg.max_def > 0) {
+      def_p = p;
+      def_end = p + pg.def_bytes;
+    }
+    p += pg.def_bytes > 0 ? pg.def_bytes : 0;
+  } else if (pg.max_def > 0) {
+    uint32_t len = load_le32_unaligned(p);
+    def_p = p + 4;
+    def_end = def_p + len;
+    p = def_end;
+  }
+  return p <= pend;
+}
+
+// One thread per data page: is it dictionary-encoded, and can it hold nulls?
+__global__ void k_classify_pages(const PageDesc* __restrict__ pages, int64_t n_pages, uint32_t* __restrict__ col_flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pages) return;
+  const PageDesc pg = pages[i];
+  uint32_t f = 0;
+  if (pg.encoding != pq::ENC_PLAIN_DICTIONARY && pg.encoding != pq::ENC_RLE_DICTIONARY) f |= PAGECLASS_NOT_DICT;
+  if (pg.max_def > 0) {
+    const uint8_t* p = pg.data;
+    const uint8_t *def_p, *def_end;
+    if (!locate_def_levels(pg, p, def_p, def_end) || !def_levels_all_valid(def_p, def_end, (uint32_t)pg.num_values))
+      f |= PAGECLASS_MAYBE_NULLS;
+  }
+  if (f) atomicOr(&col_flags[pg.col], f);
+}
+
+// value -> code of a late-materialised dictionary column (same table layout and probing as k_dict_map_all)
+__device__ __forceinline__ uint32_t carry_code(const ColumnOut& co, uint64_t v, uint32_t* d_error) {
+  if (v == ~0ull) return co.carry_empty_index;
+  const uint4* tab = reinterpret_cast<const uint4*>(co.carry_entries);
+  const uint32_t mask = co.carry_mask, vlo = (uint32_t)v, vhi = (uint32_t)(v >> 32);
+  uint32_t h = dict_hash_u64(v) & mask;
+  for (uint32_t probes = 0; probes <= mask; probes++) {
+    const uint4 e = tab[h];
+    if (e.x == vlo && e.y == vhi) return e.z;
+    if (e.x == 0xffffffffu && e.y == 0xffffffffu) break;
+    h = (h + 1) & mask;
+  }
+  set_error(d_error, DERR_DICT_INDEX, 0xffffffu);  // a chunk dictionary holds a value the union does not
+  return 0;
+}
+
 template <int W>
 __device__ __forceinline__ uint64_t load_value(const uint8_t* p) {
   if (W == 8) return load_le64_unaligned(p);
@@ -293,6 +371,11 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
     if (threadIdx.x == 0) set_error(d_error, DERR_UNSUPPORTED_ENCODING, (uint32_t)pg.encoding);
     return;
   }
+  const bool carry = W != 1 && co.carry != 0;  // emit 16-bit codes of the column-wide dictionary instead of values
+  if (carry && !is_dict) {  // the column was classified dictionary-only before decoding
+    if (threadIdx.x == 0) set_error(d_error, DERR_UNSUPPORTED_ENCODING, (uint32_t)pg.encoding);
+    return;
+  }
   // bit 1 of the column's flag word: a page that is NOT dictionary-encoded was seen (when it stays clear, the union of the
   // chunk dictionaries is a superset of the column's distinct values and the encoder can skip its full-column scan)
   if (!is_dict && threadIdx.x == 0) atomicOr(col_has_nulls, 2u);
@@ -319,37 +402,16 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
   // all-valid fast check: a single RLE run of ones covering the page
   bool has_def = def_p != nullptr;
   if (has_def) {
-    if (threadIdx.x == 0) {
-      // all-valid when the block is nothing but RLE runs of the value 1 that cover the page (writers emit one such run;
-      // this engine's own encoder emits a few, see write_plain_page_prefix)
-      const uint8_t* q = def_p;
-      uint32_t covered = 0;
-      bool all_ones = true;
-      for (int r = 0; r < 64 && covered < (uint32_t)n && all_ones; r++) {
-        uint32_t h = 0;
-        int shift = 0;
-        while (q < def_end) {
-          uint8_t b = *q++;
-          h |= (uint32_t)(b & 0x7f) << shift;
-          if (!(b & 0x80)) break;
-          shift += 7;
-          if (shift > 28) break;
-        }
-        if ((h & 1) || q >= def_end || !(*q & 1) || (h >> 1) == 0) all_ones = false;
-        else {
-          covered += h >> 1;
-          q++;
-        }
-      }
-      sm.flag = (all_ones && covered >= (uint32_t)n) ? 1u : 0u;
-    }
+    if (threadIdx.x == 0) sm.flag = def_levels_all_valid(def_p, def_end, (uint32_t)n) ? 1u : 0u;
     __syncthreads();
     if (sm.flag) has_def = false;
     __syncthreads();
   }
   // ---- dictionary -----------------------------------------------------------------------------------
   uint32_t idx_bw = 0;
-  const bool dict_in_smem = is_dict && pg.dict_count <= kSmemDict;
+  // carry mode keeps 16-bit codes in the same shared array: four times as many entries fit
+  uint16_t* const dict16 = reinterpret_cast<uint16_t*>(sm.dict);
+  const bool dict_in_smem = is_dict && pg.dict_count <= (carry ? kSmemDict * 4 : kSmemDict);
   if (is_dict) {
     if (pg.dict == nullptr) {
       if (threadIdx.x == 0) set_error(d_error, DERR_DICT_INDEX, 0);
@@ -366,7 +428,8 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
         uint64_t v;
         if (W == 1) v = (pg.dict[i >> 3] >> (i & 7)) & 1;
         else v = load_value<W>(pg.dict + (size_t)i * W);
-        sm.dict[i] = v;
+        if (carry) dict16[i] = (uint16_t)carry_code(co, v, d_error);
+        else sm.dict[i] = v;
       }
     }
     if (threadIdx.x == 0) hybrid_init(sm.idx.st, p, pend, idx_bw);
@@ -380,10 +443,19 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
       set_error(d_error, DERR_DICT_INDEX, ix);
       return 0;
     }
+    if (carry) return dict_in_smem ? (uint64_t)dict16[ix] : (uint64_t)carry_code(co, load_value<W>(pg.dict + (size_t)ix * W), d_error);
     if (dict_in_smem) return sm.dict[ix];
     if (W == 1) return (pg.dict[ix >> 3] >> (ix & 7)) & 1;
     return load_value<W>(pg.dict + (size_t)ix * W);
   };
+  auto emit = [&](int64_t row, uint64_t v) {
+    if (carry) ((uint16_t*)co.data)[row] = (uint16_t)v;
+    else store_value<W>(co.data, row, v);
+  };
+  if (carry && has_def) {  // classified free of nulls before decoding
+    if (threadIdx.x == 0) set_error(d_error, DERR_VALUE_COUNT, (uint32_t)pg.col);
+    return;
+  }
 
   // ---- fast paths: no nulls in this page -----------------------------------------------------------------------
   if (!has_def) {
@@ -450,13 +522,13 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
         const uint8_t* run = p + hdr_len;
 #pragma unroll 8
         for (int i = threadIdx.x; i < n; i += kDecodeThreads)
-          store_value<W>(co.data, row0 + i, dict_lookup(extract_bits(run, (uint64_t)i, idx_bw)));
+          emit(row0 + i, dict_lookup(extract_bits(run, (uint64_t)i, idx_bw)));
         return;
       }
       for (int base = 0; base < n; base += kTileRows) {
         const uint32_t cnt = (uint32_t)min(kTileRows, n - base);
         bool ok = hybrid_decode_next(sm.idx, cnt, [&](uint32_t i, uint32_t v) {
-          store_value<W>(co.data, row0 + base + i, dict_lookup(v));
+          emit(row0 + base + i, dict_lookup(v));
         });
         if (!ok) {
           if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
@@ -554,6 +626,13 @@ void launch_walk_pages(hs_ctx* ctx, const ChunkDesc* chunks, int n_chunks, int32
   const int threads = 64;
   k_walk_pages<<<(n_chunks + threads - 1) / threads, threads, 0, ctx->stream>>>(chunks, n_chunks, page_counts,
                                                                                 page_offsets, pages, d_error, mode);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_classify_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, uint32_t* col_flags) {
+  KernelScope _ks(ctx, "k_classify_pages");
+  if (n_pages == 0) return;
+  k_classify_pages<<<(unsigned)ceil_div(n_pages, 128), 128, 0, ctx->stream>>>(pages, n_pages, col_flags);
   HS_LAUNCH_CHECK(ctx);
 }
 

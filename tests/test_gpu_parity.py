@@ -588,3 +588,77 @@ def test_key_statistics_in_index_files(ctx):
             assert len(hit) == int((tbl.column("k").to_numpy() == probe).sum())
         assert seen == n
         res.free()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# late-materialised dictionary columns (codes instead of values between decode and encode)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _index_images(ctx, files, indexed, included, nb, uuid, **kw):
+    from hyperspace_b200 import _native
+
+    res, st = ctx.create_index(files, indexed, included, nb, output=_native.HS_OUT_HOST, job_uuid=uuid, **kw)
+    images = {f.name: res.host_bytes(i) for i, f in enumerate(res.files)}
+    return res, images, st
+
+
+def test_late_materialised_columns_give_identical_files(ctx, tmp_path, monkeypatch):
+    """The code-carrying path and the value path must produce byte-identical index files (HS_NO_CARRY switches it off)."""
+    from hyperspace_b200 import _native
+
+    rng = np.random.default_rng(41)
+    n = 120_000
+    cols = {
+        "k": rng.integers(-2**62, 2**62, size=n, dtype=np.int64),
+        "a": rng.integers(0, 900, size=n, dtype=np.int64) - 1,          # contains -1 == the hash sets' empty marker
+        "b": rng.integers(-3, 60, size=n).astype(np.int32),
+        "c": (rng.integers(0, 2000, size=n) * 0.5).astype(np.float64),
+        "d": np.where(rng.integers(0, 4, size=n) == 0, np.float32("nan"), rng.integers(0, 7, size=n).astype(np.float32)),
+        "e": rng.integers(0, 3, size=n, dtype=np.int64),                 # fifth and sixth dictionary columns: more than one
+        "f": rng.integers(0, 300, size=n).astype(np.int32),              # record holds -> mapped by the encoder instead
+        "g": rng.standard_normal(n),                                      # high cardinality: pyarrow falls back to PLAIN pages
+    }
+    included = ["a", "b", "c", "d", "e", "f", "g"]
+    paths = _write_sources(tmp_path, cols, 3, use_dictionary=True, data_page_version="1.0", row_group_size=25_000,
+                           dictionary_pagesize_limit=256 * 1024)
+    files = [_native.FileImage(path=p) for p in paths]
+    res1, img1, st1 = _index_images(ctx, files, ["k"], included, 16, "lm", rows_per_page=4096, rows_per_row_group=8192)
+    _check_index(res1, cols, ["k"], included, 16, "lm")
+    md = pq.ParquetFile(pa.BufferReader(next(iter(img1.values())))).metadata.row_group(0)
+    assert all(md.column(i).has_dictionary_page for i in range(1, 7)) and not md.column(7).has_dictionary_page
+    monkeypatch.setenv("HS_NO_CARRY", "1")
+    res2, img2, st2 = _index_images(ctx, files, ["k"], included, 16, "lm", rows_per_page=4096, rows_per_row_group=8192)
+    monkeypatch.delenv("HS_NO_CARRY")
+    assert img1.keys() == img2.keys()
+    for name in img1:
+        assert img1[name] == img2[name], name
+    res1.free()
+    res2.free()
+
+
+def test_late_materialisation_falls_back_when_pages_differ(ctx, tmp_path):
+    """A column that is dictionary-encoded in one source file and PLAIN (or nullable) in another takes the value path."""
+    from hyperspace_b200 import _native
+
+    rng = np.random.default_rng(43)
+    n = 30_000
+    cols = {"k": rng.integers(0, 10**9, size=n, dtype=np.int64), "a": rng.integers(0, 50, size=n, dtype=np.int64),
+            "b": rng.integers(0, 9, size=n).astype(np.int32)}
+    p1, p2 = str(tmp_path / "s1.parquet"), str(tmp_path / "s2.parquet")
+    half = n // 2
+    pq.write_table(pa.table({k: v[:half] for k, v in cols.items()}), p1, compression="NONE", use_dictionary=True)
+    pq.write_table(pa.table({k: v[half:] for k, v in cols.items()}), p2, compression="NONE", use_dictionary=["b"])
+    res, _ = ctx.create_index([_native.FileImage(path=p1), _native.FileImage(path=p2)], ["k"], ["a", "b"], 8,
+                              output=_native.HS_OUT_HOST, job_uuid="fb")
+    _check_index(res, cols, ["k"], ["a", "b"], 8, "fb")
+    res.free()
+    # nulls in a dictionary-encoded column: not carried, still correct (checked against pyarrow's own reading)
+    a = pa.array([None if i % 7 == 0 else int(i % 5) for i in range(n)], type=pa.int64())
+    t = pa.table({"k": cols["k"], "a": a})
+    p3 = str(tmp_path / "s3.parquet")
+    pq.write_table(t, p3, compression="NONE", use_dictionary=True)
+    res, _ = ctx.create_index([_native.FileImage(path=p3)], ["k"], ["a"], 4, output=_native.HS_OUT_HOST, job_uuid="nn")
+    got = pa.concat_tables([_read_image(res.host_bytes(i)) for i in range(len(res.files))]).sort_by("k")
+    want = t.sort_by("k")
+    assert got.column("a").to_pylist() == want.column("a").to_pylist()
+    res.free()
