@@ -355,12 +355,13 @@ int hs_create_index(hs_ctx* ctx, const hs_index_spec* spec, hs_index_result** ou
         if (cols[i] == cols[j]) fail(HS_EINVAL, "duplicate column '%s' in index config", cols[i].c_str());
     Table table;
     // Included columns whose source pages are all dictionary-encoded travel through the build as 16-bit dictionary codes
-    // (late materialisation).  Only where nothing between decode and encode needs their values: one GPU, the fused
-    // partition, no rows to drop.  HS_NO_CARRY=1 switches it off (A/B measurements).
+    // (late materialisation).  Only where nothing between decode and encode needs their values: the fused partition (on
+    // one GPU, or writing straight into the owners' memory on several), no rows to drop.  HS_NO_CARRY=1 switches it off
+    // (A/B measurements; on several GPUs every rank must be given the same setting).
     const bool no_carry = getenv("HS_NO_CARRY") != nullptr;
     CarryOptions carry;
-    if (ctx->world == 1 && !spec->disable_dictionary && spec->n_deleted_file_ids == 0 && !no_carry &&
-        fused_partition_supported(spec->num_buckets)) {
+    if ((ctx->world == 1 || p2p_exchange_supported(ctx, spec->num_buckets)) && !spec->disable_dictionary &&
+        spec->n_deleted_file_ids == 0 && !no_carry && fused_partition_supported(spec->num_buckets)) {
       carry.first_col = spec->n_indexed;
       carry.num_segments = spec->num_buckets;
     }

@@ -116,6 +116,15 @@ void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const s
 
 // ---- dictionary helpers shared by the decoder (late-materialised columns) and the page encoder -------------------------
 
+// Column order first, raw bits second: values that compare equal (-0.0 / 0.0, NaN payloads) still get one fixed order, so
+// every rank -- and every run -- numbers the same dictionary the same way.
+static void sort_dictionary(std::vector<uint64_t>& values, int type) {
+  std::sort(values.begin(), values.end(), [type](uint64_t a, uint64_t b) {
+    const uint64_t ea = sort_encode(type, a), eb = sort_encode(type, b);
+    return ea != eb ? ea < eb : a < b;
+  });
+}
+
 // The distinct values of a device hash set (state[0] of them, plus the empty marker when state[2] is set), sorted in the
 // column's order.  Synchronises the stream.
 static std::vector<uint64_t> sorted_dictionary(hs_ctx* ctx, const unsigned long long* keys, const uint32_t* state, int type) {
@@ -128,7 +137,7 @@ static std::vector<uint64_t> sorted_dictionary(hs_ctx* ctx, const unsigned long 
   if (ntab) HS_CUDA(cudaMemcpyAsync(values.data(), d_list.get(), 8 * (size_t)ntab, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
   if (state[2]) values.push_back(~0ull);
-  std::sort(values.begin(), values.end(), [type](uint64_t a, uint64_t b) { return sort_encode(type, a) < sort_encode(type, b); });
+  sort_dictionary(values, type);
   return values;
 }
 
@@ -357,16 +366,18 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   };
   const int n_chunks = (int)chunks.size();
   t_plan.stop();
-  if (n_chunks == 0 || nrows == 0) {
+  const bool want_carry = carry && carry->first_col >= 0 && !file_windows;
+  // (with several GPUs a rank without rows still takes part in the agreement on the late-materialised columns below)
+  if ((n_chunks == 0 || nrows == 0) && !(want_carry && ctx->world > 1)) {
     alloc_destinations();
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
     return;
   }
   // ---- page walk -----------------------------------------------------------------------------------------
   t_dec.start();
-  Buf<ChunkDesc> d_chunks(ctx, n_chunks);
-  Buf<int32_t> d_counts(ctx, n_chunks);
-  Buf<int64_t> d_offsets(ctx, n_chunks);
+  Buf<ChunkDesc> d_chunks(ctx, std::max(1, n_chunks));
+  Buf<int32_t> d_counts(ctx, std::max(1, n_chunks));
+  Buf<int64_t> d_offsets(ctx, std::max(1, n_chunks));
   Buf<uint32_t> d_flags(ctx, 1 + ncols);  // [0] error word, [1..] per-column has-nulls
   Buf<ColumnOut> d_cols(ctx, ncols);
   HS_CUDA(cudaMemcpyAsync(d_chunks.get(), chunks.data(), sizeof(ChunkDesc) * n_chunks, cudaMemcpyHostToDevice, ctx->stream));
@@ -437,47 +448,88 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   // ---- late-materialised dictionary columns --------------------------------------------------------------------------
   // A candidate column whose every page is dictionary-encoded and free of nulls, and whose chunk dictionaries unite to a
   // dictionary that pays off, is decoded to 16-bit codes of that dictionary: its values are never written to HBM, the
-  // partition moves 2 bytes per row instead of 4 or 8, and the page encoder finds its codes ready-made.
-  if (carry && carry->first_col >= 0 && !file_windows && ctx->world == 1 && n_pages > 0) {
-    Buf<uint32_t> d_class(ctx, ncols);
-    HS_CUDA(cudaMemsetAsync(d_class.get(), 0, 4 * (size_t)ncols, ctx->stream));
-    launch_classify_pages(ctx, d_pages.get(), n_pages, d_class.get());
-    std::vector<uint32_t> cls(ncols);
-    HS_CUDA(cudaMemcpyAsync(cls.data(), d_class.get(), 4 * (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  // partition moves 2 bytes per row instead of 4 or 8, and the page encoder finds its codes ready-made.  On several GPUs
+  // the ranks agree on the columns and on one dictionary per column (unions all-gathered and merged), so that codes mean
+  // the same everywhere and can cross NVLink in place of the values.
+  if (want_carry) {
+    const int W = ctx->world;
+    // what every rank knows about its own pages: per column the classification flags, then its row count
+    std::vector<uint32_t> mine(ncols + 2, 0u), all((size_t)(ncols + 2) * W);
+    if (n_pages > 0) {
+      Buf<uint32_t> d_class(ctx, ncols);
+      HS_CUDA(cudaMemsetAsync(d_class.get(), 0, 4 * (size_t)ncols, ctx->stream));
+      launch_classify_pages(ctx, d_pages.get(), n_pages, d_class.get());
+      HS_CUDA(cudaMemcpyAsync(mine.data(), d_class.get(), 4 * (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    mine[ncols] = (uint32_t)(nrows & 0xffffffffll);
+    mine[ncols + 1] = (uint32_t)(nrows >> 32);
+    comm_allgather_host(ctx, mine.data(), 4 * mine.size(), all.data());
+    std::vector<uint32_t> cls(ncols, 0u);
+    int64_t total_rows = 0;
+    for (int r = 0; r < W; r++) {
+      const uint32_t* a = &all[(size_t)r * (ncols + 2)];
+      for (int c = 0; c < ncols; c++) cls[c] |= a[c];
+      total_rows += (int64_t)a[ncols] | ((int64_t)a[ncols + 1] << 32);
+    }
     std::vector<int> cand;
-    for (int c = carry->first_col; c < ncols && (int)cand.size() < kMaxCarried; c++)
+    for (int c = carry->first_col; c < ncols && (int)cand.size() < kMaxCarried && total_rows > 0; c++)
       if (cls[c] == 0 && (out->cols[c].width == 4 || out->cols[c].width == 8)) cand.push_back(c);
     if (!cand.empty()) {
-      Buf<uint32_t> d_states(ctx, 4 * (size_t)ncols);
-      HS_CUDA(cudaMemsetAsync(d_states.get(), 0, 16 * (size_t)ncols, ctx->stream));
-      for (int c : cand) {
-        DevColumn& dc = out->cols[c];
-        dc.dict_keys.alloc(ctx, kDictCapacity);
-        HS_CUDA(cudaMemsetAsync(dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
-        launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, c, dc.width, dc.dict_keys.get(), kDictCapacity, kMaxDictEntries,
-                                     d_states.get() + 4 * c);
+      // union of this rank's chunk dictionaries, per candidate
+      const int nc = (int)cand.size();
+      std::vector<uint32_t> h_states(4 * (size_t)nc, 0u), all_states(4 * (size_t)nc * W);
+      if (n_pages > 0) {
+        Buf<uint32_t> d_states(ctx, 4 * (size_t)nc);
+        HS_CUDA(cudaMemsetAsync(d_states.get(), 0, 16 * (size_t)nc, ctx->stream));
+        for (int i = 0; i < nc; i++) {
+          DevColumn& dc = out->cols[cand[i]];
+          dc.dict_keys.alloc(ctx, kDictCapacity);
+          HS_CUDA(cudaMemsetAsync(dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
+          launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, cand[i], dc.width, dc.dict_keys.get(), kDictCapacity,
+                                       kMaxDictEntries, d_states.get() + 4 * i);
+        }
+        HS_CUDA(cudaMemcpyAsync(h_states.data(), d_states.get(), 16 * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+        HS_CUDA(cudaStreamSynchronize(ctx->stream));
       }
-      std::vector<uint32_t> h_states(4 * (size_t)ncols);
-      HS_CUDA(cudaMemcpyAsync(h_states.data(), d_states.get(), 16 * (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
-      for (int c : cand) {
+      comm_allgather_host(ctx, h_states.data(), 16 * (size_t)nc, all_states.data());
+      for (int i = 0; i < nc; i++) {
+        const int c = cand[i];
         DevColumn& dc = out->cols[c];
-        const uint32_t* st = &h_states[4 * (size_t)c];
-        if (st[1] == 0) {  // the union fits a dictionary page
-          std::vector<uint64_t> values = sorted_dictionary(ctx, dc.dict_keys.get(), st, dc.type);
-          const uint32_t bw = bits_for((uint32_t)values.size());
-          if (dictionary_pays_off((uint32_t)values.size(), bw, dc.width, nrows, carry->num_segments)) {
-            uint32_t mask = 0, empty_index = 0;
-            upload_lookup_table(ctx, values, &carry_tables[c], &mask, &empty_index);
-            dc.carried = true;
-            dc.dict_values = std::move(values);
-            dc.dict_bw = bw;
-            dc.codes.alloc(ctx, (size_t)nrows + 16);
-            h_cols[c] = ColumnOut{dc.codes.get(), nullptr, dc.width, dc.type, carry_tables[c].get(), mask, empty_index, 1, 0};
+        bool overflow = false;
+        uint32_t max_count = 0;
+        for (int r = 0; r < W; r++) {
+          const uint32_t* st = &all_states[((size_t)r * nc + i) * 4];
+          overflow = overflow || st[1] != 0;
+          max_count = std::max(max_count, st[0] + (st[2] ? 1u : 0u));
+        }
+        std::vector<uint64_t> values;
+        if (!overflow) {
+          if (n_pages > 0) values = sorted_dictionary(ctx, dc.dict_keys.get(), &h_states[4 * (size_t)i], dc.type);
+          if (W > 1) {  // merge the ranks' unions: [count, values...] blobs of equal size
+            std::vector<uint64_t> blob((size_t)max_count + 1, 0ull), blobs(((size_t)max_count + 1) * W);
+            blob[0] = values.size();
+            std::copy(values.begin(), values.end(), blob.begin() + 1);
+            comm_allgather_host(ctx, blob.data(), 8 * blob.size(), blobs.data());
+            values.clear();
+            for (int r = 0; r < W; r++) {
+              const uint64_t* bl = &blobs[(size_t)r * (max_count + 1)];
+              values.insert(values.end(), bl + 1, bl + 1 + bl[0]);
+            }
+            sort_dictionary(values, dc.type);
+            values.erase(std::unique(values.begin(), values.end()), values.end());
           }
         }
         dc.dict_keys.release();
+        const uint32_t bw = bits_for((uint32_t)values.size());
+        if (overflow || !dictionary_pays_off((uint32_t)values.size(), bw, dc.width, total_rows, carry->num_segments)) continue;
+        uint32_t mask = 0, empty_index = 0;
+        upload_lookup_table(ctx, values, &carry_tables[c], &mask, &empty_index);
+        dc.carried = true;
+        dc.dict_values = std::move(values);
+        dc.dict_bw = bw;
+        dc.codes.alloc(ctx, (size_t)std::max<int64_t>(1, nrows) + 16);
+        h_cols[c] = ColumnOut{dc.codes.get(), nullptr, dc.width, dc.type, carry_tables[c].get(), mask, empty_index, 1, 0};
       }
     }
   }
@@ -561,7 +613,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   Buf<KeyColumn> d_keys(ctx, nkeys);
   HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
   const bool fused = fused_partition_supported(num_buckets);
-  const int64_t ntiles = ceil_div(nrows, fused ? kFusedTile : kPartTile);
+  const int64_t ntiles = ceil_div(nrows, fused ? fused_tile_rows(false) : kPartTile);
   Buf<uint16_t> bucket;
   Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * num_buckets);
   Buf<unsigned long long> ghist(ctx, num_buckets);
@@ -571,8 +623,10 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   if (fused) {
     const unsigned long long init[2] = {0ull, ~0ull};
     HS_CUDA(cudaMemcpyAsync(d_key_bits.get(), init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    static const bool rehash = getenv("HS_PART_REHASH") != nullptr;  // A/B: hash twice instead of storing 2 B/row
+    if (!rehash) bucket.alloc(ctx, std::max<int64_t>(1, nrows));
     launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), ghist.get(), d_key_bits.get(),
-                     single_key_type_of(h_keys.data(), nkeys));
+                     single_key_type_of(h_keys.data(), nkeys), rehash ? nullptr : bucket.get());
     HS_CUDA(cudaMemcpyAsync(out->key_or_and, d_key_bits.get(), sizeof out->key_or_and, cudaMemcpyDeviceToHost, ctx->stream));
     out->have_key_bits = true;  // valid after the stream synchronisation below
   } else {
@@ -630,7 +684,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
       pack.out = out->part.rec.get();
     }
     launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), d_pc.get(), (int)h_pc.size(),
-                          nullptr, 1, single_key_type_of(h_keys.data(), nkeys), &pack);
+                          nullptr, 1, single_key_type_of(h_keys.data(), nkeys), &pack, bucket ? bucket.get() : nullptr);
   } else {
     dest.alloc(ctx, std::max<int64_t>(1, nrows));
     launch_partition_dest(ctx, bucket.get(), nrows, num_buckets, tile_hist.get(), dest.get());

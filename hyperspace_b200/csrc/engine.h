@@ -129,6 +129,8 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
 // the buckets it owns (owner(b) = b % world).  No-op when world == 1.
 void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_stats* stats);
 void comm_destroy(hs_ctx* ctx);
+// all-gather of a small host blob (out: world x bytes, rank-major); a plain copy on one GPU
+void comm_allgather_host(hs_ctx* ctx, const void* in, size_t bytes, void* out);
 // Fused alternative (NVLink peer memory): partitions by bucket and delivers every row to its final bucket-major position
 // on the owner GPU in one kernel; fills out->part / bucket_offsets so that sort_partitioned_rows can run next.
 bool p2p_exchange_supported(hs_ctx* ctx, int num_buckets);

@@ -84,6 +84,21 @@ void comm_destroy(hs_ctx* ctx) {
   }
 }
 
+// All-gather of small host blobs (every rank contributes `bytes`; out = world x bytes, rank-major).  Used for the
+// agreement steps around the data path (dictionary unions, flags); the rows themselves never come this way.
+void comm_allgather_host(hs_ctx* ctx, const void* in, size_t bytes, void* out) {
+  if (ctx->world <= 1) {
+    memcpy(out, in, bytes);
+    return;
+  }
+  if (!ctx->comm || !ctx->comm->comm) fail(HS_ECOMM, "hs_comm_init has not been called on this context");
+  Buf<uint8_t> d_in(ctx, std::max<size_t>(bytes, 16)), d_out(ctx, std::max<size_t>(bytes, 16) * ctx->world);
+  HS_CUDA(cudaMemcpyAsync(d_in.get(), in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  HS_NCCL(nccl().AllGather(d_in.get(), d_out.get(), bytes, kNcclUint8, ctx->comm->comm, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(out, d_out.get(), bytes * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_stats* stats) {
   const int world = ctx->world;
   if (world <= 1) return;
@@ -100,7 +115,7 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
   HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
-  const int64_t ntiles = ceil_div(nrows, kFusedTile);
+  const int64_t ntiles = ceil_div(nrows, fused_tile_rows(false));  // the send buffers are local memory
   Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * world);
   Buf<unsigned long long> ghist(ctx, world);
   Buf<uint64_t> d_send_off(ctx, world + 1);
@@ -301,7 +316,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
   HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
-  const int64_t ntiles = ceil_div(nrows, kFusedTile);
+  const int64_t ntiles = ceil_div(nrows, fused_tile_rows(true));  // runs leave over NVLink: the large tile shape
   Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * nb);
   // gathered payload per rank: nb bucket counts followed by ncols has-nulls flags
   const int msg = nb + ncols;
@@ -310,7 +325,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   for (int c = 0; c < ncols; c++) h_mine[nb + c] = table.cols[c].has_nulls ? 1 : 0;
   HS_CUDA(cudaMemcpyAsync(d_mine.get(), h_mine.data(), 8 * msg, cudaMemcpyHostToDevice, ctx->stream));
   launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_mine.get(), nullptr,
-                   single_key_type_of(h_keys.data(), nkeys));
+                   single_key_type_of(h_keys.data(), nkeys), nullptr, /*peer_tiles=*/true);
   HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), msg, kNcclUint64, ctx->comm->comm, ctx->stream));
   HS_CUDA(cudaMemcpyAsync(h_all.data(), d_all.get(), 8 * (size_t)msg * world, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -362,6 +377,8 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   out->part.cols.resize(ncols);
   std::vector<PartColumn> h_pc;          // what the kernel moves (data columns, then validity where needed)
   std::vector<void*> my_recv;            // receive buffer of every moved column on this rank
+  CodePackRound pack;                    // late-materialised columns: their codes leave as one record per row
+  memset(&pack, 0, sizeof pack);
   for (int c = 0; c < ncols; c++) {
     DevColumn& src = table.cols[c];
     DevColumn& dst = out->part.cols[c];
@@ -370,6 +387,15 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
     dst.width = src.width;
     dst.schema = src.schema;
     dst.has_nulls = any_nulls[c];
+    if (src.carried) {  // every rank carries the same columns with the same dictionary (decode_sources agreed on both)
+      if (c < nkeys || pack.n >= kMaxCarried) fail(HS_EINVAL, "column '%s' cannot be late-materialised here", src.name.c_str());
+      dst.carried = true;
+      dst.dict_values = std::move(src.dict_values);
+      dst.dict_bw = src.dict_bw;
+      dst.carry_slot = pack.n;
+      pack.src[pack.n++] = src.codes.get();
+      continue;
+    }
     dst.data.alloc(ctx, (size_t)n_recv * src.width + 16);
     ctx->pool.mark_exported(dst.data.get());
     h_pc.push_back(PartColumn{src.data.get(), nullptr, src.width, 0});
@@ -385,7 +411,13 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
       my_recv.push_back(dst.valid.get());
     }
   }
-  const int nmoved = (int)h_pc.size();
+  const int ncolmoved = (int)h_pc.size();  // the kernel's column rounds; the code records (if any) follow them
+  if (pack.n > 0) {
+    out->part.rec.alloc(ctx, (size_t)n_recv * 8 + 16);
+    ctx->pool.mark_exported(out->part.rec.get());
+    my_recv.push_back(out->part.rec.get());
+  }
+  const int nmoved = (int)my_recv.size();
   std::vector<cudaIpcMemHandle_t> my_handles(nmoved), all_handles((size_t)nmoved * world);
   for (int i = 0; i < nmoved; i++) HS_CUDA(cudaIpcGetMemHandle(&my_handles[i], my_recv[i]));
   const size_t hbytes = sizeof(cudaIpcMemHandle_t) * nmoved;
@@ -401,14 +433,15 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
 
   // ---- one kernel: partition + exchange ------------------------------------------------------------------------
   Buf<unsigned long long> d_base(ctx, nb);
-  Buf<PartColumn> d_pc(ctx, nmoved);
+  Buf<PartColumn> d_pc(ctx, std::max(1, ncolmoved));
   Buf<void*> d_peer(ctx, (size_t)nmoved * world);
   HS_CUDA(cudaMemcpyAsync(d_base.get(), my_base.data(), 8 * nb, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * nmoved, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * ncolmoved, cudaMemcpyHostToDevice, ctx->stream));
   HS_CUDA(cudaMemcpyAsync(d_peer.get(), h_peer.data(), sizeof(void*) * nmoved * world, cudaMemcpyHostToDevice, ctx->stream));
   launch_tile_offsets(ctx, tile_hist.get(), ntiles, nb, d_mine.get(), nullptr, d_base.get());
-  launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_pc.get(), nmoved,
-                        (void* const*)d_peer.get(), world, single_key_type_of(h_keys.data(), nkeys));
+  // the peer table holds one row of `world` pointers per column round, then one row for the code records
+  launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_pc.get(), ncolmoved,
+                        (void* const*)d_peer.get(), world, single_key_type_of(h_keys.data(), nkeys), &pack);
   // closing barrier: nobody reads its receive buffers before every peer's kernel has completed
   HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), 1, kNcclUint64, ctx->comm->comm, ctx->stream));
   t_x.stop();
@@ -416,6 +449,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data.release();
     table.cols[c].valid.release();
+    table.cols[c].codes.release();
   }
   out->bucket_offsets = my_bucket_offsets;
   out->d_bucket_offsets.alloc(ctx, nb + 1);
@@ -424,7 +458,8 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   for (int r = 0; r < world; r++)
     if (r != me)
       for (int b = r; b < nb; b += world)
-        for (int c = 0; c < ncols; c++) stats->bytes_exchanged += (int64_t)(cnt(me, b) * (table.cols[c].width + (any_nulls[c] ? 1 : 0)));
+        for (int c = 0; c < ncols; c++)
+          stats->bytes_exchanged += (int64_t)(cnt(me, b) * ((out->part.cols[c].carried ? 2 : table.cols[c].width) + (any_nulls[c] ? 1 : 0)));
   stats->ms_hash += t_hash.ms();
   stats->ms_exchange += t_x.ms();
 }

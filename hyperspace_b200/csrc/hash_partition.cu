@@ -333,10 +333,19 @@ void launch_iota_u32(hs_ctx* ctx, uint32_t* out, int64_t n) {
 namespace hs {
 namespace {
 
-constexpr int kFThreads = 512;
-constexpr int kFWarps = kFThreads / 32;
-constexpr int kFItems = kFusedTile / kFThreads;   // 16
-constexpr int kFWarpRows = kFusedTile / kFWarps;  // 512
+// Two tile shapes.  Local: 4096 rows x 256 threads, four CTAs per SM -- the kernel is bound by the latency of its phases
+// (hash, rank, one exchange round per column), and four small CTAs overlap them better than two big ones (-11 % at 1 B
+// rows).  Peer: 8192 rows x 512 threads -- when the runs leave over NVLink, twice as long a run per (tile, bucket) matters
+// more (the small tile was 16 % slower at N = 2).
+template <bool PEER>
+struct FusedCfg {
+  static constexpr int kTile = PEER ? kFusedTilePeer : kFusedTileLocal;
+  static constexpr int kThreads = PEER ? 512 : 256;
+  static constexpr int kWarps = kThreads / 32;
+  static constexpr int kItems = kTile / kThreads;   // 16
+  static constexpr int kWarpRows = kTile / kWarps;  // 512
+  static constexpr int kMinCtas = 1024 / kThreads;
+};
 
 // pmod(hash, n) and bucket % world without an integer division per row: Lemire's fastmod (M = 2^64 / n + 1; exact for
 // 32-bit operands).  The signed Murmur3 value is shifted into unsigned range first and the shift is taken out again
@@ -392,13 +401,15 @@ struct RowHasher {
   }
 };
 
-template <int KT>
-__global__ void __launch_bounds__(kFThreads) k_tile_hist(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
+template <int KT, bool PEER>
+__global__ void __launch_bounds__(FusedCfg<PEER>::kThreads) k_tile_hist(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
                                                           ModConst bucket_mod, ModConst owner_mod, int use_owner,
                                                           uint32_t* __restrict__ tile_hist,
                                                           unsigned long long* __restrict__ global_hist,
-                                                          unsigned long long* __restrict__ key_or_and) {
+                                                          unsigned long long* __restrict__ key_or_and,
+                                                          uint16_t* __restrict__ bin_ids) {
   extern __shared__ uint32_t s_hist[];  // nb
+  constexpr int kFThreads = FusedCfg<PEER>::kThreads, kFItems = FusedCfg<PEER>::kItems, kFusedTile = FusedCfg<PEER>::kTile;
   const int nb = use_owner ? (int)owner_mod.n : (int)bucket_mod.n;
   for (int i = threadIdx.x; i < nb; i += kFThreads) s_hist[i] = 0;
   __syncthreads();
@@ -413,6 +424,7 @@ __global__ void __launch_bounds__(kFThreads) k_tile_hist(const KeyColumn* __rest
       uint32_t b = fast_pmod(hasher(row, &e), bucket_mod);
       if (use_owner) b = fast_mod(b, owner_mod);
       atomicAdd(&s_hist[b], 1u);
+      if (bin_ids) bin_ids[row] = (uint16_t)b;  // the partition kernel reads 2 bytes back instead of hashing 8 again
       vor |= e;
       vand &= e;
     }
@@ -445,14 +457,16 @@ __global__ void __launch_bounds__(kFThreads) k_tile_hist(const KeyColumn* __rest
 //
 // All warp collectives run with the full mask and outside any branch: slots past the end of the last tile carry the
 // last bin and, being the last slots of the tile, rank behind every real row of that bin; they are never written out.
-template <int BITS, int KT>
-__global__ void __launch_bounds__(kFThreads, 2) k_partition_rows(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
+template <int BITS, int KT, bool PEER>
+__global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMinCtas) k_partition_rows(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
                                                                ModConst bucket_mod, ModConst owner_mod, int use_owner,
                                                                const uint32_t* __restrict__ tile_dst,
                                                                const PartColumn* __restrict__ cols, int ncols,
                                                                void* const* __restrict__ peer_out, int out_world,
-                                                               CodePackRound pack) {
+                                                               CodePackRound pack, const uint16_t* __restrict__ bin_ids) {
   extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int kFThreads = FusedCfg<PEER>::kThreads, kFItems = FusedCfg<PEER>::kItems, kFusedTile = FusedCfg<PEER>::kTile;
+  constexpr int kFWarps = FusedCfg<PEER>::kWarps, kFWarpRows = FusedCfg<PEER>::kWarpRows;
   const int nb = use_owner ? (int)owner_mod.n : (int)bucket_mod.n;
   uint64_t* xbuf = reinterpret_cast<uint64_t*>(smem);
   uint16_t* pos_bin = reinterpret_cast<uint16_t*>(smem + (size_t)kFusedTile * 8);
@@ -473,6 +487,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_partition_rows(const KeyColumn
   for (int j = 0; j < kFItems; j++) {
     bin[j] = (uint32_t)nb - 1;
     if (first + j * 32 < tile_count) {
+      if (bin_ids) {
+        bin[j] = bin_ids[wbase + j * 32];
+        continue;
+      }
 #ifdef HS_PART_OLDMOD
       uint32_t b = (uint32_t)spark_pmod(hasher(wbase + j * 32), (int32_t)bucket_mod.n);
       if (use_owner) b %= owner_mod.n;
@@ -613,34 +631,42 @@ __global__ void __launch_bounds__(kFThreads, 2) k_partition_rows(const KeyColumn
       }
     }
     __syncthreads();
-    uint64_t* out = (uint64_t*)pack.out;
+    // on several GPUs the records go to the bucket's owner like every column: their row of the peer table follows the
+    // column rounds'
+    void* const* pout = peer_out ? peer_out + (size_t)ncols * out_world : nullptr;
 #pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) out[out_adj[pos_bin[i]] + i] = xbuf[i];
+    for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
+      const uint32_t b = pos_bin[i];
+      uint64_t* out = (uint64_t*)(pout ? pout[bin_owner[b]] : pack.out);
+      out[out_adj[b] + i] = xbuf[i];
+    }
   }
 }
 
+template <bool PEER>
 size_t fused_smem_bytes(int nb) {
-  size_t cnt_entries = (size_t)kFWarps * nb;
+  size_t cnt_entries = (size_t)FusedCfg<PEER>::kWarps * nb;
   cnt_entries += cnt_entries & 1;
-  return (size_t)kFusedTile * 8 + (size_t)kFusedTile * 2 + cnt_entries * 2 + (size_t)nb * 4 * 2 + 40 * 4;
+  return (size_t)FusedCfg<PEER>::kTile * 8 + (size_t)FusedCfg<PEER>::kTile * 2 + cnt_entries * 2 + (size_t)nb * 4 * 2 + 40 * 4;
 }
 
 }  // namespace
 
 bool fused_partition_supported(int nbins) { return nbins <= kFusedMaxBins; }
 
-void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
-                      uint32_t* tile_hist, unsigned long long* global_hist, unsigned long long* key_or_and,
-                      int single_key_type) {
-  KernelScope _ks(ctx, "k_tile_hist");
-  if (nrows == 0) return;
+int fused_tile_rows(bool peer_tiles) { return peer_tiles ? kFusedTilePeer : kFusedTileLocal; }
+
+template <bool PEER>
+static void launch_tile_hist_t(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
+                               uint32_t* tile_hist, unsigned long long* global_hist, unsigned long long* key_or_and,
+                               int single_key_type, uint16_t* bin_ids) {
   const int nb = owner_mod > 0 ? owner_mod : num_buckets;
-  const int64_t ntiles = ceil_div(nrows, kFusedTile);
+  const int64_t ntiles = ceil_div(nrows, FusedCfg<PEER>::kTile);
   const ModConst bm = make_mod_const((uint32_t)num_buckets), om = make_mod_const((uint32_t)std::max(owner_mod, 1));
   const int uo = owner_mod > 0 ? 1 : 0;
-#define HS_HIST(KT)                                                                                                      \
-  k_tile_hist<KT><<<(unsigned)ntiles, kFThreads, (size_t)nb * 4, ctx->stream>>>(d_keys, nkeys, nrows, bm, om, uo, tile_hist, \
-                                                                                global_hist, key_or_and)
+#define HS_HIST(KT)                                                                                                       \
+  k_tile_hist<KT, PEER><<<(unsigned)ntiles, FusedCfg<PEER>::kThreads, (size_t)nb * 4, ctx->stream>>>(                     \
+      d_keys, nkeys, nrows, bm, om, uo, tile_hist, global_hist, key_or_and, bin_ids)
   switch (single_key_type) {
     case HS_TYPE_INT32: HS_HIST(HS_TYPE_INT32); break;
     case HS_TYPE_INT64: HS_HIST(HS_TYPE_INT64); break;
@@ -650,58 +676,76 @@ void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t n
   HS_LAUNCH_CHECK(ctx);
 }
 
-template <int BITS, int KT>
-static void launch_partition_rows_t(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets,
-                                    int owner_mod, const uint32_t* tile_dst, const PartColumn* d_cols, int ncols,
-                                    void* const* d_peer_out, int out_world, const CodePackRound& pack) {
-  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
-  const int64_t ntiles = ceil_div(nrows, kFusedTile);
+void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
+                      uint32_t* tile_hist, unsigned long long* global_hist, unsigned long long* key_or_and,
+                      int single_key_type, uint16_t* bin_ids, bool peer_tiles) {
+  KernelScope _ks(ctx, "k_tile_hist");
+  if (nrows == 0) return;
+  if (peer_tiles)
+    launch_tile_hist_t<true>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_hist, global_hist, key_or_and, single_key_type, bin_ids);
+  else
+    launch_tile_hist_t<false>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_hist, global_hist, key_or_and, single_key_type, bin_ids);
+}
+
+struct PartitionLaunch {
+  const KeyColumn* d_keys;
+  int nkeys;
+  int64_t nrows;
+  int num_buckets, owner_mod;
+  const uint32_t* tile_dst;
+  const PartColumn* d_cols;
+  int ncols;
+  void* const* d_peer_out;
+  int out_world;
+  CodePackRound pack;
+  const uint16_t* bin_ids;
+};
+
+template <int BITS, int KT, bool PEER>
+static void launch_partition_rows_t(hs_ctx* ctx, const PartitionLaunch& a) {
+  const int nb = a.owner_mod > 0 ? a.owner_mod : a.num_buckets;
+  const int64_t ntiles = ceil_div(a.nrows, FusedCfg<PEER>::kTile);
   static bool attr = false;  // one per instantiation
   if (!attr) {
-    HS_CUDA(cudaFuncSetAttribute(k_partition_rows<BITS, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)fused_smem_bytes(kFusedMaxBins)));
+    HS_CUDA(cudaFuncSetAttribute(k_partition_rows<BITS, KT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fused_smem_bytes<PEER>(kFusedMaxBins)));
     attr = true;
   }
-  k_partition_rows<BITS, KT><<<(unsigned)ntiles, kFThreads, fused_smem_bytes(nb), ctx->stream>>>(
-      d_keys, nkeys, nrows, make_mod_const((uint32_t)num_buckets), make_mod_const((uint32_t)std::max(owner_mod, 1)),
-      owner_mod > 0 ? 1 : 0, tile_dst, d_cols, ncols, d_peer_out, out_world, pack);
+  k_partition_rows<BITS, KT, PEER><<<(unsigned)ntiles, FusedCfg<PEER>::kThreads, fused_smem_bytes<PEER>(nb), ctx->stream>>>(
+      a.d_keys, a.nkeys, a.nrows, make_mod_const((uint32_t)a.num_buckets), make_mod_const((uint32_t)std::max(a.owner_mod, 1)),
+      a.owner_mod > 0 ? 1 : 0, a.tile_dst, a.d_cols, a.ncols, a.d_peer_out, a.out_world, a.pack, a.bin_ids);
   HS_LAUNCH_CHECK(ctx);
 }
 
-template <int BITS>
-static void launch_partition_rows_bits(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets,
-                                       int owner_mod, const uint32_t* tile_dst, const PartColumn* d_cols, int ncols,
-                                       void* const* d_peer_out, int out_world, int single_key_type,
-                                       const CodePackRound& pack) {
+template <int BITS, bool PEER>
+static void launch_partition_rows_bits(hs_ctx* ctx, const PartitionLaunch& a, int single_key_type) {
   switch (single_key_type) {
-    case HS_TYPE_INT32:
-      launch_partition_rows_t<BITS, HS_TYPE_INT32>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, pack);
-      break;
-    case HS_TYPE_INT64:
-      launch_partition_rows_t<BITS, HS_TYPE_INT64>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, pack);
-      break;
-    default:
-      launch_partition_rows_t<BITS, -1>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, pack);
+    case HS_TYPE_INT32: launch_partition_rows_t<BITS, HS_TYPE_INT32, PEER>(ctx, a); break;
+    case HS_TYPE_INT64: launch_partition_rows_t<BITS, HS_TYPE_INT64, PEER>(ctx, a); break;
+    default: launch_partition_rows_t<BITS, -1, PEER>(ctx, a);
   }
+}
+
+template <bool PEER>
+static void launch_partition_rows_cfg(hs_ctx* ctx, const PartitionLaunch& a, int single_key_type) {
+  const int nb = a.owner_mod > 0 ? a.owner_mod : a.num_buckets;
+  // the ranking votes once per bin-id bit: 4, 8 or 10 (kFusedMaxBins = 1024)
+  if (nb <= 16) launch_partition_rows_bits<4, PEER>(ctx, a, single_key_type);
+  else if (nb <= 256) launch_partition_rows_bits<8, PEER>(ctx, a, single_key_type);
+  else launch_partition_rows_bits<10, PEER>(ctx, a, single_key_type);
 }
 
 void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
                            const uint32_t* tile_dst, const PartColumn* d_cols, int ncols, void* const* d_peer_out,
-                           int out_world, int single_key_type, const CodePackRound* pack_round) {
+                           int out_world, int single_key_type, const CodePackRound* pack_round, const uint16_t* bin_ids) {
   KernelScope _ks(ctx, "k_partition_rows");
   if (nrows == 0) return;
-  CodePackRound pack;
-  memset(&pack, 0, sizeof pack);
-  if (pack_round) pack = *pack_round;
-  if (pack.n > 0 && d_peer_out) fail(HS_EINVAL, "code records cannot be routed to peer GPUs");
-  const int nb = owner_mod > 0 ? owner_mod : num_buckets;
-  // the ranking votes once per bin-id bit: 4, 8 or 10 (kFusedMaxBins = 1024)
-  if (nb <= 16)
-    launch_partition_rows_bits<4>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type, pack);
-  else if (nb <= 256)
-    launch_partition_rows_bits<8>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type, pack);
-  else
-    launch_partition_rows_bits<10>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, single_key_type, pack);
+  PartitionLaunch a{d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, {}, bin_ids};
+  memset(&a.pack, 0, sizeof a.pack);
+  if (pack_round) a.pack = *pack_round;
+  // tiles that leave over NVLink use the large shape (the tile histogram must have been taken with peer_tiles = true)
+  if (d_peer_out) launch_partition_rows_cfg<true>(ctx, a, single_key_type);
+  else launch_partition_rows_cfg<false>(ctx, a, single_key_type);
 }
 
 }  // namespace hs

@@ -112,10 +112,9 @@ void launch_partition_dest(hs_ctx* ctx, const uint16_t* bucket, int64_t nrows, i
 // out[dest[i]] = in[i]
 void launch_scatter_column(hs_ctx* ctx, const void* in, void* out, const uint32_t* dest, int64_t nrows, int width);
 // ---- fused partition (hash + stable rank + shared-memory exchange of every column in one kernel) ------------------
-#ifndef HS_FUSED_TILE
-#define HS_FUSED_TILE 8192
-#endif
-constexpr int kFusedTile = HS_FUSED_TILE;     // rows per tile (512 threads x 16)
+constexpr int kFusedTileLocal = 4096;  // rows per tile when the partition writes local memory (256 threads x 16)
+constexpr int kFusedTilePeer = 8192;   // ... and when it writes peer GPUs' memory over NVLink (512 threads x 16)
+int fused_tile_rows(bool peer_tiles);
 constexpr int kFusedMaxBins = 1024;  // above this the per-warp counters no longer fit next to the exchange buffer
 struct PartColumn {
   const void* in;
@@ -124,11 +123,13 @@ struct PartColumn {
   int32_t pad;
 };
 bool fused_partition_supported(int nbins);
+// bin_ids (optional): receives every row's bin so that launch_partition_rows (same argument) need not hash again
 // key_or_and (optional, {0, ~0} on entry): accumulates OR / AND of the sort-encoded values of the last key column
-// tile histograms M[tile][bin] for kFusedTile-row tiles (+ global histogram); bin = bucket, or bucket % owner_mod
+// tile histograms M[tile][bin] for fused_tile_rows(peer_tiles)-row tiles (+ global histogram); bin = bucket, or bucket % owner_mod
 void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
                       uint32_t* tile_hist, unsigned long long* global_hist,
-                      unsigned long long* key_or_and = nullptr, int single_key_type = -1);
+                      unsigned long long* key_or_and = nullptr, int single_key_type = -1, uint16_t* bin_ids = nullptr,
+                      bool peer_tiles = false);
 // single_key_type: HS_TYPE_INT32 / HS_TYPE_INT64 when there is exactly one key column, of that type and without nulls
 // (selects a kernel with the hash inlined for it); -1 otherwise.  See single_key_type_of().
 inline int single_key_type_of(const KeyColumn* h_keys, int nkeys) {
@@ -146,7 +147,8 @@ struct CodePackRound {
 };
 void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
                            const uint32_t* tile_dst, const PartColumn* d_cols, int ncols, void* const* d_peer_out = nullptr,
-                           int out_world = 1, int single_key_type = -1, const CodePackRound* pack = nullptr);
+                           int out_world = 1, int single_key_type = -1, const CodePackRound* pack = nullptr,
+                           const uint16_t* bin_ids = nullptr);
 // out[i] = sort_encode(in[src ? src[i] : i])  (+ global OR / AND reduction into or_and[0], or_and[1])
 void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* src, int64_t nrows, uint64_t* out,
                         unsigned long long* or_and);
