@@ -184,6 +184,18 @@ static void upload_lookup_table(hs_ctx* ctx, const std::vector<uint64_t>& values
   HS_CUDA(cudaStreamSynchronize(ctx->stream));  // tab goes out of scope
 }
 
+// out[dst_off .. dst_off + len) = src[0 .. len): gathers the tails / footers of device-resident file images into one
+// buffer so that they reach the host with a single copy.  One CTA per span.
+struct SpanCopy {
+  const uint8_t* src;
+  uint64_t dst_off;
+  uint32_t len;
+};
+__global__ void k_gather_spans(const SpanCopy* __restrict__ spans, uint8_t* __restrict__ out) {
+  const SpanCopy sp = spans[blockIdx.x];
+  for (uint32_t i = threadIdx.x; i < sp.len; i += blockDim.x) out[sp.dst_off + i] = sp.src[i];
+}
+
 void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceSet* set, hs_stats* stats) {
   StageTimer t_h2d(ctx);
   set->n_files = n_files;
@@ -223,14 +235,23 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
   bool any_dev = false;
   for (int f = 0; f < n_files; f++) any_dev = any_dev || (files[f].data && files[f].on_device);
   if (any_dev) {
+    // one gather kernel + one copy per round instead of one small copy per file (each costs ~4.5 us of launch overhead)
     pinned_tails.alloc(ctx, (size_t)n_files * 8, /*pinned=*/true);
+    Buf<SpanCopy> h_spans(ctx, n_files, /*pinned=*/true);
+    Buf<SpanCopy> d_spans(ctx, n_files);
+    Buf<uint8_t> d_gathered(ctx, (size_t)n_files * 8);
+    int nspans = 0;
     for (int f = 0; f < n_files; f++) {
       const hs_source_file& sf = files[f];
       if (!(sf.data && sf.on_device)) continue;
       if (((uintptr_t)sf.data & 15) != 0) fail(HS_EINVAL, "%s: device images must be 16-byte aligned", imgs[f].what.c_str());
       imgs[f].dev = (const uint8_t*)sf.data;
-      HS_CUDA(cudaMemcpyAsync(pinned_tails.get() + (size_t)f * 8, imgs[f].dev + sizes[f] - 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      h_spans.get()[nspans++] = SpanCopy{imgs[f].dev + sizes[f] - 8, (uint64_t)f * 8, 8};
     }
+    HS_CUDA(cudaMemcpyAsync(d_spans.get(), h_spans.get(), sizeof(SpanCopy) * nspans, cudaMemcpyHostToDevice, ctx->stream));
+    k_gather_spans<<<nspans, 128, 0, ctx->stream>>>(d_spans.get(), d_gathered.get());
+    HS_LAUNCH_CHECK(ctx);
+    HS_CUDA(cudaMemcpyAsync(pinned_tails.get(), d_gathered.get(), (size_t)n_files * 8, cudaMemcpyDeviceToHost, ctx->stream));
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int f = 0; f < n_files; f++) {
       const hs_source_file& sf = files[f];
@@ -243,11 +264,17 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
       footer_off[f + 1] = footer_off[f] + flen;
     }
     pinned_footers.alloc(ctx, std::max<uint64_t>(1, footer_off[n_files]), /*pinned=*/true);
+    Buf<uint8_t> d_footers(ctx, std::max<uint64_t>(1, footer_off[n_files]));
+    nspans = 0;
     for (int f = 0; f < n_files; f++) {
       const uint64_t flen = footer_off[f + 1] - footer_off[f];
-      if (flen)
-        HS_CUDA(cudaMemcpyAsync(pinned_footers.get() + footer_off[f], imgs[f].dev + sizes[f] - 8 - flen, flen,
-                                cudaMemcpyDeviceToHost, ctx->stream));
+      if (flen) h_spans.get()[nspans++] = SpanCopy{imgs[f].dev + sizes[f] - 8 - flen, footer_off[f], (uint32_t)flen};
+    }
+    if (nspans) {
+      HS_CUDA(cudaMemcpyAsync(d_spans.get(), h_spans.get(), sizeof(SpanCopy) * nspans, cudaMemcpyHostToDevice, ctx->stream));
+      k_gather_spans<<<nspans, 128, 0, ctx->stream>>>(d_spans.get(), d_footers.get());
+      HS_LAUNCH_CHECK(ctx);
+      HS_CUDA(cudaMemcpyAsync(pinned_footers.get(), d_footers.get(), footer_off[n_files], cudaMemcpyDeviceToHost, ctx->stream));
     }
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
   }

@@ -324,8 +324,9 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   std::vector<unsigned long long> h_mine(msg, 0), h_all((size_t)msg * world);
   for (int c = 0; c < ncols; c++) h_mine[nb + c] = table.cols[c].has_nulls ? 1 : 0;
   HS_CUDA(cudaMemcpyAsync(d_mine.get(), h_mine.data(), 8 * msg, cudaMemcpyHostToDevice, ctx->stream));
+  Buf<uint16_t> bin_ids(ctx, std::max<int64_t>(1, nrows));  // bucket of every row: hashed once, read back by the partition
   launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_mine.get(), nullptr,
-                   single_key_type_of(h_keys.data(), nkeys), nullptr, /*peer_tiles=*/true);
+                   single_key_type_of(h_keys.data(), nkeys), bin_ids.get(), /*peer_tiles=*/true);
   HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), msg, kNcclUint64, ctx->comm->comm, ctx->stream));
   HS_CUDA(cudaMemcpyAsync(h_all.data(), d_all.get(), 8 * (size_t)msg * world, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -441,7 +442,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   launch_tile_offsets(ctx, tile_hist.get(), ntiles, nb, d_mine.get(), nullptr, d_base.get());
   // the peer table holds one row of `world` pointers per column round, then one row for the code records
   launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_pc.get(), ncolmoved,
-                        (void* const*)d_peer.get(), world, single_key_type_of(h_keys.data(), nkeys), &pack);
+                        (void* const*)d_peer.get(), world, single_key_type_of(h_keys.data(), nkeys), &pack, bin_ids.get());
   // closing barrier: nobody reads its receive buffers before every peer's kernel has completed
   HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), 1, kNcclUint64, ctx->comm->comm, ctx->stream));
   t_x.stop();

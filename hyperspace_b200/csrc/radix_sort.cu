@@ -358,34 +358,46 @@ ChunkPlan build_chunks(hs_ctx* ctx, const std::vector<uint32_t>& seg_tile_begin)
 
 }  // namespace
 
+// tiles of one segment (one CTA per segment): the list has a quarter of a million entries at 1 B rows, so it is generated
+// where it is used instead of being built on the host and copied over from pageable memory
+__global__ void k_build_tiles(const uint64_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_tile_begin,
+                              SortTile* __restrict__ tiles) {
+  const uint32_t s = blockIdx.x;
+  const uint64_t b = seg_start[s], e = seg_start[s + 1];
+  const uint32_t t0 = seg_tile_begin[s], nt = seg_tile_begin[s + 1] - t0;
+  for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) {
+    const uint64_t p = b + (uint64_t)i * kSortTile;
+    tiles[t0 + i] = SortTile{s, (uint32_t)min((uint64_t)kSortTile, e - p), p};
+  }
+}
+
 void build_sort_plan(hs_ctx* ctx, const uint64_t* seg_offsets, int nseg, SortPlan* plan) {
-  std::vector<SortTile> tiles;
   std::vector<uint32_t> stb(nseg + 1);
   std::vector<uint64_t> sstart(nseg + 1);
+  uint64_t ntiles = 0;
   for (int s = 0; s < nseg; s++) {
-    stb[s] = (uint32_t)tiles.size();
+    stb[s] = (uint32_t)ntiles;
     sstart[s] = seg_offsets[s];
-    const uint64_t b = seg_offsets[s], e = seg_offsets[s + 1];
-    for (uint64_t p = b; p < e; p += kSortTile)
-      tiles.push_back(SortTile{(uint32_t)s, (uint32_t)std::min<uint64_t>(kSortTile, e - p), p});
+    ntiles += ceil_div(seg_offsets[s + 1] - seg_offsets[s], (uint64_t)kSortTile);
   }
-  stb[nseg] = (uint32_t)tiles.size();
+  stb[nseg] = (uint32_t)ntiles;
   sstart[nseg] = seg_offsets[nseg];
   if (seg_offsets[nseg] >= (1ull << 32)) fail(HS_EUNSUPPORTED, "more than 2^32-1 rows per GPU per call");
   plan->n = (int64_t)seg_offsets[nseg];
-  plan->ntiles = (int64_t)tiles.size();
+  plan->ntiles = (int64_t)ntiles;
   plan->nseg = nseg;
-  plan->tiles.alloc(ctx, std::max<size_t>(1, tiles.size()));
+  plan->tiles.alloc(ctx, std::max<size_t>(1, ntiles));
   plan->seg_tile_begin.alloc(ctx, stb.size());
   plan->seg_start.alloc(ctx, sstart.size());
-  plan->tile_hist.alloc(ctx, std::max<size_t>(1, tiles.size()) * 256);
-  plan->tile_dst.alloc(ctx, std::max<size_t>(1, tiles.size()) * 256);
-  if (!tiles.empty())
-    HS_CUDA(cudaMemcpyAsync(plan->tiles.get(), tiles.data(), tiles.size() * sizeof(SortTile), cudaMemcpyHostToDevice,
-                            ctx->stream));
+  plan->tile_hist.alloc(ctx, std::max<size_t>(1, ntiles) * 256);
+  plan->tile_dst.alloc(ctx, std::max<size_t>(1, ntiles) * 256);
   HS_CUDA(cudaMemcpyAsync(plan->seg_tile_begin.get(), stb.data(), stb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   HS_CUDA(cudaMemcpyAsync(plan->seg_start.get(), sstart.data(), sstart.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (nseg > 0 && ntiles > 0) {
+    k_build_tiles<<<nseg, 256, 0, ctx->stream>>>(plan->seg_start.get(), plan->seg_tile_begin.get(), plan->tiles.get());
+    HS_LAUNCH_CHECK(ctx);
+  }
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
   plan->h_seg_tile_begin = stb;
 }
 
