@@ -206,18 +206,15 @@ __device__ __forceinline__ unsigned match_any_bits(unsigned amask, unsigned v) {
 }
 
 // Full-warp variant (every lane takes part, no branch around it): bit test, ballot and the select of m / ~m are spelled
-// out in PTX so that each bit costs LOP3.P + VOTE + SEL + LOP3.
+// out in PTX; ptxas then moves the digit's bits into predicates with one R2P and spends VOTE + predicated LOP3 (NOT) +
+// LOP3 (AND) per bit -- half of what it emits for the C++ form above.
 template <int NBITS>
 __device__ __forceinline__ unsigned match_any_full(unsigned v) {
   unsigned peers = 0xffffffffu;
 #pragma unroll
   for (int b = 0; b < NBITS; b++) {
     unsigned m, x;
-#ifdef HS_ASM_NOVOLATILE
-    asm(
-#else
     asm volatile(
-#endif
         "{\n\t"
         ".reg .pred p;\n\t"
         ".reg .b32 t;\n\t"

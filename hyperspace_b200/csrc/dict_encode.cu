@@ -117,28 +117,6 @@ __global__ void k_dict_collect(const unsigned long long* __restrict__ keys, uint
   if (v != kEmpty) out[atomicAdd(counter, 1u)] = v;
 }
 
-// slot -> rank of its key in the sorted dictionary (binary search on the order-preserving encoding)
-// ... stored next to the key in one 16-byte entry, so that a look-up costs ONE 32-byte sector request
-__global__ void k_dict_slot_index(const unsigned long long* __restrict__ keys, uint32_t capacity,
-                                  const unsigned long long* __restrict__ sorted_values, uint32_t ndict, int type,
-                                  uint4* __restrict__ entries) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= capacity) return;
-  const unsigned long long v = keys[s];
-  if (v == kEmpty) {
-    entries[s] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
-    return;
-  }
-  const uint64_t e = sort_encode(type, v);
-  uint32_t lo = 0, hi = ndict;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (sort_encode(type, sorted_values[mid]) < e) lo = mid + 1;
-    else hi = mid;
-  }
-  entries[s] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), lo, 0u);
-}
-
 // ---- all dictionary columns at once ---------------------------------------------------------------------------------
 // k_dict_map_all writes ONE record per row holding the 16-bit indices of every dictionary column (4 or 8 slots), so
 // that k_dict_pack_all fetches all of a row's indices with a single 32-byte L2 sector request instead of one request per
@@ -298,12 +276,6 @@ void launch_dict_build_from_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_
 void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity, unsigned long long* out,
                          uint32_t* counter) {
   k_dict_collect<<<(capacity + 255) / 256, 256, 0, ctx->stream>>>(keys, capacity, out, counter);
-  HS_LAUNCH_CHECK(ctx);
-}
-
-void launch_dict_slot_index(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity,
-                            const unsigned long long* sorted_values, uint32_t ndict, int type, void* entries) {
-  k_dict_slot_index<<<(capacity + 255) / 256, 256, 0, ctx->stream>>>(keys, capacity, sorted_values, ndict, type, (uint4*)entries);
   HS_LAUNCH_CHECK(ctx);
 }
 

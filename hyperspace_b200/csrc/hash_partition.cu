@@ -491,13 +491,8 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
         bin[j] = bin_ids[wbase + j * 32];
         continue;
       }
-#ifdef HS_PART_OLDMOD
-      uint32_t b = (uint32_t)spark_pmod(hasher(wbase + j * 32), (int32_t)bucket_mod.n);
-      if (use_owner) b %= owner_mod.n;
-#else
       uint32_t b = fast_pmod(hasher(wbase + j * 32), bucket_mod);
       if (use_owner) b = fast_mod(b, owner_mod);
-#endif
       bin[j] = b;
     }
   }
@@ -506,27 +501,14 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
   uint16_t* wcnt = cnt + (size_t)warp * nb;
 #pragma unroll
   for (int j = 0; j < kFItems; j++) {
-#ifdef HS_PART_ASM
-    const unsigned peers = match_any_full<BITS>(bin[j]);
-#else
+    // (the PTX-spelled vote sequence that pays off in k_sort_scatter made THIS kernel 50 % slower on B200 -- 16 items per
+    // thread instead of 8 -- so the plain form stays here)
     const unsigned peers = match_any_bits<BITS>(0xffffffffu, bin[j]);
-#endif
     const uint32_t before = __popc(peers & lt);
-#ifdef HS_PART_LEADER
-    uint32_t pre = 0;
-    const int leader = __ffs(peers) - 1;
-    if (before == 0) {
-      pre = wcnt[bin[j]];
-      wcnt[bin[j]] = (uint16_t)(pre + __popc(peers));
-    }
-    pre = __shfl_sync(0xffffffffu, pre, leader);
-    __syncwarp();
-#else
     const uint32_t pre = wcnt[bin[j]];  // every peer reads the same counter (broadcast)
     __syncwarp();
     if (before == 0) wcnt[bin[j]] = (uint16_t)(pre + __popc(peers));
     __syncwarp();
-#endif
     bin[j] |= (pre + before) << 16;
   }
   __syncthreads();
@@ -589,9 +571,7 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
     // (a peer-mapped pointer: these stores go straight over NVLink into the owner's memory)
     void* const* pout = peer_out ? peer_out + (size_t)c * out_world : nullptr;
     if (pc.width == 8) {
-#ifndef HS_PART_NOUNROLL
 #pragma unroll 4
-#endif
       for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
         const uint32_t b = pos_bin[i];
         uint64_t* out = (uint64_t*)(pout ? pout[bin_owner[b]] : pc.out);
@@ -599,9 +579,7 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
       }
     } else if (pc.width == 4) {
       const uint32_t* xb = reinterpret_cast<const uint32_t*>(xbuf);
-#ifndef HS_PART_NOUNROLL
 #pragma unroll 4
-#endif
       for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
         const uint32_t b = pos_bin[i];
         uint32_t* out = (uint32_t*)(pout ? pout[bin_owner[b]] : pc.out);

@@ -226,8 +226,6 @@ void launch_dict_build_from_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_
 void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity, unsigned long long* out,
                          uint32_t* counter);
 // entries: capacity x 16 bytes {key lo, key hi, dictionary index, 0}
-void launch_dict_slot_index(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity,
-                            const unsigned long long* sorted_values, uint32_t ndict, int type, void* entries);
 // all dictionary columns of a table in one map + one pack launch (up to 8 columns per call)
 struct DictMapArgs {
   const void* src[8];

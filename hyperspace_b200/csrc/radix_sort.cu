@@ -176,11 +176,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sort_scatter(const SortTile* __
   uint32_t rank[kItems];
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
-#ifdef HS_SCATTER_NOASM
-    const unsigned peers = match_any_bits<8>(0xffffffffu, bin[j]);
-#else
     const unsigned peers = match_any_full<8>(bin[j]);
-#endif
     const uint32_t before = __popc(peers & lt);
     const uint32_t pre = cnt[bin[j]];   // every peer reads the same counter (broadcast)
     __syncwarp();
