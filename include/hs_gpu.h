@@ -11,6 +11,13 @@
  * The library owns all device memory and every handle it returns until the matching *_free call.  There is no
  * CPU fallback: without a CUDA device hs_init fails with HS_ENODEVICE and nothing else can be called.
  * One hs_ctx drives one GPU on one CUDA stream; use one ctx per host thread / per rank.
+ *
+ * Environment switches (diagnostics and A/B measurements only; results are identical either way):
+ *   HS_EXCHANGE=nccl   multi-GPU: NCCL all-to-all instead of the fused partition + NVLink peer stores
+ *   HS_NO_CARRY=1      decode dictionary-encoded included columns to values instead of carrying 16-bit codes
+ *                      (on several GPUs all ranks must agree)
+ *   HS_FULL_SORT=1     radix-sort every varying key byte instead of the high bytes + tie fix-up
+ *   HS_PART_REHASH=1   partition kernel hashes the keys again instead of reading the stored bucket ids
  */
 #ifndef HS_GPU_H
 #define HS_GPU_H

@@ -119,3 +119,22 @@ def test_create_index_cpu_path(tmp_path):
         assert np.all(k[:-1] <= k[1:])
         seen += len(k)
     assert seen == 10_000
+
+
+def test_division_free_pmod_formula_is_exact():
+    """The GPU computes Spark's pmod(hash, n) without a division (hash_partition.cu: make_mod_const / fast_pmod):
+    shift the signed hash into unsigned range, Lemire fastmod with M = 2^64 // n + 1, take the shift out again modulo n.
+    The restatement below follows that code line by line and must agree with the oracle's pmod for every bucket count."""
+    rng = np.random.default_rng(5)
+    hashes = np.concatenate([rng.integers(-2**31, 2**31, size=2000, dtype=np.int64),
+                             np.array([0, 1, -1, 2**31 - 1, -2**31, 42, -42], dtype=np.int64)])
+    mask64 = (1 << 64) - 1
+    for n in list(range(1, 300)) + [1000, 1023, 1024, 4095, 4096, 65535, 2**31 - 1]:
+        M = (mask64 // n + 1) & mask64          # wraps to 0 for n == 1
+        bias = (1 << 31) % n
+        for h in hashes.tolist():
+            u = (h & 0xffffffff) ^ 0x80000000    # h + 2^31 as an unsigned 32-bit value
+            r = (((M * u) & mask64) * n) >> 64   # fastmod: (u mod n) for every 32-bit u
+            assert r == u % n
+            got = r - bias if r >= bias else r + n - bias
+            assert got == h % n                  # Python's % is already the non-negative (pmod) remainder
