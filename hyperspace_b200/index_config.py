@@ -36,11 +36,45 @@ class CoveringIndexConfig:
                 and sorted(c.lower() for c in self.includedColumns) == sorted(c.lower() for c in o.includedColumns))
 
     def __hash__(self):
-        return hash((self.indexName.lower(), tuple(c.lower() for c in self.indexedColumns)))
+        return hash((self.indexName.lower(), tuple(c.lower() for c in self.indexedColumns),
+                     frozenset(c.lower() for c in self.includedColumns)))
 
     def __repr__(self):
         return (f"[indexName: {self.indexName}; indexedColumns: {','.join(self.indexedColumns)}; "
                 f"includedColumns: {','.join(self.includedColumns)}]")
+
+
+    # ---- builder (CoveringIndexConfig.scala:66-151): IndexConfig.builder().indexName("n").indexBy("a").include("b").create()
+    class Builder:
+        def __init__(self):
+            self._name, self._indexed, self._included = "", [], []
+
+        def indexName(self, indexName: str) -> "CoveringIndexConfig.Builder":
+            if self._name:
+                raise NotImplementedError("Index name is already set.")  # UnsupportedOperationException in the reference
+            if not indexName:
+                raise ValueError("Empty index name is not allowed.")
+            self._name = indexName
+            return self
+
+        def indexBy(self, indexedColumn: str, *indexedColumns: str) -> "CoveringIndexConfig.Builder":
+            if self._indexed:
+                raise NotImplementedError("Indexed columns are already set.")
+            self._indexed = [indexedColumn, *indexedColumns]
+            return self
+
+        def include(self, includedColumn: str, *includedColumns: str) -> "CoveringIndexConfig.Builder":
+            if self._included:
+                raise NotImplementedError("Included columns are already set.")
+            self._included = [includedColumn, *includedColumns]
+            return self
+
+        def create(self) -> "CoveringIndexConfig":
+            return CoveringIndexConfig(self._name, self._indexed, self._included)
+
+    @staticmethod
+    def builder() -> "CoveringIndexConfig.Builder":
+        return CoveringIndexConfig.Builder()
 
 
 IndexConfig = CoveringIndexConfig  # S/index/package.scala:27-33 keeps the old name as an alias

@@ -1,0 +1,359 @@
+"""The reference's data-free unit suites, restated case by case against the Python host layer (CPU only).
+
+Every test names the reference test it follows (``T/`` = ``src/test/scala/com/microsoft/hyperspace/``).  Where the reference
+mocks ``IndexLogManager`` / ``IndexDataManager`` with Mockito, small recording fakes play the same role here.
+"""
+import os
+import uuid
+
+import pytest
+
+from hyperspace_b200 import log_entry as LE
+from hyperspace_b200.hyperspace import CancelAction, VacuumAction, _Action, _StateFlip
+from hyperspace_b200.index_config import CoveringIndexConfig, IndexConfig
+from hyperspace_b200.log_entry import FileIdTracker, FileInfo, HyperspaceException, States
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _entry(state: str) -> LE.IndexLogEntry:
+    e = LE.IndexLogEntry.from_json(open(os.path.join(GOLDEN, "index_log_entry_spec.json")).read())
+    e.state = state
+    return e
+
+
+def _put(index_path, id_, content: str):
+    d = os.path.join(index_path, LE.HYPERSPACE_LOG)
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, str(id_)), "w") as f:
+        f.write(content)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/IndexLogManagerImplTest.scala
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_get_log_returns_none_if_log_not_found(tmp_path):
+    assert LE.IndexLogManager(str(tmp_path / "testPath")).get_log(0) is None
+
+
+def test_get_log_returns_entry_if_id_found(tmp_path):
+    path = str(tmp_path / "testPath")
+    _put(path, 0, _entry("ACTIVE").to_json())
+    assert LE.IndexLogManager(path).get_log(0).to_json() == _entry("ACTIVE").to_json()
+
+
+def test_get_log_fails_if_json_is_not_in_proper_form(tmp_path):
+    path = str(tmp_path / "testPath")
+    js = _entry("ACTIVE").to_json()
+    i = js.index('"source"') + 8
+    _put(path, 0, js[:i] + "\x00" + js[i:])
+    with pytest.raises(HyperspaceException):
+        LE.IndexLogManager(path).get_log(0)
+
+
+def test_write_log_passes_only_if_no_other_file_exists_with_same_name(tmp_path):
+    path = str(tmp_path / str(uuid.uuid4()))
+    assert LE.IndexLogManager(path).write_log(0, _entry("ACTIVE"))
+    assert not LE.IndexLogManager(path).write_log(0, _entry("ACTIVE"))
+
+
+def test_get_latest_id_ignores_non_numeric_names(tmp_path):
+    path = str(tmp_path / str(uuid.uuid4()))
+    for name in ("0", "1", "abc", "20"):
+        _put(path, name, "file contents")
+    assert LE.IndexLogManager(path).get_latest_id() == 20
+
+
+def test_get_latest_stable_log_returns_latest_stable_log(tmp_path):
+    path = str(tmp_path / str(uuid.uuid4()))
+    for id_, state in ((0, "CREATING"), (1, "ACTIVE"), (3, "ACTIVE"), (4, "REFRESHING"), (20, "CANCELLING")):
+        _put(path, id_, _entry(state).to_json())
+    lm = LE.IndexLogManager(path)
+    assert lm.get_latest_stable_log().to_json() == _entry("ACTIVE").to_json()
+    assert lm.get_index_versions(["ACTIVE"]) == [3, 1]
+
+
+def test_get_latest_stable_log_does_not_return_irrelevant_previous_log(tmp_path):
+    path = str(tmp_path / str(uuid.uuid4()))
+    _put(path, 8, _entry("ACTIVE").to_json())
+    _put(path, 10, _entry("VACUUMING").to_json())
+    assert LE.IndexLogManager(path).get_latest_stable_log() is None  # VACUUMING cuts the history off
+    _put(path, 12, _entry("CREATING").to_json())
+    assert LE.IndexLogManager(path).get_latest_stable_log() is None
+
+
+def test_create_latest_stable_log(tmp_path):
+    path = str(tmp_path / str(uuid.uuid4()))
+    _put(path, 0, _entry("ACTIVE").to_json())
+    assert LE.IndexLogManager(path).create_latest_stable_log(0) is True
+    assert os.path.exists(os.path.join(path, LE.HYPERSPACE_LOG, "latestStable"))
+    # ... fails if the log state is not stable
+    path2 = str(tmp_path / str(uuid.uuid4()))
+    _put(path2, 0, _entry("CANCELLING").to_json())
+    assert LE.IndexLogManager(path2).create_latest_stable_log(0) is False
+    assert not os.path.exists(os.path.join(path2, LE.HYPERSPACE_LOG, "latestStable"))
+    # ... fails with an exception if it cannot find a valid log entry
+    path3 = str(tmp_path / str(uuid.uuid4()))
+    _put(path3, 0, "Invalid Log Entry")
+    with pytest.raises(HyperspaceException):
+        LE.IndexLogManager(path3).create_latest_stable_log(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/actions/ActionTest.scala, DeleteActionTest, RestoreActionTest, VacuumActionTest, CancelActionTest
+# ---------------------------------------------------------------------------------------------------------------------
+
+class _RecordingLogManager:
+    """The Mockito mock of the reference's action tests: canned answers, calls recorded."""
+
+    def __init__(self, latest_id=None, log=None, stable=None):
+        self.latest_id, self.log, self.stable = latest_id, log, stable
+        self.calls = []
+
+    def get_latest_id(self):
+        return self.latest_id
+
+    def get_log(self, id_):
+        return self.log
+
+    def get_latest_stable_log(self):
+        return self.stable
+
+    def write_log(self, id_, entry):
+        self.calls.append(("writeLog", id_, entry.state))
+        return True
+
+    def delete_latest_stable_log(self):
+        self.calls.append(("deleteLatestStableLog",))
+        return True
+
+    def create_latest_stable_log(self, id_):
+        self.calls.append(("createLatestStableLog", id_))
+        return True
+
+
+def test_action_run_protocol():
+    """ActionTest 'verify run()': writeLog(0, CREATING), deleteLatestStableLog, writeLog(1, ACTIVE), createLatestStableLog(1)."""
+    lm = _RecordingLogManager()
+
+    class A(_Action):
+        transient_state, final_state = States.CREATING, States.ACTIVE
+
+        def log_entry(self):
+            return _entry(States.DOESNOTEXIST)
+
+    A(lm).run()
+    assert lm.calls == [("writeLog", 0, "CREATING"), ("deleteLatestStableLog",), ("writeLog", 1, "ACTIVE"),
+                        ("createLatestStableLog", 1)]
+
+
+def test_action_fails_when_the_log_slot_is_taken():
+    """Action.scala:66-70: losing the optimistic write means 'Could not acquire proper state'."""
+    lm = _RecordingLogManager()
+    lm.write_log = lambda id_, entry: False
+
+    class A(_Action):
+        transient_state, final_state = States.CREATING, States.ACTIVE
+
+        def log_entry(self):
+            return _entry(States.DOESNOTEXIST)
+
+    with pytest.raises(HyperspaceException, match="Could not acquire proper state"):
+        A(lm).run()
+
+
+def test_delete_action_validate():
+    """DeleteActionTest: passes from ACTIVE, fails otherwise with 'Delete is only supported in ACTIVE state'."""
+    _StateFlip(_RecordingLogManager(log=_entry("ACTIVE")), "ACTIVE", "DELETING", "DELETED", "Delete").validate()
+    with pytest.raises(HyperspaceException, match="Delete is only supported in ACTIVE state"):
+        _StateFlip(_RecordingLogManager(log=_entry("CREATING")), "ACTIVE", "DELETING", "DELETED", "Delete").validate()
+
+
+def test_restore_action_validate():
+    """RestoreActionTest: passes from DELETED, fails otherwise with 'Restore is only supported in DELETED state'."""
+    _StateFlip(_RecordingLogManager(log=_entry("DELETED")), "DELETED", "RESTORING", "ACTIVE", "Restore").validate()
+    with pytest.raises(HyperspaceException, match="Restore is only supported in DELETED state"):
+        _StateFlip(_RecordingLogManager(log=_entry("ACTIVE")), "DELETED", "RESTORING", "ACTIVE", "Restore").validate()
+
+
+class _RecordingDataManager:
+    def __init__(self, versions):
+        self.versions, self.deleted = list(versions), []
+
+    def get_all_version_ids(self):
+        return list(self.versions)
+
+    def get_latest_version_id(self):
+        return max(self.versions) if self.versions else None
+
+    def delete(self, id_):
+        self.deleted.append(id_)
+
+
+def test_vacuum_action_validate_and_op():
+    """VacuumActionTest: validate() passes only from DELETED; op() deletes every data version (0, 1, 2 and nothing else)."""
+    dm = _RecordingDataManager([0, 1, 2])
+    VacuumAction(_RecordingLogManager(log=_entry("DELETED")), dm).validate()
+    with pytest.raises(HyperspaceException):
+        VacuumAction(_RecordingLogManager(log=_entry("CREATING")), dm).validate()
+    VacuumAction(_RecordingLogManager(log=_entry("DELETED")), dm).op()
+    assert sorted(dm.deleted) == [0, 1, 2]
+
+
+@pytest.mark.parametrize("current,stable,final", [
+    ("ACTIVE", "ACTIVE", "ACTIVE"),            # 'Cancel leads to ACTIVE from ACTIVE state'
+    ("REFRESHING", "ACTIVE", "ACTIVE"),        # '... to last stable state from transient state if stable state exists'
+    ("VACUUMING", None, "DOESNOTEXIST"),       # '... to DoesNotExist state from VACUUMING'
+    ("REFRESHING", None, "DOESNOTEXIST"),      # '... to DoesNotExist from transient state if no stable state exists'
+])
+def test_cancel_action_final_state(current, stable, final):
+    lm = _RecordingLogManager(log=_entry(current), stable=_entry(stable) if stable else None)
+    assert CancelAction(lm).final_state == final
+
+
+def test_cancel_action_validate_rejects_stable_states():
+    """CancelAction.scala:44-52."""
+    with pytest.raises(HyperspaceException, match="Cancel\\(\\) is not supported in stable states"):
+        CancelAction(_RecordingLogManager(log=_entry("ACTIVE"), stable=_entry("ACTIVE"))).validate()
+    CancelAction(_RecordingLogManager(log=_entry("REFRESHING"), stable=_entry("ACTIVE"))).validate()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/IndexConfigTest.scala
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_index_config_empty_names_and_columns_are_not_allowed():
+    with pytest.raises(ValueError):
+        IndexConfig("", ["c1"], ["c2"])
+    with pytest.raises(ValueError):
+        IndexConfig.builder().indexName("")
+    with pytest.raises(ValueError):
+        IndexConfig("name", [], ["c1"])
+    with pytest.raises(ValueError):
+        IndexConfig.builder().indexName("name").include("c1").create()
+
+
+def test_index_config_same_column_names_case_insensitive_are_not_allowed():
+    with pytest.raises(ValueError):
+        IndexConfig("name", ["c1", "C1"], ["c2"])
+    with pytest.raises(ValueError):
+        IndexConfig.builder().indexName("name").indexBy("c1", "C1").include("c2").create()
+    with pytest.raises(ValueError):
+        IndexConfig("name", ["c1"], ["C1", "c2"])
+    with pytest.raises(ValueError):
+        IndexConfig.builder().indexName("name").indexBy("c1").include("C1", "c2").create()
+
+
+def test_index_config_equals_and_hash():
+    base = IndexConfig("name", ["c1", "c2"], ["c3", "c4"])
+    assert base != object()
+    assert base != IndexConfig("name", ["c2", "c1"], ["c3", "c4"])       # indexed column order matters
+    assert base != IndexConfig("name", ["c1", "c5"], ["c3", "c4"])
+    assert base != IndexConfig("name", ["c1", "c2"], ["c3", "c5"])
+    assert IndexConfig("Name1", ["c1", "c2"], ["c3", "c4"]) != IndexConfig("Name2", ["c1", "c2"], ["c3", "c4"])
+    assert base == IndexConfig("name", ["c1", "c2"], ["c3", "c4"])
+    assert base == IndexConfig("name", ["c1", "c2"], ["c4", "c3"])       # included columns are a set
+    assert base == IndexConfig("Name", ["C1", "C2"], ["C3", "C4"])       # everything is case-insensitive
+    a, b = IndexConfig("name1", ["c1"], ["c2"]), IndexConfig("name1", ["C1"], ["c2"])
+    assert a == b and hash(a) == hash(b)
+    c, d = IndexConfig("name3", ["c1"], ["c3", "c4"]), IndexConfig("name3", ["C1"], ["c4", "c3"])
+    assert c == d and hash(c) == hash(d)
+
+
+def test_index_config_builder():
+    cfg = IndexConfig.builder().indexName("Name").indexBy("C1", "c2", "C3").include("C4", "c5", "C6").create()
+    assert isinstance(cfg, CoveringIndexConfig)
+    assert cfg.indexName == "Name" and cfg.indexedColumns == ["C1", "c2", "C3"] and cfg.includedColumns == ["C4", "c5", "C6"]
+    # 'Test exception on multiple indexBy, include and index name on IndexConfig builder.'
+    with pytest.raises(NotImplementedError):
+        IndexConfig.builder().indexName("name1").indexName("name2")
+    with pytest.raises(NotImplementedError):
+        IndexConfig.builder().indexName("name").indexBy("c1").indexBy("c2")
+    with pytest.raises(NotImplementedError):
+        IndexConfig.builder().indexName("name").indexBy("c1").include("c3").include("c4")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/FileIdTrackerTest.scala
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_file_id_tracker_new_instance():
+    t = FileIdTracker()
+    assert t.max_file_id == -1 and t.id_to_file() == {}
+    assert t.get_file_id("abc", 123, 555) is None
+    t.add_file_info([])
+    assert t.max_file_id == -1 and t.id_to_file() == {}
+
+
+def test_file_id_tracker_add_file_info():
+    t = FileIdTracker()
+    with pytest.raises(HyperspaceException, match="Cannot add file info with unknown id"):
+        t.add_file_info([FileInfo("abc", 123, 555, LE.UNKNOWN_FILE_ID)])
+    # a conflict raises, but what was added before the conflict stays
+    t = FileIdTracker()
+    t.add_file_info([FileInfo("def", 123, 555, 10)])
+    with pytest.raises(HyperspaceException, match="Adding file info with a conflicting id"):
+        t.add_file_info(sorted([FileInfo("abc", 100, 555, 15), FileInfo("def", 123, 555, 11)], key=lambda f: f.name))
+    assert t.get_file_id("abc", 100, 555) == 15
+    # success: records added, max id raised
+    t = FileIdTracker()
+    t.add_file_info([FileInfo("abc", 123, 555, 10), FileInfo("def", 234, 777, 5)])
+    assert t.get_file_id("abc", 123, 555) == 10 and t.get_file_id("def", 234, 777) == 5 and t.max_file_id == 10
+
+
+def test_file_id_tracker_add_file():
+    t = FileIdTracker()
+    t.add_file_info([FileInfo("abc", 123, 555, 10)])
+    assert t.add_file("abc", 123, 555) == 10 and t.max_file_id == 10  # existing id, max unchanged
+    t = FileIdTracker()
+    assert t.add_file("abc", 123, 555) == 0
+    assert t.add_file("def", 123, 555) == 1
+    assert t.add_file("xyz", 124, 777) == 2
+    assert t.max_file_id == 2
+    assert (t.get_file_id("abc", 123, 555), t.get_file_id("def", 123, 555), t.get_file_id("xyz", 124, 777)) == (0, 1, 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/IndexCollectionManagerTest.scala (the manager's role is played by the Hyperspace facade + PathResolver)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _active_index(system_path, name):
+    e = _entry("ACTIVE")
+    e.name = name
+    lm = LE.IndexLogManager(os.path.join(system_path, name))
+    assert lm.write_log(0, e) and lm.create_latest_stable_log(0)
+
+
+def test_get_indexes_returns_all_indexes(tmp_path):
+    """'getIndexes() returns seq of Indexes': every index directory under the system path is listed with its entry."""
+    from hyperspace_b200.hyperspace import Hyperspace
+    from hyperspace_b200.session import HyperspaceSession
+
+    system_path = str(tmp_path / "indexes")
+    for n in ("idx1", "idx2", "idx3"):
+        _active_index(system_path, n)
+    hs = Hyperspace(HyperspaceSession({"spark.hyperspace.system.path": system_path}))
+    got = hs.indexes()
+    assert [i["name"] for i in got] == ["idx1", "idx2", "idx3"]
+    assert all(i["state"] == "ACTIVE" and i["indexedColumns"] == ["col1"] and i["numBuckets"] == 200 for i in got)
+
+
+@pytest.mark.parametrize("call", [
+    lambda hs: hs.deleteIndex("idx4"),                      # 'delete() throws exception if index is not found'
+    lambda hs: hs.vacuumIndex("idx4"),                      # 'vacuum() ...'
+    lambda hs: hs.restoreIndex("idx4"),                     # 'restore() ...'
+    lambda hs: hs.refreshIndex("idx4", "full"),             # "refresh() with mode = 'full' ..."
+    lambda hs: hs.refreshIndex("idx4", "incremental"),      # "refresh() with mode = 'incremental' ..."
+    lambda hs: hs.optimizeIndex("idx4"),
+    lambda hs: hs.cancel("idx4"),
+    lambda hs: hs.index("idx4"),
+])
+def test_operations_on_a_missing_index_raise(tmp_path, call):
+    from hyperspace_b200.hyperspace import Hyperspace
+    from hyperspace_b200.session import HyperspaceSession
+
+    system_path = str(tmp_path / "indexes")
+    _active_index(system_path, "idx1")
+    with pytest.raises(HyperspaceException, match="could not be found"):
+        call(Hyperspace(HyperspaceSession({"spark.hyperspace.system.path": system_path})))
