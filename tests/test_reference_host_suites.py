@@ -357,3 +357,120 @@ def test_operations_on_a_missing_index_raise(tmp_path, call):
     _active_index(system_path, "idx1")
     with pytest.raises(HyperspaceException, match="could not be found"):
         call(Hyperspace(HyperspaceSession({"spark.hyperspace.system.path": system_path})))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/IndexLogEntryTest.scala -- Content / Directory cases
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _tree(d: LE.Directory):
+    """Order-insensitive shape of a Directory (the reference's directoryEquals compares files and subDirs as sets)."""
+    return (d.name, frozenset((f.name, f.size, f.modifiedTime, f.id) for f in d.files), frozenset(_tree(s) for s in d.subDirs))
+
+
+def _under_root(path: str, leaf: LE.Directory) -> LE.Directory:
+    """createDirectory(path, leaf) of the reference test: wrap `leaf` (the directory at `path`) up to the file-system root."""
+    parts = [p for p in os.path.dirname(os.path.abspath(path)).split("/") if p]
+    cur = leaf
+    for name in reversed(parts):
+        cur = LE.Directory(name, subDirs=[cur])
+    return LE.Directory("file:/", subDirs=[cur])
+
+
+def _touch(p, text="x"):
+    os.makedirs(os.path.dirname(p), exist_ok=True)
+    with open(p, "w") as f:
+        f.write(text)
+    return LE.file_status(p)
+
+
+def test_content_files_lists_all_files():
+    u = LE.UNKNOWN_FILE_ID
+    content = LE.Content(LE.Directory("file:/", subDirs=[LE.Directory(
+        "a", files=[FileInfo("f1", 0, 0, u), FileInfo("f2", 0, 0, u)],
+        subDirs=[LE.Directory("b", files=[FileInfo("f3", 0, 0, u), FileInfo("f4", 0, 0, u)])])]))
+    assert set(content.files) == {"file:/a/f1", "file:/a/f2", "file:/a/b/f3", "file:/a/b/f4"}
+
+
+def test_directory_from_leaf_files_builds_exactly_the_given_tree(tmp_path):
+    test_dir = str(tmp_path / "testDir")
+    f1, f2 = _touch(f"{test_dir}/f1"), _touch(f"{test_dir}/f2")
+    f3, f4 = _touch(f"{test_dir}/nested/f3"), _touch(f"{test_dir}/nested/f4")
+    t = FileIdTracker()
+
+    def info(st):
+        return FileInfo(os.path.basename(st[0]), st[1], st[2], t.add_file(*st))
+
+    expected = _under_root(test_dir, LE.Directory("testDir", [info(f1), info(f2)], [LE.Directory("nested", [info(f3), info(f4)])]))
+    assert _tree(LE.Directory.from_leaf_files([f1, f2, f3, f4], t)) == _tree(expected)
+    assert _tree(LE.Directory.from_directory(test_dir, t)) == _tree(expected)
+    # 'fromLeafFiles api does not include other files in the directory.'
+    expected = _under_root(test_dir, LE.Directory("testDir", [info(f1)], [LE.Directory("nested", [info(f4)])]))
+    assert _tree(LE.Directory.from_leaf_files([f1, f4], t)) == _tree(expected)
+    # 'Content.fromDirectory api creates the correct Content object.'
+    expected = _under_root(f"{test_dir}/nested", LE.Directory("nested", [info(f3), info(f4)]))
+    assert _tree(LE.Content.from_directory(f"{test_dir}/nested", t).root) == _tree(expected)
+    assert _tree(LE.Content.from_leaf_files([f3, f4], t).root) == _tree(expected)
+
+
+def test_directory_from_directory_empty_or_nonexistent(tmp_path):
+    empty = str(tmp_path / "testDir" / "empty")
+    expected = _under_root(empty, LE.Directory("empty"))
+    t = FileIdTracker()
+    assert _tree(LE.Directory.from_directory(empty, t)) == _tree(expected)   # nonexistent
+    os.makedirs(empty)
+    assert _tree(LE.Directory.from_directory(empty, t)) == _tree(expected)   # empty
+
+
+def test_directory_with_a_gap_and_with_multiple_subdirectories(tmp_path):
+    t = FileIdTracker()
+
+    def info(st):
+        return FileInfo(os.path.basename(st[0]), st[1], st[2], t.add_file(*st))
+
+    # testDir/temp/a/f1, testDir/temp/b/c/f2
+    temp = str(tmp_path / "testDir" / "temp")
+    f1, f2 = _touch(f"{temp}/a/f1"), _touch(f"{temp}/b/c/f2")
+    expected = _under_root(temp, LE.Directory("temp", subDirs=[
+        LE.Directory("a", [info(f1)]), LE.Directory("b", subDirs=[LE.Directory("c", [info(f2)])])]))
+    assert _tree(LE.Directory.from_leaf_files([f1, f2], t)) == _tree(expected)
+    assert _tree(LE.Directory.from_directory(temp, t)) == _tree(expected)
+    # testDir/temp2/a/f1, a/b/f2, a/c/f3
+    temp2 = str(tmp_path / "testDir" / "temp2")
+    g1, g2, g3 = _touch(f"{temp2}/a/f1"), _touch(f"{temp2}/a/b/f2"), _touch(f"{temp2}/a/c/f3")
+    expected = _under_root(temp2, LE.Directory("temp2", subDirs=[
+        LE.Directory("a", [info(g1)], [LE.Directory("b", [info(g2)]), LE.Directory("c", [info(g3)])])]))
+    assert _tree(LE.Directory.from_leaf_files([g1, g2, g3], t)) == _tree(expected)
+    assert _tree(LE.Directory.from_directory(f"{temp2}/a", t)) == _tree(expected)
+
+
+def test_directory_path_filter_adds_only_valid_files(tmp_path):
+    """'Directory Test: pathfilter adds only valid files': names starting with '_' or '.' are not data files."""
+    d = str(tmp_path / "testDir")
+    keep = _touch(f"{d}/f1")
+    for hidden in ("_SUCCESS", ".f2.crc", "_committed_1", ".hidden"):
+        _touch(f"{d}/{hidden}")
+    t = FileIdTracker()
+    got = LE.Directory.from_directory(d, t)
+    assert [os.path.basename(f) for f in LE.Content(got).files] == ["f1"]
+    assert t.get_file_id(*keep) == 0 and t.max_file_id == 0
+
+
+def test_directory_merge_cases():
+    F = lambda n, i: FileInfo(n, 100, 100, i)  # noqa: E731
+    d1 = LE.Directory("a", [F("f1", 1), F("f2", 2)])
+    d2 = LE.Directory("a", subDirs=[LE.Directory("b", [F("f3", 3), F("f4", 4)])])
+    expected = LE.Directory("a", [F("f1", 1), F("f2", 2)], [LE.Directory("b", [F("f3", 3), F("f4", 4)])])
+    assert _tree(d1.merge(d2)) == _tree(expected) and _tree(d2.merge(d1)) == _tree(expected)
+    # overlapping directories
+    d1 = LE.Directory("a", [F("f1", 1), F("f2", 2)], [LE.Directory("b", [F("f3", 3)])])
+    d2 = LE.Directory("a", [F("f4", 4)], [LE.Directory("b", [F("f5", 5), F("f6", 6)], [LE.Directory("c", [F("f7", 7)])])])
+    expected = LE.Directory("a", [F("f1", 1), F("f2", 2), F("f4", 4)],
+                            [LE.Directory("b", [F("f3", 3), F("f5", 5), F("f6", 6)], [LE.Directory("c", [F("f7", 7)])])])
+    assert _tree(d1.merge(d2)) == _tree(expected) and _tree(d2.merge(d1)) == _tree(expected)
+    # different names
+    a, b = LE.Directory("a", [F("f1", 1)]), LE.Directory("b", [F("f3", 3)])
+    with pytest.raises(HyperspaceException, match="Merging directories with names a and b failed."):
+        a.merge(b)
+    with pytest.raises(HyperspaceException, match="Merging directories with names b and a failed."):
+        b.merge(a)
