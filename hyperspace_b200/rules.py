@@ -272,34 +272,74 @@ class BucketJoinExec:
 # the rules
 # ---------------------------------------------------------------------------------------------------------------------
 
+def rank_filter_candidates(session, cands: Sequence[Candidate]) -> Optional[Candidate]:
+    """FilterIndexRanker.rank (covering/FilterIndexRanker.scala:43-64): the smallest index wins; under Hybrid Scan the index
+    with the most source bytes in common with the relation wins instead (first one on a tie, like Scala's maxBy/minBy)."""
+    if not cands:
+        return None
+    if session.conf.hybrid_scan_enabled:
+        return max(cands, key=lambda c: c.common_bytes)
+    return min(cands, key=lambda c: c.entry.index_files_size_in_bytes)
+
+
+def rank_join_pairs(session, pairs: Sequence[Tuple[Candidate, Candidate]]) -> List[Tuple[Candidate, Candidate]]:
+    """JoinIndexRanker.rank (covering/JoinIndexRanker.scala:52-90), best pair first: pairs with equal bucket counts come
+    before unequal ones; among equal-bucket pairs more buckets is better -- unless Hybrid Scan is on and the pairs differ in
+    common source bytes, then more common bytes is better; unequal-bucket pairs keep their order (more common bytes first
+    under Hybrid Scan).  Stable, like Scala's sortWith on a Seq."""
+    import functools
+
+    hybrid = session.conf.hybrid_scan_enabled
+
+    def before(p1, p2) -> bool:
+        (l1, r1), (l2, r2) = p1, p2
+        c1, c2 = l1.common_bytes + r1.common_bytes, l2.common_bytes + r2.common_bytes
+        eq1, eq2 = l1.entry.numBuckets == r1.entry.numBuckets, l2.entry.numBuckets == r2.entry.numBuckets
+        if eq1 and eq2:
+            if not hybrid or c1 == c2:
+                return l1.entry.numBuckets > l2.entry.numBuckets
+            return c1 > c2
+        if eq1:
+            return True
+        if eq2:
+            return False
+        return (not hybrid) or c1 > c2
+
+    def cmp(p1, p2) -> int:
+        if before(p1, p2):
+            return -1
+        if before(p2, p1):
+            return 1
+        return 0
+
+    # Scala: indexPairs.sortWith(before) = a stable sort under Ordering.fromLessThan(before), restated literally
+    return sorted(pairs, key=functools.cmp_to_key(cmp))
+
+
 def filter_index_rule(session, lin: Linear) -> Optional[Candidate]:
     """FilterIndexRule: the first indexed column must appear in the filter, and the index must cover every referenced
-    column (FilterIndexRule.scala:60-103); rank = smallest index, or most common bytes under Hybrid Scan
-    (FilterIndexRanker.scala:43-64)."""
+    column (FilterIndexRule.scala:60-103); ranked by rank_filter_candidates."""
     if not lin.predicate:
         return None
     fcols = {c.lower() for c in lin.predicate.columns}
     good = [c for c in candidates_for(session, lin.relation)
             if c.entry.indexedColumns[0].lower() in fcols and _covers(c.entry, lin.referenced())]
-    if not good:
-        return None
-    if session.conf.hybrid_scan_enabled:
-        return max(good, key=lambda c: c.common_bytes)
-    return min(good, key=lambda c: c.entry.index_files_size_in_bytes)
+    return rank_filter_candidates(session, good)
 
 
 def join_index_rule(session, left: Linear, right: Linear, lkey: str, rkey: str):
     """JoinIndexRule: join columns == indexed columns on both sides, each index covers its side's referenced columns
-    (JoinIndexRule.scala:325-513); among compatible pairs prefer equal bucket counts, then more buckets
-    (JoinIndexRanker.scala:52-90)."""
+    (JoinIndexRule.scala:325-513); pairs ranked by rank_join_pairs.  The GPU merge join needs both sides bucketed alike,
+    so only the best EQUAL-bucket pair is used (the reference would re-shuffle one side of an unequal pair; here the
+    query then runs without indexes)."""
     lc = [c for c in candidates_for(session, left.relation)
           if [x.lower() for x in c.entry.indexedColumns] == [lkey.lower()] and _covers(c.entry, left.referenced())]
     rc = [c for c in candidates_for(session, right.relation)
           if [x.lower() for x in c.entry.indexedColumns] == [rkey.lower()] and _covers(c.entry, right.referenced())]
-    pairs = [(a, b) for a in lc for b in rc if a.entry.numBuckets == b.entry.numBuckets]
-    if not pairs:
+    ranked = rank_join_pairs(session, [(a, b) for a in lc for b in rc])
+    if not ranked or ranked[0][0].entry.numBuckets != ranked[0][1].entry.numBuckets:
         return None
-    return max(pairs, key=lambda p: (p[0].entry.numBuckets, p[0].common_bytes + p[1].common_bytes))
+    return ranked[0]
 
 
 def plan_query(session, plan):

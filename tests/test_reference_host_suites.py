@@ -474,3 +474,69 @@ def test_directory_merge_cases():
         a.merge(b)
     with pytest.raises(HyperspaceException, match="Merging directories with names b and a failed."):
         b.merge(a)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/covering/FilterIndexRankerTest.scala, JoinIndexRankerTest.scala
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _cand(name, num_buckets=200, index_file_sizes=(10,), common_bytes=0):
+    from hyperspace_b200 import rules as R
+
+    e = _entry("ACTIVE")
+    e.name, e.numBuckets = name, num_buckets
+    files = [(f"file:/indexes/{name}/v__=0/f{i}.parquet", s, 1) for i, s in enumerate(index_file_sizes)]
+    e.content = LE.Content.from_leaf_files(files, FileIdTracker())
+    return R.Candidate(e, [], [], common_bytes)
+
+
+def _session(hybrid=False):
+    from hyperspace_b200.session import HyperspaceSession
+
+    s = HyperspaceSession()
+    s.conf.set("spark.hyperspace.index.hybridscan.enabled", "true" if hybrid else "false")
+    assert s.conf.hybrid_scan_enabled == hybrid
+    return s
+
+
+def test_filter_ranker_prefers_the_smallest_index_by_default():
+    """'rank() should return the index with smallest size by default.' (ind1: 2 files, ind2: 1 file, ind3: 3 files)"""
+    from hyperspace_b200 import rules as R
+
+    ind1, ind2, ind3 = _cand("ind1", index_file_sizes=(10, 10)), _cand("ind2", index_file_sizes=(10,)), _cand("ind3", index_file_sizes=(10, 10, 10))
+    assert R.rank_filter_candidates(_session(), [ind1, ind2, ind3]) is ind2
+    assert R.rank_filter_candidates(_session(), []) is None
+
+
+def test_filter_ranker_prefers_largest_common_bytes_under_hybrid_scan():
+    """'rank() should return the index with the largest common bytes of source files if HybridScan is enabled.'"""
+    from hyperspace_b200 import rules as R
+
+    ind1, ind2, ind3 = _cand("ind1", common_bytes=2), _cand("ind2", common_bytes=4), _cand("ind3", common_bytes=2)
+    assert R.rank_filter_candidates(_session(hybrid=True), [ind1, ind2, ind3]) is ind2
+    assert R.rank_filter_candidates(_session(hybrid=False), [ind1, ind2, ind3]) is ind1  # equal sizes: the first one
+
+
+def test_join_ranker_prefers_equal_bucket_pairs_then_more_buckets():
+    from hyperspace_b200 import rules as R
+
+    l10, l20, r10, r20 = _cand("l1", 10), _cand("l2", 20), _cand("r1", 10), _cand("r2", 20)
+    # 'rank() should prefer equal-bucket index pairs over unequal-bucket.'
+    assert R.rank_join_pairs(_session(), [(l10, r20), (l20, r20)]) == [(l20, r20), (l10, r20)]
+    # 'rank() should prefer higher number of buckets if multiple equal-bucket index pairs found.'
+    assert R.rank_join_pairs(_session(), [(l10, r10), (l10, r20), (l20, r20)]) == [(l20, r20), (l10, r10), (l10, r20)]
+
+
+def test_join_ranker_prefers_largest_common_bytes_under_hybrid_scan():
+    """'rank() should prefer the largest common bytes if HybridScan is enabled.' (fileList1 = 3 bytes, fileList2 = 2 bytes)"""
+    from hyperspace_b200 import rules as R
+
+    l10, l20 = _cand("l1", 10, common_bytes=3), _cand("l2", 20, common_bytes=2)
+    r10, r20 = _cand("r1", 10, common_bytes=3), _cand("r2", 20, common_bytes=2)
+    pairs = [(l10, r10), (l10, r20), (l20, r20)]
+    assert R.rank_join_pairs(_session(hybrid=False), pairs) == [(l20, r20), (l10, r10), (l10, r20)]
+    assert R.rank_join_pairs(_session(hybrid=True), pairs) == [(l10, r10), (l20, r20), (l10, r20)]
+    # 'If both indexes have the same amount of common bytes, follow the original algorithm.'
+    l10, l20, r10, r20 = (_cand(n, b, common_bytes=3) for n, b in (("l1", 10), ("l2", 20), ("r1", 10), ("r2", 20)))
+    pairs = [(l10, r10), (l10, r20), (l20, r20)]
+    assert R.rank_join_pairs(_session(hybrid=True), pairs) == [(l20, r20), (l10, r10), (l10, r20)]
