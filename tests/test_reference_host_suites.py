@@ -540,3 +540,52 @@ def test_join_ranker_prefers_largest_common_bytes_under_hybrid_scan():
     l10, l20, r10, r20 = (_cand(n, b, common_bytes=3) for n, b in (("l1", 10), ("l2", 20), ("r1", 10), ("r2", 20)))
     pairs = [(l10, r10), (l10, r20), (l20, r20)]
     assert R.rank_join_pairs(_session(hybrid=True), pairs) == [(l20, r20), (l10, r10), (l10, r20)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/FileBasedSignatureProviderTest.scala, IndexSignatureProviderTest.scala, T/util/HashingUtilsTest.scala
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _relation(files):
+    from hyperspace_b200.session import RelationNode
+
+    return RelationNode(["file:/data"], [(f"file:{p}", size, mtime) for size, mtime, p in files], [("c", "long")])
+
+
+def test_md5_hashing_is_a_function_of_its_input():
+    a, b = str(uuid.uuid4()), str(uuid.uuid4())
+    assert LE.md5_hex(a) == LE.md5_hex(a) and LE.md5_hex(a) != LE.md5_hex(b)
+    assert LE.md5_hex("") == "d41d8cd98f00b204e9800998ecf8427e"  # RFC 1321 test vector: commons-codec md5Hex agrees
+
+
+def test_file_based_signature():
+    length, mtime, path, new_path = 100, 10_000, "/data/f1", "/data/f2"
+    sig = lambda files: _relation(files).signature  # noqa: E731
+    assert sig([(length, mtime, path)]) == sig([(length, mtime, path)])                   # same file
+    assert sig([(length, mtime, path)]) != sig([(length + 10, mtime, path)])              # different length
+    assert sig([(length, mtime, path)]) != sig([(length, mtime + 3600, path)])            # different modification time
+    assert sig([(length, mtime, path)]) != sig([(length, mtime, new_path)])               # different path
+    two = [(length, mtime, path), (length + 10, mtime + 3600, new_path)]
+    assert sig(two) == sig(list(two)) == sig(list(reversed(two)))                         # same files (sorted by path first)
+    assert sig([(length, mtime, path), (length + 10, mtime, new_path)]) != sig([(length, mtime, path), (length, mtime + 3600, new_path)])
+
+
+def test_index_signature_combines_file_and_plan_signatures():
+    """IndexSignatureProvider.scala:33-51: md5(fileBasedSignature + planSignature); equal for equal relations only."""
+    from hyperspace_b200 import rules as R
+
+    r1, r1b, r2 = _relation([(100, 1, "/data/f1")]), _relation([(100, 1, "/data/f1")]), _relation([(101, 1, "/data/f1")])
+    assert R.index_signature(r1) == R.index_signature(r1b) != R.index_signature(r2)
+    assert R.index_signature(r1) == LE.md5_hex(LE.md5_hex(r1.signature) + LE.md5_hex("LogicalRelation"))
+
+
+def test_json_round_trip_of_an_index_log_entry():
+    """T/util/JsonUtilsTest.scala 'Test for JsonUtils.': fromJson(toJson(entry)) == entry, for an entry with no relations."""
+    schema = {"type": "struct", "fields": [{"name": n, "type": t, "nullable": True, "metadata": {}}
+                                           for n, t in (("id", "integer"), ("name", "string"), ("school", "string"))]}
+    index = LE.IndexLogEntry(name="myIndex", indexedColumns=["id"], includedColumns=["name", "school"], schema=schema,
+                             numBuckets=10, derived_properties={}, content=LE.Content(LE.Directory("path")), relations=[],
+                             signatures=[LE.Signature("signatureProvider", "dfSignature")], state=States.ACTIVE)
+    back = LE.IndexLogEntry.from_json(index.to_json())
+    assert back == index and back.to_json() == index.to_json()
+    assert back.numBuckets == 10 and back.schema == schema and back.state == "ACTIVE"
