@@ -228,20 +228,31 @@ class DataFrame:
         self.plan = plan
 
     # ---- transformations ------------------------------------------------------------------------------------
+    def _resolve(self, name: str) -> str:
+        """Column names resolve case-insensitively (Spark's default, spark.sql.caseSensitive=false; the reference does the
+        same for index configs in util/ResolverUtils.scala) and come out in the schema's own spelling."""
+        hits = [c for c in self.columns if c.lower() == name.lower()]
+        if not hits:
+            raise LE.HyperspaceException(f"cannot resolve column '{name}' among ({', '.join(self.columns)})")
+        if len(hits) > 1 and name not in hits:
+            raise LE.HyperspaceException(f"Reference '{name}' is ambiguous, could be: {', '.join(hits)}")
+        return name if name in hits else hits[0]
+
     def filter(self, predicate: Predicate) -> "DataFrame":
-        return DataFrame(self.session, FilterNode(self.plan, predicate))
+        resolved = Predicate({self._resolve(c): b for c, b in predicate.bounds.items()})
+        return DataFrame(self.session, FilterNode(self.plan, resolved))
 
     where = filter
 
     def select(self, *columns: str) -> "DataFrame":
         cols = list(columns[0]) if len(columns) == 1 and isinstance(columns[0], (list, tuple)) else list(columns)
-        return DataFrame(self.session, ProjectNode(self.plan, cols))
+        return DataFrame(self.session, ProjectNode(self.plan, [self._resolve(c) for c in cols]))
 
     def join(self, other: "DataFrame", on, how: str = "inner") -> "DataFrame":
         if how != "inner":
             raise LE.HyperspaceException("only inner equi-joins are handled by the GPU path")
         lk, rk = (on, on) if isinstance(on, str) else on
-        return DataFrame(self.session, JoinNode(self.plan, other.plan, lk, rk))
+        return DataFrame(self.session, JoinNode(self.plan, other.plan, self._resolve(lk), other._resolve(rk)))
 
     # ---- introspection ------------------------------------------------------------------------------------
     @property

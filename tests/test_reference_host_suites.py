@@ -589,3 +589,110 @@ def test_json_round_trip_of_an_index_log_entry():
     back = LE.IndexLogEntry.from_json(index.to_json())
     assert back == index and back.to_json() == index.to_json()
     assert back.numBuckets == 10 and back.schema == schema and back.state == "ACTIVE"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/covering/FilterIndexRuleTest.scala (same index set-up: index1 on (c3, c2) incl. c1; index2, index3 on (c4, c2)
+# incl. c1, c3; the transformed plan is recognised by the index name in the scan node)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _filter_rule_fixture(tmp_path):
+    from hyperspace_b200 import rules as R
+    from hyperspace_b200.session import DataFrame, HyperspaceSession, RelationNode
+
+    s = HyperspaceSession({"spark.hyperspace.system.path": str(tmp_path / "indexes")}).enableHyperspace()
+    rel = RelationNode([f"file:{tmp_path}/baseTableLocation"], [(f"file:{tmp_path}/baseTableLocation/f1", 100, 1)],
+                       [("c1", "long"), ("c2", "long"), ("c3", "long"), ("c4", "integer")])  # literals are ints here: the GPU scan takes int keys
+
+    def make(name, indexed, included):
+        e = _entry("ACTIVE")
+        e.name, e.indexedColumns, e.includedColumns, e.id = name, indexed, included, 1
+        e.content = LE.Content.from_leaf_files([(f"file:{tmp_path}/indexes/{name}/v__=0/part-00000-x_00000.c000.parquet", 10, 1)],
+                                               FileIdTracker())
+        e.relations = [LE.Relation(rel.root_paths, LE.Content.from_leaf_files(rel.files, FileIdTracker()),
+                                   {"type": "struct", "fields": []}, "parquet")]
+        e.signatures = [LE.Signature(LE.INDEX_SIGNATURE_PROVIDER, R.index_signature(rel))]
+        lm = LE.IndexLogManager(os.path.join(str(tmp_path / "indexes"), name))
+        assert lm.write_log(1, e) and lm.create_latest_stable_log(1)
+
+    make("index1", ["c3", "c2"], ["c1"])
+    make("index2", ["c4", "c2"], ["c1", "c3"])
+    make("index3", ["c4", "c2"], ["c1", "c3"])
+    return s, DataFrame(s, rel)
+
+
+def test_filter_index_rule_cases(tmp_path):
+    from hyperspace_b200.session import col
+
+    s, df = _filter_rule_fixture(tmp_path)
+    # 'Verify FilterIndex rule is applied correctly.'
+    assert "Name: index1" in df.filter(col("c3") == 7).select("c2", "c3").explain()
+    # '... for case insensitive query.'
+    assert "Name: index1" in df.filter(col("C3") == 7).select("C2", "C3").explain()
+    # '... does not apply if all columns are not covered.' (c4 is not covered by index1; index2/3 do not start with c3)
+    plan = df.filter(col("c3") == 7).select("c2", "c3", "c4").explain()
+    assert "Name: index" not in plan and "GpuSourceScan" in plan
+    # '... does not apply if filter does not contain first indexed column.' (c2 is not a first indexed column)
+    plan = df.filter(col("c2") == 9).select("c2", "c3").explain()
+    assert "Name: index" not in plan
+    # '... is applied when all columns are selected.' (index2 and index3 tie; the first one is taken)
+    assert "Name: index2" in df.filter(col("c4") == 10).explain()
+    # disabled session: untouched plan
+    s.disableHyperspace()
+    assert "Name: index" not in df.filter(col("c4") == 10).explain()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/covering/JoinIndexRuleTest.scala (cases expressible as single-column inner equi-joins, which is what the GPU
+# merge join takes; same five indexes as the reference's fixture)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _join_rule_fixture(tmp_path):
+    from hyperspace_b200 import rules as R
+    from hyperspace_b200.session import DataFrame, HyperspaceSession, RelationNode
+
+    s = HyperspaceSession({"spark.hyperspace.system.path": str(tmp_path / "indexes")}).enableHyperspace()
+
+    def rel(t):
+        return RelationNode([f"file:{tmp_path}/{t}"], [(f"file:{tmp_path}/{t}/f1", 100, 1)],
+                            [(f"{t}c{i}", "long") for i in (1, 2, 3, 4)])
+
+    def make(name, r, indexed, included):
+        e = _entry("ACTIVE")
+        e.name, e.indexedColumns, e.includedColumns, e.id = name, indexed, included, 1
+        e.content = LE.Content.from_leaf_files([(f"file:{tmp_path}/indexes/{name}/v__=0/part-00000-x_00000.c000.parquet", 10, 1)],
+                                               FileIdTracker())
+        e.relations = [LE.Relation(r.root_paths, LE.Content.from_leaf_files(r.files, FileIdTracker()),
+                                   {"type": "struct", "fields": []}, "parquet")]
+        e.signatures = [LE.Signature(LE.INDEX_SIGNATURE_PROVIDER, R.index_signature(r))]
+        lm = LE.IndexLogManager(os.path.join(str(tmp_path / "indexes"), name))
+        assert lm.write_log(1, e) and lm.create_latest_stable_log(1)
+
+    t1, t2 = rel("t1"), rel("t2")
+    make("t1i1", t1, ["t1c1"], ["t1c3"])
+    make("t1i2", t1, ["t1c1", "t1c2"], ["t1c3"])
+    make("t1i3", t1, ["t1c2"], ["t1c3"])
+    make("t2i1", t2, ["t2c1"], ["t2c3"])
+    make("t2i2", t2, ["t2c1", "t2c2"], ["t2c3"])
+    return s, DataFrame(s, t1), DataFrame(s, t2)
+
+
+def test_join_index_rule_cases(tmp_path):
+    s, t1, t2 = _join_rule_fixture(tmp_path)
+    # 'Join rule works if indexes exist and configs are set correctly.': t1i1 and t2i1 (indexed columns == join columns)
+    plan = t1.join(t2, on=("t1c1", "t2c1")).select("t1c3", "t2c3").explain()
+    assert "Name: t1i1" in plan and "Name: t2i1" in plan and "exchange=none" in plan
+    # '... for case insensitive index and query.'
+    plan = t1.join(t2, on=("T1C1", "T2C1")).select("T1C3", "T2C3").explain()
+    assert "Name: t1i1" in plan and "Name: t2i1" in plan
+    # "... does not update plan if index doesn't exist for either table." (t1i3 is keyed on t1c2, nothing is on t2c2)
+    plan = t1.join(t2, on=("t1c2", "t2c2")).select("t1c3", "t2c3").explain()
+    assert "Name:" not in plan and "GpuShuffle" in plan
+    # a column outside the indexes' coverage on one side keeps that side (and so the join) off the indexes
+    plan = t1.join(t2, on=("t1c1", "t2c1")).select("t1c4", "t2c3").explain()
+    assert "Name:" not in plan
+    # only inner joins reach the rule at all
+    with pytest.raises(HyperspaceException):
+        t1.join(t2, on=("t1c1", "t2c1"), how="left")
+    s.disableHyperspace()
+    assert "Name:" not in t1.join(t2, on=("t1c1", "t2c1")).select("t1c3", "t2c3").explain()
