@@ -696,3 +696,60 @@ def test_join_index_rule_cases(tmp_path):
         t1.join(t2, on=("t1c1", "t2c1"), how="left")
     s.disableHyperspace()
     assert "Name:" not in t1.join(t2, on=("t1c1", "t2c1")).select("t1c3", "t2c3").explain()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/index/rules/CandidateIndexCollectorTest.scala 'Verify CandidateIndexCollector for hybrid scan.'
+# (indexes fabricated over a 4-file relation, one with the lineage column and one without; thresholds as in the reference)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_candidate_index_collector_for_hybrid_scan(tmp_path):
+    from hyperspace_b200 import rules as R
+    from hyperspace_b200.session import HyperspaceSession, RelationNode
+
+    base = [(f"file:{tmp_path}/data/f{i}", 100, 10 + i) for i in range(4)]
+
+    def rel(files):
+        return RelationNode([f"file:{tmp_path}/data"], list(files), [("id", "long")])
+
+    s = HyperspaceSession({"spark.hyperspace.system.path": str(tmp_path / "indexes")}).enableHyperspace()
+    for name, lineage in (("index1", True), ("index2", False)):
+        e = _entry("ACTIVE")
+        e.name, e.indexedColumns, e.includedColumns, e.id = name, ["id"], [], 1
+        e.derived_properties = {LE.LINEAGE_PROPERTY: "true" if lineage else "false"}
+        e.content = LE.Content.from_leaf_files([(f"file:{tmp_path}/indexes/{name}/v__=0/part-00000-x_00000.c000.parquet", 10, 1)],
+                                               FileIdTracker())
+        e.relations = [LE.Relation([f"file:{tmp_path}/data"], LE.Content.from_leaf_files(base, FileIdTracker()),
+                                   {"type": "struct", "fields": []}, "parquet")]
+        e.signatures = [LE.Signature(LE.INDEX_SIGNATURE_PROVIDER, R.index_signature(rel(base)))]
+        lm = LE.IndexLogManager(os.path.join(str(tmp_path / "indexes"), name))
+        assert lm.write_log(1, e) and lm.create_latest_stable_log(1)
+
+    def verify(files, hybrid, delete_enabled, expected_names, expected_hybrid_required=None, expected_common=None):
+        s.conf.set("spark.hyperspace.index.hybridscan.enabled", "true" if hybrid else "false")
+        s.conf.set("spark.hyperspace.index.hybridscan.maxAppendedRatio", "0.99")
+        s.conf.set("spark.hyperspace.index.hybridscan.maxDeletedRatio", "0.99" if delete_enabled else "0")
+        cands = R.candidates_for(s, rel(files))
+        assert sorted(c.entry.name for c in cands) == sorted(expected_names)
+        for c in cands:
+            if expected_hybrid_required is not None:
+                assert bool(c.appended or c.deleted_ids) == expected_hybrid_required
+            if expected_common is not None:
+                assert c.common_bytes == expected_common
+
+    # unmodified source: candidates whether Hybrid Scan is enabled or not
+    verify(base, False, False, ["index1", "index2"])
+    verify(base, True, False, ["index1", "index2"], expected_hybrid_required=False, expected_common=400)
+    # Scenario #1: append new files
+    appended = base + [(f"file:{tmp_path}/data/g{i}", 100, 50 + i) for i in range(4)]
+    verify(appended, False, False, [])
+    verify(appended, True, False, ["index1", "index2"], expected_hybrid_required=True, expected_common=400)
+    # Scenario #2: delete one file (needs the lineage column and a non-zero delete threshold)
+    deleted = appended[1:]
+    verify(deleted, False, False, [])
+    verify(deleted, True, False, [])
+    verify(deleted, True, True, ["index1"], expected_hybrid_required=True, expected_common=300)
+    # Scenario #3: replace all files
+    replaced = [(f"file:{tmp_path}/data/h{i}", 100, 90 + i) for i in range(4)]
+    verify(replaced, False, False, [])
+    verify(replaced, True, True, [])
