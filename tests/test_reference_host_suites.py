@@ -753,3 +753,85 @@ def test_candidate_index_collector_for_hybrid_scan(tmp_path):
     replaced = [(f"file:{tmp_path}/data/h{i}", 100, 90 + i) for i in range(4)]
     verify(replaced, False, False, [])
     verify(replaced, True, True, [])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/HyperspaceConfTest.scala 'Test configs that support legacy configs'
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_num_buckets_conf_supports_the_legacy_key():
+    from hyperspace_b200 import session as S
+
+    conf = S.HyperspaceSession().conf
+    legacy, new = S.INDEX_NUM_BUCKETS_LEGACY, S.INDEX_NUM_BUCKETS
+
+    def clear():
+        conf.unset(legacy)
+        conf.unset(new)
+
+    clear()
+    assert conf.num_buckets == S.INDEX_NUM_BUCKETS_DEFAULT == 200   # default if no key is set
+    conf.set(legacy, 10)
+    assert conf.num_buckets == 10                                   # only the legacy key
+    clear()
+    conf.set(new, 5)
+    assert conf.num_buckets == 5                                    # only the new key
+    clear()
+    conf.set(legacy, 10)
+    conf.set(new, 5)
+    assert conf.num_buckets == 5                                    # both: the new key wins
+    assert (legacy, new) == ("spark.hyperspace.index.num.buckets", "spark.hyperspace.index.numBuckets")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/actions/RefreshActionTest.scala (validate() only: no data path involved)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _refresh_fixture(tmp_path, state):
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    from hyperspace_b200.session import HyperspaceSession
+
+    data = tmp_path / "sampleparquet"
+    data.mkdir(exist_ok=True)
+    pq.write_table(pa.table({"clicks": np.arange(10, dtype=np.int32), "imprs": np.arange(10, dtype=np.int64)}), str(data / "part-0.parquet"))
+    files = [LE.file_status(str(data / "part-0.parquet"))]
+    e = _entry(state)
+    e.name, e.indexedColumns, e.includedColumns, e.numBuckets = "index1", ["clicks"], [], 10
+    e.relations = [LE.Relation([LE.to_uri(str(data))], LE.Content.from_leaf_files(files, FileIdTracker()),
+                               {"type": "struct", "fields": []}, "parquet")]
+    lm = _RecordingLogManager(latest_id=None, log=e)
+    dm = _RecordingDataManager([])
+    dm.get_path = lambda id_: str(tmp_path / "indexPath")
+    return HyperspaceSession(), lm, dm, data
+
+
+def _append_source_file(data):
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    pq.write_table(pa.table({"clicks": np.arange(5, dtype=np.int32), "imprs": np.arange(5, dtype=np.int64)}), str(data / "part-1.parquet"))
+
+
+def test_refresh_action_validate(tmp_path):
+    from hyperspace_b200.hyperspace import NoChangesException, RefreshAction
+
+    # 'validate() passes if old index logs are found with ACTIVE state'
+    s, lm, dm, data = _refresh_fixture(tmp_path, "ACTIVE")
+    _append_source_file(data)
+    RefreshAction(s, lm, dm).validate()
+    # 'validate() fails if old index logs found with non-ACTIVE state'
+    s, lm, dm, data = _refresh_fixture(tmp_path, "CREATING")
+    with pytest.raises(HyperspaceException, match="Refresh is only supported in ACTIVE state"):
+        RefreshAction(s, lm, dm).validate()
+    # 'validate() fails if there is no source data change.'
+    (data / "part-1.parquet").unlink()
+    s, lm, dm, data = _refresh_fixture(tmp_path, "ACTIVE")
+    with pytest.raises(NoChangesException, match="Refresh full aborted as no source data changed."):
+        RefreshAction(s, lm, dm).validate()
+    # and run() treats that as a no-op: nothing is written to the log (Action.scala:96-99)
+    RefreshAction(s, lm, dm).run()
+    assert lm.calls == []
