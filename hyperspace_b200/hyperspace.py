@@ -130,9 +130,9 @@ class CreateAction(_DataAction):
                                       "Source plan must be a bare relation (spark.read.parquet).")
         have = {c.lower() for c in self.df.plan.column_names}
         missing = [c for c in self.config.referencedColumns if c.lower() not in have]
-        if missing:
-            raise HyperspaceException(f"Columns '{','.join(missing)}' could not be resolved from available source columns "
-                                      f"'{','.join(self.df.plan.column_names)}'")
+        if missing:  # same first sentence as CreateAction.scala:63-65; the rest tells which columns
+            raise HyperspaceException(f"Index config is not applicable to dataframe schema. Columns '{','.join(missing)}' could "
+                                      f"not be resolved from available source columns '{','.join(self.df.plan.column_names)}'")
         latest = self.log_manager.get_latest_log()
         if latest is not None and latest.state != States.DOESNOTEXIST:
             raise HyperspaceException(f"Another Index with name {self.config.indexName} already exists")

@@ -835,3 +835,39 @@ def test_refresh_action_validate(tmp_path):
     # and run() treats that as a no-op: nothing is written to the log (Action.scala:96-99)
     RefreshAction(s, lm, dm).run()
     assert lm.calls == []
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/actions/CreateActionTest.scala (validate() cases)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_create_action_validate(tmp_path):
+    from hyperspace_b200.hyperspace import CreateAction
+    from hyperspace_b200.session import DataFrame
+
+    s, lm, dm, data = _refresh_fixture(tmp_path, "ACTIVE")
+    df = s.read.parquet(str(data))
+    cfg = IndexConfig("index1", ["clicks"], ["imprs"])
+    lm.get_latest_log = lambda: None
+    # 'validate passes for valid index config and df' / '... if no earlier index logs are found'
+    CreateAction(s, df, cfg, lm, dm).validate()
+    # 'validate() fails if df is not logical plan' (here: anything but a bare file-based relation)
+    with pytest.raises(HyperspaceException, match="Only creating index over HDFS file based scan nodes is supported."):
+        CreateAction(s, df.select("clicks"), IndexConfig("name", ["clicks"]), lm, dm).validate()
+    # "validate() fails if index config doesn't contain columns from df"
+    with pytest.raises(HyperspaceException, match="Index config is not applicable to dataframe schema"):
+        CreateAction(s, df, IndexConfig("name", ["c1"], ["c2"]), lm, dm).validate()
+    # 'validate() passes if old index logs are found with DOESNOTEXIST state'
+    lm.get_latest_log = lambda: _entry("DOESNOTEXIST")
+    CreateAction(s, df, cfg, lm, dm).validate()
+    # 'validate() fails if old index logs found with non-DOESNOTEXIST state'
+    lm.get_latest_log = lambda: _entry("ACTIVE")
+    with pytest.raises(HyperspaceException, match="Another Index with name index1 already exists"):
+        CreateAction(s, df, cfg, lm, dm).validate()
+    # index config columns resolve case-insensitively and the log entry keeps the source's spelling (ResolverUtils)
+    lm.get_latest_log = lambda: None
+    a = CreateAction(s, df, IndexConfig("index1", ["CLICKS"], ["Imprs"]), lm, dm)
+    a.validate()
+    e = a.log_entry()
+    assert e.indexedColumns == ["clicks"] and e.includedColumns == ["imprs"] and e.numBuckets == 200
+    assert isinstance(df, DataFrame)
