@@ -353,7 +353,8 @@ class VacuumOutdatedAction(_Action):
 
     def validate(self) -> None:
         if self.prev is None or self.prev.state != States.ACTIVE:
-            raise HyperspaceException(f"VacuumOutdated is only supported in {States.ACTIVE} state.")
+            cur = self.prev.state if self.prev else States.DOESNOTEXIST
+            raise HyperspaceException(f"VacuumOutdated is only supported in {States.ACTIVE} state. Current state is {cur}.")
 
     def log_entry(self):
         return self.prev.copy()

@@ -871,3 +871,49 @@ def test_create_action_validate(tmp_path):
     e = a.log_entry()
     assert e.indexedColumns == ["clicks"] and e.includedColumns == ["imprs"] and e.numBuckets == 200
     assert isinstance(df, DataFrame)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# T/actions/VacuumOutdatedActionTest.scala
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_vacuum_outdated_action(tmp_path):
+    from hyperspace_b200.hyperspace import VacuumOutdatedAction
+
+    dm0 = _RecordingDataManager([])
+    # validate(): ACTIVE only, with the reference's message
+    VacuumOutdatedAction(_RecordingLogManager(log=_entry("ACTIVE")), dm0).validate()
+    with pytest.raises(HyperspaceException, match="VacuumOutdated is only supported in ACTIVE state. Current state is CREATING."):
+        VacuumOutdatedAction(_RecordingLogManager(log=_entry("CREATING")), dm0).validate()
+
+    def fixture(all_versions, live_files):
+        index_path = str(tmp_path / str(uuid.uuid4()))
+        for v in all_versions:
+            _touch(os.path.join(index_path, f"v__={v}", f"stale-{v}.parquet"))
+        statuses = [_touch(os.path.join(index_path, rel)) for rel in live_files]
+        e = _entry("ACTIVE")
+        e.content = LE.Content.from_leaf_files(statuses, FileIdTracker())
+        return index_path, LE.IndexDataManager(index_path), _RecordingLogManager(log=e)
+
+    # 'op() calls which deletes nothing since every data is up-to-date' (versions 0, 1, 2 all referenced)
+    path, dm, lm = fixture([0, 1, 2], ["v__=0/a.parquet", "v__=1/b.parquet", "v__=2/part-00053-.c000.snappy.parquet"])
+    VacuumOutdatedAction(lm, dm).op()
+    assert dm.get_all_version_ids() == [0, 1, 2]
+    # 'op() calls delete for all outdated data': versions 0 and 1 go, 2 and 3 stay -- minus the files the entry does not list
+    path, dm, lm = fixture([0, 1, 2, 3], ["v__=2/part-00053-.c000.snappy.parquet", "v__=2/part-00027-.c000.snappy.parquet",
+                                           "v__=3/part-00001-.c000.snappy.parquet"])
+    VacuumOutdatedAction(lm, dm).op()
+    assert dm.get_all_version_ids() == [2, 3]
+    assert sorted(os.listdir(os.path.join(path, "v__=2"))) == ["part-00027-.c000.snappy.parquet", "part-00053-.c000.snappy.parquet"]
+    assert os.listdir(os.path.join(path, "v__=3")) == ["part-00001-.c000.snappy.parquet"]
+
+
+def test_index_version_directories_of_a_log_entry():
+    """'versionInfos gets correct version info.': the v__=N directories the entry's content refers to."""
+    u = LE.UNKNOWN_FILE_ID
+    version_dirs = [LE.Directory(f"v__={v}", files=[FileInfo(f"index_{v}", 0, 0, u)]) for v in (4, 5)]
+    e = _entry("ACTIVE")
+    e.content = LE.Content(LE.Directory("file:/", subDirs=[LE.Directory(
+        "a", files=[FileInfo("f1", 0, 0, u), FileInfo("f2", 0, 0, u)],
+        subDirs=[LE.Directory("b", files=[FileInfo("f3", 0, 0, u), FileInfo("f4", 0, 0, u)], subDirs=version_dirs)])]))
+    assert e.index_version_dirs() == [4, 5]
