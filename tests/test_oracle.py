@@ -138,3 +138,14 @@ def test_division_free_pmod_formula_is_exact():
             assert r == u % n
             got = r - bias if r >= bias else r + n - bias
             assert got == h % n                  # Python's % is already the non-negative (pmod) remainder
+
+
+def test_spark_documented_hash_example():
+    """Spark's own documentation of the function the reference buckets with (Murmur3Hash's ExpressionDescription, Spark
+    3.1.1 `sql/catalyst/.../expressions/hash.scala`): SELECT hash('Spark', array(123), 2) -> -1321691492.
+    It exercises hashUnsafeBytes (5 bytes: one 4-byte block + the per-byte tail), hashInt and the seed fold, seed 42."""
+    L = O.lib()
+    h = L.hso_hash_bytes(b"Spark", 5, 42)
+    h = L.hso_hash_int(123, h)   # an array hashes its elements in order, each seeded with the running hash
+    h = L.hso_hash_int(2, h)
+    assert h == -1321691492
