@@ -16,6 +16,8 @@ VECTORS = {
                           "per_partition_key_sums_of_union": [0, 6, 0, 0, 4, 0, 0, 0, 0, 0]},
     "hash_long_seed42": {"0": -1670924195, "1": -1712319331, "2": -797927272, "3": 519220707, "-1": -939490007},
     "pmod200_of_hash_long": {"0": 5, "1": 69, "2": 128, "3": 107, "-1": 193},
+    # Spark 3.1.1 Murmur3Hash ExpressionDescription (the functions documentation): bytes + int + seed fold
+    "spark_docs_hash_example": {"sql": "SELECT hash('Spark', array(123), 2)", "seed": 42, "result": -1321691492},
 }
 
 if __name__ == "__main__":
@@ -23,6 +25,8 @@ if __name__ == "__main__":
     for k, h in VECTORS["hash_long_seed42"].items():
         assert O.lib().hso_hash_long(int(k), 42) == h, k
         assert int(O.bucket_ids([np.array([int(k)], dtype=np.int64)], 200)[0]) == VECTORS["pmod200_of_hash_long"][k]
+    L = O.lib()
+    assert L.hso_hash_int(2, L.hso_hash_int(123, L.hso_hash_bytes(b"Spark", 5, 42))) == VECTORS["spark_docs_hash_example"]["result"]
     with open(os.path.join(os.path.dirname(__file__), "spark_hash_vectors.json"), "w") as f:
         json.dump(VECTORS, f, indent=2)
     print("ok")
