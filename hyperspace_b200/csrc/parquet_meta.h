@@ -59,6 +59,17 @@ struct FileMeta {
   std::vector<std::pair<std::string, std::string>> key_values;
 };
 
+// A list header read from an untrusted footer: every element occupies at least one byte, so a count larger than what is
+// left of the buffer is corrupt (a mutated footer must not make the parser allocate billions of elements).
+inline uint32_t read_list_header(thrift::Reader& r, uint8_t& etype) {
+  const uint32_t n = r.list(etype);
+  if (r.bad || (uint64_t)n > (uint64_t)(r.end - r.p)) {
+    r.bad = true;
+    return 0;
+  }
+  return n;
+}
+
 inline std::string read_string(thrift::Reader& r) {
   uint64_t n = r.varint();
   if ((uint64_t)(r.end - r.p) < n) {
@@ -124,7 +135,7 @@ inline void parse_row_group(thrift::Reader& r, RowGroupMeta& g) {
     if (t == thrift::T_STOP || r.bad) break;
     if (fid == 1 && t == thrift::T_LIST) {
       uint8_t et;
-      uint32_t n = r.list(et);
+      uint32_t n = read_list_header(r, et);
       g.columns.resize(n);
       for (uint32_t i = 0; i < n && !r.bad; i++) parse_column_chunk(r, g.columns[i]);
     } else if (fid == 3) {
@@ -147,7 +158,7 @@ inline FileMeta parse_footer_bytes(const uint8_t* footer, uint32_t flen, const c
     switch (fid) {
       case 2: {
         uint8_t et;
-        uint32_t n = r.list(et);
+        uint32_t n = read_list_header(r, et);
         elems.resize(n);
         for (uint32_t i = 0; i < n && !r.bad; i++) parse_schema_element(r, elems[i]);
         break;
@@ -155,14 +166,14 @@ inline FileMeta parse_footer_bytes(const uint8_t* footer, uint32_t flen, const c
       case 3: fm.num_rows = r.zigzag(); break;
       case 4: {
         uint8_t et;
-        uint32_t n = r.list(et);
+        uint32_t n = read_list_header(r, et);
         fm.row_groups.resize(n);
         for (uint32_t i = 0; i < n && !r.bad; i++) parse_row_group(r, fm.row_groups[i]);
         break;
       }
       case 5: {
         uint8_t et;
-        uint32_t n = r.list(et);
+        uint32_t n = read_list_header(r, et);
         for (uint32_t i = 0; i < n && !r.bad; i++) {
           std::string k, v;
           int16_t f2 = 0;

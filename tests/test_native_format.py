@@ -27,6 +27,21 @@ def roundtrip(tmp_path_factory):
     return out, report
 
 
+def test_footer_reader_rejects_mutated_footers_without_crashing(roundtrip, tmp_path):
+    """20 000 deterministic mutations of a valid footer (byte flips, false lengths, truncations, 0xff / 0x00 runs): the
+    engine's reader must return or raise its own error every time -- no crash, no hang, no allocation sized by an untrusted
+    count (a list count larger than the bytes that are left is corrupt by definition)."""
+    out, _ = roundtrip
+    exe = str(tmp_path / "footer_fuzz")
+    subprocess.check_call(["nvcc", "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "native", "footer_fuzz.cu")])
+    report = subprocess.run([exe, out, "20000"], text=True, capture_output=True, timeout=120)
+    assert report.returncode == 0, report.stdout + report.stderr
+    fields = dict(kv.split("=") for kv in report.stdout.split())
+    assert int(fields["rounds"]) == 20000 and int(fields["rejected"]) + int(fields["accepted"]) == 20000
+    assert int(fields["rejected"]) > 5000  # most mutations are detected as corrupt
+
+
 def test_engine_footer_reader_parses_what_the_engine_writer_wrote(roundtrip):
     _, report = roundtrip
     lines = report.splitlines()
