@@ -422,6 +422,16 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   Buf<PageDesc> d_pages(ctx, std::max<int64_t>(1, n_pages));
   HS_CUDA(cudaMemcpyAsync(d_offsets.get(), offsets.data(), sizeof(int64_t) * n_chunks, cudaMemcpyHostToDevice, ctx->stream));
   launch_walk_pages(ctx, d_chunks.get(), n_chunks, d_counts.get(), d_offsets.get(), d_pages.get(), d_flags.get(), 1);
+  {  // a chunk whose page headers do not add up must not reach the decoder: its pages would write outside the columns
+    uint32_t walk_error = 0;
+    HS_CUDA(cudaMemcpyAsync(&walk_error, d_flags.get(), sizeof walk_error, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (walk_error) {
+      const uint32_t code = walk_error >> 24, detail = walk_error & 0xffffffu;
+      fail(code == DERR_COMPRESSED ? HS_EUNSUPPORTED : HS_EFORMAT, "Parquet page walk failed: %s (column chunk %u)",
+           decode_error_text(code), detail);
+    }
+  }
   // ---- snappy: decompress the compressed page bodies (and dictionary pages) into a scratch buffer, repoint the pages ----
   Buf<uint8_t> d_scratch;
   if (any_compressed && n_pages > 0) {
