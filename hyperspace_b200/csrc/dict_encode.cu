@@ -285,7 +285,8 @@ void launch_dict_pack(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const 
   KernelScope _ks(ctx, "k_dict_pack");
   if (ntiles == 0) return;
   const size_t smem = (size_t)pack_args.ncols * (kSortTile / 8 * 16);
-  static bool attr = false;
+  static DeviceOnce attr_once;
+  bool& attr = attr_once(ctx->device);
   if (!attr) {
     HS_CUDA(cudaFuncSetAttribute(k_dict_pack_all<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (kSortTile / 8 * 16)));
     HS_CUDA(cudaFuncSetAttribute(k_dict_pack_all<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (kSortTile / 8 * 16)));

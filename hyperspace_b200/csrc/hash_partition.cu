@@ -244,7 +244,8 @@ void launch_bucket_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t
   if (nrows == 0) return;
   const int64_t ntiles = ceil_div(nrows, kPartTile);
   const size_t smem = (size_t)kWarps * num_buckets * sizeof(uint16_t);
-  static bool attr = false;
+  static DeviceOnce attr_once;
+  bool& attr = attr_once(ctx->device);
   if (!attr) {
     HS_CUDA(cudaFuncSetAttribute(k_bucket_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kMaxBuckets * 2));
     HS_CUDA(cudaFuncSetAttribute(k_partition_dest, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kMaxBuckets * 2));
@@ -683,7 +684,8 @@ template <int BITS, int KT, bool PEER>
 static void launch_partition_rows_t(hs_ctx* ctx, const PartitionLaunch& a) {
   const int nb = a.owner_mod > 0 ? a.owner_mod : a.num_buckets;
   const int64_t ntiles = ceil_div(a.nrows, FusedCfg<PEER>::kTile);
-  static bool attr = false;  // one per instantiation
+  static DeviceOnce attr_once;  // one per instantiation
+  bool& attr = attr_once(ctx->device);
   if (!attr) {
     HS_CUDA(cudaFuncSetAttribute(k_partition_rows<BITS, KT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)fused_smem_bytes<PEER>(kFusedMaxBins)));

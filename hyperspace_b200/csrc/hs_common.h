@@ -208,6 +208,13 @@ struct StageTimer {
 };
 
 // RAII: brackets the kernel launches issued in its scope with CUDA events on the ctx stream when profiling is on.
+// Per-device "done once" flag for settings that live in a device's context (cudaFuncSetAttribute): one process may hold
+// contexts on several GPUs (one hs_ctx per host thread), and an attribute set for device 0 says nothing about device 1.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool& operator()(int device) { return done[device & 63]; }
+};
+
 struct KernelScope {
   hs_ctx* ctx;
   size_t idx = (size_t)-1;

@@ -640,7 +640,8 @@ void launch_decode_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, co
                          uint32_t* col_has_nulls, const int64_t* row_window, uint32_t* d_error) {
   KernelScope _ks(ctx, "k_decode_pages");
   if (n_pages == 0) return;
-  static bool attr_set = false;
+  static DeviceOnce attr_set_once;
+  bool& attr_set = attr_set_once(ctx->device);
   if (!attr_set) {
     HS_CUDA(cudaFuncSetAttribute(k_decode_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared)));
     attr_set = true;

@@ -309,7 +309,8 @@ void run_pass(hs_ctx* ctx, SortPlan* plan, const SortChunk* chunks, int64_t nchu
   k_seg_apply<<<(unsigned)nchunks, 1024, 0, ctx->stream>>>(chunks, plan->tile_hist.get(), plan->tile_dst.get(), chunk_sums);
   HS_LAUNCH_CHECK(ctx);
   delete _scan;
-  static bool attr = false;  // one per (Src, Digit) instantiation
+  static DeviceOnce attr_once;  // one per (Src, Digit) instantiation
+  bool& attr = attr_once(ctx->device);
   if (!attr) {
     HS_CUDA(cudaFuncSetAttribute(k_sort_scatter<Src, Digit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(ScatterShared)));
