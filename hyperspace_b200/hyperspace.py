@@ -89,10 +89,13 @@ class _DataAction(_Action):
     def _build_entry(self, name, indexed, included, num_buckets, lineage: bool, rel: RelationNode, content: LE.Content,
                      properties: Optional[Dict[str, str]] = None, update: Optional[LE.Update] = None) -> LE.IndexLogEntry:
         type_of = {n.lower(): t for n, t in rel.schema}
-        inc = list(included)
-        if lineage and LE.DATA_FILE_NAME_ID not in inc:
-            inc = inc + [LE.DATA_FILE_NAME_ID]
+        # includedColumns stays the user's resolved columns; the lineage column is recorded only in `schema`, as
+        # CoveringIndex.createIndexData does (index/covering/CoveringIndex.scala:152-186) -- a reference reader of this log
+        # would otherwise try to resolve `_data_file_id` against the source on refresh
+        inc = [c for c in included if c != LE.DATA_FILE_NAME_ID]
         schema = [(c, type_of.get(c.lower(), "long")) for c in list(indexed) + inc]
+        if lineage:
+            schema.append((LE.DATA_FILE_NAME_ID, "long"))
         source_content = LE.Content.from_leaf_files(rel.files, self.tracker)
         relation = LE.Relation(rel.root_paths, source_content, _struct_type(rel.schema), "parquet", {}, update)
         derived = {LE.LINEAGE_PROPERTY: str(lineage).lower(), LE.HAS_PARQUET_AS_SOURCE_FORMAT_PROPERTY: "true",
@@ -292,7 +295,12 @@ class OptimizeAction(_DataAction):
 
     def op(self) -> None:
         files = [(f.name, f.size, f.modifiedTime) for f in self.to_optimize]
-        self._write(files, self.prev.indexedColumns, self.prev.includedColumns, self.prev.numBuckets, False, self.index_data_path)
+        # index files of a lineage index carry `_data_file_id` (it is in the schema, not in includedColumns): re-read it as a
+        # plain column so that the compacted files keep it
+        inc = [c for c in self.prev.includedColumns if c != LE.DATA_FILE_NAME_ID]
+        if self.prev.has_lineage_column:
+            inc = inc + [LE.DATA_FILE_NAME_ID]
+        self._write(files, self.prev.indexedColumns, inc, self.prev.numBuckets, False, self.index_data_path)
 
     def log_entry(self):
         new_content = LE.Content.from_directory(self.index_data_path, LE.FileIdTracker())
@@ -364,13 +372,16 @@ class VacuumOutdatedAction(_Action):
         for v in self.data_manager.get_all_version_ids():
             if v not in used_versions:
                 self.data_manager.delete(v)
-        live = {LE.from_uri(f) for f in self.prev.index_files}
+        # both sides canonical: the log holds abspath-normalised URIs, the data manager builds its paths from the raw
+        # spark.hyperspace.system.path (relative, '//', trailing '/', '..', symlinks) -- comparing the two as strings
+        # once classified every live file as outdated
+        live = {os.path.realpath(LE.from_uri(f)) for f in self.prev.index_files}
         for v in used_versions:
             d = self.data_manager.get_path(v)
             if os.path.isdir(d):
                 for fn in os.listdir(d):
                     p = os.path.join(d, fn)
-                    if not fn.startswith(("_", ".")) and p not in live:
+                    if not fn.startswith(("_", ".")) and os.path.realpath(p) not in live:
                         os.remove(p)
 
 

@@ -69,8 +69,18 @@ def _candidate(session, rel: RelationNode, e: LE.IndexLogEntry) -> Optional[Cand
     cur = {LE.FileInfo(u, s, m) for u, s, m in rel.files}
     indexed = {f: f.id for f in e.source_file_infos}
     # quick refresh bookkeeping: files recorded in Update are already known appended / deleted
-    if any(s.value == index_signature(rel) for s in e.signatures) and not e.appended_files and not e.deleted_files:
+    sig_match = any(s.value == index_signature(rel) for s in e.signatures)
+    if sig_match and not e.appended_files and not e.deleted_files:
         return Candidate(e, [], [], sum(f.size for f in indexed))
+    if sig_match:
+        # refreshIndex(mode = "quick") recorded the appended / deleted source files in Update and re-signed the entry: the
+        # reference then applies the Hybrid Scan transformation from those recorded files whether or not
+        # spark.hyperspace.index.hybridscan.enabled is set (CoveringIndexRuleUtils.scala:68-84, RefreshQuickAction.scala:32-80)
+        recorded_deleted = e.deleted_files
+        if not recorded_deleted or e.has_lineage_column:
+            common = cur & set(indexed)
+            return Candidate(e, sorted((f.name, f.size, f.modifiedTime) for f in e.appended_files),
+                             sorted(f.id for f in recorded_deleted), sum(f.size for f in common))
     if not session.conf.hybrid_scan_enabled:
         return None
     common = cur & set(indexed)
@@ -332,10 +342,15 @@ def join_index_rule(session, left: Linear, right: Linear, lkey: str, rkey: str):
     (JoinIndexRule.scala:325-513); pairs ranked by rank_join_pairs.  The GPU merge join needs both sides bucketed alike,
     so only the best EQUAL-bucket pair is used (the reference would re-shuffle one side of an unequal pair; here the
     query then runs without indexes)."""
+    # (an index whose source lost files would need the lineage NOT-IN filter below the merge join, which the GPU join does
+    # not apply: such a candidate is skipped and the query falls back to the next pair / to no index, as the fail-open rule
+    # layer of the reference would -- ApplyHyperspace.scala:57-64)
     lc = [c for c in candidates_for(session, left.relation)
-          if [x.lower() for x in c.entry.indexedColumns] == [lkey.lower()] and _covers(c.entry, left.referenced())]
+          if [x.lower() for x in c.entry.indexedColumns] == [lkey.lower()] and _covers(c.entry, left.referenced())
+          and not c.deleted_ids]
     rc = [c for c in candidates_for(session, right.relation)
-          if [x.lower() for x in c.entry.indexedColumns] == [rkey.lower()] and _covers(c.entry, right.referenced())]
+          if [x.lower() for x in c.entry.indexedColumns] == [rkey.lower()] and _covers(c.entry, right.referenced())
+          and not c.deleted_ids]
     ranked = rank_join_pairs(session, [(a, b) for a in lc for b in rc])
     if not ranked or ranked[0][0].entry.numBuckets != ranked[0][1].entry.numBuckets:
         return None

@@ -17,6 +17,7 @@ files the native call reads -- the same decision FilterIndexRule / JoinIndexRule
 """
 from __future__ import annotations
 
+import math
 import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -111,23 +112,27 @@ class Column:
     def __init__(self, name: str):
         self.name = name
 
+    # integer key columns: a non-integral literal is rounded in the direction that keeps the predicate's meaning
+    # (k < 1.5  <=>  k <= 1;  k >= 1.5  <=>  k >= 2)
     def __ge__(self, v):
-        return Predicate({self.name: (int(v), None)})
+        return Predicate({self.name: (math.ceil(v), None)})
 
     def __gt__(self, v):
-        return Predicate({self.name: (int(v) + 1, None)})
+        return Predicate({self.name: (math.floor(v) + 1, None)})
 
     def __le__(self, v):
-        return Predicate({self.name: (None, int(v))})
+        return Predicate({self.name: (None, math.floor(v))})
 
     def __lt__(self, v):
-        return Predicate({self.name: (None, int(v) - 1)})
+        return Predicate({self.name: (None, math.ceil(v) - 1)})
 
     def __eq__(self, v):  # noqa: A003
+        if v != math.floor(v):
+            return Predicate({self.name: (1, 0)})  # an integer never equals a fraction: empty range
         return Predicate({self.name: (int(v), int(v))})
 
     def between(self, lo, hi):
-        return Predicate({self.name: (int(lo), int(hi))})
+        return Predicate({self.name: (math.ceil(lo), math.floor(hi))})
 
 
 def col(name: str) -> Column:
