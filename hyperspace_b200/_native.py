@@ -78,6 +78,17 @@ class JoinSpec(C.Structure):
                 ("right_columns", C.POINTER(C.c_char_p)), ("n_right_columns", C.c_int32)]
 
 
+class VerifyReport(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("bucket_mismatches", C.c_int64), ("order_violations", C.c_int64),
+                ("row_checksum", C.c_uint64), ("column_checksum", C.c_uint64 * 16), ("n_columns", C.c_int32),
+                ("reserved", C.c_int32)]
+
+    def as_dict(self) -> Dict[str, object]:
+        return {"rows": self.rows, "bucket_mismatches": self.bucket_mismatches, "order_violations": self.order_violations,
+                "row_checksum": int(self.row_checksum),
+                "column_checksum": [int(self.column_checksum[i]) for i in range(self.n_columns)]}
+
+
 class HostColumn(C.Structure):
     _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("data", C.c_void_p), ("valid", C.c_void_p)]
 
@@ -88,6 +99,8 @@ EXPORTED_SYMBOLS = [
     "hs_comm_unique_id", "hs_comm_init", "hs_create_index", "hs_result_num_files", "hs_result_file", "hs_result_free",
     "hs_filter_scan", "hs_bucket_join", "hs_batch_num_rows", "hs_batch_num_columns", "hs_batch_column", "hs_batch_free",
     "hs_k_bucket_ids", "hs_k_sort_perm", "hs_synth_table",
+    "hs_stage_sources", "hs_staged_num_files", "hs_staged_file", "hs_staged_wait", "hs_staged_free",
+    "hs_create_index_async", "hs_pending_wait", "hs_pending_cancel", "hs_verify_index", "hs_synth_checksum",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -152,6 +165,27 @@ def load_library() -> C.CDLL:
     L.hs_synth_table.restype = C.c_int
     L.hs_synth_table.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.POINTER(C.c_void_p), *err]
+    L.hs_stage_sources.restype = C.c_int
+    L.hs_stage_sources.argtypes = [C.c_void_p, C.POINTER(SourceFile), C.c_int32, C.POINTER(C.c_void_p), *err]
+    L.hs_staged_num_files.restype = C.c_int32
+    L.hs_staged_num_files.argtypes = [C.c_void_p]
+    L.hs_staged_file.restype = C.c_int
+    L.hs_staged_file.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SourceFile)]
+    L.hs_staged_wait.restype = C.c_int
+    L.hs_staged_wait.argtypes = [C.c_void_p]
+    L.hs_staged_free.restype = None
+    L.hs_staged_free.argtypes = [C.c_void_p]
+    L.hs_create_index_async.restype = C.c_int
+    L.hs_create_index_async.argtypes = [C.c_void_p, C.POINTER(IndexSpec), C.POINTER(C.c_void_p), *err]
+    L.hs_pending_wait.restype = C.c_int
+    L.hs_pending_wait.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(Stats), *err]
+    L.hs_pending_cancel.restype = None
+    L.hs_pending_cancel.argtypes = [C.c_void_p]
+    L.hs_verify_index.restype = C.c_int
+    L.hs_verify_index.argtypes = [C.c_void_p, C.POINTER(SourceFile), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_char_p), C.c_int32,
+                                  C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.POINTER(VerifyReport), *err]
+    L.hs_synth_checksum.restype = C.c_int
+    L.hs_synth_checksum.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.POINTER(VerifyReport), *err]
     if L.hs_abi_version() != 1:
         raise HyperspaceGpuError(HS_EINVAL, f"ABI version mismatch: library {L.hs_abi_version()}, binding 1")
     _lib = L
@@ -246,6 +280,68 @@ class IndexResult:
     def free(self) -> None:
         if self._h:
             load_library().hs_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Staged:
+    """Source file images on their way to device memory (hs_stage_sources); ``as_sources()`` feeds create_index[_async]."""
+
+    def __init__(self, ctx: "Context", handle: int, keep):
+        self._ctx, self._h, self._keep = ctx, handle, keep
+        ctx._results.add(self)
+        L = load_library()
+        self.files: List[FileImage] = []
+        for i in range(L.hs_staged_num_files(handle)):
+            sf = SourceFile()
+            L.hs_staged_file(handle, i, C.byref(sf))
+            self.files.append(FileImage(path=sf.path.decode() if sf.path else None, data=sf.data, size=sf.size,
+                                        file_id=sf.file_id, on_device=True))
+
+    def as_sources(self) -> List[FileImage]:
+        return list(self.files)
+
+    def wait(self) -> None:
+        if self._h and load_library().hs_staged_wait(self._h) != HS_OK:
+            raise HyperspaceGpuError(HS_ECUDA, "hs_staged_wait failed")
+
+    def free(self) -> None:
+        if self._h:
+            load_library().hs_staged_free(self._h)
+            self._h = None
+            self._keep = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Pending:
+    """A createIndex whose index files are draining to the host (hs_create_index_async); ``wait()`` yields the result."""
+
+    def __init__(self, ctx: "Context", handle: int, output: int, keep):
+        self._ctx, self._h, self.output, self._keep = ctx, handle, output, keep
+        ctx._results.add(self)
+
+    def wait(self) -> Tuple[IndexResult, Dict[str, float]]:
+        assert self._h, "already waited for"
+        res, st = C.c_void_p(), Stats()
+        err = C.create_string_buffer(1024)
+        h, self._h = self._h, None
+        _check(load_library().hs_pending_wait(h, C.byref(res), C.byref(st), err, len(err)), err)
+        self._keep = None
+        return IndexResult(self._ctx, res.value, self.output), st.as_dict()
+
+    def free(self) -> None:
+        if self._h:
+            load_library().hs_pending_cancel(self._h)
             self._h = None
 
     def __del__(self):
@@ -365,6 +461,58 @@ class Context:
         self.rank, self.world = rank, world
 
     # ---- write side ----------------------------------------------------------------------------------
+    def stage_sources(self, files: Sequence[FileImage]) -> Staged:
+        """Starts copying host / file-system Parquet images to the device on the ctx's H2D copy stream."""
+        src, keep = _source_array(files)
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        _check(load_library().hs_stage_sources(self._h, src, len(files), C.byref(h), err, len(err)), err)
+        return Staged(self, h.value, (src, keep, list(files)))
+
+    def create_index_async(self, files: Sequence[FileImage], indexed: Sequence[str], included: Sequence[str], num_buckets: int,
+                           **kw) -> Pending:
+        """create_index up to the encoded files in device memory; the device->host copy continues on the D2H copy stream."""
+        spec, keep = self._index_spec(files, indexed, included, num_buckets, **kw)
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        _check(load_library().hs_create_index_async(self._h, C.byref(spec), C.byref(h), err, len(err)), err)
+        return Pending(self, h.value, spec.output, keep)
+
+    def verify_index(self, files: Sequence[FileImage], buckets: Sequence[int], indexed: Sequence[str], included: Sequence[str],
+                     num_buckets: int) -> Dict[str, object]:
+        src, keep = _source_array(files)
+        ic, nc = _cstr_array(indexed), _cstr_array(included)
+        bk = (C.c_int32 * max(1, len(buckets)))(*buckets)
+        rep = VerifyReport()
+        err = C.create_string_buffer(1024)
+        _check(load_library().hs_verify_index(self._h, src, bk, len(files), ic, len(indexed), nc, len(included), num_buckets,
+                                              C.byref(rep), err, len(err)), err)
+        return rep.as_dict()
+
+    def synth_checksum(self, first_row: int, nrows: int, ncols: int = 5) -> Dict[str, object]:
+        rep = VerifyReport()
+        err = C.create_string_buffer(1024)
+        _check(load_library().hs_synth_checksum(self._h, first_row, nrows, ncols, C.byref(rep), err, len(err)), err)
+        return rep.as_dict()
+
+    def _index_spec(self, files, indexed, included, num_buckets, out_dir=None, output=HS_OUT_FILES, job_uuid=None,
+                    save_mode=HS_SAVE_OVERWRITE, lineage=False, deleted_file_ids=(), rows_per_page=0, rows_per_row_group=0,
+                    dictionary=True):
+        src, keep = _source_array(files)
+        ic, nc = _cstr_array(indexed), _cstr_array(included)
+        spec = IndexSpec()
+        spec.files, spec.n_files = src, len(files)
+        spec.indexed_columns, spec.n_indexed = ic, len(indexed)
+        spec.included_columns, spec.n_included = nc, len(included)
+        spec.num_buckets, spec.save_mode, spec.output, spec.lineage = num_buckets, save_mode, output, 1 if lineage else 0
+        spec.out_dir = out_dir.encode() if out_dir else None
+        spec.job_uuid = job_uuid.encode() if job_uuid else None
+        spec.rows_per_page, spec.rows_per_row_group = rows_per_page, rows_per_row_group
+        dl = (C.c_int64 * max(1, len(deleted_file_ids)))(*deleted_file_ids)
+        spec.deleted_file_ids, spec.n_deleted_file_ids = dl, len(deleted_file_ids)
+        spec.disable_dictionary = 0 if dictionary else 1
+        return spec, (src, keep, ic, nc, dl)
+
     def create_index(self, files: Sequence[FileImage], indexed: Sequence[str], included: Sequence[str], num_buckets: int,
                      out_dir: Optional[str] = None, output: int = HS_OUT_FILES, job_uuid: Optional[str] = None,
                      save_mode: int = HS_SAVE_OVERWRITE, lineage: bool = False, deleted_file_ids: Sequence[int] = (),

@@ -170,6 +170,24 @@ std::vector<std::string> names_of(const char* const* a, int na, const char* cons
   return v;
 }
 
+// HS_OUT_FILES: the file images in res->h_arena become <out_dir>/<name>, all or nothing
+void write_result_files(hs_index_result* res, const std::string& dir, int save_mode) {
+  if (dir.empty()) fail(HS_EINVAL, "HS_OUT_FILES needs out_dir");
+  mkdirs(dir);
+  if (save_mode == HS_SAVE_OVERWRITE) remove_data_files(dir);
+  std::vector<std::string> written;
+  try {
+    for (const OutFile& f : res->files) {
+      write_file_atomic(dir, f.name, res->h_arena.get() + f.offset, f.size);
+      written.push_back(dir + "/" + f.name);
+    }
+  } catch (...) {
+    for (auto& p : written) unlink(p.c_str());  // all-or-nothing
+    throw;
+  }
+  res->h_arena.release();
+}
+
 void finish_result(hs_ctx* ctx, EncodedFiles& enc, int output, const char* out_dir, int save_mode, hs_index_result* res,
                    hs_stats* st) {
   res->ctx = ctx;
@@ -187,23 +205,22 @@ void finish_result(hs_ctx* ctx, EncodedFiles& enc, int output, const char* out_d
   t.stop();
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
   st->ms_d2h += t.ms();
-  if (output == HS_OUT_FILES) {
-    if (!out_dir) fail(HS_EINVAL, "HS_OUT_FILES needs out_dir");
-    const std::string dir(out_dir);
-    mkdirs(dir);
-    if (save_mode == HS_SAVE_OVERWRITE) remove_data_files(dir);
-    std::vector<std::string> written;
-    try {
-      for (const OutFile& f : res->files) {
-        write_file_atomic(dir, f.name, res->h_arena.get() + f.offset, f.size);
-        written.push_back(dir + "/" + f.name);
-      }
-    } catch (...) {
-      for (auto& p : written) unlink(p.c_str());  // all-or-nothing
-      throw;
+  if (output == HS_OUT_FILES) write_result_files(res, out_dir ? out_dir : "", save_mode);
+}
+
+void read_file_into(const char* path, uint8_t* dst, uint64_t size) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) fail(HS_EIO, "cannot open %s", path);
+  uint64_t got = 0;
+  while (got < size) {
+    ssize_t r = read(fd, dst + got, size - got);
+    if (r <= 0) {
+      close(fd);
+      fail(HS_EIO, "short read on %s", path);
     }
-    res->h_arena.release();
+    got += (uint64_t)r;
   }
+  close(fd);
 }
 
 }  // namespace
@@ -249,7 +266,8 @@ int hs_init(int device_id, void* cuda_stream, hs_ctx** out, char* err, size_t er
       HS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
       ctx->own_stream = true;
     }
-    HS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    HS_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    HS_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
   });
   if (rc != HS_OK) {
     delete ctx;
@@ -265,7 +283,14 @@ void hs_shutdown(hs_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   comm_destroy(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->h2d_stream) {
+    cudaStreamSynchronize(ctx->h2d_stream);
+    cudaStreamDestroy(ctx->h2d_stream);
+  }
+  if (ctx->d2h_stream) {
+    cudaStreamSynchronize(ctx->d2h_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
+  }
   delete ctx;
 }
 
@@ -337,75 +362,243 @@ void hs_host_free(hs_ctx* ctx, void* p) {
   if (ctx && p) ctx->pool.put(p);
 }
 
-int hs_create_index(hs_ctx* ctx, const hs_index_spec* spec, hs_index_result** out, hs_stats* stats, char* err,
-                    size_t errlen) {
+// ---- staging: host file images -> device, asynchronously on the H2D copy stream -----------------------------------------
+
+int hs_stage_sources(hs_ctx* ctx, const hs_source_file* files, int32_t n_files, hs_staged** out, char* err, size_t errlen) {
+  if (!ctx || !out || n_files < 0 || (n_files > 0 && !files)) return HS_EINVAL;
+  *out = nullptr;
+  std::unique_ptr<hs_staged> sg(new hs_staged());
+  sg->ctx = ctx;
+  int rc = guarded(ctx, err, errlen, [&] {
+    const int launches_before = ctx->launches;
+    std::vector<uint64_t> sizes(n_files), off(n_files);
+    uint64_t total = 0;
+    for (int f = 0; f < n_files; f++) {
+      const hs_source_file& sf = files[f];
+      if (sf.data && sf.on_device) fail(HS_EINVAL, "source file %d is already on the device", f);
+      if (sf.data) {
+        sizes[f] = sf.size;
+      } else {
+        if (!sf.path) fail(HS_EINVAL, "source file %d has neither data nor path", f);
+        struct stat st;
+        if (stat(sf.path, &st) != 0) fail(HS_EIO, "cannot stat %s", sf.path);
+        sizes[f] = (uint64_t)st.st_size;
+      }
+      if (sizes[f] < 12) fail(HS_EFORMAT, "source file %d: too small to be a Parquet file", f);
+      off[f] = total;
+      total += round_up(sizes[f], 16) + 16;
+    }
+    sg->d_images.alloc(ctx, std::max<uint64_t>(total, 16));
+    sg->files.resize(n_files);
+    sg->names.resize(n_files);
+    sg->metas.resize(n_files);
+    for (int f = 0; f < n_files; f++) {
+      const hs_source_file& sf = files[f];
+      sg->names[f] = sf.path ? sf.path : ("<memory file " + std::to_string(f) + ">");
+      const uint8_t* host = (const uint8_t*)sf.data;
+      if (!host) {  // file system source: read into pinned memory first (kept until the copy has completed)
+        sg->staging.emplace_back(ctx, sizes[f], /*pinned=*/true);
+        read_file_into(sf.path, sg->staging.back().get(), sizes[f]);
+        host = sg->staging.back().get();
+      }
+      // the footer is parsed here, from host memory, so that the build never has to fetch it back from the device
+      sg->metas[f] = std::make_shared<hs::pq::FileMeta>(hs::pq::parse_footer(host, sizes[f], sg->names[f].c_str()));
+      HS_CUDA(cudaMemcpyAsync(sg->d_images.get() + off[f], host, sizes[f], cudaMemcpyHostToDevice, ctx->h2d_stream));
+      hs_source_file& o = sg->files[f];
+      o.path = nullptr;  // patched to names[f].c_str() by hs_staged_file (the vector may still move here)
+      o.data = sg->d_images.get() + off[f];
+      o.size = sizes[f];
+      o.file_id = sf.file_id;
+      o.on_device = 1;
+      o.reserved = 0;
+      sg->bytes += sizes[f];
+    }
+    HS_CUDA(cudaEventCreateWithFlags(&sg->ready, cudaEventDisableTiming));
+    HS_CUDA(cudaEventRecord(sg->ready, ctx->h2d_stream));
+    ctx->staged_ready.push_back(sg->ready);
+    for (int f = 0; f < n_files; f++) ctx->staged_meta[sg->files[f].data] = sg->metas[f];
+    ctx->launches = launches_before;
+  });
+  if (rc == HS_OK) *out = sg.release();
+  return rc;
+}
+
+int32_t hs_staged_num_files(const hs_staged* s) { return s ? (int32_t)s->files.size() : 0; }
+
+int hs_staged_file(const hs_staged* s, int32_t i, hs_source_file* out) {
+  if (!s || !out || i < 0 || i >= (int32_t)s->files.size()) return HS_EINVAL;
+  *out = s->files[i];
+  out->path = s->names[i].c_str();
+  return HS_OK;
+}
+
+int hs_staged_wait(hs_staged* s) {
+  if (!s) return HS_EINVAL;
+  cudaSetDevice(s->ctx->device);
+  return cudaEventSynchronize(s->ready) == cudaSuccess ? HS_OK : HS_ECUDA;
+}
+
+void hs_staged_free(hs_staged* s) {
+  if (!s) return;
+  hs_ctx* ctx = s->ctx;
+  cudaSetDevice(ctx->device);
+  if (s->ready) {
+    cudaEventSynchronize(s->ready);  // the copies read caller memory / pinned staging and write d_images
+    auto& v = ctx->staged_ready;
+    v.erase(std::remove(v.begin(), v.end(), s->ready), v.end());
+    cudaEventDestroy(s->ready);
+  }
+  for (const hs_source_file& f : s->files) ctx->staged_meta.erase(f.data);
+  cudaStreamSynchronize(ctx->stream);  // a build that decodes these images may still be running
+  delete s;
+}
+
+// ---- createIndex -----------------------------------------------------------------------------------------------------
+
+int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** out, char* err, size_t errlen) {
   if (!ctx || !spec || !out) return HS_EINVAL;
   *out = nullptr;
-  hs_stats st;
+  std::unique_ptr<hs_pending> pd(new hs_pending());
+  pd->ctx = ctx;
+  pd->res.reset(new hs_index_result());
+  hs_stats& st = pd->st;
   memset(&st, 0, sizeof st);
-  std::unique_ptr<hs_index_result> res(new hs_index_result());
+  hs_index_result* res = pd->res.get();
   int rc = guarded(ctx, err, errlen, [&] {
     if (spec->n_indexed < 1) fail(HS_EINVAL, "at least one indexed column is required");
     if (spec->n_files < 0 || (spec->n_files > 0 && !spec->files)) fail(HS_EINVAL, "bad source file list");
-    StageTimer total(ctx);
-    total.start();
+    if (spec->output == HS_OUT_FILES && !spec->out_dir) fail(HS_EINVAL, "HS_OUT_FILES needs out_dir");
+    HS_CUDA(cudaEventCreate(&pd->t_begin));
+    HS_CUDA(cudaEventCreate(&pd->t_compute_end));
+    HS_CUDA(cudaEventRecord(pd->t_begin, ctx->stream));
     std::vector<std::string> cols = names_of(spec->indexed_columns, spec->n_indexed, spec->included_columns, spec->n_included);
     for (size_t i = 0; i < cols.size(); i++)
       for (size_t j = i + 1; j < cols.size(); j++)
         if (cols[i] == cols[j]) fail(HS_EINVAL, "duplicate column '%s' in index config", cols[i].c_str());
-    Table table;
-    // Included columns whose source pages are all dictionary-encoded travel through the build as 16-bit dictionary codes
-    // (late materialisation).  Only where nothing between decode and encode needs their values: the fused partition (on
-    // one GPU, or writing straight into the owners' memory on several), no rows to drop.  HS_NO_CARRY=1 switches it off
-    // (A/B measurements; on several GPUs every rank must be given the same setting).
-    const bool no_carry = getenv("HS_NO_CARRY") != nullptr;
-    CarryOptions carry;
-    if ((ctx->world == 1 || p2p_exchange_supported(ctx, spec->num_buckets)) && !spec->disable_dictionary &&
-        spec->n_deleted_file_ids == 0 && !no_carry && fused_partition_supported(spec->num_buckets)) {
-      carry.first_col = spec->n_indexed;
-      carry.num_segments = spec->num_buckets;
-    }
-    load_sources(ctx, spec->files, spec->n_files, cols, &table, &st, &carry);
-    if (spec->lineage) fill_lineage(ctx, table, spec->files, spec->n_files);
-    if (spec->n_deleted_file_ids > 0) drop_deleted_rows(ctx, table, spec->deleted_file_ids, spec->n_deleted_file_ids);
-    IndexedRows rows;
-    if (p2p_exchange_supported(ctx, spec->num_buckets)) {
-      // partition + exchange fused over NVLink peer memory, then the local sort
-      exchange_partition_p2p(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
-      sort_partitioned_rows(ctx, spec->n_indexed, spec->num_buckets, &rows, &st);
-    } else {
-      if (ctx->world > 1) exchange_rows(ctx, table, spec->n_indexed, spec->num_buckets, &st);  // NCCL all-to-all
-      index_rows(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
-    }
-
-    EncodeRequest req;
-    req.table = &rows.part;
-    req.d_perm = rows.sorted_perm;
-    req.d_sorted_keys = rows.sorted_keys;
-    req.plan = &rows.plan;
-    req.seg_offsets = rows.bucket_offsets;
-    req.rows_per_page = spec->rows_per_page;
-    req.rows_per_row_group = spec->rows_per_row_group;
-    req.use_dictionary = spec->disable_dictionary == 0;
-    const std::string uuid = spec->job_uuid ? spec->job_uuid : make_uuid();
-    req.seg_names.resize(spec->num_buckets);
-    for (int b = 0; b < spec->num_buckets; b++) {
-      // Spark FileFormatWriter: part-<task>-<jobUUID>_<bucket>.c000<codec ext>.parquet ; bucket id parsed back by
-      // BucketingUtils.getBucketId (relied on by actions/OptimizeAction.scala:110)
-      char nm[160];
-      snprintf(nm, sizeof nm, "part-%05d-%s_%05d.c000.parquet", b, uuid.c_str(), b);
-      req.seg_names[b] = nm;
-    }
     EncodedFiles enc;
-    encode_segments(ctx, req, &enc, &st);
-    st.rows_out = rows.part.nrows;
-    finish_result(ctx, enc, spec->output, spec->out_dir, spec->save_mode, res.get(), &st);
-    total.stop();
-    st.ms_total = total.ms();
+    {
+      Table table;
+      // Included columns whose source pages are all dictionary-encoded travel through the build as 16-bit dictionary codes
+      // (late materialisation).  Only where nothing between decode and encode needs their values: the fused partition (on
+      // one GPU, or writing straight into the owners' memory on several), no rows to drop.  HS_NO_CARRY=1 switches it off
+      // (A/B measurements; on several GPUs every rank must be given the same setting).
+      const bool no_carry = getenv("HS_NO_CARRY") != nullptr;
+      CarryOptions carry;
+      if ((ctx->world == 1 || p2p_exchange_supported(ctx, spec->num_buckets)) && !spec->disable_dictionary &&
+          spec->n_deleted_file_ids == 0 && !no_carry && fused_partition_supported(spec->num_buckets)) {
+        carry.first_col = spec->n_indexed;
+        carry.num_segments = spec->num_buckets;
+      }
+      load_sources(ctx, spec->files, spec->n_files, cols, &table, &st, &carry);
+      if (spec->lineage) fill_lineage(ctx, table, spec->files, spec->n_files);
+      if (spec->n_deleted_file_ids > 0) drop_deleted_rows(ctx, table, spec->deleted_file_ids, spec->n_deleted_file_ids);
+      IndexedRows rows;
+      if (p2p_exchange_supported(ctx, spec->num_buckets)) {
+        // partition + exchange fused over NVLink peer memory, then the local sort
+        exchange_partition_p2p(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
+        sort_partitioned_rows(ctx, spec->n_indexed, spec->num_buckets, &rows, &st);
+      } else {
+        if (ctx->world > 1) exchange_rows(ctx, table, spec->n_indexed, spec->num_buckets, &st);  // NCCL all-to-all
+        index_rows(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
+      }
+
+      EncodeRequest req;
+      req.table = &rows.part;
+      req.d_perm = rows.sorted_perm;
+      req.d_sorted_keys = rows.sorted_keys;
+      req.plan = &rows.plan;
+      req.seg_offsets = rows.bucket_offsets;
+      req.rows_per_page = spec->rows_per_page;
+      req.rows_per_row_group = spec->rows_per_row_group;
+      req.use_dictionary = spec->disable_dictionary == 0;
+      const std::string uuid = spec->job_uuid ? spec->job_uuid : make_uuid();
+      req.seg_names.resize(spec->num_buckets);
+      for (int b = 0; b < spec->num_buckets; b++) {
+        // Spark FileFormatWriter: part-<task>-<jobUUID>_<bucket>.c000<codec ext>.parquet ; bucket id parsed back by
+        // BucketingUtils.getBucketId (relied on by actions/OptimizeAction.scala:110)
+        char nm[160];
+        snprintf(nm, sizeof nm, "part-%05d-%s_%05d.c000.parquet", b, uuid.c_str(), b);
+        req.seg_names[b] = nm;
+      }
+      encode_segments(ctx, req, &enc, &st);  // synchronises the stream before it returns
+      st.rows_out = rows.part.nrows;
+      // the decoded / partitioned / sorted intermediates go back to the pool here: while this call's index files drain to
+      // the host, the next call can already build in the same memory
+    }
+    HS_CUDA(cudaEventRecord(pd->t_compute_end, ctx->stream));
+    res->ctx = ctx;
+    res->output = spec->output;
+    res->files = enc.files;
+    pd->save_mode = spec->save_mode;
+    if (spec->out_dir) pd->out_dir = spec->out_dir;
     st.gpu_launches = ctx->launches;
+    if (spec->output == HS_OUT_DEVICE) {
+      res->d_arena = std::move(enc.arena);
+      return;
+    }
+    // device -> host on the D2H copy stream; hs_pending_wait picks it up
+    pd->d_arena = std::move(enc.arena);
+    res->h_arena.alloc(ctx, std::max<uint64_t>(enc.arena_bytes, 16), /*pinned=*/true);
+    HS_CUDA(cudaEventCreate(&pd->t_d2h_begin));
+    HS_CUDA(cudaEventCreate(&pd->t_d2h_end));
+    HS_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, pd->t_compute_end, 0));
+    HS_CUDA(cudaEventRecord(pd->t_d2h_begin, ctx->d2h_stream));
+    if (enc.arena_bytes)
+      HS_CUDA(cudaMemcpyAsync(res->h_arena.get(), pd->d_arena.get(), enc.arena_bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    HS_CUDA(cudaEventRecord(pd->t_d2h_end, ctx->d2h_stream));
+    pd->has_d2h = true;
   });
-  if (stats) *stats = st;
-  if (rc == HS_OK) *out = res.release();
+  if (rc == HS_OK) *out = pd.release();
+  return rc;
+}
+
+int hs_pending_wait(hs_pending* p, hs_index_result** out, hs_stats* stats, char* err, size_t errlen) {
+  if (!p || !out) return HS_EINVAL;
+  *out = nullptr;
+  std::unique_ptr<hs_pending> pd(p);  // consumed either way
+  hs_ctx* ctx = pd->ctx;
+  const int launches = ctx->launches;
+  int rc = guarded(ctx, err, errlen, [&] {
+    hs_stats& st = pd->st;
+    float ms = 0;
+    if (pd->has_d2h) {
+      HS_CUDA(cudaEventSynchronize(pd->t_d2h_end));
+      HS_CUDA(cudaEventElapsedTime(&ms, pd->t_d2h_begin, pd->t_d2h_end));
+      st.ms_d2h += ms;
+      HS_CUDA(cudaEventElapsedTime(&ms, pd->t_begin, pd->t_d2h_end));
+      st.ms_total = ms;
+      pd->d_arena.release();
+    } else {
+      HS_CUDA(cudaEventSynchronize(pd->t_compute_end));
+      HS_CUDA(cudaEventElapsedTime(&ms, pd->t_begin, pd->t_compute_end));
+      st.ms_total = ms;
+    }
+    if (pd->res->output == HS_OUT_FILES) write_result_files(pd->res.get(), pd->out_dir, pd->save_mode);
+  });
+  ctx->launches = launches;
+  if (stats) *stats = pd->st;
+  if (rc == HS_OK) *out = pd->res.release();
+  return rc;
+}
+
+void hs_pending_cancel(hs_pending* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  if (p->has_d2h) cudaEventSynchronize(p->t_d2h_end);
+  delete p;
+}
+
+int hs_create_index(hs_ctx* ctx, const hs_index_spec* spec, hs_index_result** out, hs_stats* stats, char* err,
+                    size_t errlen) {
+  if (!ctx || !spec || !out) return HS_EINVAL;
+  *out = nullptr;
+  if (stats) memset(stats, 0, sizeof *stats);
+  hs_pending* pd = nullptr;
+  int rc = hs_create_index_async(ctx, spec, &pd, err, errlen);
+  if (rc != HS_OK) return rc;
+  const int launches = ctx->launches;
+  rc = hs_pending_wait(pd, out, stats, err, errlen);
+  if (stats) stats->gpu_launches = launches;
   return rc;
 }
 

@@ -234,7 +234,26 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
   Buf<uint8_t> pinned_tails, pinned_footers;
   bool any_dev = false;
   for (int f = 0; f < n_files; f++) any_dev = any_dev || (files[f].data && files[f].on_device);
-  if (any_dev) {
+  // images staged by hs_stage_sources may still be on their way: everything this call enqueues waits for those copies
+  if (any_dev)
+    for (cudaEvent_t ev : ctx->staged_ready) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
+  // ... and their footers were parsed from host memory when they were staged
+  std::vector<std::shared_ptr<pq::FileMeta>> cached(n_files);
+  bool fetch_footers = false;
+  for (int f = 0; f < n_files; f++) {
+    if (!(files[f].data && files[f].on_device)) continue;
+    auto it = ctx->staged_meta.find(files[f].data);
+    if (it != ctx->staged_meta.end()) cached[f] = it->second;
+    else fetch_footers = true;
+  }
+  if (any_dev && !fetch_footers) {
+    for (int f = 0; f < n_files; f++)
+      if (cached[f]) {
+        if (((uintptr_t)files[f].data & 15) != 0) fail(HS_EINVAL, "%s: device images must be 16-byte aligned", imgs[f].what.c_str());
+        imgs[f].dev = (const uint8_t*)files[f].data;
+      }
+  }
+  if (any_dev && fetch_footers) {
     // one gather kernel + one copy per round instead of one small copy per file (each costs ~4.5 us of launch overhead)
     pinned_tails.alloc(ctx, (size_t)n_files * 8, /*pinned=*/true);
     Buf<SpanCopy> h_spans(ctx, n_files, /*pinned=*/true);
@@ -282,8 +301,10 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
     const hs_source_file& sf = files[f];
     const uint8_t* host = nullptr;
     if (sf.data && sf.on_device) {
-      imgs[f].meta = pq::parse_footer_bytes(pinned_footers.get() + footer_off[f], (uint32_t)(footer_off[f + 1] - footer_off[f]),
-                                            imgs[f].what.c_str());
+      if (!fetch_footers) imgs[f].meta = *cached[f];
+      else
+        imgs[f].meta = pq::parse_footer_bytes(pinned_footers.get() + footer_off[f], (uint32_t)(footer_off[f + 1] - footer_off[f]),
+                                              imgs[f].what.c_str());
     } else {
       if (sf.data) host = (const uint8_t*)sf.data;
       else {

@@ -150,6 +150,34 @@ struct hs_index_result {
   std::vector<hs::OutFile> files;
 };
 
+// Source file images on their way to (or already in) device memory: hs_stage_sources.
+struct hs_staged {
+  hs_ctx* ctx = nullptr;
+  hs::Buf<uint8_t> d_images;
+  std::vector<hs_source_file> files;   // on_device descriptors pointing into d_images
+  std::vector<std::string> names;
+  std::vector<std::shared_ptr<hs::pq::FileMeta>> metas;
+  std::vector<hs::Buf<uint8_t>> staging;  // pinned copies of file-system sources
+  cudaEvent_t ready = nullptr;          // recorded on ctx->h2d_stream behind the last copy
+  uint64_t bytes = 0;
+};
+
+// A createIndex whose kernels have run and whose index files are draining to the host: hs_create_index_async.
+struct hs_pending {
+  hs_ctx* ctx = nullptr;
+  std::unique_ptr<hs_index_result> res;
+  hs_stats st;
+  hs::Buf<uint8_t> d_arena;             // device file images until the copy has completed
+  cudaEvent_t t_begin = nullptr, t_compute_end = nullptr, t_d2h_begin = nullptr, t_d2h_end = nullptr;
+  bool has_d2h = false;
+  std::string out_dir;
+  int save_mode = 0;
+  ~hs_pending() {
+    for (cudaEvent_t e : {t_begin, t_compute_end, t_d2h_begin, t_d2h_end})
+      if (e) cudaEventDestroy(e);
+  }
+};
+
 struct hs_batch {
   hs_ctx* ctx = nullptr;
   int64_t nrows = 0;

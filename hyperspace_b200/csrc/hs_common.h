@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <set>
 #include <mutex>
 #include <stdexcept>
@@ -113,12 +114,22 @@ class BufferPool {
 }  // namespace hs
 
 struct hs_comm_state;  // exchange.cu
+namespace hs {
+namespace pq {
+struct FileMeta;  // parquet_meta.h
+}
+}  // namespace hs
 
 struct hs_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaStream_t copy_stream = nullptr;  // H2D/D2H overlap
+  // Copy engines of their own, so that the host->device staging of the NEXT call's source files and the device->host
+  // drain of the PREVIOUS call's index files overlap this call's kernels and each other (PCIe is full duplex).
+  cudaStream_t h2d_stream = nullptr;   // hs_stage_sources
+  cudaStream_t d2h_stream = nullptr;   // hs_create_index_async -> hs_pending_wait
+  std::vector<cudaEvent_t> staged_ready;  // "copied" events of the live hs_staged handles: device images wait on them
+  std::map<const void*, std::shared_ptr<hs::pq::FileMeta>> staged_meta;  // footers of staged images, parsed on the host
   int sm_count = 148;
   hs::BufferPool pool;
   int launches = 0;  // kernels launched by the current call (hs_stats.gpu_launches)

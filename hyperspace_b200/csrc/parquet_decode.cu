@@ -89,11 +89,32 @@ __global__ void k_walk_pages(const ChunkDesc* __restrict__ chunks, int n_chunks,
   int64_t out = mode ? page_offsets[c] : 0;
   while (r.p < r.end && values_seen < ch.num_values) {
     PageHeaderInfo h;
-    if (!parse_page_header(r, h) || h.compressed_size < 0 || (int64_t)(r.end - r.p) < h.compressed_size) {
+    if (!parse_page_header(r, h) || h.compressed_size < 0 || h.uncompressed_size < 0 || h.num_values < 0 ||
+        (int64_t)(r.end - r.p) < h.compressed_size) {
       set_error(d_error, DERR_BAD_HEADER, (uint32_t)c);
       break;
     }
     const uint8_t* body = r.p;
+    // Every field a decoder will index with is range-checked HERE, before any page is decoded: a page header is
+    // untrusted input, and a chunk that fails stops the whole call (decode_sources reads the error word first).
+    if (h.type == pq::DATA_PAGE || h.type == pq::DATA_PAGE_V2) {
+      bool ok = values_seen + h.num_values <= ch.num_values;  // a page never writes past its chunk's rows
+      if (h.type == pq::DATA_PAGE_V2)
+        ok = ok && h.rep_bytes >= 0 && h.def_bytes >= 0 && (int64_t)h.rep_bytes + h.def_bytes <= h.compressed_size &&
+             (int64_t)h.rep_bytes + h.def_bytes <= h.uncompressed_size;
+      if (!ok) {
+        set_error(d_error, DERR_BAD_HEADER, (uint32_t)c);
+        break;
+      }
+    } else if (h.type == pq::DICTIONARY_PAGE) {
+      // dictionary entries are PLAIN values: all of them must lie inside the (decompressed) page
+      const int64_t vw = (ch.phys_type == pq::INT64 || ch.phys_type == pq::DOUBLE) ? 8 : (ch.phys_type == pq::BOOLEAN ? 0 : 4);
+      const int64_t need = vw ? (int64_t)h.num_values * vw : ((int64_t)h.num_values + 7) / 8;
+      if (need > h.uncompressed_size) {
+        set_error(d_error, DERR_BAD_HEADER, (uint32_t)c);
+        break;
+      }
+    }
     if (h.type == pq::DICTIONARY_PAGE) {
       dict = body;
       dict_count = h.num_values;
@@ -204,11 +225,21 @@ __device__ void hybrid_fill_table(HybridShared& hs, uint32_t want) {
       }
       if (h & 1) {  // bit-packed: (h >> 1) groups of 8 values
         uint32_t groups = h >> 1;
+        // a run header may claim more groups than the stream holds: only what is there is decoded (the caller then
+        // sees the stream end early and reports DERR_OVERRUN), nothing past `end` is read
+        const uint64_t avail = st.bw ? (uint64_t)(st.end - st.p) / st.bw : 0xffffffffu / 8;
+        const bool claimed = groups > 0;
+        if (groups > avail) groups = (uint32_t)avail;
+        if (groups > 0xffffffffu / 8) groups = 0xffffffffu / 8;
         st.run_is_rle = 0;
         st.run_left = groups * 8;
         st.run_pos = 0;
         st.run_data = st.p;
         st.p += (size_t)groups * st.bw;
+        if (claimed && groups == 0) {  // nothing decodable is left
+          st.bad = 1;
+          break;
+        }
       } else {
         st.run_is_rle = 1;
         st.run_left = h >> 1;
@@ -295,7 +326,9 @@ __device__ __forceinline__ bool locate_def_levels(const PageDesc& pg, const uint
     }
     p += pg.def_bytes > 0 ? pg.def_bytes : 0;
   } else if (pg.max_def > 0) {
+    if (pend - p < 4) return false;
     uint32_t len = load_le32_unaligned(p);
+    if ((uint64_t)len > (uint64_t)(pend - p - 4)) return false;
     def_p = p + 4;
     def_end = def_p + len;
     p = def_end;
@@ -382,20 +415,7 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
   // ---- definition levels -----------------------------------------------------------------------------------
   const uint8_t* def_p = nullptr;
   const uint8_t* def_end = nullptr;
-  if (pg.page_type == pq::DATA_PAGE_V2) {
-    p += pg.rep_bytes;
-    if (pg.max_def > 0) {
-      def_p = p;
-      def_end = p + pg.def_bytes;
-    }
-    p += pg.def_bytes > 0 ? pg.def_bytes : 0;
-  } else if (pg.max_def > 0) {
-    uint32_t len = load_le32_unaligned(p);
-    def_p = p + 4;
-    def_end = def_p + len;
-    p = def_end;
-  }
-  if (p > pend) {
+  if (n < 0 || pg.size < 0 || !locate_def_levels(pg, p, def_p, def_end)) {  // level bytes reach past the page
     if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
     return;
   }
@@ -417,8 +437,12 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
       if (threadIdx.x == 0) set_error(d_error, DERR_DICT_INDEX, 0);
       return;
     }
-    idx_bw = n > 0 && p < pend ? *p : 0;
-    p += 1;
+    if (n > 0 && p >= pend) {  // no room for the bit-width byte
+      if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+      return;
+    }
+    idx_bw = n > 0 ? *p : 0;
+    if (n > 0) p += 1;
     if (idx_bw > 32) {
       if (threadIdx.x == 0) set_error(d_error, DERR_UNSUPPORTED_ENCODING, idx_bw);
       return;
@@ -461,6 +485,10 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
   if (!has_def) {
     if (!is_dict) {
       if (W == 1) {
+        if ((int64_t)(pend - p) < ((int64_t)n + 7) / 8) {
+          if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+          return;
+        }
         for (int i = threadIdx.x; i < n; i += blockDim.x) store_value<1>(co.data, row0 + i, (p[i >> 3] >> (i & 7)) & 1);
       } else {
         if ((int64_t)(pend - p) < (int64_t)n * W) {
@@ -570,6 +598,12 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
       ok = hybrid_decode_next(sm.idx, total, [&](uint32_t j, uint32_t v) { sm.tile_idx[j] = v; });
       __syncthreads();
       if (!ok) {
+        if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+        return;
+      }
+    } else {  // the tile's dense PLAIN values must lie inside the page
+      const int64_t have = (int64_t)(pend - p), upto = val_cursor + total;
+      if (W == 1 ? (upto + 7) / 8 > have : upto * W > have) {
         if (threadIdx.x == 0) set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
         return;
       }

@@ -150,6 +150,37 @@ typedef struct {
 int hs_create_index(hs_ctx* ctx, const hs_index_spec* spec, hs_index_result** out, hs_stats* stats, char* err,
                     size_t errlen);
 
+/* ---- software pipelining across calls -------------------------------------------------------------------------------
+ * One createIndex cannot overlap its own input and output copies: every index file depends on every source file (the hash
+ * repartition), so the device->host drain of a call starts after its last source byte has arrived.  What CAN overlap are
+ * the copies of NEIGHBOURING calls, in both directions at once (PCIe is full duplex) -- the overlap Spark gets from running
+ * the scan tasks of one job beside the write tasks of another (index/DataFrameWriterExtensions.scala:76-80 hands the write
+ * to Spark's task scheduler).  Three steps, each on its own CUDA stream of the ctx:
+ *
+ *   hs_stage_sources       host (or file system) Parquet images -> device, asynchronously on the H2D copy stream; footers
+ *                          are parsed from host memory on the way.  The handle's descriptors (on_device = 1) are valid
+ *                          inputs of hs_create_index[_async], hs_filter_scan and hs_bucket_join, which wait for the copy.
+ *                          The caller's host images must stay valid until hs_staged_wait / hs_staged_free returns or a
+ *                          call that consumed the descriptors has returned.
+ *   hs_create_index_async  everything hs_create_index does up to the encoded index files in device memory (returns when
+ *                          the kernels have run), then starts the device->host copy on the D2H copy stream.
+ *   hs_pending_wait        waits for that copy (and writes the files for HS_OUT_FILES); yields the result + stats.
+ *                          Consumes the handle, also on failure.
+ *
+ *   staged[i+1] = hs_stage_sources(...);  pending[i] = hs_create_index_async(staged[i]...);  hs_pending_wait(pending[i-1])
+ *
+ * keeps the H2D engine, the SMs and the D2H engine busy at the same time.  hs_create_index == async + wait. */
+typedef struct hs_staged hs_staged;
+typedef struct hs_pending hs_pending;
+int hs_stage_sources(hs_ctx* ctx, const hs_source_file* files, int32_t n_files, hs_staged** out, char* err, size_t errlen);
+int32_t hs_staged_num_files(const hs_staged* s);
+int hs_staged_file(const hs_staged* s, int32_t i, hs_source_file* out); /* out->path points into the handle */
+int hs_staged_wait(hs_staged* s);  /* blocks until the copies have completed */
+void hs_staged_free(hs_staged* s); /* waits for the copies and for the ctx stream, then releases the device images */
+int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** out, char* err, size_t errlen);
+int hs_pending_wait(hs_pending* p, hs_index_result** out, hs_stats* stats, char* err, size_t errlen);
+void hs_pending_cancel(hs_pending* p); /* waits for the copy and drops the result */
+
 int32_t hs_result_num_files(const hs_index_result* r);
 /* File i of the result: bucket id, file name (no directory), image pointer (host or device, NULL for
  * HS_OUT_FILES), image size, row count. */
@@ -209,6 +240,32 @@ int32_t hs_batch_num_columns(const hs_batch* b);
 int hs_batch_column(const hs_batch* b, int32_t i, const char** name, int32_t* type, const void** data,
                     const uint8_t** valid);
 void hs_batch_free(hs_batch* b);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Verification of a written index (any size; bench.py checks the 1 B-row benchmark output with it on every run)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  int64_t rows;               /* rows found in the files */
+  int64_t bucket_mismatches;  /* rows whose pmod(murmur3(indexed columns, 42), num_buckets) != bucket id of their file */
+  int64_t order_violations;   /* adjacent rows of one file whose indexed columns are not ascending, nulls first */
+  uint64_t row_checksum;      /* sum over rows, mod 2^64, of a 64-bit mix of all the row's values (indexed ++ included order):
+                                 independent of row order; changes when a value moves to another row */
+  uint64_t column_checksum[16]; /* the same per column */
+  int32_t n_columns;
+  int32_t reserved;
+} hs_verify_report;
+
+/* The three properties the reference's write-path test pins (T/index/DataFrameWriterExtensionsTest.scala:93-158: bucket id
+ * of every row == HashPartitioning's, every file sorted on the indexed columns, row multiset preserved), evaluated on the
+ * GPU over whole index files.  buckets[i] is the bucket id of files[i] (BucketingUtils.getBucketId of its name). */
+int hs_verify_index(hs_ctx* ctx, const hs_source_file* files, const int32_t* buckets, int32_t n_files,
+                    const char* const* indexed_columns, int32_t n_indexed, const char* const* included_columns,
+                    int32_t n_included, int32_t num_buckets, hs_verify_report* out, char* err, size_t errlen);
+/* rows / row_checksum / column_checksum of rows [first_row, first_row + nrows) of the synthetic table T as generated
+ * (never encoded): what hs_verify_index must report for an index built over those rows. */
+int hs_synth_checksum(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, hs_verify_report* out, char* err,
+                      size_t errlen);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Kernel-level entry points (host arrays in, host arrays out).  They exist so the parity tests can pin each

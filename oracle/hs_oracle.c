@@ -355,3 +355,62 @@ uint64_t hso_splitmix64(uint64_t seed, uint64_t i) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
+
+/* Rows of the synthetic table T (k_i = splitmix64(42, i)) that fall into `bucket`, in source order.  Two passes over
+ * [first_row, first_row + nrows) in 1 M-row chunks: count, then fill -- what a scan of the whole table followed by
+ * `WHERE pmod(hash(k), n) = bucket` yields, without materialising the table (bench.py checks whole buckets of the
+ * 1 B-row build against it). */
+typedef struct {
+  uint64_t first_row;
+  int64_t nrows;
+  int32_t nb, bucket;
+  int64_t* counts;   /* per chunk */
+  int64_t* offsets;  /* per chunk, exclusive prefix (fill pass) */
+  int64_t* out;
+  int64_t cap;
+} synth_bucket_arg;
+
+#define SYNTH_CHUNK (1 << 20)
+
+static inline int32_t synth_row_bucket(uint64_t i, int32_t nb) {
+  int32_t h = hso_hash_long((int64_t)hso_splitmix64(42, i), 42);
+  int32_t r = h % nb;
+  return r < 0 ? r + nb : r;
+}
+
+static void synth_bucket_count(int64_t lo, int64_t hi, void* vp) {
+  synth_bucket_arg* a = (synth_bucket_arg*)vp;
+  for (int64_t c = lo; c < hi; c++) {
+    int64_t r0 = c * SYNTH_CHUNK, r1 = r0 + SYNTH_CHUNK < a->nrows ? r0 + SYNTH_CHUNK : a->nrows, n = 0;
+    for (int64_t r = r0; r < r1; r++) n += synth_row_bucket(a->first_row + (uint64_t)r, a->nb) == a->bucket;
+    a->counts[c] = n;
+  }
+}
+
+static void synth_bucket_fill(int64_t lo, int64_t hi, void* vp) {
+  synth_bucket_arg* a = (synth_bucket_arg*)vp;
+  for (int64_t c = lo; c < hi; c++) {
+    int64_t r0 = c * SYNTH_CHUNK, r1 = r0 + SYNTH_CHUNK < a->nrows ? r0 + SYNTH_CHUNK : a->nrows, o = a->offsets[c];
+    for (int64_t r = r0; r < r1; r++)
+      if (synth_row_bucket(a->first_row + (uint64_t)r, a->nb) == a->bucket) {
+        if (o < a->cap) a->out[o] = (int64_t)(a->first_row + (uint64_t)r);
+        o++;
+      }
+  }
+}
+
+int64_t hso_synth_bucket_rows(uint64_t first_row, int64_t nrows, int32_t num_buckets, int32_t bucket, int64_t* out_rows,
+                              int64_t cap, int32_t nthreads) {
+  int64_t nchunks = (nrows + SYNTH_CHUNK - 1) / SYNTH_CHUNK;
+  if (nchunks <= 0) return 0;
+  synth_bucket_arg a = {first_row, nrows, num_buckets, bucket, NULL, NULL, out_rows, cap};
+  a.counts = (int64_t*)calloc((size_t)nchunks, sizeof(int64_t));
+  a.offsets = (int64_t*)calloc((size_t)nchunks + 1, sizeof(int64_t));
+  hso_parallel_for(nchunks, 1, nthreads, synth_bucket_count, &a);
+  for (int64_t c = 0; c < nchunks; c++) a.offsets[c + 1] = a.offsets[c] + a.counts[c];
+  int64_t total = a.offsets[nchunks];
+  if (out_rows) hso_parallel_for(nchunks, 1, nthreads, synth_bucket_fill, &a);
+  free(a.counts);
+  free(a.offsets);
+  return total;
+}

@@ -76,6 +76,12 @@ int64_t hso_merge_join_i64(const int64_t* lk, int64_t nl, const int64_t* rk, int
 /* splitmix64 generator used by the synthetic tables of SURVEY.md section 8d: value i of stream `seed` */
 uint64_t hso_splitmix64(uint64_t seed, uint64_t i);
 
+/* Global row numbers of the rows of the synthetic table T (k_i = splitmix64(42, i), i in [first_row, first_row + nrows))
+ * whose bucket pmod(hashLong(k_i, 42), num_buckets) == bucket, in source order; writes at most cap of them, returns how
+ * many there are. */
+int64_t hso_synth_bucket_rows(uint64_t first_row, int64_t nrows, int32_t num_buckets, int32_t bucket, int64_t* out_rows,
+                              int64_t cap, int32_t nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,9 @@ def lib() -> ctypes.CDLL:
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         L.hso_splitmix64.restype = ctypes.c_uint64
         L.hso_splitmix64.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
+        L.hso_synth_bucket_rows.restype = ctypes.c_int64
+        L.hso_synth_bucket_rows.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                            ctypes.c_int64, ctypes.c_int32]
         _lib = L
     return _lib
 
@@ -283,6 +286,33 @@ def synthetic_table(first_row: int, nrows: int, ncols: int = 5) -> Dict[str, np.
     if ncols >= 5:
         cols["v4"] = (i % np.uint64(4096)).astype(np.float32) * np.float32(0.25)
     return cols
+
+
+def synthetic_rows_at(rows: np.ndarray, ncols: int = 5) -> Dict[str, np.ndarray]:
+    """Columns of table T at the given global row numbers (any order)."""
+    i = np.asarray(rows).astype(np.uint64)
+    cols = {"k": splitmix64(42, i).view(np.int64)}
+    if ncols >= 2:
+        cols["v1"] = (splitmix64(43, i) % np.uint64(1000)).astype(np.int64)
+    if ncols >= 3:
+        cols["v2"] = i.astype(np.float64) * 1e-3
+    if ncols >= 4:
+        cols["v3"] = (i % np.uint64(100)).astype(np.int32)
+    if ncols >= 5:
+        cols["v4"] = (i % np.uint64(4096)).astype(np.float32) * np.float32(0.25)
+    return cols
+
+
+def synthetic_bucket(first_row: int, nrows: int, num_buckets: int, bucket: int, ncols: int = 5,
+                     nthreads: int = 1) -> Dict[str, np.ndarray]:
+    """What the index file of ``bucket`` must hold for createIndex(T[first_row : first_row + nrows], indexed = k):
+    the table's rows with pmod(hash(k), num_buckets) == bucket, ordered by (k, source row) -- without materialising T."""
+    n = lib().hso_synth_bucket_rows(first_row, nrows, num_buckets, bucket, None, 0, nthreads)
+    rows = np.empty(n, dtype=np.int64)
+    lib().hso_synth_bucket_rows(first_row, nrows, num_buckets, bucket, rows.ctypes.data, n, nthreads)
+    k = splitmix64(42, rows.astype(np.uint64)).view(np.int64)
+    order = np.argsort(k, kind="stable")
+    return synthetic_rows_at(rows[order], ncols)
 
 
 # ----------------------------------------------------------------------------------------------

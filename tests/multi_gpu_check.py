@@ -46,6 +46,29 @@ def main():
             assert got.tobytes() == want.tobytes(), (rank, f.bucket, name)
         seen.add(f.bucket)
     assert seen == {b for b in owned if offs[b + 1] > offs[b]}
+    # the staged / asynchronous API on several GPUs: two builds in flight per rank, byte-identical files
+    want = {f.name: res.host_bytes(i) for i, f in enumerate(res.files)}
+    hsrc = ctx.synth_table(my[0] * rows_per_file, len(my) * rows_per_file, 5, n_files=len(my), row_groups_per_file=2,
+                           output=N.HS_OUT_HOST)
+    s1 = ctx.stage_sources(hsrc.as_sources())
+    s2 = ctx.stage_sources(hsrc.as_sources())
+    p1 = ctx.create_index_async(s1.as_sources(), ["k"], ["v1", "v2", "v3", "v4"], nb, output=N.HS_OUT_HOST, job_uuid="mg")
+    p2 = ctx.create_index_async(s2.as_sources(), ["k"], ["v1", "v2", "v3", "v4"], nb, output=N.HS_OUT_HOST, job_uuid="mg")
+    for p in (p1, p2):
+        r, _ = p.wait()
+        assert {f.name: r.host_bytes(i) for i, f in enumerate(r.files)} == want, rank
+        r.free()
+    s1.free()
+    s2.free()
+    # whole-index verification across ranks: checksums add up to the generator's
+    rep = ctx.verify_index(res.as_sources(), [f.bucket for f in res.files], ["k"], ["v1", "v2", "v3", "v4"], nb)
+    gen = ctx.synth_checksum(my[0] * rows_per_file, len(my) * rows_per_file, 5)
+    allr = [None] * world
+    dist.all_gather_object(allr, (rep, gen))
+    assert sum(a[0]["bucket_mismatches"] + a[0]["order_violations"] for a in allr) == 0
+    assert sum(a[0]["row_checksum"] for a in allr) % 2**64 == sum(a[1]["row_checksum"] for a in allr) % 2**64
+    assert sum(a[0]["rows"] for a in allr) == n_files * rows_per_file
+    hsrc.free()
     counts = torch.tensor([st["rows_in"], st["rows_out"], st["bytes_exchanged"]], device="cuda", dtype=torch.float64)
     dist.all_reduce(counts)
     if rank == 0:
