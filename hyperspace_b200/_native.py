@@ -65,14 +65,14 @@ class ScanSpec(C.Structure):
     _fields_ = [("files", C.POINTER(SourceFile)), ("n_files", C.c_int32), ("sorted_on_key", C.c_int32),
                 ("key_column", C.c_char_p), ("projected_columns", C.POINTER(C.c_char_p)), ("n_projected", C.c_int32),
                 ("has_lo", C.c_int32), ("has_hi", C.c_int32), ("lo", C.c_int64), ("hi", C.c_int64),
-                ("deleted_file_ids", C.POINTER(C.c_int64)), ("n_deleted_file_ids", C.c_int32), ("reserved", C.c_int32)]
+                ("deleted_file_ids", C.POINTER(C.c_int64)), ("n_deleted_file_ids", C.c_int32), ("output", C.c_int32)]
 
 
 class JoinSpec(C.Structure):
     _fields_ = [("left_files", C.POINTER(SourceFile)), ("n_left", C.c_int32),
                 ("right_files", C.POINTER(SourceFile)), ("n_right", C.c_int32),
                 ("left_buckets", C.POINTER(C.c_int32)), ("right_buckets", C.POINTER(C.c_int32)),
-                ("num_buckets", C.c_int32), ("reserved", C.c_int32),
+                ("num_buckets", C.c_int32), ("output", C.c_int32),
                 ("left_key", C.c_char_p), ("right_key", C.c_char_p),
                 ("left_columns", C.POINTER(C.c_char_p)), ("n_left_columns", C.c_int32),
                 ("right_columns", C.POINTER(C.c_char_p)), ("n_right_columns", C.c_int32)]
@@ -97,7 +97,7 @@ class HostColumn(C.Structure):
 EXPORTED_SYMBOLS = [
     "hs_abi_version", "hs_build_info", "hs_init", "hs_shutdown", "hs_trim", "hs_host_alloc", "hs_host_free", "hs_profile_enable", "hs_profile_report",
     "hs_comm_unique_id", "hs_comm_init", "hs_create_index", "hs_result_num_files", "hs_result_file", "hs_result_free",
-    "hs_filter_scan", "hs_bucket_join", "hs_batch_num_rows", "hs_batch_num_columns", "hs_batch_column", "hs_batch_free",
+    "hs_filter_scan", "hs_bucket_join", "hs_batch_num_rows", "hs_batch_on_device", "hs_batch_num_columns", "hs_batch_column", "hs_batch_free",
     "hs_k_bucket_ids", "hs_k_sort_perm", "hs_synth_table",
     "hs_stage_sources", "hs_staged_num_files", "hs_staged_file", "hs_staged_wait", "hs_staged_free",
     "hs_create_index_async", "hs_pending_wait", "hs_pending_cancel", "hs_verify_index", "hs_synth_checksum",
@@ -151,6 +151,8 @@ def load_library() -> C.CDLL:
     L.hs_bucket_join.argtypes = [C.c_void_p, C.POINTER(JoinSpec), C.POINTER(C.c_void_p), C.POINTER(Stats), *err]
     L.hs_batch_num_rows.restype = C.c_int64
     L.hs_batch_num_rows.argtypes = [C.c_void_p]
+    L.hs_batch_on_device.restype = C.c_int32
+    L.hs_batch_on_device.argtypes = [C.c_void_p]
     L.hs_batch_num_columns.restype = C.c_int32
     L.hs_batch_num_columns.argtypes = [C.c_void_p]
     L.hs_batch_column.restype = C.c_int
@@ -361,11 +363,16 @@ class Batch:
         if ctx is not None:
             ctx._results.add(self)
         self.num_rows = L.hs_batch_num_rows(handle)
+        self.on_device = bool(L.hs_batch_on_device(handle))
         self.columns: List[Tuple[str, np.ndarray, Optional[np.ndarray]]] = []
+        self.device_columns: List[Tuple[str, int, int]] = []  # (name, HS_TYPE_*, device pointer) when on_device
         n = self.num_rows
         for i in range(L.hs_batch_num_columns(handle)):
             nm, ty, d, v = C.c_char_p(), C.c_int32(), C.c_void_p(), C.c_void_p()
             L.hs_batch_column(handle, i, C.byref(nm), C.byref(ty), C.byref(d), C.byref(v))
+            if self.on_device:
+                self.device_columns.append((nm.value.decode(), ty.value, d.value))
+                continue
             dt = np.dtype(_NP_OF_TYPE[ty.value])
             if n:
                 data = np.ctypeslib.as_array((C.c_uint8 * (n * dt.itemsize)).from_address(d.value)).view(dt)
@@ -548,8 +555,8 @@ class Context:
 
     # ---- read side ----------------------------------------------------------------------------------
     def filter_scan(self, files: Sequence[FileImage], key: str, projected: Sequence[str], lo: Optional[int] = None,
-                    hi: Optional[int] = None, sorted_on_key: bool = True, deleted_file_ids: Sequence[int] = ()
-                    ) -> Tuple[Batch, Dict[str, float]]:
+                    hi: Optional[int] = None, sorted_on_key: bool = True, deleted_file_ids: Sequence[int] = (),
+                    output: int = HS_OUT_HOST) -> Tuple[Batch, Dict[str, float]]:
         L = load_library()
         src, keep = _source_array(files)
         pc = _cstr_array(projected)
@@ -561,6 +568,7 @@ class Context:
         spec.lo, spec.hi = lo or 0, hi or 0
         dl = (C.c_int64 * max(1, len(deleted_file_ids)))(*deleted_file_ids)
         spec.deleted_file_ids, spec.n_deleted_file_ids = dl, len(deleted_file_ids)
+        spec.output = output
         res, st = C.c_void_p(), Stats()
         err = C.create_string_buffer(1024)
         _check(L.hs_filter_scan(self._h, C.byref(spec), C.byref(res), C.byref(st), err, len(err)), err)
@@ -568,7 +576,8 @@ class Context:
 
     def bucket_join(self, left: Sequence[FileImage], left_buckets: Sequence[int], right: Sequence[FileImage],
                     right_buckets: Sequence[int], num_buckets: int, left_key: str, right_key: str,
-                    left_columns: Sequence[str], right_columns: Sequence[str]) -> Tuple[Batch, Dict[str, float]]:
+                    left_columns: Sequence[str], right_columns: Sequence[str], output: int = HS_OUT_HOST
+                    ) -> Tuple[Batch, Dict[str, float]]:
         L = load_library()
         ls, k1 = _source_array(left)
         rs, k2 = _source_array(right)
@@ -581,6 +590,7 @@ class Context:
         spec.left_key, spec.right_key = left_key.encode(), right_key.encode()
         spec.left_columns, spec.n_left_columns = lc, len(left_columns)
         spec.right_columns, spec.n_right_columns = rc, len(right_columns)
+        spec.output = output
         res, st = C.c_void_p(), Stats()
         err = C.create_string_buffer(1024)
         _check(L.hs_bucket_join(self._h, C.byref(spec), C.byref(res), C.byref(st), err, len(err)), err)

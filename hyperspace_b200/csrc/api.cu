@@ -635,26 +635,38 @@ void hs_result_free(hs_index_result* r) {
 
 static void batch_from_gather(hs_ctx* ctx, const Table& t, const std::vector<int>& col_idx, const uint32_t* d_idx,
                               int64_t n_out, hs_batch* b) {
+  // all gathers first, then all copies, one synchronisation at the end
+  std::vector<Buf<uint8_t>> d_data, d_valid;
   for (int ci : col_idx) {
     const DevColumn& c = t.cols[ci];
-    Buf<uint8_t> d(ctx, (size_t)std::max<int64_t>(1, n_out) * c.width);
-    launch_gather_plain(ctx, c.data.get(), d_idx, n_out, c.width, d.get());
+    d_data.emplace_back(ctx, (size_t)std::max<int64_t>(1, n_out) * c.width);
+    launch_gather_plain(ctx, c.data.get(), d_idx, n_out, c.width, d_data.back().get());
+    d_valid.emplace_back();
+    if (c.has_nulls) {
+      d_valid.back().alloc(ctx, (size_t)std::max<int64_t>(1, n_out));
+      launch_gather_plain(ctx, c.valid.get(), d_idx, n_out, 1, d_valid.back().get());
+    }
+  }
+  for (size_t i = 0; i < col_idx.size(); i++) {
+    const DevColumn& c = t.cols[col_idx[i]];
     hs_batch::Col bc;
     bc.name = c.name;
     bc.type = c.type;
-    bc.data.alloc(ctx, (size_t)std::max<int64_t>(1, n_out) * c.width, true);
-    if (n_out) HS_CUDA(cudaMemcpyAsync(bc.data.get(), d.get(), (size_t)n_out * c.width, cudaMemcpyDeviceToHost, ctx->stream));
-    if (c.has_nulls) {
-      Buf<uint8_t> dv(ctx, (size_t)std::max<int64_t>(1, n_out));
-      launch_gather_plain(ctx, c.valid.get(), d_idx, n_out, 1, dv.get());
-      bc.valid.alloc(ctx, (size_t)std::max<int64_t>(1, n_out), true);
-      if (n_out) HS_CUDA(cudaMemcpyAsync(bc.valid.get(), dv.get(), (size_t)n_out, cudaMemcpyDeviceToHost, ctx->stream));
-      bc.has_valid = true;
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    bc.has_valid = c.has_nulls;
+    if (b->on_device) {  // the next GPU operator consumes the columns where they are
+      bc.data = std::move(d_data[i]);
+      if (c.has_nulls) bc.valid = std::move(d_valid[i]);
+    } else {
+      bc.data.alloc(ctx, (size_t)std::max<int64_t>(1, n_out) * c.width, true);
+      if (n_out) HS_CUDA(cudaMemcpyAsync(bc.data.get(), d_data[i].get(), (size_t)n_out * c.width, cudaMemcpyDeviceToHost, ctx->stream));
+      if (c.has_nulls) {
+        bc.valid.alloc(ctx, (size_t)std::max<int64_t>(1, n_out), true);
+        if (n_out) HS_CUDA(cudaMemcpyAsync(bc.valid.get(), d_valid[i].get(), (size_t)n_out, cudaMemcpyDeviceToHost, ctx->stream));
+      }
     }
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
     b->cols.push_back(std::move(bc));
   }
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
   b->nrows = n_out;
 }
 
@@ -693,6 +705,7 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
   memset(&st, 0, sizeof st);
   std::unique_ptr<hs_batch> res(new hs_batch());
   res->ctx = ctx;
+  res->on_device = spec->output == HS_OUT_DEVICE;
   int rc = guarded(ctx, err, errlen, [&] {
     StageTimer total(ctx);
     total.start();
@@ -885,6 +898,7 @@ int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_sta
   memset(&st, 0, sizeof st);
   std::unique_ptr<hs_batch> res(new hs_batch());
   res->ctx = ctx;
+  res->on_device = spec->output == HS_OUT_DEVICE;
   int rc = guarded(ctx, err, errlen, [&] {
     StageTimer total(ctx);
     total.start();
@@ -958,6 +972,7 @@ int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_sta
 }
 
 int64_t hs_batch_num_rows(const hs_batch* b) { return b ? b->nrows : 0; }
+int32_t hs_batch_on_device(const hs_batch* b) { return b && b->on_device ? 1 : 0; }
 int32_t hs_batch_num_columns(const hs_batch* b) { return b ? (int32_t)b->cols.size() : 0; }
 int hs_batch_column(const hs_batch* b, int32_t i, const char** name, int32_t* type, const void** data,
                     const uint8_t** valid) {
@@ -971,7 +986,10 @@ int hs_batch_column(const hs_batch* b, int32_t i, const char** name, int32_t* ty
 }
 void hs_batch_free(hs_batch* b) {
   if (!b) return;
-  if (b->ctx) cudaSetDevice(b->ctx->device);
+  if (b->ctx) {
+    cudaSetDevice(b->ctx->device);
+    if (b->on_device) cudaStreamSynchronize(b->ctx->stream);
+  }
   delete b;
 }
 

@@ -181,6 +181,7 @@ struct hs_pending {
 struct hs_batch {
   hs_ctx* ctx = nullptr;
   int64_t nrows = 0;
+  bool on_device = false;
   struct Col {
     std::string name;
     int32_t type;

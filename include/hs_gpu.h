@@ -204,7 +204,8 @@ typedef struct {
   int64_t lo, hi;
   const int64_t* deleted_file_ids; /* Hybrid Scan: NOT (_data_file_id IN ids) (covering/CoveringIndexRuleUtils.scala:244-253) */
   int32_t n_deleted_file_ids;
-  int32_t reserved;
+  int32_t output;              /* HS_OUT_HOST (or 0): result columns in pinned host memory; HS_OUT_DEVICE: left in device
+                                  memory for the next GPU operator (hs_batch_column then yields device pointers) */
 } hs_scan_spec;
 
 /* Executes the scan FilterIndexRule.applyIndex substitutes for the source scan
@@ -219,7 +220,7 @@ typedef struct {
   const int32_t* left_buckets;       /* bucket id per left file  (BucketingUtils.getBucketId on the file name) */
   const int32_t* right_buckets;
   int32_t num_buckets;
-  int32_t reserved;
+  int32_t output;                    /* HS_OUT_HOST (or 0) / HS_OUT_DEVICE, as in hs_scan_spec */
   const char* left_key;              /* single integer join key on each side */
   const char* right_key;
   const char* const* left_columns;   /* projected from the left side */
@@ -234,9 +235,10 @@ typedef struct {
 int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_stats* stats, char* err, size_t errlen);
 
 int64_t hs_batch_num_rows(const hs_batch* b);
+int32_t hs_batch_on_device(const hs_batch* b); /* != 0: the column pointers are device pointers (output = HS_OUT_DEVICE) */
 int32_t hs_batch_num_columns(const hs_batch* b);
-/* Column i: name, HS_TYPE_*, host pointer to num_rows values, host pointer to one validity byte per row
- * (NULL when the column has no nulls). */
+/* Column i: name, HS_TYPE_*, pointer to num_rows values, pointer to one validity byte per row (NULL when the column
+ * has no nulls); host pointers unless hs_batch_on_device. */
 int hs_batch_column(const hs_batch* b, int32_t i, const char** name, int32_t* type, const void** data,
                     const uint8_t** valid);
 void hs_batch_free(hs_batch* b);
