@@ -159,6 +159,7 @@ def cpu_write_sources(sample_rows: int, n_files: int, nthreads: int, workdir: st
 
 def cpu_create_index(paths, nthreads: int, workdir: str):
     """Times the oracle port (CPU restatement of the reference path) over the given source files.  Returns seconds."""
+    import numpy as np
     import pyarrow as pa
     import pyarrow.parquet as pq
     from concurrent.futures import ThreadPoolExecutor
@@ -169,11 +170,20 @@ def cpu_create_index(paths, nthreads: int, workdir: str):
     out_dir = os.path.join(workdir, "idx")
     t0 = time.perf_counter()
     order = INDEXED + INCLUDED
-    # one decode task per file over all cores (Spark: one scan task per file split)
+    # one decode task per file over all cores (Spark: one scan task per file split); every task writes its rows straight
+    # into the table-wide column arrays, so nothing is concatenated on one thread afterwards
+    counts = [pq.ParquetFile(p).metadata.num_rows for p in paths]
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    schema = pq.ParquetFile(paths[0]).schema_arrow
+    cols = {name: np.empty(int(starts[-1]), dtype=schema.field(name).type.to_pandas_dtype()) for name in order}
+
+    def decode(i):
+        t = pq.read_table(paths[i], columns=order, use_threads=False)
+        for name in order:
+            cols[name][starts[i]:starts[i + 1]] = t.column(name).to_numpy()
+
     with ThreadPoolExecutor(max_workers=max(1, min(nthreads, len(paths)))) as ex:
-        tables = list(ex.map(lambda p: pq.read_table(p, columns=order, use_threads=False), paths))
-    t = pa.concat_tables(tables).combine_chunks()
-    cols = {name: t.column(name).chunk(0).to_numpy() for name in order}
+        list(ex.map(decode, range(len(paths))))
     perm, offs, _ = O.index_rows(cols, INDEXED, INCLUDED, NUM_BUCKETS, nthreads=nthreads)
     os.makedirs(out_dir, exist_ok=True)
 

@@ -415,8 +415,7 @@ int hs_stage_sources(hs_ctx* ctx, const hs_source_file* files, int32_t n_files, 
     }
     HS_CUDA(cudaEventCreateWithFlags(&sg->ready, cudaEventDisableTiming));
     HS_CUDA(cudaEventRecord(sg->ready, ctx->h2d_stream));
-    ctx->staged_ready.push_back(sg->ready);
-    for (int f = 0; f < n_files; f++) ctx->staged_meta[sg->files[f].data] = sg->metas[f];
+    for (int f = 0; f < n_files; f++) ctx->staged[sg->files[f].data] = hs_ctx::StagedImage{sg->metas[f], sg->ready};
     ctx->launches = launches_before;
   });
   if (rc == HS_OK) *out = sg.release();
@@ -444,11 +443,9 @@ void hs_staged_free(hs_staged* s) {
   cudaSetDevice(ctx->device);
   if (s->ready) {
     cudaEventSynchronize(s->ready);  // the copies read caller memory / pinned staging and write d_images
-    auto& v = ctx->staged_ready;
-    v.erase(std::remove(v.begin(), v.end(), s->ready), v.end());
     cudaEventDestroy(s->ready);
   }
-  for (const hs_source_file& f : s->files) ctx->staged_meta.erase(f.data);
+  for (const hs_source_file& f : s->files) ctx->staged.erase(f.data);
   cudaStreamSynchronize(ctx->stream);  // a build that decodes these images may still be running
   delete s;
 }

@@ -234,17 +234,26 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
   Buf<uint8_t> pinned_tails, pinned_footers;
   bool any_dev = false;
   for (int f = 0; f < n_files; f++) any_dev = any_dev || (files[f].data && files[f].on_device);
-  // images staged by hs_stage_sources may still be on their way: everything this call enqueues waits for those copies
-  if (any_dev)
-    for (cudaEvent_t ev : ctx->staged_ready) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
-  // ... and their footers were parsed from host memory when they were staged
+  // images staged by hs_stage_sources may still be on their way: everything this call enqueues waits for THEIR copies (and
+  // only theirs: the images of the next call are being staged at this very moment); their footers were parsed from host
+  // memory when they were staged
   std::vector<std::shared_ptr<pq::FileMeta>> cached(n_files);
   bool fetch_footers = false;
-  for (int f = 0; f < n_files; f++) {
-    if (!(files[f].data && files[f].on_device)) continue;
-    auto it = ctx->staged_meta.find(files[f].data);
-    if (it != ctx->staged_meta.end()) cached[f] = it->second;
-    else fetch_footers = true;
+  {
+    cudaEvent_t last_ev = nullptr;
+    for (int f = 0; f < n_files; f++) {
+      if (!(files[f].data && files[f].on_device)) continue;
+      auto it = ctx->staged.find(files[f].data);
+      if (it == ctx->staged.end()) {
+        fetch_footers = true;
+        continue;
+      }
+      cached[f] = it->second.meta;
+      if (it->second.ready != last_ev) {
+        last_ev = it->second.ready;
+        HS_CUDA(cudaStreamWaitEvent(ctx->stream, last_ev, 0));
+      }
+    }
   }
   if (any_dev && !fetch_footers) {
     for (int f = 0; f < n_files; f++)

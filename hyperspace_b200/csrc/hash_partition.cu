@@ -453,8 +453,29 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads) k_tile_hist(const Ke
   }
 }
 
-// dynamic shared memory layout: [exchange buffer kFusedTile * 8 B][pos_bin u16 kFusedTile][cnt u16 kFWarps*nb]
-// [out_adj u32 nb][bin_owner u32 nb][warp_sums 40 u32]
+// ---- bulk asynchronous stores (TMA engine, 1-D): shared memory -> global / peer memory ----------------------------------
+// A bucket's rows leave the tile as ONE cp.async.bulk per column instead of one 8-byte store per row: the copy engine reads
+// the run from shared memory and writes it as full-width transactions -- over NVLink that is one packet stream per run
+// instead of a sector-sized write per warp slice -- and the issuing thread is free at once.  Both addresses and the size must
+// be multiples of 16 bytes: runs are laid out in the exchange buffer with the same 16-byte phase as their destination (see
+// the padded layout below); an odd head / tail element goes out as a plain store.
+__device__ __forceinline__ void bulk_store_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory source of every committed group has been read (the global writes may still be in flight)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (the copy engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// dynamic shared memory layout: [exchange buffer XN * 8 B][pos_bin u16 XN][cnt u16 kFWarps*nb][out_adj u32 nb]
+// [bin_owner u32 nb][run_start u16 nb][run_len u16 nb][warp_sums 40 u32], XN = kFusedTile + 2 nb + 2
+//
+// Padded layout of the exchange buffer: bin b's run starts at s_b = P_b + 2 b + ((P_b ^ d_b) & 1), P_b = rows of the bins
+// before it, d_b = its destination element index.  Runs never overlap (s_b - end of run b-1 is 1, 2 or 3) and s_b has the
+// parity of d_b, so an 8-byte column's run and its destination share their 16-byte phase.
 //
 // All warp collectives run with the full mask and outside any branch: slots past the end of the last tile carry the
 // last bin and, being the last slots of the tile, rank behind every real row of that bin; they are never written out.
@@ -464,20 +485,25 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
                                                                const uint32_t* __restrict__ tile_dst,
                                                                const PartColumn* __restrict__ cols, int ncols,
                                                                void* const* __restrict__ peer_out, int out_world,
-                                                               CodePackRound pack, const uint16_t* __restrict__ bin_ids) {
+                                                               CodePackRound pack, const uint16_t* __restrict__ bin_ids,
+                                                               int bulk) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int kFThreads = FusedCfg<PEER>::kThreads, kFItems = FusedCfg<PEER>::kItems, kFusedTile = FusedCfg<PEER>::kTile;
   constexpr int kFWarps = FusedCfg<PEER>::kWarps, kFWarpRows = FusedCfg<PEER>::kWarpRows;
   const int nb = use_owner ? (int)owner_mod.n : (int)bucket_mod.n;
+  const uint32_t XN = (uint32_t)kFusedTile + 2u * (uint32_t)nb + 2u;
   uint64_t* xbuf = reinterpret_cast<uint64_t*>(smem);
-  uint16_t* pos_bin = reinterpret_cast<uint16_t*>(smem + (size_t)kFusedTile * 8);
-  uint16_t* cnt = pos_bin + kFusedTile;
-  uint32_t* out_adj = reinterpret_cast<uint32_t*>(cnt + (size_t)kFWarps * nb + ((kFWarps * nb) & 1));
+  uint16_t* pos_bin = reinterpret_cast<uint16_t*>(smem + (size_t)XN * 8);
+  uint16_t* cnt = pos_bin + XN;
+  uint32_t* out_adj = reinterpret_cast<uint32_t*>(cnt + (size_t)kFWarps * nb + ((XN + (size_t)kFWarps * nb) & 1));
   uint32_t* bin_owner = out_adj + nb;
-  uint32_t* warp_sums = bin_owner + nb;
+  uint16_t* run_start = reinterpret_cast<uint16_t*>(bin_owner + nb);
+  uint16_t* run_len = run_start + nb;
+  uint32_t* warp_sums = reinterpret_cast<uint32_t*>(run_len + nb + (nb & 1));
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1;
   for (int i = threadIdx.x; i < kFWarps * nb; i += kFThreads) cnt[i] = 0;
+  for (uint32_t i = threadIdx.x; i < XN; i += kFThreads) pos_bin[i] = 0xffffu;  // padding slots belong to no bin
   const int64_t tile_base = (int64_t)blockIdx.x * kFusedTile;
   const uint32_t first = warp * kFWarpRows + lane;  // tile-relative row of this thread's item 0
   const int64_t wbase = tile_base + first;
@@ -513,7 +539,7 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
     bin[j] |= (pre + before) << 16;
   }
   __syncthreads();
-  // per bin: exclusive prefix over warps and bins -> first in-tile position of every (warp, bin)
+  // per bin: exclusive prefix over warps and bins -> first position of every (warp, bin) in the padded exchange buffer
   uint32_t carry = 0;
   for (int b0 = 0; b0 < nb; b0 += kFThreads) {
     const int b = b0 + threadIdx.x;
@@ -525,9 +551,14 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
     uint32_t chunk_total = 0;
     const uint32_t ex = block_exclusive_scan(total, warp_sums, &chunk_total);
     if (b < nb) {
-      uint32_t run = carry + ex;
-      out_adj[b] = tile_dst[(size_t)blockIdx.x * nb + b] - run;
+      const uint32_t P = carry + ex;
+      const uint32_t dst = tile_dst[(size_t)blockIdx.x * nb + b];
+      uint32_t run = P + 2u * (uint32_t)b + ((P ^ dst) & 1u);
+      out_adj[b] = dst - run;
       bin_owner[b] = out_world > 1 ? (uint32_t)b % (uint32_t)out_world : 0u;
+      run_start[b] = (uint16_t)run;
+      // the phantom slots of a partial last tile sit at the end of the last bin's run
+      run_len[b] = (uint16_t)(b == nb - 1 ? total - ((uint32_t)kFusedTile - tile_count) : total);
 #pragma unroll
       for (int w = 0; w < kFWarps; w++) {
         const uint16_t c = cnt[(size_t)w * nb + b];
@@ -538,13 +569,34 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
     carry += chunk_total;
   }
   __syncthreads();
+  const uint32_t x_end = (uint32_t)run_start[nb - 1] + run_len[nb - 1];  // positions in use: [0, x_end)
 #pragma unroll
   for (int j = 0; j < kFItems; j++) {
     const uint32_t b = bin[j] & 0xffffu;
     bin[j] = wcnt[b] + (bin[j] >> 16);
-    pos_bin[bin[j]] = (uint16_t)b;
+    if (first + j * 32 < tile_count) pos_bin[bin[j]] = (uint16_t)b;
   }
   const uint32_t(&pos)[kFItems] = bin;
+  // one bin's run of an 8-byte column: [odd head element] [16-byte aligned body as ONE bulk copy] [odd tail element]
+  auto store_runs = [&](void* const* pout, void* local_out) {
+    for (int b = threadIdx.x; b < nb; b += kFThreads) {
+      const uint32_t n = run_len[b];
+      if (n == 0) continue;
+      const uint32_t s = run_start[b];
+      uint64_t* dst = (uint64_t*)(pout ? pout[bin_owner[b]] : local_out) + (out_adj[b] + s);
+      const uint32_t h = (uint32_t)(((uintptr_t)dst >> 3) & 1u);
+      if ((h ^ s) & 1u) {  // output base not 16-byte aligned (never the case for pool buffers): plain stores
+        for (uint32_t i = 0; i < n; i++) dst[i] = xbuf[s + i];
+        continue;
+      }
+      if (h) dst[0] = xbuf[s];
+      const uint32_t body = (n - h) & ~1u;
+      if (body) bulk_store_s2g(dst + h, xbuf + s + h, body * 8u);
+      if ((n - h) & 1u) dst[n - 1] = xbuf[s + n - 1];
+    }
+    bulk_commit();
+    bulk_wait_read();  // the runs have left shared memory: the next round may overwrite the buffer
+  };
   // ---- move every column through the exchange buffer -----------------------------------------------------------
   for (int c = 0; c < ncols; c++) {
     const PartColumn pc = cols[c];
@@ -567,29 +619,37 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
       for (int j = 0; j < kFItems; j++)
         if (first + j * 32 < tile_count) xb[pos[j]] = in[j * 32];
     }
+    if (bulk && pc.width == 8) fence_async_smem();
     __syncthreads();
     // peer_out != nullptr: bucket b lives on GPU (b % out_world); its column c buffer is peer_out[c * out_world + owner]
     // (a peer-mapped pointer: these stores go straight over NVLink into the owner's memory)
     void* const* pout = peer_out ? peer_out + (size_t)c * out_world : nullptr;
     if (pc.width == 8) {
+      if (bulk) {
+        store_runs(pout, pc.out);
+      } else {
 #pragma unroll 4
-      for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
-        const uint32_t b = pos_bin[i];
-        uint64_t* out = (uint64_t*)(pout ? pout[bin_owner[b]] : pc.out);
-        out[out_adj[b] + i] = xbuf[i];
+        for (uint32_t i = threadIdx.x; i < x_end; i += kFThreads) {
+          const uint32_t b = pos_bin[i];
+          if (b == 0xffffu) continue;
+          uint64_t* out = (uint64_t*)(pout ? pout[bin_owner[b]] : pc.out);
+          out[out_adj[b] + i] = xbuf[i];
+        }
       }
     } else if (pc.width == 4) {
       const uint32_t* xb = reinterpret_cast<const uint32_t*>(xbuf);
 #pragma unroll 4
-      for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
+      for (uint32_t i = threadIdx.x; i < x_end; i += kFThreads) {
         const uint32_t b = pos_bin[i];
+        if (b == 0xffffu) continue;
         uint32_t* out = (uint32_t*)(pout ? pout[bin_owner[b]] : pc.out);
         out[out_adj[b] + i] = xb[i];
       }
     } else {
       const uint8_t* xb = reinterpret_cast<const uint8_t*>(xbuf);
-      for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
+      for (uint32_t i = threadIdx.x; i < x_end; i += kFThreads) {
         const uint32_t b = pos_bin[i];
+        if (b == 0xffffu) continue;
         uint8_t* out = (uint8_t*)(pout ? pout[bin_owner[b]] : pc.out);
         out[out_adj[b] + i] = xb[i];
       }
@@ -609,24 +669,31 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
         xbuf[pos[j]] = (uint64_t)lo | ((uint64_t)hi << 32);
       }
     }
+    if (bulk) fence_async_smem();
     __syncthreads();
     // on several GPUs the records go to the bucket's owner like every column: their row of the peer table follows the
     // column rounds'
     void* const* pout = peer_out ? peer_out + (size_t)ncols * out_world : nullptr;
+    if (bulk) {
+      store_runs(pout, pack.out);
+    } else {
 #pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < tile_count; i += kFThreads) {
-      const uint32_t b = pos_bin[i];
-      uint64_t* out = (uint64_t*)(pout ? pout[bin_owner[b]] : pack.out);
-      out[out_adj[b] + i] = xbuf[i];
+      for (uint32_t i = threadIdx.x; i < x_end; i += kFThreads) {
+        const uint32_t b = pos_bin[i];
+        if (b == 0xffffu) continue;
+        uint64_t* out = (uint64_t*)(pout ? pout[bin_owner[b]] : pack.out);
+        out[out_adj[b] + i] = xbuf[i];
+      }
     }
   }
 }
 
 template <bool PEER>
 size_t fused_smem_bytes(int nb) {
-  size_t cnt_entries = (size_t)FusedCfg<PEER>::kWarps * nb;
-  cnt_entries += cnt_entries & 1;
-  return (size_t)FusedCfg<PEER>::kTile * 8 + (size_t)FusedCfg<PEER>::kTile * 2 + cnt_entries * 2 + (size_t)nb * 4 * 2 + 40 * 4;
+  const size_t XN = (size_t)FusedCfg<PEER>::kTile + 2 * (size_t)nb + 2;
+  size_t u16s = XN + (size_t)FusedCfg<PEER>::kWarps * nb;
+  u16s += u16s & 1;
+  return XN * 8 + u16s * 2 + (size_t)nb * 4 * 2 + ((size_t)nb * 2 + (nb & 1)) * 2 + 40 * 4;
 }
 
 }  // namespace
@@ -678,6 +745,7 @@ struct PartitionLaunch {
   int out_world;
   CodePackRound pack;
   const uint16_t* bin_ids;
+  int bulk;
 };
 
 template <int BITS, int KT, bool PEER>
@@ -693,7 +761,7 @@ static void launch_partition_rows_t(hs_ctx* ctx, const PartitionLaunch& a) {
   }
   k_partition_rows<BITS, KT, PEER><<<(unsigned)ntiles, FusedCfg<PEER>::kThreads, fused_smem_bytes<PEER>(nb), ctx->stream>>>(
       a.d_keys, a.nkeys, a.nrows, make_mod_const((uint32_t)a.num_buckets), make_mod_const((uint32_t)std::max(a.owner_mod, 1)),
-      a.owner_mod > 0 ? 1 : 0, a.tile_dst, a.d_cols, a.ncols, a.d_peer_out, a.out_world, a.pack, a.bin_ids);
+      a.owner_mod > 0 ? 1 : 0, a.tile_dst, a.d_cols, a.ncols, a.d_peer_out, a.out_world, a.pack, a.bin_ids, a.bulk);
   HS_LAUNCH_CHECK(ctx);
 }
 
@@ -720,7 +788,10 @@ void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int6
                            int out_world, int single_key_type, const CodePackRound* pack_round, const uint16_t* bin_ids) {
   KernelScope _ks(ctx, "k_partition_rows");
   if (nrows == 0) return;
-  PartitionLaunch a{d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, {}, bin_ids};
+  // HS_PART_BULK=0|1: plain 8-byte stores or cp.async.bulk runs (A/B switch; default: bulk when the runs leave over NVLink)
+  static const char* bulk_env = getenv("HS_PART_BULK");
+  const int bulk = bulk_env ? atoi(bulk_env) : (d_peer_out ? 1 : 0);
+  PartitionLaunch a{d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, {}, bin_ids, bulk};
   memset(&a.pack, 0, sizeof a.pack);
   if (pack_round) a.pack = *pack_round;
   // tiles that leave over NVLink use the large shape (the tile histogram must have been taken with peer_tiles = true)

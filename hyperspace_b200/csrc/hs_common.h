@@ -128,8 +128,14 @@ struct hs_ctx {
   // drain of the PREVIOUS call's index files overlap this call's kernels and each other (PCIe is full duplex).
   cudaStream_t h2d_stream = nullptr;   // hs_stage_sources
   cudaStream_t d2h_stream = nullptr;   // hs_create_index_async -> hs_pending_wait
-  std::vector<cudaEvent_t> staged_ready;  // "copied" events of the live hs_staged handles: device images wait on them
-  std::map<const void*, std::shared_ptr<hs::pq::FileMeta>> staged_meta;  // footers of staged images, parsed on the host
+  // device images staged by hs_stage_sources, by address: the footer parsed from host memory on the way, and the event
+  // behind the copy (a call that reads the image makes its stream wait for exactly that event -- not for the copies of
+  // images staged for LATER calls, which are already in flight at that point)
+  struct StagedImage {
+    std::shared_ptr<hs::pq::FileMeta> meta;
+    cudaEvent_t ready;
+  };
+  std::map<const void*, StagedImage> staged;
   int sm_count = 148;
   hs::BufferPool pool;
   int launches = 0;  // kernels launched by the current call (hs_stats.gpu_launches)
