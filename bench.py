@@ -502,6 +502,8 @@ def run_create_index(rig, args):
                 res.free()
             return st
 
+        copy_ms = {"h2d": [], "d2h": [], "build": []}
+
         def pipelined(steps, keep_last=False):
             """stage(i+1) | build(i) | drain(i-1): three calls in flight, each step's copies inside this function."""
             nxt = ctx.stage_sources(host_in)
@@ -509,9 +511,12 @@ def run_create_index(rig, args):
             for i in range(steps):
                 cur, nxt = nxt, (ctx.stage_sources(host_in) if i + 1 < steps else None)
                 pend = ctx.create_index_async(cur.as_sources(), INDEXED, INCLUDED, NUM_BUCKETS, output=N.HS_OUT_HOST, **kw)
+                copy_ms["h2d"].append(cur.wait())
                 cur.free()
                 if prev is not None:
-                    consume(prev)
+                    st = consume(prev)
+                    copy_ms["d2h"].append(st["ms_d2h"])
+                    copy_ms["build"].append(st["ms_total"] - st["ms_d2h"])
                 prev = pend
             consume(prev, keep=keep_last)
 
@@ -523,7 +528,10 @@ def run_create_index(rig, args):
             return st
 
         pipelined(max(2, args.warmup))
+        for v in copy_ms.values():
+            v.clear()
         ms_pipe, _ = rig.timed(lambda: pipelined(args.steps, keep_last=not args.no_verify))
+        avg = lambda v: (sum(v) / len(v)) if v else None  # noqa: E731
         ms_e2e = ms_pipe / args.steps
         single_call()
         ms_single, st_single = rig.timed(single_call)
@@ -531,6 +539,7 @@ def run_create_index(rig, args):
                "d2h_bytes_per_step": int(out_bytes[0]), "ms_per_step": ms_e2e,
                "h2d_GBps_per_rank": src_bytes / (ms_e2e / 1e3) / 1e9, "d2h_GBps_per_rank": out_bytes[0] / (ms_e2e / 1e3) / 1e9,
                "calls_in_flight": 3, "single_call_ms": ms_single,
+               "pipelined_ms": {"h2d_copy": avg(copy_ms["h2d"]), "d2h_copy": avg(copy_ms["d2h"]), "build": avg(copy_ms["build"])},
                "single_call_copy_ms": {"h2d": st_single.get("ms_h2d"), "d2h": st_single.get("ms_d2h")},
                "note": "pinned HOST Parquet images in, HOST index images out, per-rank bytes; timed over K steps software-pipelined "
                        "through hs_stage_sources / hs_create_index_async / hs_pending_wait (H2D of step i+1 and D2H of step i-1 "

@@ -174,7 +174,7 @@ def load_library() -> C.CDLL:
     L.hs_staged_file.restype = C.c_int
     L.hs_staged_file.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SourceFile)]
     L.hs_staged_wait.restype = C.c_int
-    L.hs_staged_wait.argtypes = [C.c_void_p]
+    L.hs_staged_wait.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.hs_staged_free.restype = None
     L.hs_staged_free.argtypes = [C.c_void_p]
     L.hs_create_index_async.restype = C.c_int
@@ -308,9 +308,12 @@ class Staged:
     def as_sources(self) -> List[FileImage]:
         return list(self.files)
 
-    def wait(self) -> None:
-        if self._h and load_library().hs_staged_wait(self._h) != HS_OK:
+    def wait(self) -> float:
+        """Blocks until the copies have completed; returns their duration on the H2D stream in ms."""
+        ms = C.c_float(0)
+        if self._h and load_library().hs_staged_wait(self._h, C.byref(ms)) != HS_OK:
             raise HyperspaceGpuError(HS_ECUDA, "hs_staged_wait failed")
+        return float(ms.value)
 
     def free(self) -> None:
         if self._h:

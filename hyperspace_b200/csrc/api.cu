@@ -36,12 +36,12 @@ int guarded(hs_ctx* ctx, char* err, size_t errlen, F&& f) {
     return HS_OK;
   } catch (const hs::Error& e) {
     set_err(err, errlen, e.what());
-    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (ctx) xfer_abort(ctx);
     cudaGetLastError();
     return e.code;
   } catch (const std::exception& e) {
     set_err(err, errlen, e.what());
-    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (ctx) xfer_abort(ctx);
     cudaGetLastError();
     return HS_EINVAL;
   }
@@ -150,14 +150,14 @@ void drop_deleted_rows(hs_ctx* ctx, Table& t, const int64_t* deleted, int ndelet
   Buf<uint32_t> mask(ctx, n);
   Buf<uint64_t> offs(ctx, n + 1);
   Buf<int64_t> d_del(ctx, ndeleted);
-  HS_CUDA(cudaMemcpyAsync(d_del.get(), deleted, sizeof(int64_t) * ndeleted, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_del.get(), deleted, sizeof(int64_t) * ndeleted);
   k_fill_u32<<<(int)std::min<int64_t>(ceil_div(n, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(mask.get(), n, 1u);
   HS_LAUNCH_CHECK(ctx);
   launch_not_in_mask(ctx, (const int64_t*)t.cols[lc].data.get(), n, d_del.get(), ndeleted, mask.get());
   exclusive_scan_u32_u64(ctx, mask.get(), n, offs.get());
   uint64_t kept = 0;
-  HS_CUDA(cudaMemcpyAsync(&kept, offs.get() + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  copy_d2h(ctx, &kept, offs.get() + n, 8);
+  sync_stream(ctx);
   Buf<uint32_t> idx(ctx, std::max<uint64_t>(1, kept));
   launch_compact_indices(ctx, mask.get(), offs.get(), n, idx.get());
   gather_table(ctx, t, idx.get(), (int64_t)kept);
@@ -201,9 +201,9 @@ void finish_result(hs_ctx* ctx, EncodedFiles& enc, int output, const char* out_d
   t.start();
   res->h_arena.alloc(ctx, std::max<uint64_t>(enc.arena_bytes, 16), /*pinned=*/true);
   if (enc.arena_bytes)
-    HS_CUDA(cudaMemcpyAsync(res->h_arena.get(), enc.arena.get(), enc.arena_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    copy_d2h(ctx, res->h_arena.get(), enc.arena.get(), enc.arena_bytes);
   t.stop();
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  sync_stream(ctx);
   st->ms_d2h += t.ms();
   if (output == HS_OUT_FILES) write_result_files(res, out_dir ? out_dir : "", save_mode);
 }
@@ -280,7 +280,7 @@ int hs_init(int device_id, void* cuda_stream, hs_ctx** out, char* err, size_t er
 void hs_shutdown(hs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  xfer_release(ctx);
   comm_destroy(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   if (ctx->h2d_stream) {
@@ -389,6 +389,8 @@ int hs_stage_sources(hs_ctx* ctx, const hs_source_file* files, int32_t n_files, 
       total += round_up(sizes[f], 16) + 16;
     }
     sg->d_images.alloc(ctx, std::max<uint64_t>(total, 16));
+    HS_CUDA(cudaEventCreate(&sg->begin));
+    HS_CUDA(cudaEventRecord(sg->begin, ctx->h2d_stream));
     sg->files.resize(n_files);
     sg->names.resize(n_files);
     sg->metas.resize(n_files);
@@ -413,7 +415,7 @@ int hs_stage_sources(hs_ctx* ctx, const hs_source_file* files, int32_t n_files, 
       o.reserved = 0;
       sg->bytes += sizes[f];
     }
-    HS_CUDA(cudaEventCreateWithFlags(&sg->ready, cudaEventDisableTiming));
+    HS_CUDA(cudaEventCreate(&sg->ready));
     HS_CUDA(cudaEventRecord(sg->ready, ctx->h2d_stream));
     for (int f = 0; f < n_files; f++) ctx->staged[sg->files[f].data] = hs_ctx::StagedImage{sg->metas[f], sg->ready};
     ctx->launches = launches_before;
@@ -431,10 +433,27 @@ int hs_staged_file(const hs_staged* s, int32_t i, hs_source_file* out) {
   return HS_OK;
 }
 
-int hs_staged_wait(hs_staged* s) {
+// HS_TIMELINE=1: begin / end of every staged copy, build and drain relative to the first event seen, on stderr
+static void timeline(hs_ctx* ctx, const char* what, cudaEvent_t a, cudaEvent_t b) {
+  static const bool on = getenv("HS_TIMELINE") != nullptr;
+  if (!on || !a || !b) return;
+  static cudaEvent_t base = nullptr;
+  if (!base) base = a;  // (leaks one reference to an event that may be destroyed later: diagnostics only, first event kept alive)
+  float t0 = 0, t1 = 0;
+  if (cudaEventElapsedTime(&t0, base, a) != cudaSuccess || cudaEventElapsedTime(&t1, base, b) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  fprintf(stderr, "[hs timeline] %-8s %10.2f -> %10.2f  (%8.2f ms)\n", what, t0, t1, t1 - t0);
+}
+
+int hs_staged_wait(hs_staged* s, float* ms_copy) {
   if (!s) return HS_EINVAL;
   cudaSetDevice(s->ctx->device);
-  return cudaEventSynchronize(s->ready) == cudaSuccess ? HS_OK : HS_ECUDA;
+  if (cudaEventSynchronize(s->ready) != cudaSuccess) return HS_ECUDA;
+  if (ms_copy && cudaEventElapsedTime(ms_copy, s->begin, s->ready) != cudaSuccess) *ms_copy = 0;
+  timeline(s->ctx, "H2D", s->begin, s->ready);
+  return HS_OK;
 }
 
 void hs_staged_free(hs_staged* s) {
@@ -445,6 +464,7 @@ void hs_staged_free(hs_staged* s) {
     cudaEventSynchronize(s->ready);  // the copies read caller memory / pinned staging and write d_images
     cudaEventDestroy(s->ready);
   }
+  if (s->begin && !getenv("HS_TIMELINE")) cudaEventDestroy(s->begin);  // (the timeline's base event is one of these)
   for (const hs_source_file& f : s->files) ctx->staged.erase(f.data);
   cudaStreamSynchronize(ctx->stream);  // a build that decodes these images may still be running
   delete s;
@@ -564,6 +584,8 @@ int hs_pending_wait(hs_pending* p, hs_index_result** out, hs_stats* stats, char*
       st.ms_d2h += ms;
       HS_CUDA(cudaEventElapsedTime(&ms, pd->t_begin, pd->t_d2h_end));
       st.ms_total = ms;
+      timeline(ctx, "build", pd->t_begin, pd->t_compute_end);
+      timeline(ctx, "D2H", pd->t_d2h_begin, pd->t_d2h_end);
       pd->d_arena.release();
     } else {
       HS_CUDA(cudaEventSynchronize(pd->t_compute_end));
@@ -655,15 +677,15 @@ static void batch_from_gather(hs_ctx* ctx, const Table& t, const std::vector<int
       if (c.has_nulls) bc.valid = std::move(d_valid[i]);
     } else {
       bc.data.alloc(ctx, (size_t)std::max<int64_t>(1, n_out) * c.width, true);
-      if (n_out) HS_CUDA(cudaMemcpyAsync(bc.data.get(), d_data[i].get(), (size_t)n_out * c.width, cudaMemcpyDeviceToHost, ctx->stream));
+      if (n_out) copy_d2h(ctx, bc.data.get(), d_data[i].get(), (size_t)n_out * c.width);
       if (c.has_nulls) {
         bc.valid.alloc(ctx, (size_t)std::max<int64_t>(1, n_out), true);
-        if (n_out) HS_CUDA(cudaMemcpyAsync(bc.valid.get(), d_valid[i].get(), (size_t)n_out, cudaMemcpyDeviceToHost, ctx->stream));
+        if (n_out) copy_d2h(ctx, bc.valid.get(), d_valid[i].get(), (size_t)n_out);
       }
     }
     b->cols.push_back(std::move(bc));
   }
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  sync_stream(ctx);
   b->nrows = n_out;
 }
 
@@ -764,11 +786,11 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
       for (int f = 0; f <= nseg; f++) seg[f] = (uint64_t)t.file_row_begin[f];
       Buf<uint64_t> d_seg(ctx, nseg + 1);
       Buf<int64_t> d_bounds(ctx, 2 * std::max(1, nseg));
-      HS_CUDA(cudaMemcpyAsync(d_seg.get(), seg.data(), 8 * (nseg + 1), cudaMemcpyHostToDevice, ctx->stream));
+      copy_h2d(ctx, d_seg.get(), seg.data(), 8 * (nseg + 1));
       launch_range_bounds(ctx, d_keys, d_seg.get(), nseg, spec->has_lo, spec->lo, spec->has_hi, spec->hi, d_bounds.get());
       std::vector<int64_t> bounds(2 * std::max(1, nseg));
-      HS_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds.get(), 16 * nseg, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      copy_d2h(ctx, bounds.data(), d_bounds.get(), 16 * nseg);
+      sync_stream(ctx);
       std::vector<uint64_t> oo(nseg + 1, 0);
       for (int f = 0; f < nseg; f++) oo[f + 1] = oo[f] + (uint64_t)(bounds[2 * f + 1] - bounds[2 * f]);
       if (cols.size() > 1) {  // phase 2: decode the other columns, only the pages inside each file's [first, last)
@@ -781,13 +803,13 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
       }
       n_out = (int64_t)oo[nseg];
       Buf<uint64_t> d_oo(ctx, nseg + 1);
-      HS_CUDA(cudaMemcpyAsync(d_oo.get(), oo.data(), 8 * (nseg + 1), cudaMemcpyHostToDevice, ctx->stream));
+      copy_h2d(ctx, d_oo.get(), oo.data(), 8 * (nseg + 1));
       idx.alloc(ctx, std::max<int64_t>(1, n_out));
       if (nseg) {
         k_ranges_to_indices<<<nseg, 256, 0, ctx->stream>>>(d_bounds.get(), d_seg.get(), d_oo.get(), nseg, idx.get());
         HS_LAUNCH_CHECK(ctx);
       }
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      sync_stream(ctx);
     } else {
       // full predicate scan (appended source files under Hybrid Scan, or lineage NOT-IN filter)
       Buf<uint32_t> mask(ctx, std::max<int64_t>(1, n));
@@ -796,23 +818,23 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
                          spec->has_hi, spec->hi, mask.get());
       if (spec->n_deleted_file_ids > 0) {
         Buf<int64_t> d_del(ctx, spec->n_deleted_file_ids);
-        HS_CUDA(cudaMemcpyAsync(d_del.get(), spec->deleted_file_ids, 8 * spec->n_deleted_file_ids, cudaMemcpyHostToDevice, ctx->stream));
+        copy_h2d(ctx, d_del.get(), spec->deleted_file_ids, 8 * spec->n_deleted_file_ids);
         launch_not_in_mask(ctx, (const int64_t*)t.cols[lineage_col].data.get(), n, d_del.get(), spec->n_deleted_file_ids, mask.get());
-        HS_CUDA(cudaStreamSynchronize(ctx->stream));
+        sync_stream(ctx);
       }
       exclusive_scan_u32_u64(ctx, mask.get(), n, offs.get());
       uint64_t kept = 0;
-      HS_CUDA(cudaMemcpyAsync(&kept, offs.get() + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      copy_d2h(ctx, &kept, offs.get() + n, 8);
+      sync_stream(ctx);
       n_out = (int64_t)kept;
       idx.alloc(ctx, std::max<int64_t>(1, n_out));
       launch_compact_indices(ctx, mask.get(), offs.get(), n, idx.get());
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      sync_stream(ctx);
     }
     t_scan.stop();
     batch_from_gather(ctx, t, proj_idx, idx.get(), n_out, res.get());
     total.stop();
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    sync_stream(ctx);
     st.ms_sort += t_scan.ms();
     st.rows_out = n_out;
     st.ms_total = total.ms();
@@ -932,15 +954,15 @@ int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_sta
     StageTimer t_join(ctx);
     t_join.start();
     Buf<uint64_t> d_lseg(ctx, nb + 1), d_rseg(ctx, nb + 1);
-    HS_CUDA(cudaMemcpyAsync(d_lseg.get(), lseg.data(), 8 * (nb + 1), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(d_rseg.get(), rseg.data(), 8 * (nb + 1), cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_lseg.get(), lseg.data(), 8 * (nb + 1));
+    copy_h2d(ctx, d_rseg.get(), rseg.data(), 8 * (nb + 1));
     Buf<uint32_t> counts(ctx, std::max<int64_t>(1, nl)), first(ctx, std::max<int64_t>(1, nl));
     Buf<uint64_t> offs(ctx, nl + 1);
     launch_join_count(ctx, lkeys, d_lseg.get(), rkeys, d_rseg.get(), nb, nl, counts.get(), first.get());
     exclusive_scan_u32_u64(ctx, counts.get(), nl, offs.get());
     uint64_t total_out = 0;
-    HS_CUDA(cudaMemcpyAsync(&total_out, offs.get() + nl, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    copy_d2h(ctx, &total_out, offs.get() + nl, 8);
+    sync_stream(ctx);
     if (total_out >= (1ull << 32)) fail(HS_EUNSUPPORTED, "join output larger than 2^32-1 rows per call");
     Buf<uint32_t> li(ctx, std::max<uint64_t>(1, total_out)), ri(ctx, std::max<uint64_t>(1, total_out));
     launch_join_emit(ctx, counts.get(), first.get(), offs.get(), nl, li.get(), ri.get());
@@ -957,7 +979,7 @@ int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_sta
     batch_from_gather(ctx, lt, lproj, lrow.get(), (int64_t)total_out, res.get());
     batch_from_gather(ctx, rt, rproj, rrow.get(), (int64_t)total_out, res.get());
     total.stop();
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    sync_stream(ctx);
     st.ms_sort += t_join.ms();
     st.rows_out = (int64_t)total_out;
     st.ms_total = total.ms();
@@ -1004,14 +1026,14 @@ static void upload_table(hs_ctx* ctx, const hs_host_column* keys, int nkeys, int
     c.width = type_width(c.type);
     if (c.width == 0) fail(HS_EUNSUPPORTED, "key type %d is not handled by the GPU path", c.type);
     c.data.alloc(ctx, (size_t)nrows * c.width + 16);
-    if (nrows) HS_CUDA(cudaMemcpyAsync(c.data.get(), keys[k].data, (size_t)nrows * c.width, cudaMemcpyHostToDevice, ctx->stream));
+    if (nrows) copy_h2d(ctx, c.data.get(), keys[k].data, (size_t)nrows * c.width);
     if (keys[k].valid) {
       c.valid.alloc(ctx, (size_t)nrows + 16);
-      if (nrows) HS_CUDA(cudaMemcpyAsync(c.valid.get(), keys[k].valid, (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
+      if (nrows) copy_h2d(ctx, c.valid.get(), keys[k].valid, (size_t)nrows);
       c.has_nulls = true;
     }
   }
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  sync_stream(ctx);
 }
 
 int hs_k_bucket_ids(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64_t nrows, int32_t num_buckets,
@@ -1025,17 +1047,17 @@ int hs_k_bucket_ids(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int6
     for (int k = 0; k < nkeys; k++)
       h_keys[k] = KeyColumn{t.cols[k].data.get(), t.cols[k].has_nulls ? t.cols[k].valid.get() : nullptr, t.cols[k].type, t.cols[k].width};
     Buf<KeyColumn> d_keys(ctx, nkeys);
-    HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys);
     const int64_t ntiles = ceil_div(nrows, kPartTile);
     Buf<uint16_t> bucket(ctx, std::max<int64_t>(1, nrows));
     Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * num_buckets);
     Buf<unsigned long long> ghist(ctx, num_buckets);
-    HS_CUDA(cudaMemsetAsync(ghist.get(), 0, 8 * num_buckets, ctx->stream));
+    fill_bytes(ctx, ghist.get(), 0, 8 * num_buckets);
     launch_bucket_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, bucket.get(), tile_hist.get(), ghist.get());
     std::vector<uint16_t> hb(nrows);
-    if (nrows) HS_CUDA(cudaMemcpyAsync(hb.data(), bucket.get(), 2 * nrows, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_hist) HS_CUDA(cudaMemcpyAsync(out_hist, ghist.get(), 8 * num_buckets, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (nrows) copy_d2h(ctx, hb.data(), bucket.get(), 2 * nrows);
+    if (out_hist) copy_d2h(ctx, out_hist, ghist.get(), 8 * num_buckets);
+    sync_stream(ctx);
     if (out_bucket) for (int64_t i = 0; i < nrows; i++) out_bucket[i] = hb[i];
   });
 }
@@ -1061,8 +1083,8 @@ int hs_k_sort_perm(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64
     Buf<uint8_t> orig(ctx, (size_t)std::max<int64_t>(1, nrows) * 4);
     launch_gather_plain(ctx, rows.part.cols[nkeys].data.get(), rows.sorted_perm, nrows, 4, orig.get());
     std::vector<uint32_t> h(nrows);
-    if (nrows) HS_CUDA(cudaMemcpyAsync(h.data(), orig.get(), 4 * nrows, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (nrows) copy_d2h(ctx, h.data(), orig.get(), 4 * nrows);
+    sync_stream(ctx);
     for (int64_t i = 0; i < nrows; i++) out_perm[i] = h[i];
     for (int b = 0; b <= num_buckets; b++) out_bucket_offsets[b] = (int64_t)rows.bucket_offsets[b];
   });

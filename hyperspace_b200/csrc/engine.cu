@@ -131,11 +131,11 @@ static std::vector<uint64_t> sorted_dictionary(hs_ctx* ctx, const unsigned long 
   const uint32_t ntab = state[0];
   Buf<unsigned long long> d_list(ctx, std::max<uint32_t>(1, ntab) + 1);
   Buf<uint32_t> d_counter(ctx, 1);
-  HS_CUDA(cudaMemsetAsync(d_counter.get(), 0, 4, ctx->stream));
+  fill_bytes(ctx, d_counter.get(), 0, 4);
   launch_dict_collect(ctx, keys, kDictCapacity, d_list.get(), d_counter.get());
   std::vector<uint64_t> values(ntab);
-  if (ntab) HS_CUDA(cudaMemcpyAsync(values.data(), d_list.get(), 8 * (size_t)ntab, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ntab) copy_d2h(ctx, values.data(), d_list.get(), 8 * (size_t)ntab);
+  sync_stream(ctx);
   if (state[2]) values.push_back(~0ull);
   sort_dictionary(values, type);
   return values;
@@ -180,8 +180,8 @@ static void upload_lookup_table(hs_ctx* ctx, const std::vector<uint64_t>& values
     tab[(size_t)h * 4 + 2] = i;
   }
   entries->alloc(ctx, (size_t)cap * 16);
-  HS_CUDA(cudaMemcpyAsync(entries->get(), tab.data(), (size_t)cap * 16, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // tab goes out of scope
+  copy_h2d(ctx, entries->get(), tab.data(), (size_t)cap * 16);
+  sync_stream(ctx);  // tab goes out of scope
 }
 
 // out[dst_off .. dst_off + len) = src[0 .. len): gathers the tails / footers of device-resident file images into one
@@ -276,11 +276,11 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
       imgs[f].dev = (const uint8_t*)sf.data;
       h_spans.get()[nspans++] = SpanCopy{imgs[f].dev + sizes[f] - 8, (uint64_t)f * 8, 8};
     }
-    HS_CUDA(cudaMemcpyAsync(d_spans.get(), h_spans.get(), sizeof(SpanCopy) * nspans, cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_spans.get(), h_spans.get(), sizeof(SpanCopy) * nspans);
     k_gather_spans<<<nspans, 128, 0, ctx->stream>>>(d_spans.get(), d_gathered.get());
     HS_LAUNCH_CHECK(ctx);
-    HS_CUDA(cudaMemcpyAsync(pinned_tails.get(), d_gathered.get(), (size_t)n_files * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    copy_d2h(ctx, pinned_tails.get(), d_gathered.get(), (size_t)n_files * 8);
+    sync_stream(ctx);
     for (int f = 0; f < n_files; f++) {
       const hs_source_file& sf = files[f];
       footer_off[f + 1] = footer_off[f];
@@ -299,12 +299,12 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
       if (flen) h_spans.get()[nspans++] = SpanCopy{imgs[f].dev + sizes[f] - 8 - flen, footer_off[f], (uint32_t)flen};
     }
     if (nspans) {
-      HS_CUDA(cudaMemcpyAsync(d_spans.get(), h_spans.get(), sizeof(SpanCopy) * nspans, cudaMemcpyHostToDevice, ctx->stream));
+      copy_h2d(ctx, d_spans.get(), h_spans.get(), sizeof(SpanCopy) * nspans);
       k_gather_spans<<<nspans, 128, 0, ctx->stream>>>(d_spans.get(), d_footers.get());
       HS_LAUNCH_CHECK(ctx);
-      HS_CUDA(cudaMemcpyAsync(pinned_footers.get(), d_footers.get(), footer_off[n_files], cudaMemcpyDeviceToHost, ctx->stream));
+      copy_d2h(ctx, pinned_footers.get(), d_footers.get(), footer_off[n_files]);
     }
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    sync_stream(ctx);
   }
   for (int f = 0; f < n_files; f++) {
     const hs_source_file& sf = files[f];
@@ -323,12 +323,12 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
       }
       imgs[f].meta = pq::parse_footer(host, sizes[f], imgs[f].what.c_str());
       imgs[f].dev = d_images.get() + dev_off[f];
-      HS_CUDA(cudaMemcpyAsync(d_images.get() + dev_off[f], host, sizes[f], cudaMemcpyHostToDevice, ctx->stream));
+      copy_h2d(ctx, d_images.get() + dev_off[f], host, sizes[f]);
     }
     stats->bytes_in += (int64_t)sizes[f];
   }
   t_h2d.stop();
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // pinned staging buffers and caller memory are free to go
+  sync_stream(ctx);  // pinned staging buffers and caller memory are free to go
   stats->ms_h2d += t_h2d.ms();
 }
 
@@ -416,7 +416,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       dc.data.alloc(ctx, (size_t)nrows * dc.width + 16);
       if (col_optional[c]) {
         dc.valid.alloc(ctx, (size_t)nrows + 16);
-        HS_CUDA(cudaMemsetAsync(dc.valid.get(), 1, (size_t)nrows + 16, ctx->stream));
+        fill_bytes(ctx, dc.valid.get(), 1, (size_t)nrows + 16);
       }
       h_cols[c] = ColumnOut{dc.data.get(), col_optional[c] ? dc.valid.get() : nullptr, dc.width, dc.type, nullptr, 0u, 0u, 0, 0};
     }
@@ -427,7 +427,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   // (with several GPUs a rank without rows still takes part in the agreement on the late-materialised columns below)
   if ((n_chunks == 0 || nrows == 0) && !(want_carry && ctx->world > 1)) {
     alloc_destinations();
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    sync_stream(ctx);
     return;
   }
   // ---- page walk -----------------------------------------------------------------------------------------
@@ -437,12 +437,12 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   Buf<int64_t> d_offsets(ctx, std::max(1, n_chunks));
   Buf<uint32_t> d_flags(ctx, 1 + ncols);  // [0] error word, [1..] per-column has-nulls
   Buf<ColumnOut> d_cols(ctx, ncols);
-  HS_CUDA(cudaMemcpyAsync(d_chunks.get(), chunks.data(), sizeof(ChunkDesc) * n_chunks, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaMemsetAsync(d_flags.get(), 0, sizeof(uint32_t) * (1 + ncols), ctx->stream));
+  copy_h2d(ctx, d_chunks.get(), chunks.data(), sizeof(ChunkDesc) * n_chunks);
+  fill_bytes(ctx, d_flags.get(), 0, sizeof(uint32_t) * (1 + ncols));
   launch_walk_pages(ctx, d_chunks.get(), n_chunks, d_counts.get(), nullptr, nullptr, d_flags.get(), 0);
   std::vector<int32_t> counts(n_chunks);
-  HS_CUDA(cudaMemcpyAsync(counts.data(), d_counts.get(), sizeof(int32_t) * n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  copy_d2h(ctx, counts.data(), d_counts.get(), sizeof(int32_t) * n_chunks);
+  sync_stream(ctx);
   std::vector<int64_t> offsets(n_chunks);
   int64_t n_pages = 0;
   for (int i = 0; i < n_chunks; i++) {
@@ -450,12 +450,12 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
     n_pages += counts[i];
   }
   Buf<PageDesc> d_pages(ctx, std::max<int64_t>(1, n_pages));
-  HS_CUDA(cudaMemcpyAsync(d_offsets.get(), offsets.data(), sizeof(int64_t) * n_chunks, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_offsets.get(), offsets.data(), sizeof(int64_t) * n_chunks);
   launch_walk_pages(ctx, d_chunks.get(), n_chunks, d_counts.get(), d_offsets.get(), d_pages.get(), d_flags.get(), 1);
   {  // a chunk whose page headers do not add up must not reach the decoder: its pages would write outside the columns
     uint32_t walk_error = 0;
-    HS_CUDA(cudaMemcpyAsync(&walk_error, d_flags.get(), sizeof walk_error, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    copy_d2h(ctx, &walk_error, d_flags.get(), sizeof walk_error);
+    sync_stream(ctx);
     if (walk_error) {
       const uint32_t code = walk_error >> 24, detail = walk_error & 0xffffffu;
       fail(code == DERR_COMPRESSED ? HS_EUNSUPPORTED : HS_EFORMAT, "Parquet page walk failed: %s (column chunk %u)",
@@ -466,8 +466,8 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   Buf<uint8_t> d_scratch;
   if (any_compressed && n_pages > 0) {
     std::vector<PageDesc> h_pages((size_t)n_pages);
-    HS_CUDA(cudaMemcpyAsync(h_pages.data(), d_pages.get(), sizeof(PageDesc) * (size_t)n_pages, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    copy_d2h(ctx, h_pages.data(), d_pages.get(), sizeof(PageDesc) * (size_t)n_pages);
+    sync_stream(ctx);
     std::vector<SnappyBlob> blobs;
     std::map<const uint8_t*, uint64_t> dict_off;  // stored dictionary page -> scratch offset of its decompressed copy
     uint64_t cursor = 0;
@@ -507,10 +507,10 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       }
     }
     Buf<SnappyBlob> d_blobs(ctx, std::max<size_t>(1, blobs.size()));
-    HS_CUDA(cudaMemcpyAsync(d_blobs.get(), blobs.data(), sizeof(SnappyBlob) * blobs.size(), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(d_pages.get(), h_pages.data(), sizeof(PageDesc) * (size_t)n_pages, cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_blobs.get(), blobs.data(), sizeof(SnappyBlob) * blobs.size());
+    copy_h2d(ctx, d_pages.get(), h_pages.data(), sizeof(PageDesc) * (size_t)n_pages);
     launch_snappy_decompress(ctx, d_blobs.get(), (int64_t)blobs.size(), d_scratch.get(), d_flags.get());
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    sync_stream(ctx);  // host vectors go out of scope
   }
   // ---- late-materialised dictionary columns --------------------------------------------------------------------------
   // A candidate column whose every page is dictionary-encoded and free of nulls, and whose chunk dictionaries unite to a
@@ -524,10 +524,10 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
     std::vector<uint32_t> mine(ncols + 2, 0u), all((size_t)(ncols + 2) * W);
     if (n_pages > 0) {
       Buf<uint32_t> d_class(ctx, ncols);
-      HS_CUDA(cudaMemsetAsync(d_class.get(), 0, 4 * (size_t)ncols, ctx->stream));
+      fill_bytes(ctx, d_class.get(), 0, 4 * (size_t)ncols);
       launch_classify_pages(ctx, d_pages.get(), n_pages, d_class.get());
-      HS_CUDA(cudaMemcpyAsync(mine.data(), d_class.get(), 4 * (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      copy_d2h(ctx, mine.data(), d_class.get(), 4 * (size_t)ncols);
+      sync_stream(ctx);
     }
     mine[ncols] = (uint32_t)(nrows & 0xffffffffll);
     mine[ncols + 1] = (uint32_t)(nrows >> 32);
@@ -548,16 +548,16 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       std::vector<uint32_t> h_states(4 * (size_t)nc, 0u), all_states(4 * (size_t)nc * W);
       if (n_pages > 0) {
         Buf<uint32_t> d_states(ctx, 4 * (size_t)nc);
-        HS_CUDA(cudaMemsetAsync(d_states.get(), 0, 16 * (size_t)nc, ctx->stream));
+        fill_bytes(ctx, d_states.get(), 0, 16 * (size_t)nc);
         for (int i = 0; i < nc; i++) {
           DevColumn& dc = out->cols[cand[i]];
           dc.dict_keys.alloc(ctx, kDictCapacity);
-          HS_CUDA(cudaMemsetAsync(dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
+          fill_bytes(ctx, dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
           launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, cand[i], dc.width, dc.dict_keys.get(), kDictCapacity,
                                        kMaxDictEntries, d_states.get() + 4 * i);
         }
-        HS_CUDA(cudaMemcpyAsync(h_states.data(), d_states.get(), 16 * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
-        HS_CUDA(cudaStreamSynchronize(ctx->stream));
+        copy_d2h(ctx, h_states.data(), d_states.get(), 16 * (size_t)nc);
+        sync_stream(ctx);
       }
       comm_allgather_host(ctx, h_states.data(), 16 * (size_t)nc, all_states.data());
       for (int i = 0; i < nc; i++) {
@@ -601,7 +601,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
     }
   }
   alloc_destinations();
-  HS_CUDA(cudaMemcpyAsync(d_cols.get(), h_cols.data(), sizeof(ColumnOut) * ncols, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_cols.get(), h_cols.data(), sizeof(ColumnOut) * ncols);
   // ---- decode -----------------------------------------------------------------------------------------
   // optional per-file row windows (file-relative -> global): pages that do not intersect their file's window are skipped
   Buf<int64_t> d_window;
@@ -612,15 +612,15 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       w[2 * f + 1] = out->file_row_begin[f] + (*file_windows)[f].second;
     }
     d_window.alloc(ctx, w.size());
-    HS_CUDA(cudaMemcpyAsync(d_window.get(), w.data(), 8 * w.size(), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    copy_h2d(ctx, d_window.get(), w.data(), 8 * w.size());
+    sync_stream(ctx);
   }
   launch_decode_pages(ctx, d_pages.get(), n_pages, d_cols.get(), d_flags.get() + 1, file_windows ? d_window.get() : nullptr,
                       d_flags.get());
   std::vector<uint32_t> flags(1 + ncols);
-  HS_CUDA(cudaMemcpyAsync(flags.data(), d_flags.get(), sizeof(uint32_t) * (1 + ncols), cudaMemcpyDeviceToHost, ctx->stream));
+  copy_d2h(ctx, flags.data(), d_flags.get(), sizeof(uint32_t) * (1 + ncols));
   t_dec.stop();
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  sync_stream(ctx);
   if (flags[0]) {
     const uint32_t code = flags[0] >> 24, detail = flags[0] & 0xffffffu;
     const int ecode = (code == DERR_COMPRESSED || code == DERR_UNSUPPORTED_ENCODING || code == DERR_UNSUPPORTED_TYPE)
@@ -633,20 +633,20 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   if (!file_windows && ctx->world == 1) {
     std::vector<int> cand;
     Buf<uint32_t> d_states(ctx, 4 * (size_t)std::max(1, ncols));
-    HS_CUDA(cudaMemsetAsync(d_states.get(), 0, 16 * (size_t)std::max(1, ncols), ctx->stream));
+    fill_bytes(ctx, d_states.get(), 0, 16 * (size_t)std::max(1, ncols));
     for (int c = 0; c < ncols; c++) {
       DevColumn& dc = out->cols[c];
       if (dc.carried || (flags[1 + c] & 2u) || (dc.width != 4 && dc.width != 8)) continue;
       dc.dict_keys.alloc(ctx, kDictCapacity);
-      HS_CUDA(cudaMemsetAsync(dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
+      fill_bytes(ctx, dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
       launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, c, dc.width, dc.dict_keys.get(), kDictCapacity, kMaxDictEntries,
                                    d_states.get() + 4 * c);
       cand.push_back(c);
     }
     if (!cand.empty()) {
       std::vector<uint32_t> h_states(4 * (size_t)ncols);
-      HS_CUDA(cudaMemcpyAsync(h_states.data(), d_states.get(), 16 * (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      copy_d2h(ctx, h_states.data(), d_states.get(), 16 * (size_t)ncols);
+      sync_stream(ctx);
       for (int c : cand) {
         DevColumn& dc = out->cols[c];
         memcpy(dc.dict_state, &h_states[4 * c], 16);
@@ -678,23 +678,23 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
     h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width};
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
-  HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys);
   const bool fused = fused_partition_supported(num_buckets);
   const int64_t ntiles = ceil_div(nrows, fused ? fused_tile_rows(false) : kPartTile);
   Buf<uint16_t> bucket;
   Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * num_buckets);
   Buf<unsigned long long> ghist(ctx, num_buckets);
   out->d_bucket_offsets.alloc(ctx, num_buckets + 1);
-  HS_CUDA(cudaMemsetAsync(ghist.get(), 0, sizeof(unsigned long long) * num_buckets, ctx->stream));
+  fill_bytes(ctx, ghist.get(), 0, sizeof(unsigned long long) * num_buckets);
   Buf<unsigned long long> d_key_bits(ctx, 2);
   if (fused) {
     const unsigned long long init[2] = {0ull, ~0ull};
-    HS_CUDA(cudaMemcpyAsync(d_key_bits.get(), init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_key_bits.get(), init, sizeof init);
     static const bool rehash = getenv("HS_PART_REHASH") != nullptr;  // A/B: hash twice instead of storing 2 B/row
     if (!rehash) bucket.alloc(ctx, std::max<int64_t>(1, nrows));
     launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, 0, tile_hist.get(), ghist.get(), d_key_bits.get(),
                      single_key_type_of(h_keys.data(), nkeys), rehash ? nullptr : bucket.get());
-    HS_CUDA(cudaMemcpyAsync(out->key_or_and, d_key_bits.get(), sizeof out->key_or_and, cudaMemcpyDeviceToHost, ctx->stream));
+    copy_d2h(ctx, out->key_or_and, d_key_bits.get(), sizeof out->key_or_and);
     out->have_key_bits = true;  // valid after the stream synchronisation below
   } else {
     bucket.alloc(ctx, std::max<int64_t>(1, nrows));
@@ -703,8 +703,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   launch_tile_offsets(ctx, tile_hist.get(), ntiles, num_buckets, ghist.get(),
                       (unsigned long long*)out->d_bucket_offsets.get());
   out->bucket_offsets.assign(num_buckets + 1, 0);
-  HS_CUDA(cudaMemcpyAsync(out->bucket_offsets.data(), out->d_bucket_offsets.get(), sizeof(uint64_t) * (num_buckets + 1),
-                          cudaMemcpyDeviceToHost, ctx->stream));
+  copy_d2h(ctx, out->bucket_offsets.data(), out->d_bucket_offsets.get(), sizeof(uint64_t) * (num_buckets + 1));
   t_hash.stop();
 
   // ---- K3: stable partition -----------------------------------------------------------------------------------
@@ -745,7 +744,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   Buf<uint32_t> dest;
   Buf<PartColumn> d_pc(ctx, h_pc.size());
   if (fused) {
-    HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * h_pc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_pc.get(), h_pc.data(), sizeof(PartColumn) * h_pc.size());
     if (pack.n > 0) {
       out->part.rec.alloc(ctx, (size_t)nrows * 8 + 16);
       pack.out = out->part.rec.get();
@@ -758,7 +757,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
     for (const PartColumn& pc : h_pc) launch_scatter_column(ctx, pc.in, pc.out, dest.get(), nrows, pc.width);
   }
   t_part.stop();
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // h_pc is read by the async copy; bucket_offsets now valid on the host
+  sync_stream(ctx);  // h_pc is read by the async copy; bucket_offsets now valid on the host
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data.release();
     table.cols[c].valid.release();
@@ -798,10 +797,10 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
       or_and[1] = out->key_or_and[1];
     } else {
       const unsigned long long init[2] = {0ull, ~0ull};
-      HS_CUDA(cudaMemcpyAsync(d_or_and.get(), init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+      copy_h2d(ctx, d_or_and.get(), init, sizeof init);
       launch_encode_keys(ctx, kc.data.get(), kc.type, from_raw ? nullptr : perm, nrows, from_raw ? nullptr : keys, d_or_and.get());
-      HS_CUDA(cudaMemcpyAsync(or_and, d_or_and.get(), sizeof or_and, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      copy_d2h(ctx, or_and, d_or_and.get(), sizeof or_and);
+      sync_stream(ctx);
     }
     const uint64_t varying = nrows ? (or_and[0] ^ or_and[1]) : 0;
     // Keys with more than four varying bytes: LSD passes over the top four varying bytes only, then fix up the (rare,
@@ -831,11 +830,11 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
       const uint64_t low_mask = ~high_mask;
       segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying & high_mask, first_src);
       Buf<uint32_t> d_flag(ctx, 1);
-      HS_CUDA(cudaMemsetAsync(d_flag.get(), 0, 4, ctx->stream));
+      fill_bytes(ctx, d_flag.get(), 0, 4);
       launch_fix_runs(ctx, &out->plan, keys, perm, high_mask, low_mask, 64, d_flag.get());
       uint32_t flag = 0;
-      HS_CUDA(cudaMemcpyAsync(&flag, d_flag.get(), 4, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      copy_d2h(ctx, &flag, d_flag.get(), 4);
+      sync_stream(ctx);
       if (flag) segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying);
     } else {
       segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying, first_src);
@@ -846,7 +845,7 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
   out->sorted_keys = keys;
   out->sorted_perm = perm;
   t_sort.stop();
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  sync_stream(ctx);
   stats->ms_sort += t_sort.ms();
 }
 
@@ -896,9 +895,9 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       tile_val_off[c].assign(ntiles, 0);
       tile_def_off[c].assign(ntiles, 0);
       if (ntiles)
-        HS_CUDA(cudaMemcpyAsync(tile_valid[c].data(), d_counts[c].get(), sizeof(uint32_t) * ntiles, cudaMemcpyDeviceToHost, ctx->stream));
+        copy_d2h(ctx, tile_valid[c].data(), d_counts[c].get(), sizeof(uint32_t) * ntiles);
     }
-    if (any) HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (any) sync_stream(ctx);
   }
   const std::vector<uint32_t>& seg_tile_begin = req.plan->h_seg_tile_begin;
 
@@ -940,16 +939,16 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       } else {
         cd.keys.alloc(ctx, kDictCapacity);
         cd.keys_ptr = cd.keys.get();
-        HS_CUDA(cudaMemsetAsync(cd.keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity, ctx->stream));
+        fill_bytes(ctx, cd.keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
       }
-      HS_CUDA(cudaMemsetAsync(d_state.get(), 0, 16, ctx->stream));
+      fill_bytes(ctx, d_state.get(), 0, 16);
       if (!ready) {
       // staged sampling: 16 K rows that are (nearly) all distinct mark a key-like column at once; a 256 K-row sample then
       // lets the remaining high-cardinality columns overflow cheaply (the overflow path serialises on one counter)
       const int64_t mini = std::min<int64_t>(total_rows, 1 << 14);
       launch_dict_build(ctx, dc.data.get(), dc.width, 0, mini, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state.get());
-      HS_CUDA(cudaMemcpyAsync(st, d_state.get(), 16, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      copy_d2h(ctx, st, d_state.get(), 16);
+      sync_stream(ctx);
       if (total_rows > (1 << 20) && st[0] + st[2] > 0.95 * mini) {
         cd.keys.release();
         continue;
@@ -957,14 +956,14 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       const int64_t sample = std::min<int64_t>(total_rows, 1 << 18);
       if (sample > mini) {
         launch_dict_build(ctx, dc.data.get(), dc.width, mini, sample, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state.get());
-        HS_CUDA(cudaMemcpyAsync(st, d_state.get(), 16, cudaMemcpyDeviceToHost, ctx->stream));
-        HS_CUDA(cudaStreamSynchronize(ctx->stream));
+        copy_d2h(ctx, st, d_state.get(), 16);
+        sync_stream(ctx);
       }
       if (!st[1] && sample < total_rows) {
         launch_dict_build(ctx, dc.data.get(), dc.width, sample, total_rows, cd.keys.get(), kDictCapacity, kMaxDictEntries,
                           d_state.get());
-        HS_CUDA(cudaMemcpyAsync(st, d_state.get(), 16, cudaMemcpyDeviceToHost, ctx->stream));
-        HS_CUDA(cudaStreamSynchronize(ctx->stream));
+        copy_d2h(ctx, st, d_state.get(), 16);
+        sync_stream(ctx);
       }
       }  // !ready
       if (st[1]) {
@@ -1140,14 +1139,13 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
   Buf<uint32_t> d_page_begin(ctx, seg_page_begin.size());
   Buf<uint64_t> d_pvo(ctx, std::max<size_t>(1, (size_t)ncols * page_counter));
   if (!skeleton.empty())
-    HS_CUDA(cudaMemcpyAsync(d_skel.get(), skeleton.data(), skeleton.size(), cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_skel.get(), skeleton.data(), skeleton.size());
   if (!copies.empty())
-    HS_CUDA(cudaMemcpyAsync(d_copies.get(), copies.data(), copies.size() * sizeof(ByteCopy), cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(d_page_begin.get(), seg_page_begin.data(), seg_page_begin.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_copies.get(), copies.data(), copies.size() * sizeof(ByteCopy));
+  copy_h2d(ctx, d_page_begin.get(), seg_page_begin.data(), seg_page_begin.size() * 4);
   for (int c = 0; c < ncols; c++)
     if (page_counter)
-      HS_CUDA(cudaMemcpyAsync(d_pvo.get() + (size_t)c * page_counter, page_value_offset[c].data(), (size_t)page_counter * 8,
-                              cudaMemcpyHostToDevice, ctx->stream));
+      copy_h2d(ctx, d_pvo.get() + (size_t)c * page_counter, page_value_offset[c].data(), (size_t)page_counter * 8);
   t_plan.stop();
 
   // ---- K5+K6 -----------------------------------------------------------------------------------------
@@ -1165,8 +1163,8 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     if (dc.has_nulls) {
       Buf<uint64_t> d_voff(ctx, std::max<int64_t>(1, ntiles)), d_doff(ctx, std::max<int64_t>(1, ntiles));
       if (ntiles) {
-        HS_CUDA(cudaMemcpyAsync(d_voff.get(), tile_val_off[c].data(), 8 * ntiles, cudaMemcpyHostToDevice, ctx->stream));
-        HS_CUDA(cudaMemcpyAsync(d_doff.get(), tile_def_off[c].data(), 8 * ntiles, cudaMemcpyHostToDevice, ctx->stream));
+        copy_h2d(ctx, d_voff.get(), tile_val_off[c].data(), 8 * ntiles);
+        copy_h2d(ctx, d_doff.get(), tile_def_off[c].data(), 8 * ntiles);
       }
       launch_gather_encode_nullable(ctx, req.plan->tiles.get(), ntiles, req.d_perm, dc.data.get(), dc.valid.get(), dc.width,
                                     d_voff.get(), d_doff.get(), out->arena.get());
@@ -1178,7 +1176,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
   }
   if (!stat_patches.empty()) {
     Buf<StatPatch> d_sp(ctx, stat_patches.size());
-    HS_CUDA(cudaMemcpyAsync(d_sp.get(), stat_patches.data(), sizeof(StatPatch) * stat_patches.size(), cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_sp.get(), stat_patches.data(), sizeof(StatPatch) * stat_patches.size());
     launch_patch_key_stats(ctx, d_sp.get(), (int64_t)stat_patches.size(), req.d_sorted_keys, table.cols[0].type, out->arena.get());
   }
   {  // dictionary columns, up to 8 per launch pair
@@ -1220,7 +1218,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     }
   }
   t_enc.stop();
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host plan vectors are about to go out of scope
+  sync_stream(ctx);  // host plan vectors are about to go out of scope
   stats->ms_plan += t_plan.ms();
   stats->ms_encode += t_enc.ms();
   stats->bytes_out += (int64_t)cursor;

@@ -158,7 +158,7 @@ struct hs_staged {
   std::vector<std::string> names;
   std::vector<std::shared_ptr<hs::pq::FileMeta>> metas;
   std::vector<hs::Buf<uint8_t>> staging;  // pinned copies of file-system sources
-  cudaEvent_t ready = nullptr;          // recorded on ctx->h2d_stream behind the last copy
+  cudaEvent_t begin = nullptr, ready = nullptr;  // recorded on ctx->h2d_stream around the copies
   uint64_t bytes = 0;
 };
 
@@ -173,6 +173,7 @@ struct hs_pending {
   std::string out_dir;
   int save_mode = 0;
   ~hs_pending() {
+    if (getenv("HS_TIMELINE")) return;  // diagnostics: the timeline's base event may be one of these
     for (cudaEvent_t e : {t_begin, t_compute_end, t_d2h_begin, t_d2h_end})
       if (e) cudaEventDestroy(e);
   }

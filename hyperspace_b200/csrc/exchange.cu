@@ -93,10 +93,10 @@ void comm_allgather_host(hs_ctx* ctx, const void* in, size_t bytes, void* out) {
   }
   if (!ctx->comm || !ctx->comm->comm) fail(HS_ECOMM, "hs_comm_init has not been called on this context");
   Buf<uint8_t> d_in(ctx, std::max<size_t>(bytes, 16)), d_out(ctx, std::max<size_t>(bytes, 16) * ctx->world);
-  HS_CUDA(cudaMemcpyAsync(d_in.get(), in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_in.get(), in, bytes);
   HS_NCCL(nccl().AllGather(d_in.get(), d_out.get(), bytes, kNcclUint8, ctx->comm->comm, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(out, d_out.get(), bytes * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  copy_d2h(ctx, out, d_out.get(), bytes * ctx->world);
+  sync_stream(ctx);
 }
 
 void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_stats* stats) {
@@ -114,12 +114,12 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
     h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width};
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
-  HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys);
   const int64_t ntiles = ceil_div(nrows, fused_tile_rows(false));  // the send buffers are local memory
   Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * world);
   Buf<unsigned long long> ghist(ctx, world);
   Buf<uint64_t> d_send_off(ctx, world + 1);
-  HS_CUDA(cudaMemsetAsync(ghist.get(), 0, 8 * world, ctx->stream));
+  fill_bytes(ctx, ghist.get(), 0, 8 * world);
   launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, tile_hist.get(), ghist.get(), nullptr,
                    single_key_type_of(h_keys.data(), nkeys));
   launch_tile_offsets(ctx, tile_hist.get(), ntiles, world, ghist.get(), (unsigned long long*)d_send_off.get());
@@ -127,9 +127,9 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   Buf<uint64_t> d_matrix(ctx, (size_t)world * world);  // row r = counts rank r sends to each destination
   HS_NCCL(nccl().AllGather(ghist.get(), d_matrix.get(), world, kNcclUint64, ctx->comm->comm, ctx->stream));
   std::vector<uint64_t> matrix((size_t)world * world), send_off(world + 1);
-  HS_CUDA(cudaMemcpyAsync(matrix.data(), d_matrix.get(), 8 * (size_t)world * world, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(send_off.data(), d_send_off.get(), 8 * (world + 1), cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  copy_d2h(ctx, matrix.data(), d_matrix.get(), 8 * (size_t)world * world);
+  copy_d2h(ctx, send_off.data(), d_send_off.get(), 8 * (world + 1));
+  sync_stream(ctx);
   std::vector<uint64_t> recv_off(world + 1, 0);
   for (int r = 0; r < world; r++) recv_off[r + 1] = recv_off[r] + matrix[(size_t)r * world + ctx->rank];
   const int64_t n_recv = (int64_t)recv_off[world];
@@ -139,10 +139,10 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   Buf<uint64_t> d_nulls(ctx, (size_t)ncols), d_nulls_all(ctx, (size_t)ncols * world);
   std::vector<uint64_t> h_nulls(ncols), h_nulls_all((size_t)ncols * world);
   for (int c = 0; c < ncols; c++) h_nulls[c] = table.cols[c].has_nulls ? 1 : 0;
-  HS_CUDA(cudaMemcpyAsync(d_nulls.get(), h_nulls.data(), 8 * ncols, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_nulls.get(), h_nulls.data(), 8 * ncols);
   HS_NCCL(nccl().AllGather(d_nulls.get(), d_nulls_all.get(), ncols, kNcclUint64, ctx->comm->comm, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(h_nulls_all.data(), d_nulls_all.get(), 8 * (size_t)ncols * world, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  copy_d2h(ctx, h_nulls_all.data(), d_nulls_all.get(), 8 * (size_t)ncols * world);
+  sync_stream(ctx);
   // ---- partition into send buffers (rank-major, stable) ---------------------------------------------------------
   std::vector<Buf<uint8_t>> send_data(ncols), send_valid(ncols), recv_data(ncols), recv_valid(ncols);
   std::vector<bool> any_nulls(ncols, false);
@@ -157,14 +157,14 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
       send_valid[c].alloc(ctx, (size_t)nrows + 16);
       recv_valid[c].alloc(ctx, (size_t)n_recv + 16);
       if (col.valid) h_pc.push_back(PartColumn{col.valid.get(), send_valid[c].get(), 1, 0});
-      else HS_CUDA(cudaMemsetAsync(send_valid[c].get(), 1, (size_t)nrows + 16, ctx->stream));
+      else fill_bytes(ctx, send_valid[c].get(), 1, (size_t)nrows + 16);
     }
   }
   Buf<PartColumn> d_pc(ctx, h_pc.size());
-  HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * h_pc.size(), cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_pc.get(), h_pc.data(), sizeof(PartColumn) * h_pc.size());
   launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, num_buckets, world, tile_hist.get(), d_pc.get(), (int)h_pc.size(),
                         nullptr, 1, single_key_type_of(h_keys.data(), nkeys));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  sync_stream(ctx);
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data.release();
     table.cols[c].valid.release();
@@ -193,7 +193,7 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   }
   HS_NCCL(nccl().GroupEnd());
   t_x.stop();
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  sync_stream(ctx);
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data = std::move(recv_data[c]);
     table.cols[c].has_nulls = any_nulls[c];
@@ -315,7 +315,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
     h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width};
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
-  HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys);
   const int64_t ntiles = ceil_div(nrows, fused_tile_rows(true));  // runs leave over NVLink: the large tile shape
   Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * nb);
   // gathered payload per rank: nb bucket counts followed by ncols has-nulls flags
@@ -323,13 +323,13 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   Buf<unsigned long long> d_mine(ctx, msg), d_all(ctx, (size_t)msg * world);
   std::vector<unsigned long long> h_mine(msg, 0), h_all((size_t)msg * world);
   for (int c = 0; c < ncols; c++) h_mine[nb + c] = table.cols[c].has_nulls ? 1 : 0;
-  HS_CUDA(cudaMemcpyAsync(d_mine.get(), h_mine.data(), 8 * msg, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_mine.get(), h_mine.data(), 8 * msg);
   Buf<uint16_t> bin_ids(ctx, std::max<int64_t>(1, nrows));  // bucket of every row: hashed once, read back by the partition
   launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_mine.get(), nullptr,
                    single_key_type_of(h_keys.data(), nkeys), bin_ids.get(), /*peer_tiles=*/true);
   HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), msg, kNcclUint64, ctx->comm->comm, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(h_all.data(), d_all.get(), 8 * (size_t)msg * world, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  copy_d2h(ctx, h_all.data(), d_all.get(), 8 * (size_t)msg * world);
+  sync_stream(ctx);
   t_hash.stop();
 
   // ---- layout of every owner's receive buffers ------------------------------------------------------------------
@@ -406,7 +406,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
       ctx->pool.mark_exported(dst.valid.get());
       if (!src.valid) {  // this rank saw no nulls in the column but another did: ship all-ones
         src.valid.alloc(ctx, (size_t)nrows + 16);
-        HS_CUDA(cudaMemsetAsync(src.valid.get(), 1, (size_t)nrows + 16, ctx->stream));
+        fill_bytes(ctx, src.valid.get(), 1, (size_t)nrows + 16);
       }
       h_pc.push_back(PartColumn{src.valid.get(), nullptr, 1, 0});
       my_recv.push_back(dst.valid.get());
@@ -423,10 +423,10 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   for (int i = 0; i < nmoved; i++) HS_CUDA(cudaIpcGetMemHandle(&my_handles[i], my_recv[i]));
   const size_t hbytes = sizeof(cudaIpcMemHandle_t) * nmoved;
   Buf<uint8_t> d_h(ctx, hbytes), d_hall(ctx, hbytes * world);
-  HS_CUDA(cudaMemcpyAsync(d_h.get(), my_handles.data(), hbytes, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_h.get(), my_handles.data(), hbytes);
   HS_NCCL(nccl().AllGather(d_h.get(), d_hall.get(), hbytes, kNcclUint8, ctx->comm->comm, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(all_handles.data(), d_hall.get(), hbytes * world, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  copy_d2h(ctx, all_handles.data(), d_hall.get(), hbytes * world);
+  sync_stream(ctx);
   std::vector<void*> h_peer((size_t)nmoved * world);
   for (int i = 0; i < nmoved; i++)
     for (int r = 0; r < world; r++)
@@ -436,9 +436,9 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   Buf<unsigned long long> d_base(ctx, nb);
   Buf<PartColumn> d_pc(ctx, std::max(1, ncolmoved));
   Buf<void*> d_peer(ctx, (size_t)nmoved * world);
-  HS_CUDA(cudaMemcpyAsync(d_base.get(), my_base.data(), 8 * nb, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(d_pc.get(), h_pc.data(), sizeof(PartColumn) * ncolmoved, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(d_peer.get(), h_peer.data(), sizeof(void*) * nmoved * world, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, d_base.get(), my_base.data(), 8 * nb);
+  copy_h2d(ctx, d_pc.get(), h_pc.data(), sizeof(PartColumn) * ncolmoved);
+  copy_h2d(ctx, d_peer.get(), h_peer.data(), sizeof(void*) * nmoved * world);
   launch_tile_offsets(ctx, tile_hist.get(), ntiles, nb, d_mine.get(), nullptr, d_base.get());
   // the peer table holds one row of `world` pointers per column round, then one row for the code records
   launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_pc.get(), ncolmoved,
@@ -446,7 +446,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   // closing barrier: nobody reads its receive buffers before every peer's kernel has completed
   HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), 1, kNcclUint64, ctx->comm->comm, ctx->stream));
   t_x.stop();
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  sync_stream(ctx);
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data.release();
     table.cols[c].valid.release();
@@ -454,8 +454,8 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   }
   out->bucket_offsets = my_bucket_offsets;
   out->d_bucket_offsets.alloc(ctx, nb + 1);
-  HS_CUDA(cudaMemcpyAsync(out->d_bucket_offsets.get(), my_bucket_offsets.data(), 8 * (nb + 1), cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  copy_h2d(ctx, out->d_bucket_offsets.get(), my_bucket_offsets.data(), 8 * (nb + 1));
+  sync_stream(ctx);
   for (int r = 0; r < world; r++)
     if (r != me)
       for (int b = r; b < nb; b += world)

@@ -479,19 +479,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 //
 // All warp collectives run with the full mask and outside any branch: slots past the end of the last tile carry the
 // last bin and, being the last slots of the tile, rank behind every real row of that bin; they are never written out.
-template <int BITS, int KT, bool PEER>
+template <int BITS, int KT, bool PEER, bool BULK>
 __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMinCtas) k_partition_rows(const KeyColumn* __restrict__ keys, int nkeys, int64_t nrows,
                                                                ModConst bucket_mod, ModConst owner_mod, int use_owner,
                                                                const uint32_t* __restrict__ tile_dst,
                                                                const PartColumn* __restrict__ cols, int ncols,
                                                                void* const* __restrict__ peer_out, int out_world,
-                                                               CodePackRound pack, const uint16_t* __restrict__ bin_ids,
-                                                               int bulk) {
+                                                               CodePackRound pack, const uint16_t* __restrict__ bin_ids) {
+  constexpr bool bulk = BULK;  // compile-time: the plain-store instantiation carries none of the bulk layout's bookkeeping
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int kFThreads = FusedCfg<PEER>::kThreads, kFItems = FusedCfg<PEER>::kItems, kFusedTile = FusedCfg<PEER>::kTile;
   constexpr int kFWarps = FusedCfg<PEER>::kWarps, kFWarpRows = FusedCfg<PEER>::kWarpRows;
   const int nb = use_owner ? (int)owner_mod.n : (int)bucket_mod.n;
-  const uint32_t XN = (uint32_t)kFusedTile + 2u * (uint32_t)nb + 2u;
+  const uint32_t XN = (uint32_t)kFusedTile + (bulk ? 2u * (uint32_t)nb + 2u : 0u);
   uint64_t* xbuf = reinterpret_cast<uint64_t*>(smem);
   uint16_t* pos_bin = reinterpret_cast<uint16_t*>(smem + (size_t)XN * 8);
   uint16_t* cnt = pos_bin + XN;
@@ -499,11 +499,12 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
   uint32_t* bin_owner = out_adj + nb;
   uint16_t* run_start = reinterpret_cast<uint16_t*>(bin_owner + nb);
   uint16_t* run_len = run_start + nb;
-  uint32_t* warp_sums = reinterpret_cast<uint32_t*>(run_len + nb + (nb & 1));
+  uint32_t* warp_sums = reinterpret_cast<uint32_t*>(run_len + nb);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1;
   for (int i = threadIdx.x; i < kFWarps * nb; i += kFThreads) cnt[i] = 0;
-  for (uint32_t i = threadIdx.x; i < XN; i += kFThreads) pos_bin[i] = 0xffffu;  // padding slots belong to no bin
+  if (bulk)
+    for (uint32_t i = threadIdx.x; i < XN; i += kFThreads) pos_bin[i] = 0xffffu;  // padding slots belong to no bin
   const int64_t tile_base = (int64_t)blockIdx.x * kFusedTile;
   const uint32_t first = warp * kFWarpRows + lane;  // tile-relative row of this thread's item 0
   const int64_t wbase = tile_base + first;
@@ -553,12 +554,15 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
     if (b < nb) {
       const uint32_t P = carry + ex;
       const uint32_t dst = tile_dst[(size_t)blockIdx.x * nb + b];
-      uint32_t run = P + 2u * (uint32_t)b + ((P ^ dst) & 1u);
+      // padded layout only when the runs leave as bulk copies; plain stores keep the tile dense
+      uint32_t run = bulk ? P + 2u * (uint32_t)b + ((P ^ dst) & 1u) : P;
       out_adj[b] = dst - run;
       bin_owner[b] = out_world > 1 ? (uint32_t)b % (uint32_t)out_world : 0u;
-      run_start[b] = (uint16_t)run;
-      // the phantom slots of a partial last tile sit at the end of the last bin's run
-      run_len[b] = (uint16_t)(b == nb - 1 ? total - ((uint32_t)kFusedTile - tile_count) : total);
+      if (bulk) {
+        run_start[b] = (uint16_t)run;
+        // the phantom slots of a partial last tile sit at the end of the last bin's run
+        run_len[b] = (uint16_t)(b == nb - 1 ? total - ((uint32_t)kFusedTile - tile_count) : total);
+      }
 #pragma unroll
       for (int w = 0; w < kFWarps; w++) {
         const uint16_t c = cnt[(size_t)w * nb + b];
@@ -569,12 +573,13 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
     carry += chunk_total;
   }
   __syncthreads();
-  const uint32_t x_end = (uint32_t)run_start[nb - 1] + run_len[nb - 1];  // positions in use: [0, x_end)
+  // positions in use: [0, x_end); the dense layout ends with the tile's last real row
+  const uint32_t x_end = bulk ? (uint32_t)run_start[nb - 1] + run_len[nb - 1] : tile_count;
 #pragma unroll
   for (int j = 0; j < kFItems; j++) {
     const uint32_t b = bin[j] & 0xffffu;
     bin[j] = wcnt[b] + (bin[j] >> 16);
-    if (first + j * 32 < tile_count) pos_bin[bin[j]] = (uint16_t)b;
+    if (!bulk || first + j * 32 < tile_count) pos_bin[bin[j]] = (uint16_t)b;
   }
   const uint32_t(&pos)[kFItems] = bin;
   // one bin's run of an 8-byte column: [odd head element] [16-byte aligned body as ONE bulk copy] [odd tail element]
@@ -631,7 +636,6 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
 #pragma unroll 4
         for (uint32_t i = threadIdx.x; i < x_end; i += kFThreads) {
           const uint32_t b = pos_bin[i];
-          if (b == 0xffffu) continue;
           uint64_t* out = (uint64_t*)(pout ? pout[bin_owner[b]] : pc.out);
           out[out_adj[b] + i] = xbuf[i];
         }
@@ -640,18 +644,22 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
       const uint32_t* xb = reinterpret_cast<const uint32_t*>(xbuf);
 #pragma unroll 4
       for (uint32_t i = threadIdx.x; i < x_end; i += kFThreads) {
-        const uint32_t b = pos_bin[i];
-        if (b == 0xffffu) continue;
+        const uint32_t b0 = pos_bin[i];
+        const bool real = b0 != 0xffffu;  // padding slot of the bulk layout
+        const uint32_t b = real ? b0 : 0u;
         uint32_t* out = (uint32_t*)(pout ? pout[bin_owner[b]] : pc.out);
-        out[out_adj[b] + i] = xb[i];
+        const uint32_t v = xb[i];
+        if (real) out[out_adj[b] + i] = v;
       }
     } else {
       const uint8_t* xb = reinterpret_cast<const uint8_t*>(xbuf);
       for (uint32_t i = threadIdx.x; i < x_end; i += kFThreads) {
-        const uint32_t b = pos_bin[i];
-        if (b == 0xffffu) continue;
+        const uint32_t b0 = pos_bin[i];
+        const bool real = b0 != 0xffffu;
+        const uint32_t b = real ? b0 : 0u;
         uint8_t* out = (uint8_t*)(pout ? pout[bin_owner[b]] : pc.out);
-        out[out_adj[b] + i] = xb[i];
+        const uint8_t v = xb[i];
+        if (real) out[out_adj[b] + i] = v;
       }
     }
   }
@@ -680,7 +688,6 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
 #pragma unroll 4
       for (uint32_t i = threadIdx.x; i < x_end; i += kFThreads) {
         const uint32_t b = pos_bin[i];
-        if (b == 0xffffu) continue;
         uint64_t* out = (uint64_t*)(pout ? pout[bin_owner[b]] : pack.out);
         out[out_adj[b] + i] = xbuf[i];
       }
@@ -689,11 +696,11 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
 }
 
 template <bool PEER>
-size_t fused_smem_bytes(int nb) {
-  const size_t XN = (size_t)FusedCfg<PEER>::kTile + 2 * (size_t)nb + 2;
+size_t fused_smem_bytes(int nb, bool bulk = true) {
+  const size_t XN = (size_t)FusedCfg<PEER>::kTile + (bulk ? 2 * (size_t)nb + 2 : 0);
   size_t u16s = XN + (size_t)FusedCfg<PEER>::kWarps * nb;
   u16s += u16s & 1;
-  return XN * 8 + u16s * 2 + (size_t)nb * 4 * 2 + ((size_t)nb * 2 + (nb & 1)) * 2 + 40 * 4;
+  return XN * 8 + u16s * 2 + (size_t)nb * 4 * 2 + (size_t)nb * 2 * 2 + 40 * 4;
 }
 
 }  // namespace
@@ -748,21 +755,27 @@ struct PartitionLaunch {
   int bulk;
 };
 
-template <int BITS, int KT, bool PEER>
-static void launch_partition_rows_t(hs_ctx* ctx, const PartitionLaunch& a) {
+template <int BITS, int KT, bool PEER, bool BULK>
+static void launch_partition_rows_tb(hs_ctx* ctx, const PartitionLaunch& a) {
   const int nb = a.owner_mod > 0 ? a.owner_mod : a.num_buckets;
   const int64_t ntiles = ceil_div(a.nrows, FusedCfg<PEER>::kTile);
   static DeviceOnce attr_once;  // one per instantiation
   bool& attr = attr_once(ctx->device);
   if (!attr) {
-    HS_CUDA(cudaFuncSetAttribute(k_partition_rows<BITS, KT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)fused_smem_bytes<PEER>(kFusedMaxBins)));
+    HS_CUDA(cudaFuncSetAttribute(k_partition_rows<BITS, KT, PEER, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fused_smem_bytes<PEER>(kFusedMaxBins, BULK)));
     attr = true;
   }
-  k_partition_rows<BITS, KT, PEER><<<(unsigned)ntiles, FusedCfg<PEER>::kThreads, fused_smem_bytes<PEER>(nb), ctx->stream>>>(
+  k_partition_rows<BITS, KT, PEER, BULK><<<(unsigned)ntiles, FusedCfg<PEER>::kThreads, fused_smem_bytes<PEER>(nb, BULK), ctx->stream>>>(
       a.d_keys, a.nkeys, a.nrows, make_mod_const((uint32_t)a.num_buckets), make_mod_const((uint32_t)std::max(a.owner_mod, 1)),
-      a.owner_mod > 0 ? 1 : 0, a.tile_dst, a.d_cols, a.ncols, a.d_peer_out, a.out_world, a.pack, a.bin_ids, a.bulk);
+      a.owner_mod > 0 ? 1 : 0, a.tile_dst, a.d_cols, a.ncols, a.d_peer_out, a.out_world, a.pack, a.bin_ids);
   HS_LAUNCH_CHECK(ctx);
+}
+
+template <int BITS, int KT, bool PEER>
+static void launch_partition_rows_t(hs_ctx* ctx, const PartitionLaunch& a) {
+  if (a.bulk) launch_partition_rows_tb<BITS, KT, PEER, true>(ctx, a);
+  else launch_partition_rows_tb<BITS, KT, PEER, false>(ctx, a);
 }
 
 template <int BITS, bool PEER>

@@ -149,9 +149,29 @@ struct hs_ctx {
   std::vector<cudaEvent_t> event_pool;
   hs_comm_state* comm = nullptr;
   int rank = 0, world = 1;
+  // small host <-> device transfers that bypass the copy engines (xfer.cu)
+  struct PendingD2H {
+    void* dst;
+    const uint8_t* slot;
+    size_t bytes;
+  };
+  uint8_t* xfer_ring = nullptr;       // pinned, device-accessible
+  size_t xfer_cap = 0, xfer_head = 0;
+  std::vector<uint8_t*> xfer_retired; // outgrown rings, recycled at the next synchronisation
+  std::vector<PendingD2H> xfer_pending;
 };
 
 namespace hs {
+
+// Small transfers on the ctx stream without the copy engines (xfer.cu).  copy_h2d snapshots the host bytes at once; the
+// result of copy_d2h is in place after the next sync_stream(ctx).  Every synchronisation of ctx->stream inside a call goes
+// through sync_stream; error paths use xfer_abort (synchronises, drops undelivered results).
+void copy_h2d(hs_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+void copy_d2h(hs_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+void fill_bytes(hs_ctx* ctx, void* dst, int value, size_t bytes);  // cudaMemsetAsync without a copy engine
+void sync_stream(hs_ctx* ctx);
+void xfer_abort(hs_ctx* ctx);
+void xfer_release(hs_ctx* ctx);
 
 // RAII handle on a pooled buffer.
 template <typename T>

@@ -346,10 +346,9 @@ ChunkPlan build_chunks(hs_ctx* ctx, const std::vector<uint32_t>& seg_tile_begin)
   cp.seg_chunk_begin.alloc(ctx, scb.size());
   cp.chunk_sums.alloc(ctx, std::max<size_t>(1, chunks.size()) * 256);
   if (!chunks.empty())
-    HS_CUDA(cudaMemcpyAsync(cp.chunks.get(), chunks.data(), chunks.size() * sizeof(SortChunk), cudaMemcpyHostToDevice,
-                            ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(cp.seg_chunk_begin.get(), scb.data(), scb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    copy_h2d(ctx, cp.chunks.get(), chunks.data(), chunks.size() * sizeof(SortChunk));
+  copy_h2d(ctx, cp.seg_chunk_begin.get(), scb.data(), scb.size() * 4);
+  sync_stream(ctx);  // host vectors go out of scope
   return cp;
 }
 
@@ -388,13 +387,13 @@ void build_sort_plan(hs_ctx* ctx, const uint64_t* seg_offsets, int nseg, SortPla
   plan->seg_start.alloc(ctx, sstart.size());
   plan->tile_hist.alloc(ctx, std::max<size_t>(1, ntiles) * 256);
   plan->tile_dst.alloc(ctx, std::max<size_t>(1, ntiles) * 256);
-  HS_CUDA(cudaMemcpyAsync(plan->seg_tile_begin.get(), stb.data(), stb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(plan->seg_start.get(), sstart.data(), sstart.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  copy_h2d(ctx, plan->seg_tile_begin.get(), stb.data(), stb.size() * 4);
+  copy_h2d(ctx, plan->seg_start.get(), sstart.data(), sstart.size() * 8);
   if (nseg > 0 && ntiles > 0) {
     k_build_tiles<<<nseg, 256, 0, ctx->stream>>>(plan->seg_start.get(), plan->seg_tile_begin.get(), plan->tiles.get());
     HS_LAUNCH_CHECK(ctx);
   }
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+  sync_stream(ctx);  // the host vectors go out of scope
   plan->h_seg_tile_begin = stb;
 }
 

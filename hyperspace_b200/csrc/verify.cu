@@ -147,7 +147,7 @@ int guarded_call(hs_ctx* ctx, char* err, size_t errlen, F&& f) {
       strncpy(err, e.what(), errlen - 1);
       err[errlen - 1] = 0;
     }
-    cudaStreamSynchronize(ctx->stream);
+    xfer_abort(ctx);
     cudaGetLastError();
     return e.code;
   }
@@ -181,7 +181,7 @@ int hs_verify_index(hs_ctx* ctx, const hs_source_file* files, const int32_t* buc
     load_sources(ctx, files, n_files, cols, &t, &st);
     out->rows = t.nrows;
     Buf<unsigned long long> d_sums(ctx, 2 + 1 + kMaxVerifyCols);
-    HS_CUDA(cudaMemsetAsync(d_sums.get(), 0, 8 * (3 + kMaxVerifyCols), ctx->stream));
+    fill_bytes(ctx, d_sums.get(), 0, 8 * (3 + kMaxVerifyCols));
     checksum_table(ctx, t, d_sums.get() + 2);
     std::vector<KeyColumn> h_keys(n_indexed);
     for (int k = 0; k < n_indexed; k++) {
@@ -191,9 +191,9 @@ int hs_verify_index(hs_ctx* ctx, const hs_source_file* files, const int32_t* buc
     Buf<KeyColumn> d_keys(ctx, n_indexed);
     Buf<int64_t> d_frb(ctx, n_files + 1);
     Buf<int32_t> d_fb(ctx, n_files);
-    HS_CUDA(cudaMemcpyAsync(d_keys.get(), h_keys.data(), sizeof(KeyColumn) * n_indexed, cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(d_frb.get(), t.file_row_begin.data(), 8 * (size_t)(n_files + 1), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(d_fb.get(), buckets, 4 * (size_t)n_files, cudaMemcpyHostToDevice, ctx->stream));
+    copy_h2d(ctx, d_keys.get(), h_keys.data(), sizeof(KeyColumn) * n_indexed);
+    copy_h2d(ctx, d_frb.get(), t.file_row_begin.data(), 8 * (size_t)(n_files + 1));
+    copy_h2d(ctx, d_fb.get(), buckets, 4 * (size_t)n_files);
     if (t.nrows) {
       const int grid = (int)std::min<int64_t>(ceil_div(t.nrows, 256), (int64_t)ctx->sm_count * 8);
       k_check_rows<<<grid, 256, 0, ctx->stream>>>(d_keys.get(), n_indexed, t.nrows, num_buckets, d_frb.get(), d_fb.get(), n_files,
@@ -201,8 +201,8 @@ int hs_verify_index(hs_ctx* ctx, const hs_source_file* files, const int32_t* buc
       HS_LAUNCH_CHECK(ctx);
     }
     unsigned long long h[3 + kMaxVerifyCols];
-    HS_CUDA(cudaMemcpyAsync(h, d_sums.get(), sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    copy_d2h(ctx, h, d_sums.get(), sizeof h);
+    sync_stream(ctx);
     out->bucket_mismatches = (int64_t)h[0];
     out->order_violations = (int64_t)h[1];
     out->row_checksum = h[2];
@@ -219,7 +219,7 @@ int hs_synth_checksum(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t nco
     out->n_columns = ncols;
     out->rows = nrows;
     Buf<unsigned long long> d_sums(ctx, 1 + kMaxVerifyCols);
-    HS_CUDA(cudaMemsetAsync(d_sums.get(), 0, 8 * (1 + kMaxVerifyCols), ctx->stream));
+    fill_bytes(ctx, d_sums.get(), 0, 8 * (1 + kMaxVerifyCols));
     const int64_t chunk = 1ll << 26;  // generated and summed 64 M rows at a time: no table-sized allocation
     Table t;
     t.cols.resize(ncols);
@@ -234,8 +234,8 @@ int hs_synth_checksum(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t nco
       checksum_table(ctx, t, d_sums.get());
     }
     unsigned long long h[1 + kMaxVerifyCols];
-    HS_CUDA(cudaMemcpyAsync(h, d_sums.get(), sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    copy_d2h(ctx, h, d_sums.get(), sizeof h);
+    sync_stream(ctx);
     out->row_checksum = h[0];
     for (int c = 0; c < ncols; c++) out->column_checksum[c] = h[1 + c];
   });

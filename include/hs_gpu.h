@@ -175,7 +175,8 @@ typedef struct hs_pending hs_pending;
 int hs_stage_sources(hs_ctx* ctx, const hs_source_file* files, int32_t n_files, hs_staged** out, char* err, size_t errlen);
 int32_t hs_staged_num_files(const hs_staged* s);
 int hs_staged_file(const hs_staged* s, int32_t i, hs_source_file* out); /* out->path points into the handle */
-int hs_staged_wait(hs_staged* s);  /* blocks until the copies have completed */
+int hs_staged_wait(hs_staged* s, float* ms_copy); /* blocks until the copies have completed; ms_copy (optional): their
+                                                      duration on the H2D stream */
 void hs_staged_free(hs_staged* s); /* waits for the copies and for the ctx stream, then releases the device images */
 int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** out, char* err, size_t errlen);
 int hs_pending_wait(hs_pending* p, hs_index_result** out, hs_stats* stats, char* err, size_t errlen);
