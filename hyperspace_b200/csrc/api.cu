@@ -506,7 +506,16 @@ int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** o
         carry.first_col = spec->n_indexed;
         carry.num_segments = spec->num_buckets;
       }
-      load_sources(ctx, spec->files, spec->n_files, cols, &table, &st, &carry);
+      // PLAIN, null-free, value-aligned columns are not decoded either: hash and partition read them in place from the file
+      // images (zero copy), which therefore stay alive until the rows have been partitioned.  HS_NO_ZEROCOPY=1: A/B switch.
+      if (fused_partition_supported(spec->num_buckets) && spec->n_deleted_file_ids == 0 && !getenv("HS_NO_ZEROCOPY")) {
+        carry.zc_tile_rows = fused_tile_rows(p2p_exchange_supported(ctx, spec->num_buckets));
+        carry.zc_first_col = spec->n_indexed;
+        carry.zc_key = spec->n_indexed == 1;
+      }
+      SourceSet src;
+      open_sources(ctx, spec->files, spec->n_files, &src, &st);
+      decode_sources(ctx, src, cols, nullptr, &table, &st, &carry);
       if (spec->lineage) fill_lineage(ctx, table, spec->files, spec->n_files);
       if (spec->n_deleted_file_ids > 0) drop_deleted_rows(ctx, table, spec->deleted_file_ids, spec->n_deleted_file_ids);
       IndexedRows rows;
@@ -518,6 +527,7 @@ int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** o
         if (ctx->world > 1) exchange_rows(ctx, table, spec->n_indexed, spec->num_buckets, &st);  // NCCL all-to-all
         index_rows(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
       }
+      src.release_images();  // every column is materialised bucket-major now
 
       EncodeRequest req;
       req.table = &rows.part;

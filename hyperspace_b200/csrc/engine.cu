@@ -106,6 +106,7 @@ struct SourceSet::Impl {
 };
 SourceSet::SourceSet() : impl(new Impl()) {}
 SourceSet::~SourceSet() { delete impl; }
+void SourceSet::release_images() { impl->d_images.release(); }
 
 void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const std::vector<std::string>& columns,
                   Table* out, hs_stats* stats, const CarryOptions* carry) {
@@ -412,7 +413,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   auto alloc_destinations = [&]() {
     for (int c = 0; c < ncols; c++) {
       DevColumn& dc = out->cols[c];
-      if (dc.carried) continue;
+      if (dc.carried || dc.zero_copy) continue;
       dc.data.alloc(ctx, (size_t)nrows * dc.width + 16);
       if (col_optional[c]) {
         dc.valid.alloc(ctx, (size_t)nrows + 16);
@@ -518,17 +519,20 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   // partition moves 2 bytes per row instead of 4 or 8, and the page encoder finds its codes ready-made.  On several GPUs
   // the ranks agree on the columns and on one dictionary per column (unions all-gathered and merged), so that codes mean
   // the same everywhere and can cross NVLink in place of the values.
+  const bool want_zc = carry && carry->zc_tile_rows > 0 && !file_windows && n_pages > 0 && nrows > 0;
+  std::vector<uint32_t> local_cls(ncols, 0u);  // classification of this rank's own pages, per column
+  if ((want_carry || want_zc) && n_pages > 0) {
+    Buf<uint32_t> d_class(ctx, ncols);
+    fill_bytes(ctx, d_class.get(), 0, 4 * (size_t)ncols);
+    launch_classify_pages(ctx, d_pages.get(), n_pages, d_class.get(), want_zc ? carry->zc_tile_rows : 0);
+    copy_d2h(ctx, local_cls.data(), d_class.get(), 4 * (size_t)ncols);
+    sync_stream(ctx);
+  }
   if (want_carry) {
     const int W = ctx->world;
     // what every rank knows about its own pages: per column the classification flags, then its row count
     std::vector<uint32_t> mine(ncols + 2, 0u), all((size_t)(ncols + 2) * W);
-    if (n_pages > 0) {
-      Buf<uint32_t> d_class(ctx, ncols);
-      fill_bytes(ctx, d_class.get(), 0, 4 * (size_t)ncols);
-      launch_classify_pages(ctx, d_pages.get(), n_pages, d_class.get());
-      copy_d2h(ctx, mine.data(), d_class.get(), 4 * (size_t)ncols);
-      sync_stream(ctx);
-    }
+    for (int c = 0; c < ncols; c++) mine[c] = local_cls[c] & (PAGECLASS_NOT_DICT | PAGECLASS_MAYBE_NULLS);
     mine[ncols] = (uint32_t)(nrows & 0xffffffffll);
     mine[ncols + 1] = (uint32_t)(nrows >> 32);
     comm_allgather_host(ctx, mine.data(), 4 * mine.size(), all.data());
@@ -600,6 +604,32 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       }
     }
   }
+  // ---- zero-copy PLAIN columns -------------------------------------------------------------------------------------
+  // A column whose every page is PLAIN, stored, free of nulls, value-aligned and at least one partition tile long is not
+  // decoded at all: the hash and partition kernels read its values where they lie (a local decision: it only changes where
+  // this rank's kernels load from).  For table T that is k and v2: 32 of the 42 GB the decoder used to move per 1 B rows.
+  Buf<ZcTile*> d_tile_src;
+  if (want_zc) {
+    std::vector<ZcTile*> h_tile_src(ncols, nullptr);
+    const int64_t T = carry->zc_tile_rows;
+    bool any = false;
+    for (int c = 0; c < ncols; c++) {
+      DevColumn& dc = out->cols[c];
+      const bool candidate = c >= carry->zc_first_col || (c == 0 && carry->zc_key && (dc.type == HS_TYPE_INT32 || dc.type == HS_TYPE_INT64));
+      if (!candidate || dc.carried || (dc.width != 4 && dc.width != 8)) continue;
+      if (local_cls[c] & (PAGECLASS_NOT_IN_PLACE | PAGECLASS_MAYBE_NULLS)) continue;
+      dc.zero_copy = true;
+      dc.zc_tiles.alloc(ctx, (size_t)ceil_div(nrows, T));
+      h_tile_src[c] = dc.zc_tiles.get();
+      h_cols[c] = ColumnOut{nullptr, nullptr, dc.width, dc.type, nullptr, 0u, 0u, 0, 1};
+      any = true;
+    }
+    if (any) {
+      d_tile_src.alloc(ctx, ncols);
+      copy_h2d(ctx, d_tile_src.get(), h_tile_src.data(), sizeof(ZcTile*) * ncols);
+      launch_fill_zc_tiles(ctx, d_pages.get(), n_pages, d_tile_src.get(), (int)T, nrows);
+    }
+  }
   alloc_destinations();
   copy_h2d(ctx, d_cols.get(), h_cols.data(), sizeof(ColumnOut) * ncols);
   // ---- decode -----------------------------------------------------------------------------------------
@@ -636,7 +666,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
     fill_bytes(ctx, d_states.get(), 0, 16 * (size_t)std::max(1, ncols));
     for (int c = 0; c < ncols; c++) {
       DevColumn& dc = out->cols[c];
-      if (dc.carried || (flags[1 + c] & 2u) || (dc.width != 4 && dc.width != 8)) continue;
+      if (dc.carried || dc.zero_copy || (flags[1 + c] & 2u) || (dc.width != 4 && dc.width != 8)) continue;
       dc.dict_keys.alloc(ctx, kDictCapacity);
       fill_bytes(ctx, dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
       launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, c, dc.width, dc.dict_keys.get(), kDictCapacity, kMaxDictEntries,
@@ -675,7 +705,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
   std::vector<KeyColumn> h_keys(nkeys);
   for (int k = 0; k < nkeys; k++) {
     DevColumn& c = table.cols[k];
-    h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width};
+    h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width, c.zero_copy ? c.zc_tiles.get() : nullptr};
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
   copy_h2d(ctx, d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys);
@@ -735,7 +765,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
       continue;
     }
     dst.data.alloc(ctx, (size_t)nrows * src.width + 16);
-    h_pc.push_back(PartColumn{src.data.get(), dst.data.get(), src.width, 0});
+    h_pc.push_back(PartColumn{src.data.get(), dst.data.get(), src.width, 0, src.zero_copy ? src.zc_tiles.get() : nullptr});
     if (src.has_nulls) {
       dst.valid.alloc(ctx, (size_t)nrows + 16);
       h_pc.push_back(PartColumn{src.valid.get(), dst.valid.get(), 1, 0});
@@ -762,6 +792,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
     table.cols[c].data.release();
     table.cols[c].valid.release();
     table.cols[c].codes.release();
+    table.cols[c].zc_tiles.release();
   }
 
   stats->ms_hash += t_hash.ms();

@@ -28,6 +28,10 @@ struct DevColumn {
   // nulls, so the column travels as 16-bit codes of one column-wide sorted dictionary and its values are never written
   // to HBM.  `data` stays empty.  Before the partition `codes` holds one code per row; the partition packs the codes of
   // all carried columns of a row into one 8-byte record (Table::rec, slot `carry_slot`) that the page encoder bit-packs.
+  // Zero-copy PLAIN column: never decoded; the hash and partition kernels read its values in place from the page bodies
+  // inside the source file images (`data` stays empty until the partition has materialised the column bucket-major).
+  bool zero_copy = false;
+  Buf<ZcTile> zc_tiles;
   bool carried = false;
   Buf<uint16_t> codes;
   std::vector<uint64_t> dict_values;  // sorted dictionary, raw value bits; code = position
@@ -48,6 +52,11 @@ struct Table {
 struct CarryOptions {
   int first_col = -1;   // columns [first_col, ncols) are candidates (the indexed columns never are)
   int num_segments = 1; // output files: every one repeats the dictionary page, which enters the size criterion
+  // zero-copy PLAIN columns (0 = off): rows per tile of the partition kernel that will read them; the included columns
+  // [zc_first_col, ncols) are candidates, and column 0 too when zc_key is set (a single int32 / int64 key)
+  int zc_tile_rows = 0;
+  int zc_first_col = 0;
+  bool zc_key = false;
 };
 
 // Rows in bucket-major, key-sorted order (result of K2-K4).
@@ -92,6 +101,7 @@ struct SourceSet {
   int n_files = 0;
   SourceSet();
   ~SourceSet();
+  void release_images();  // frees the device copies of host-supplied images (zero-copy columns point into them until then)
   SourceSet(const SourceSet&) = delete;
   SourceSet& operator=(const SourceSet&) = delete;
 };

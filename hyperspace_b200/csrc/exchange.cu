@@ -111,7 +111,7 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   std::vector<KeyColumn> h_keys(nkeys);
   for (int k = 0; k < nkeys; k++) {
     DevColumn& c = table.cols[k];
-    h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width};
+    h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width, c.zero_copy ? c.zc_tiles.get() : nullptr};
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
   copy_h2d(ctx, d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys);
@@ -152,7 +152,7 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
     DevColumn& col = table.cols[c];
     send_data[c].alloc(ctx, (size_t)nrows * col.width + 16);
     recv_data[c].alloc(ctx, (size_t)n_recv * col.width + 16);
-    h_pc.push_back(PartColumn{col.data.get(), send_data[c].get(), col.width, 0});
+    h_pc.push_back(PartColumn{col.data.get(), send_data[c].get(), col.width, 0, col.zero_copy ? col.zc_tiles.get() : nullptr});
     if (any_nulls[c]) {
       send_valid[c].alloc(ctx, (size_t)nrows + 16);
       recv_valid[c].alloc(ctx, (size_t)n_recv + 16);
@@ -196,6 +196,8 @@ void exchange_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, hs_sta
   sync_stream(ctx);
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data = std::move(recv_data[c]);
+    table.cols[c].zero_copy = false;  // materialised by the exchange
+    table.cols[c].zc_tiles.release();
     table.cols[c].has_nulls = any_nulls[c];
     if (any_nulls[c]) table.cols[c].valid = std::move(recv_valid[c]);
   }
@@ -312,7 +314,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   std::vector<KeyColumn> h_keys(nkeys);
   for (int k = 0; k < nkeys; k++) {
     DevColumn& c = table.cols[k];
-    h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width};
+    h_keys[k] = KeyColumn{c.data.get(), c.has_nulls ? c.valid.get() : nullptr, c.type, c.width, c.zero_copy ? c.zc_tiles.get() : nullptr};
   }
   Buf<KeyColumn> d_keys(ctx, nkeys);
   copy_h2d(ctx, d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys);
@@ -399,7 +401,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
     }
     dst.data.alloc(ctx, (size_t)n_recv * src.width + 16);
     ctx->pool.mark_exported(dst.data.get());
-    h_pc.push_back(PartColumn{src.data.get(), nullptr, src.width, 0});
+    h_pc.push_back(PartColumn{src.data.get(), nullptr, src.width, 0, src.zero_copy ? src.zc_tiles.get() : nullptr});
     my_recv.push_back(dst.data.get());
     if (any_nulls[c]) {
       dst.valid.alloc(ctx, (size_t)n_recv + 16);
@@ -451,6 +453,7 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
     table.cols[c].data.release();
     table.cols[c].valid.release();
     table.cols[c].codes.release();
+    table.cols[c].zc_tiles.release();
   }
   out->bucket_offsets = my_bucket_offsets;
   out->d_bucket_offsets.alloc(ctx, nb + 1);

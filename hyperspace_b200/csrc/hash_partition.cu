@@ -385,16 +385,32 @@ __device__ __forceinline__ uint32_t row_hash(const KeyColumn* keys, int nkeys, i
 
 // KT >= 0: exactly one indexed column, of HS_TYPE KT and without nulls -- its descriptor is read once per thread and the
 // hash is straight-line code, so a thread's key loads issue back to back.  KT < 0: any number / type of key columns.
+// A single-key column may be zero-copy (KeyColumn::tiles): the tile's values then lie in at most two page bodies of the
+// source images, addressed by global row through rebased pointers (ZcTile); a decoded column is the same with one "page".
 template <int KT>
 struct RowHasher {
   const KeyColumn* keys;
   int nkeys;
-  const void* k0;
-  __device__ __forceinline__ RowHasher(const KeyColumn* k, int n) : keys(k), nkeys(n), k0(KT >= 0 ? k[0].data : nullptr) {}
+  const uint8_t *p0, *p1;
+  int64_t split;
+  __device__ __forceinline__ RowHasher(const KeyColumn* k, int n, int64_t tile) : keys(k), nkeys(n), p0(nullptr), p1(nullptr), split(INT64_MAX) {
+    if (KT >= 0) {
+      const KeyColumn kc = k[0];
+      if (kc.tiles) {
+        const ZcTile z = kc.tiles[tile];
+        p0 = z.p0;
+        p1 = z.p1;
+        split = z.split;
+      } else {
+        p0 = p1 = (const uint8_t*)kc.data;
+      }
+    }
+  }
   __device__ __forceinline__ uint32_t operator()(int64_t row, uint64_t* last_encoded = nullptr) const {
     if (KT >= 0) {
-      const uint64_t raw = (KT == HS_TYPE_INT64 || KT == HS_TYPE_DOUBLE) ? ((const uint64_t*)k0)[row]
-                                                                         : (uint64_t)((const uint32_t*)k0)[row];
+      const uint8_t* b = row < split ? p0 : p1;
+      const uint64_t raw = (KT == HS_TYPE_INT64 || KT == HS_TYPE_DOUBLE) ? *(const uint64_t*)(b + row * 8)
+                                                                         : (uint64_t) * (const uint32_t*)(b + row * 4);
       if (last_encoded) *last_encoded = sort_encode(KT, raw);
       return mm3_hash_value(KT, raw, 42u);
     }
@@ -415,7 +431,7 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads) k_tile_hist(const Ke
   for (int i = threadIdx.x; i < nb; i += kFThreads) s_hist[i] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * kFusedTile;
-  const RowHasher<KT> hasher(keys, nkeys);
+  const RowHasher<KT> hasher(keys, nkeys, blockIdx.x);
   uint64_t vor = 0, vand = ~0ull;
 #pragma unroll 4
   for (int j = 0; j < kFItems; j++) {
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
   const int64_t wbase = tile_base + first;
   const uint32_t tile_count = (uint32_t)min((int64_t)kFusedTile, nrows - tile_base);
   uint32_t bin[kFItems];  // bin id in the low half; the in-warp rank joins it in the high half; finally the position
-  const RowHasher<KT> hasher(keys, nkeys);
+  const RowHasher<KT> hasher(keys, nkeys, blockIdx.x);
 #pragma unroll
   for (int j = 0; j < kFItems; j++) {
     bin[j] = (uint32_t)nb - 1;
@@ -606,7 +622,25 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
   for (int c = 0; c < ncols; c++) {
     const PartColumn pc = cols[c];
     __syncthreads();  // previous column's readers are done with xbuf (and pos_bin is complete)
-    if (pc.width == 8) {
+    if (pc.tiles) {  // zero-copy column: the tile's values lie in one or two page bodies of the source images
+      const ZcTile z = pc.tiles[blockIdx.x];
+      if (pc.width == 8) {
+#pragma unroll
+        for (int j = 0; j < kFItems; j++)
+          if (first + j * 32 < tile_count) {
+            const int64_t row = wbase + j * 32;
+            xbuf[pos[j]] = *(const uint64_t*)((row < z.split ? z.p0 : z.p1) + row * 8);
+          }
+      } else {
+        uint32_t* xb = reinterpret_cast<uint32_t*>(xbuf);
+#pragma unroll
+        for (int j = 0; j < kFItems; j++)
+          if (first + j * 32 < tile_count) {
+            const int64_t row = wbase + j * 32;
+            xb[pos[j]] = *(const uint32_t*)((row < z.split ? z.p0 : z.p1) + row * 4);
+          }
+      }
+    } else if (pc.width == 8) {
       const uint64_t* in = (const uint64_t*)pc.in + wbase;
 #pragma unroll
       for (int j = 0; j < kFItems; j++)

@@ -51,12 +51,26 @@ struct ColumnOut {          // decoded column destination
   uint32_t carry_mask;
   uint32_t carry_empty_index;  // code of the value 0xFFFF...F, which the look-up table cannot hold
   int32_t carry;
-  int32_t pad;
+  int32_t skip;                // != 0: zero-copy column, its pages are not decoded at all
 };
 
 // Per-column OR over the column's data pages (k_classify_pages), read before decoding to pick late-materialised columns
-enum : uint32_t { PAGECLASS_NOT_DICT = 1u, PAGECLASS_MAYBE_NULLS = 2u };
-void launch_classify_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, uint32_t* col_flags);
+// PAGECLASS_NOT_IN_PLACE: the page cannot be read where it lies -- it is not a PLAIN, stored (uncompressed), null-free
+// page of 4- or 8-byte values whose body is value-aligned, large enough, and at least one partition tile long
+enum : uint32_t { PAGECLASS_NOT_DICT = 1u, PAGECLASS_MAYBE_NULLS = 2u, PAGECLASS_NOT_IN_PLACE = 4u };
+void launch_classify_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, uint32_t* col_flags, int zc_tile_rows);
+// Zero-copy PLAIN columns: a column whose every page passes the PAGECLASS_NOT_IN_PLACE test is never decoded.  Its values
+// are read by the hash and partition kernels straight from the page bodies inside the source file images.  Per partition
+// tile (zc_tile_rows rows: 4096, or 8192 when the rows leave over NVLink) they need to know where the tile's values lie:
+// pages are at least one tile long, so a tile touches at most two of them.
+struct ZcTile {
+  const uint8_t* p0;  // page body of the tile's first row, rebased: the value of GLOBAL row r is at p0 + r * width ...
+  const uint8_t* p1;  // ... for r < split, and at p1 + r * width from row `split` on (the next page)
+  int64_t split;
+};
+// entries of every page of a column with tile_src[col] != nullptr
+void launch_fill_zc_tiles(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, ZcTile* const* tile_src, int zc_tile_rows,
+                          int64_t nrows);
 
 // device error word: 0 = ok, else (code << 24 | detail)
 enum DecodeError : uint32_t {
@@ -90,6 +104,9 @@ struct KeyColumn {
   const uint8_t* valid;  // nullptr -> no nulls
   int32_t type;
   int32_t width;
+  // zero-copy column (data == nullptr): where each partition tile's values lie inside the source images.  Only a single
+  // int32 / int64 key without nulls may come this way (the specialised hash kernels handle it).
+  const ZcTile* tiles = nullptr;
 };
 
 constexpr int kPartTile = 4096;   // rows per partition tile (256 threads x 16)
@@ -121,6 +138,7 @@ struct PartColumn {
   void* out;
   int32_t width;  // 8, 4 or 1 (validity bytes travel as width-1 columns)
   int32_t pad;
+  const ZcTile* tiles = nullptr;  // zero-copy source (in == nullptr), see KeyColumn::tiles
 };
 bool fused_partition_supported(int nbins);
 // bin_ids (optional): receives every row's bin so that launch_partition_rows (same argument) need not hash again

@@ -337,7 +337,8 @@ __device__ __forceinline__ bool locate_def_levels(const PageDesc& pg, const uint
 }
 
 // One thread per data page: is it dictionary-encoded, and can it hold nulls?
-__global__ void k_classify_pages(const PageDesc* __restrict__ pages, int64_t n_pages, uint32_t* __restrict__ col_flags) {
+__global__ void k_classify_pages(const PageDesc* __restrict__ pages, int64_t n_pages, uint32_t* __restrict__ col_flags,
+                                 int zc_tile_rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pages) return;
   const PageDesc pg = pages[i];
@@ -349,7 +350,47 @@ __global__ void k_classify_pages(const PageDesc* __restrict__ pages, int64_t n_p
     if (!locate_def_levels(pg, p, def_p, def_end) || !def_levels_all_valid(def_p, def_end, (uint32_t)pg.num_values))
       f |= PAGECLASS_MAYBE_NULLS;
   }
+  // readable in place?
+  {
+    const int W = (pg.phys_type == pq::INT64 || pg.phys_type == pq::DOUBLE) ? 8 : ((pg.phys_type == pq::INT32 || pg.phys_type == pq::FLOAT) ? 4 : 0);
+    bool in_place = W != 0 && pg.encoding == pq::ENC_PLAIN && !pg.is_compressed && pg.size == pg.uncompressed_size &&
+                    (f & PAGECLASS_MAYBE_NULLS) == 0 && zc_tile_rows > 0 && pg.num_values >= zc_tile_rows;
+    if (in_place) {
+      const uint8_t* p = pg.data;
+      const uint8_t *def_p, *def_end;
+      in_place = locate_def_levels(pg, p, def_p, def_end) && ((uintptr_t)p % W) == 0 &&
+                 (int64_t)(pg.data + pg.size - p) >= (int64_t)pg.num_values * W;
+    }
+    if (!in_place) f |= PAGECLASS_NOT_IN_PLACE;
+  }
   if (f) atomicOr(&col_flags[pg.col], f);
+}
+
+// one CTA per page: the page's share of the tile table (see ZcTile)
+__global__ void k_fill_zc_tiles(const PageDesc* __restrict__ pages, ZcTile* const* __restrict__ tile_src, int T, int64_t nrows) {
+  const PageDesc pg = pages[blockIdx.x];
+  ZcTile* dst = tile_src[pg.col];
+  if (!dst || pg.num_values <= 0) return;
+  const int W = (pg.phys_type == pq::INT64 || pg.phys_type == pq::DOUBLE) ? 8 : 4;
+  const uint8_t* p = pg.data;
+  const uint8_t *def_p, *def_end;
+  locate_def_levels(pg, p, def_p, def_end);  // validated by k_classify_pages
+  const int64_t r0 = pg.first_row, r1 = pg.first_row + pg.num_values;  // rows [r0, r1)
+  const uint8_t* rebased = p - (size_t)r0 * W;
+  for (int64_t t = r0 / T + threadIdx.x; t * T < r1; t += blockDim.x) {
+    const int64_t first = t * T, last = min(first + T, nrows) - 1;
+    if (first >= r0) {  // the tile starts in this page
+      dst[t].p0 = rebased;
+      if (last < r1) {  // ... and ends in it
+        dst[t].p1 = rebased;
+        dst[t].split = INT64_MAX;
+      }
+    }
+    if (last < r1 && first < r0) {  // the tile started in the page before
+      dst[t].p1 = rebased;
+      dst[t].split = r0;
+    }
+  }
 }
 
 // value -> code of a late-materialised dictionary column (same table layout and probing as k_dict_map_all)
@@ -640,6 +681,7 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_pages(const PageDesc*
     if (pg.first_row + pg.num_values <= lo || pg.first_row >= hi) return;
   }
   const ColumnOut co = cols[pg.col];
+  if (co.skip) return;  // zero-copy column: read in place by the partition
   switch (pg.phys_type) {
     case pq::INT64:
     case pq::DOUBLE: decode_page<8>(pg, co, col_has_nulls + pg.col, d_error, sm); break;
@@ -663,10 +705,18 @@ void launch_walk_pages(hs_ctx* ctx, const ChunkDesc* chunks, int n_chunks, int32
   HS_LAUNCH_CHECK(ctx);
 }
 
-void launch_classify_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, uint32_t* col_flags) {
+void launch_classify_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, uint32_t* col_flags, int zc_tile_rows) {
   KernelScope _ks(ctx, "k_classify_pages");
   if (n_pages == 0) return;
-  k_classify_pages<<<(unsigned)ceil_div(n_pages, 128), 128, 0, ctx->stream>>>(pages, n_pages, col_flags);
+  k_classify_pages<<<(unsigned)ceil_div(n_pages, 128), 128, 0, ctx->stream>>>(pages, n_pages, col_flags, zc_tile_rows);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_fill_zc_tiles(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, ZcTile* const* tile_src, int zc_tile_rows,
+                          int64_t nrows) {
+  KernelScope _ks(ctx, "k_fill_zc_tiles");
+  if (n_pages == 0) return;
+  k_fill_zc_tiles<<<(unsigned)n_pages, 32, 0, ctx->stream>>>(pages, tile_src, zc_tile_rows, nrows);
   HS_LAUNCH_CHECK(ctx);
 }
 

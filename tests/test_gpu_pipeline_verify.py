@@ -186,3 +186,44 @@ def test_multi_gpu_parity_under_torchrun():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "multi-gpu parity ok" in r.stdout
+
+
+def test_zero_copy_plain_columns_give_byte_identical_files(ctx):
+    """PLAIN, null-free, value-aligned columns are read in place by the hash / partition kernels (no decode pass).  Files
+    whose row counts are no multiple of the partition tile make tiles straddle two pages (two files)."""
+    from hyperspace_b200 import _native as N
+
+    n, nb = 777_777, 64  # 7 files x 111 111 rows: every file boundary falls inside a partition tile
+    for dictionary in (True, False):
+        src = ctx.synth_table(3, n, 5, n_files=7, row_groups_per_file=1, output=N.HS_OUT_DEVICE, dictionary=dictionary)
+        ctx.profile_enable(True)
+        zc, _ = ctx.create_index(src.as_sources(), INDEXED, INCLUDED, nb, output=N.HS_OUT_HOST, job_uuid="z")
+        kernels = ctx.profile_report()
+        ctx.profile_enable(False)
+        assert "k_fill_zc_tiles" in kernels, sorted(kernels)
+        os.environ["HS_NO_ZEROCOPY"] = "1"
+        try:
+            ctx.profile_enable(True)
+            ref, _ = ctx.create_index(src.as_sources(), INDEXED, INCLUDED, nb, output=N.HS_OUT_HOST, job_uuid="z")
+            assert "k_fill_zc_tiles" not in ctx.profile_report()
+            ctx.profile_enable(False)
+        finally:
+            del os.environ["HS_NO_ZEROCOPY"]
+        assert _files_bytes(zc) == _files_bytes(ref)
+        rep = ctx.verify_index(zc.as_sources(), [f.bucket for f in zc.files], INDEXED, INCLUDED, nb)
+        gen = ctx.synth_checksum(3, n, 5)
+        assert rep["bucket_mismatches"] == 0 and rep["order_violations"] == 0 and rep["row_checksum"] == gen["row_checksum"]
+        zc.free()
+        ref.free()
+        src.free()
+    # a pyarrow file with small pages (fewer rows than a tile) or nulls is not eligible and must still come out right
+    cols = O.synthetic_table(0, 50_000, 3)
+    buf = pa.BufferOutputStream()
+    pq.write_table(pa.table(cols), buf, compression="NONE", use_dictionary=False, data_page_size=8192)
+    res, _ = ctx.create_index([N.FileImage(data=buf.getvalue().to_pybytes())], ["k"], ["v1", "v2"], 5, output=N.HS_OUT_HOST)
+    perm, offs, order = O.index_rows(cols, ["k"], ["v1", "v2"], 5)
+    for i, f in enumerate(res.files):
+        t = pq.ParquetFile(pa.BufferReader(res.host_bytes(i))).read()
+        for c in order:
+            assert t.column(c).to_numpy().tobytes() == cols[c][perm[int(offs[f.bucket]):int(offs[f.bucket + 1])]].tobytes()
+    res.free()
