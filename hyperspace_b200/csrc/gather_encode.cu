@@ -35,6 +35,30 @@ __global__ void __launch_bounds__(kThreads) k_gather_encode(const SortTile* __re
   uint8_t* const base = arena + col.page_value_offset[bucket_page_begin[t.seg] + page] + (lr0 - page * (uint64_t)rows_per_page) * W;
   // the host pads the definition-level block so that page bodies are 8-byte aligned whenever the page is large enough
   const bool aligned = ((uintptr_t)base & (W - 1)) == 0;
+  if (aligned && t.count == kSortTile) {
+    // Full tile, aligned body (all but a bucket's last tile): every thread's row indices are loaded first, then all its
+    // gathers are in flight together, then the stores -- the gather is latency-bound (ncu: 89 % of the stalls on the
+    // dependent perm -> value load pair with one pair per thread in flight)
+    constexpr int kPer = kSortTile / kThreads;
+    uint64_t v[kPer];
+    if (col.sorted_keys) {
+#pragma unroll
+      for (int it = 0; it < kPer; it++) v[it] = sort_decode_int(col.key_type, col.sorted_keys[t.start + it * kThreads + threadIdx.x]);
+    } else {
+      uint32_t r[kPer];
+#pragma unroll
+      for (int it = 0; it < kPer; it++) r[it] = perm[t.start + it * kThreads + threadIdx.x];
+#pragma unroll
+      for (int it = 0; it < kPer; it++) v[it] = W == 8 ? ((const uint64_t*)col.src)[r[it]] : ((const uint32_t*)col.src)[r[it]];
+    }
+#pragma unroll
+    for (int it = 0; it < kPer; it++) {
+      const uint32_t i = it * kThreads + threadIdx.x;
+      if (W == 8) reinterpret_cast<uint64_t*>(base)[i] = v[it];
+      else reinterpret_cast<uint32_t*>(base)[i] = (uint32_t)v[it];
+    }
+    return;
+  }
   const uint32_t iters = (t.count + kThreads - 1) / kThreads;
   for (uint32_t it = 0; it < iters; it++) {
     const uint32_t i = it * kThreads + threadIdx.x;

@@ -239,20 +239,43 @@ __global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ t
                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                    uint64_t high_mask, uint64_t low_mask, uint32_t max_run,
                                                    uint32_t* __restrict__ flag) {
+  // The tile's keys are staged in shared memory with all of a thread's loads in flight at once: s_key[1 + i] = key of row i
+  // of the tile, [0] / [count + 1] = the rows just outside it (or a key with a different prefix where the segment ends).
+  // Run detection, the walk to the end of a run and the order test then never leave shared memory; global memory is touched
+  // again only for the rows an out-of-order run actually moves.  With 5 M-row buckets one row in eight heads a run: doing
+  // all of that through dependent global loads was latency-bound (4.9 ms per 1 B rows for 8 B/row of traffic).
+  __shared__ uint64_t s_key[kSortTile + 2];
   __shared__ uint16_t s_heads[kSortTile / 2 + 32];
   __shared__ uint32_t s_n;
   const SortTile t = tiles[blockIdx.x];
   const uint64_t segb = seg_start[t.seg], sege = seg_start[t.seg + 1];
   const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1;
-  if (threadIdx.x == 0) s_n = 0;
+  constexpr int kPer = kSortTile / 256;
+  {
+    uint64_t k[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+      const uint32_t i = j * 256 + threadIdx.x;
+      k[j] = i < t.count ? keys[t.start + i] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; j++) s_key[1 + j * 256 + threadIdx.x] = k[j];
+  }
   __syncthreads();
-  for (uint32_t i0 = 0; i0 < t.count; i0 += 256) {  // uniform trip count: the ballot below needs whole warps
+  if (threadIdx.x == 0) {
+    s_n = 0;
+    const uint64_t flip = high_mask & (~high_mask + 1);  // lowest bit of the prefix: flipping it makes a different prefix
+    s_key[0] = t.start > segb ? keys[t.start - 1] : (s_key[1] ^ flip);
+    s_key[t.count + 1] = t.start + t.count < sege ? keys[t.start + t.count] : (s_key[t.count] ^ flip);
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (uint32_t i0 = 0; i0 < kSortTile; i0 += 256) {  // uniform trip count: the ballot below needs whole warps
     const uint32_t i = i0 + threadIdx.x;
     bool head = false;
     if (i < t.count) {
-      const uint64_t p = t.start + i;
-      const uint64_t kh = keys[p] & high_mask;
-      head = (p == segb || (keys[p - 1] & high_mask) != kh) && p + 1 < sege && (keys[p + 1] & high_mask) == kh;
+      const uint64_t kh = s_key[1 + i] & high_mask;
+      head = (s_key[i] & high_mask) != kh && (s_key[2 + i] & high_mask) == kh;
     }
     const unsigned m = __ballot_sync(0xffffffffu, head);
     if (m) {
@@ -265,29 +288,61 @@ __global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ t
   __syncthreads();
   const uint32_t nheads = s_n;
   for (uint32_t e = threadIdx.x; e < nheads; e += 256) {
-    const uint64_t p = t.start + s_heads[e];
-    const uint64_t kh = keys[p] & high_mask;
-    uint64_t q = p + 2;  // p + 1 is known to belong to the run
-    while (q < sege && q - p <= max_run && (keys[q] & high_mask) == kh) q++;
-    const uint32_t len = (uint32_t)(q - p);
+    const uint32_t i = s_heads[e];
+    const uint64_t p = t.start + i;
+    uint64_t* sk = s_key + 1 + i;  // the run starts at sk[0]
+    const uint64_t kh = sk[0] & high_mask;
+    uint32_t len = 1;
+    while (i + len < t.count && len <= max_run && (sk[len] & high_mask) == kh) len++;
+    if (i + len == t.count && (sk[len] & high_mask) == kh) {  // sk[len] is the next tile's first key here
+      // the run continues into the next tile (at most one per tile): settle it in global memory, as a whole.  The next
+      // tile never touches these rows -- none of them heads a run there -- and reads only their (unchanging) prefixes.
+      uint64_t q = p + len;
+      while (q < sege && q - p <= max_run && (keys[q] & high_mask) == kh) q++;
+      const uint32_t glen = (uint32_t)(q - p);
+      if (glen > max_run) {
+        *flag = 1;
+        continue;
+      }
+      for (uint32_t a = 1; a < glen; a++) {  // stable insertion sort on the low bits
+        const uint64_t ka = keys[p + a];
+        const uint32_t va = vals[p + a];
+        const uint64_t la = ka & low_mask;
+        uint32_t b = a;
+        while (b > 0 && (keys[p + b - 1] & low_mask) > la) {
+          keys[p + b] = keys[p + b - 1];
+          vals[p + b] = vals[p + b - 1];
+          b--;
+        }
+        if (b != a) {
+          keys[p + b] = ka;
+          vals[p + b] = va;
+        }
+      }
+      continue;
+    }
     if (len > max_run) {
       *flag = 1;
       continue;
     }
-    for (uint32_t a = 1; a < len; a++) {  // stable insertion sort on the low bits
-      const uint64_t ka = keys[p + a];
-      const uint32_t va = vals[p + a];
+    // the run lies inside the tile: stable insertion sort on the low bits, keys in shared memory; the rows that move are
+    // written through to global memory (their row indices are fetched only then)
+    for (uint32_t a = 1; a < len; a++) {
+      const uint64_t ka = sk[a];
       const uint64_t la = ka & low_mask;
       uint32_t b = a;
-      while (b > 0 && (keys[p + b - 1] & low_mask) > la) {
-        keys[p + b] = keys[p + b - 1];
-        vals[p + b] = vals[p + b - 1];
-        b--;
+      while (b > 0 && (sk[b - 1] & low_mask) > la) b--;
+      if (b == a) continue;
+      const uint32_t va = vals[p + a];
+      for (uint32_t c = a; c > b; c--) {
+        const uint64_t kc = sk[c - 1];
+        sk[c] = kc;
+        keys[p + c] = kc;
+        vals[p + c] = vals[p + c - 1];
       }
-      if (b != a) {
-        keys[p + b] = ka;
-        vals[p + b] = va;
-      }
+      sk[b] = ka;
+      keys[p + b] = ka;
+      vals[p + b] = va;
     }
   }
 }
