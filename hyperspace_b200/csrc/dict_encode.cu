@@ -110,11 +110,14 @@ __global__ void __launch_bounds__(kThreads) k_dict_build_from_pages(const PageDe
 
 // distinct values out of the hash set (order arbitrary; the host sorts the small list)
 __global__ void k_dict_collect(const unsigned long long* __restrict__ keys, uint32_t capacity,
-                               unsigned long long* __restrict__ out, uint32_t* __restrict__ counter) {
+                               unsigned long long* __restrict__ out, uint32_t* __restrict__ counter, uint32_t max_out) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= capacity) return;
   const unsigned long long v = keys[s];
-  if (v != kEmpty) out[atomicAdd(counter, 1u)] = v;
+  if (v != kEmpty) {
+    const uint32_t at = atomicAdd(counter, 1u);
+    if (at < max_out) out[at] = v;
+  }
 }
 
 // ---- all dictionary columns at once ---------------------------------------------------------------------------------
@@ -274,8 +277,8 @@ void launch_dict_build_from_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_
 }
 
 void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity, unsigned long long* out,
-                         uint32_t* counter) {
-  k_dict_collect<<<(capacity + 255) / 256, 256, 0, ctx->stream>>>(keys, capacity, out, counter);
+                         uint32_t* counter, uint32_t max_out) {
+  k_dict_collect<<<(capacity + 255) / 256, 256, 0, ctx->stream>>>(keys, capacity, out, counter, max_out);
   HS_LAUNCH_CHECK(ctx);
 }
 

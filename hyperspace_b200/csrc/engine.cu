@@ -158,7 +158,7 @@ static uint32_t bits_for(uint32_t ndict) {
 
 // value -> code look-up table (open addressing, linear probing, 16-byte {key lo, key hi, code, 0} entries), built on the
 // host (<= 65536 inserts) and sized to the dictionary (load <= 0.5) so that it stays resident in L1 while rows stream
-// through it.  The empty marker ~0 cannot be stored: *empty_index receives its code instead.  Synchronises the stream.
+// through it.  The empty marker ~0 cannot be stored: *empty_index receives its code instead.
 static void upload_lookup_table(hs_ctx* ctx, const std::vector<uint64_t>& values, Buf<uint8_t>* entries, uint32_t* mask,
                                 uint32_t* empty_index) {
   const uint32_t ndict = (uint32_t)values.size();
@@ -181,8 +181,7 @@ static void upload_lookup_table(hs_ctx* ctx, const std::vector<uint64_t>& values
     tab[(size_t)h * 4 + 2] = i;
   }
   entries->alloc(ctx, (size_t)cap * 16);
-  copy_h2d(ctx, entries->get(), tab.data(), (size_t)cap * 16);
-  sync_stream(ctx);  // tab goes out of scope
+  copy_h2d(ctx, entries->get(), tab.data(), (size_t)cap * 16);  // snapshot: tab may go out of scope
 }
 
 // out[dst_off .. dst_off + len) = src[0 .. len): gathers the tails / footers of device-resident file images into one
@@ -453,22 +452,27 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   Buf<PageDesc> d_pages(ctx, std::max<int64_t>(1, n_pages));
   copy_h2d(ctx, d_offsets.get(), offsets.data(), sizeof(int64_t) * n_chunks);
   launch_walk_pages(ctx, d_chunks.get(), n_chunks, d_counts.get(), d_offsets.get(), d_pages.get(), d_flags.get(), 1);
-  {  // a chunk whose page headers do not add up must not reach the decoder: its pages would write outside the columns
-    uint32_t walk_error = 0;
-    copy_d2h(ctx, &walk_error, d_flags.get(), sizeof walk_error);
-    sync_stream(ctx);
+  // a chunk whose page headers do not add up must not reach the decoder (its pages would write outside the columns): the
+  // error word is read back with the next results the host needs anyway, and checked before any page is decoded
+  uint32_t walk_error = 0;
+  bool walk_checked = false;
+  copy_d2h(ctx, &walk_error, d_flags.get(), sizeof walk_error);
+  auto check_walk = [&]() {
+    if (walk_checked) return;
+    walk_checked = true;
     if (walk_error) {
       const uint32_t code = walk_error >> 24, detail = walk_error & 0xffffffu;
       fail(code == DERR_COMPRESSED ? HS_EUNSUPPORTED : HS_EFORMAT, "Parquet page walk failed: %s (column chunk %u)",
            decode_error_text(code), detail);
     }
-  }
+  };
   // ---- snappy: decompress the compressed page bodies (and dictionary pages) into a scratch buffer, repoint the pages ----
   Buf<uint8_t> d_scratch;
   if (any_compressed && n_pages > 0) {
     std::vector<PageDesc> h_pages((size_t)n_pages);
     copy_d2h(ctx, h_pages.data(), d_pages.get(), sizeof(PageDesc) * (size_t)n_pages);
     sync_stream(ctx);
+    check_walk();
     std::vector<SnappyBlob> blobs;
     std::map<const uint8_t*, uint64_t> dict_off;  // stored dictionary page -> scratch offset of its decompressed copy
     uint64_t cursor = 0;
@@ -519,89 +523,109 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   // partition moves 2 bytes per row instead of 4 or 8, and the page encoder finds its codes ready-made.  On several GPUs
   // the ranks agree on the columns and on one dictionary per column (unions all-gathered and merged), so that codes mean
   // the same everywhere and can cross NVLink in place of the values.
+  //
+  // One device round and ONE all-gather: the page classification and, speculatively, the dictionary union of every
+  // candidate column are computed back to back and fetched with a single synchronisation; each rank then contributes one
+  // fixed-size message (flags, row count, per candidate its type and up to kAgreeCap dictionary values) and every rank
+  // derives the same decisions from the gathered messages.  (The first version took a host round trip per step and per
+  // candidate: 2 + 2 x candidates all-gathers, each with its own synchronisation -- a quarter of an 8-GPU build.)
   const bool want_zc = carry && carry->zc_tile_rows > 0 && !file_windows && n_pages > 0 && nrows > 0;
   std::vector<uint32_t> local_cls(ncols, 0u);  // classification of this rank's own pages, per column
+  constexpr uint32_t kAgreeCap = 8192;  // dictionary values per candidate carried by the message (larger unions: no carry)
+  constexpr int kMaxSpec = 6;           // candidates examined (kMaxCarried of them can be carried)
+  std::vector<int> spec;                // candidate columns, the same list on every rank
+  if (want_carry)
+    for (int c = carry->first_col; c < ncols && (int)spec.size() < kMaxSpec; c++) spec.push_back(c);
+  const int nspec = (int)spec.size();
+  std::vector<uint32_t> spec_state(4 * (size_t)std::max(1, nspec), 0u), spec_count(std::max(1, nspec), 0u);
+  std::vector<uint64_t> spec_vals((size_t)std::max(1, nspec) * kAgreeCap);
   if ((want_carry || want_zc) && n_pages > 0) {
     Buf<uint32_t> d_class(ctx, ncols);
     fill_bytes(ctx, d_class.get(), 0, 4 * (size_t)ncols);
     launch_classify_pages(ctx, d_pages.get(), n_pages, d_class.get(), want_zc ? carry->zc_tile_rows : 0);
     copy_d2h(ctx, local_cls.data(), d_class.get(), 4 * (size_t)ncols);
+    Buf<uint32_t> d_states(ctx, 4 * (size_t)std::max(1, nspec)), d_cnt(ctx, std::max(1, nspec));
+    Buf<unsigned long long> d_vals(ctx, (size_t)std::max(1, nspec) * kAgreeCap);
+    std::vector<Buf<unsigned long long>> sets(nspec);
+    if (nspec) {
+      fill_bytes(ctx, d_states.get(), 0, 16 * (size_t)nspec);
+      fill_bytes(ctx, d_cnt.get(), 0, 4 * (size_t)nspec);
+      for (int i = 0; i < nspec; i++) {
+        const DevColumn& dc = out->cols[spec[i]];
+        if (dc.width != 4 && dc.width != 8) continue;
+        sets[i].alloc(ctx, kDictCapacity);
+        fill_bytes(ctx, sets[i].get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
+        launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, spec[i], dc.width, sets[i].get(), kDictCapacity, kMaxDictEntries,
+                                     d_states.get() + 4 * i);
+        launch_dict_collect(ctx, sets[i].get(), kDictCapacity, d_vals.get() + (size_t)i * kAgreeCap, d_cnt.get() + i, kAgreeCap);
+      }
+      copy_d2h(ctx, spec_state.data(), d_states.get(), 16 * (size_t)nspec);
+      copy_d2h(ctx, spec_count.data(), d_cnt.get(), 4 * (size_t)nspec);
+      copy_d2h(ctx, spec_vals.data(), d_vals.get(), 8 * (size_t)nspec * kAgreeCap);
+    }
+    sync_stream(ctx);
+  } else {
     sync_stream(ctx);
   }
+  check_walk();
   if (want_carry) {
     const int W = ctx->world;
-    // what every rank knows about its own pages: per column the classification flags, then its row count
-    std::vector<uint32_t> mine(ncols + 2, 0u), all((size_t)(ncols + 2) * W);
+    // message: [ncols class flags][rows][per candidate: type, width, distinct count, overflow, holds ~0, values...]
+    const size_t per_cand = 5 + kAgreeCap, words = (size_t)ncols + 1 + (size_t)nspec * per_cand;
+    std::vector<uint64_t> mine(words, 0ull), all(words * W);
     for (int c = 0; c < ncols; c++) mine[c] = local_cls[c] & (PAGECLASS_NOT_DICT | PAGECLASS_MAYBE_NULLS);
-    mine[ncols] = (uint32_t)(nrows & 0xffffffffll);
-    mine[ncols + 1] = (uint32_t)(nrows >> 32);
-    comm_allgather_host(ctx, mine.data(), 4 * mine.size(), all.data());
+    mine[ncols] = (uint64_t)nrows;
+    for (int i = 0; i < nspec; i++) {
+      const DevColumn& dc = out->cols[spec[i]];
+      uint64_t* m = &mine[(size_t)ncols + 1 + (size_t)i * per_cand];
+      m[0] = (uint64_t)(int64_t)dc.type;
+      m[1] = (uint64_t)dc.width;
+      m[2] = spec_state[4 * i];                                                    // distinct values in the set (excl. ~0)
+      m[3] = (spec_state[4 * i + 1] || spec_count[i] > kAgreeCap) ? 1 : 0;         // overflow: no carry for this column
+      m[4] = spec_state[4 * i + 2];                                                // the value ~0 occurs
+      const uint32_t nv = std::min<uint32_t>(spec_count[i], kAgreeCap);
+      for (uint32_t j = 0; j < nv; j++) m[5 + j] = spec_vals[(size_t)i * kAgreeCap + j];
+      m[2] = nv;
+    }
+    comm_allgather_host(ctx, mine.data(), 8 * words, all.data());
     std::vector<uint32_t> cls(ncols, 0u);
     int64_t total_rows = 0;
     for (int r = 0; r < W; r++) {
-      const uint32_t* a = &all[(size_t)r * (ncols + 2)];
-      for (int c = 0; c < ncols; c++) cls[c] |= a[c];
-      total_rows += (int64_t)a[ncols] | ((int64_t)a[ncols + 1] << 32);
+      const uint64_t* a = &all[(size_t)r * words];
+      for (int c = 0; c < ncols; c++) cls[c] |= (uint32_t)a[c];
+      total_rows += (int64_t)a[ncols];
     }
-    std::vector<int> cand;
-    for (int c = carry->first_col; c < ncols && (int)cand.size() < kMaxCarried && total_rows > 0; c++)
-      if (cls[c] == 0 && (out->cols[c].width == 4 || out->cols[c].width == 8)) cand.push_back(c);
-    if (!cand.empty()) {
-      // union of this rank's chunk dictionaries, per candidate
-      const int nc = (int)cand.size();
-      std::vector<uint32_t> h_states(4 * (size_t)nc, 0u), all_states(4 * (size_t)nc * W);
-      if (n_pages > 0) {
-        Buf<uint32_t> d_states(ctx, 4 * (size_t)nc);
-        fill_bytes(ctx, d_states.get(), 0, 16 * (size_t)nc);
-        for (int i = 0; i < nc; i++) {
-          DevColumn& dc = out->cols[cand[i]];
-          dc.dict_keys.alloc(ctx, kDictCapacity);
-          fill_bytes(ctx, dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
-          launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, cand[i], dc.width, dc.dict_keys.get(), kDictCapacity,
-                                       kMaxDictEntries, d_states.get() + 4 * i);
-        }
-        copy_d2h(ctx, h_states.data(), d_states.get(), 16 * (size_t)nc);
-        sync_stream(ctx);
+    out->global_rows = total_rows;
+    int ncarried = 0;
+    for (int i = 0; i < nspec && ncarried < kMaxCarried && total_rows > 0; i++) {
+      const int c = spec[i];
+      DevColumn& dc = out->cols[c];
+      if (cls[c] != 0) continue;
+      int type = -1, width = 0;
+      bool overflow = false, has_empty = false;
+      std::vector<uint64_t> values;
+      for (int r = 0; r < W; r++) {
+        const uint64_t* m = &all[(size_t)r * words + (size_t)ncols + 1 + (size_t)i * per_cand];
+        if ((int64_t)m[0] >= 0) type = (int)(int64_t)m[0];
+        width = std::max(width, (int)m[1]);
+        overflow = overflow || m[3] != 0;
+        has_empty = has_empty || m[4] != 0;
+        values.insert(values.end(), m + 5, m + 5 + m[2]);
       }
-      comm_allgather_host(ctx, h_states.data(), 16 * (size_t)nc, all_states.data());
-      for (int i = 0; i < nc; i++) {
-        const int c = cand[i];
-        DevColumn& dc = out->cols[c];
-        bool overflow = false;
-        uint32_t max_count = 0;
-        for (int r = 0; r < W; r++) {
-          const uint32_t* st = &all_states[((size_t)r * nc + i) * 4];
-          overflow = overflow || st[1] != 0;
-          max_count = std::max(max_count, st[0] + (st[2] ? 1u : 0u));
-        }
-        std::vector<uint64_t> values;
-        if (!overflow) {
-          if (n_pages > 0) values = sorted_dictionary(ctx, dc.dict_keys.get(), &h_states[4 * (size_t)i], dc.type);
-          if (W > 1) {  // merge the ranks' unions: [count, values...] blobs of equal size
-            std::vector<uint64_t> blob((size_t)max_count + 1, 0ull), blobs(((size_t)max_count + 1) * W);
-            blob[0] = values.size();
-            std::copy(values.begin(), values.end(), blob.begin() + 1);
-            comm_allgather_host(ctx, blob.data(), 8 * blob.size(), blobs.data());
-            values.clear();
-            for (int r = 0; r < W; r++) {
-              const uint64_t* bl = &blobs[(size_t)r * (max_count + 1)];
-              values.insert(values.end(), bl + 1, bl + 1 + bl[0]);
-            }
-            sort_dictionary(values, dc.type);
-            values.erase(std::unique(values.begin(), values.end()), values.end());
-          }
-        }
-        dc.dict_keys.release();
-        const uint32_t bw = bits_for((uint32_t)values.size());
-        if (overflow || !dictionary_pays_off((uint32_t)values.size(), bw, dc.width, total_rows, carry->num_segments)) continue;
-        uint32_t mask = 0, empty_index = 0;
-        upload_lookup_table(ctx, values, &carry_tables[c], &mask, &empty_index);
-        dc.carried = true;
-        dc.dict_values = std::move(values);
-        dc.dict_bw = bw;
-        dc.codes.alloc(ctx, (size_t)std::max<int64_t>(1, nrows) + 16);
-        h_cols[c] = ColumnOut{dc.codes.get(), nullptr, dc.width, dc.type, carry_tables[c].get(), mask, empty_index, 1, 0};
-      }
+      if (overflow || type < 0 || (width != 4 && width != 8)) continue;
+      if (has_empty) values.push_back(~0ull);
+      sort_dictionary(values, type);
+      values.erase(std::unique(values.begin(), values.end()), values.end());
+      const uint32_t bw = bits_for((uint32_t)values.size());
+      if (!dictionary_pays_off((uint32_t)values.size(), bw, width, total_rows, carry->num_segments)) continue;
+      uint32_t mask = 0, empty_index = 0;
+      upload_lookup_table(ctx, values, &carry_tables[c], &mask, &empty_index);
+      dc.carried = true;
+      dc.dict_values = std::move(values);
+      dc.dict_bw = bw;
+      dc.codes.alloc(ctx, (size_t)std::max<int64_t>(1, nrows) + 16);
+      h_cols[c] = ColumnOut{dc.codes.get(), nullptr, dc.width, dc.type, carry_tables[c].get(), mask, empty_index, 1, 0};
+      ncarried++;
     }
   }
   // ---- zero-copy PLAIN columns -------------------------------------------------------------------------------------
@@ -878,6 +902,8 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
   t_sort.stop();
   sync_stream(ctx);
   stats->ms_sort += t_sort.ms();
+  for (auto& d : out->pending_timers) stats->*(d.field) += d.t->ms();
+  out->pending_timers.clear();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -957,46 +983,55 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     carried_cols[dc.carry_slot] = c;
   }
   if (req.use_dictionary && total_rows > 0) {
-    Buf<uint32_t> d_state(ctx, 4);
+    // staged sampling: 16 K rows that are (nearly) all distinct mark a key-like column at once; a 256 K-row sample then
+    // lets the remaining high-cardinality columns overflow cheaply (the overflow path serialises on one counter).  The
+    // first stage runs for ALL columns before the host looks at any result: one synchronisation instead of one per column.
+    Buf<uint32_t> d_states(ctx, 4 * (size_t)ncols);
+    std::vector<uint32_t> h_states(4 * (size_t)ncols, 0u);
+    fill_bytes(ctx, d_states.get(), 0, 16 * (size_t)ncols);
+    const int64_t mini = std::min<int64_t>(total_rows, 1 << 14);
+    bool any_sampled = false;
     for (int c = 0; c < ncols; c++) {
       const DevColumn& dc = table.cols[c];
       if (dc.has_nulls || dc.carried) continue;
       ColDict& cd = dicts[c];
-      uint32_t st[4] = {0, 0, 0, 0};
-      const bool ready = dc.dict_ready && dc.dict_keys;
-      if (ready) {
+      if (dc.dict_ready && dc.dict_keys) {
         cd.keys_ptr = dc.dict_keys.get();
-        memcpy(st, dc.dict_state, 16);
-      } else {
-        cd.keys.alloc(ctx, kDictCapacity);
-        cd.keys_ptr = cd.keys.get();
-        fill_bytes(ctx, cd.keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
-      }
-      fill_bytes(ctx, d_state.get(), 0, 16);
-      if (!ready) {
-      // staged sampling: 16 K rows that are (nearly) all distinct mark a key-like column at once; a 256 K-row sample then
-      // lets the remaining high-cardinality columns overflow cheaply (the overflow path serialises on one counter)
-      const int64_t mini = std::min<int64_t>(total_rows, 1 << 14);
-      launch_dict_build(ctx, dc.data.get(), dc.width, 0, mini, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state.get());
-      copy_d2h(ctx, st, d_state.get(), 16);
-      sync_stream(ctx);
-      if (total_rows > (1 << 20) && st[0] + st[2] > 0.95 * mini) {
-        cd.keys.release();
+        memcpy(&h_states[4 * (size_t)c], dc.dict_state, 16);
         continue;
       }
-      const int64_t sample = std::min<int64_t>(total_rows, 1 << 18);
-      if (sample > mini) {
-        launch_dict_build(ctx, dc.data.get(), dc.width, mini, sample, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state.get());
-        copy_d2h(ctx, st, d_state.get(), 16);
-        sync_stream(ctx);
+      cd.keys.alloc(ctx, kDictCapacity);
+      cd.keys_ptr = cd.keys.get();
+      fill_bytes(ctx, cd.keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
+      launch_dict_build(ctx, dc.data.get(), dc.width, 0, mini, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_states.get() + 4 * c);
+      copy_d2h(ctx, &h_states[4 * (size_t)c], d_states.get() + 4 * c, 16);
+      any_sampled = true;
+    }
+    if (any_sampled) sync_stream(ctx);
+    for (int c = 0; c < ncols; c++) {
+      const DevColumn& dc = table.cols[c];
+      if (dc.has_nulls || dc.carried) continue;
+      ColDict& cd = dicts[c];
+      uint32_t* st = &h_states[4 * (size_t)c];
+      const bool ready = dc.dict_ready && dc.dict_keys;
+      if (!ready) {
+        uint32_t* d_state = d_states.get() + 4 * c;
+        if (total_rows > (1 << 20) && st[0] + st[2] > 0.95 * mini) {
+          cd.keys.release();
+          continue;
+        }
+        const int64_t sample = std::min<int64_t>(total_rows, 1 << 18);
+        if (sample > mini) {
+          launch_dict_build(ctx, dc.data.get(), dc.width, mini, sample, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state);
+          copy_d2h(ctx, st, d_state, 16);
+          sync_stream(ctx);
+        }
+        if (!st[1] && sample < total_rows) {
+          launch_dict_build(ctx, dc.data.get(), dc.width, sample, total_rows, cd.keys.get(), kDictCapacity, kMaxDictEntries, d_state);
+          copy_d2h(ctx, st, d_state, 16);
+          sync_stream(ctx);
+        }
       }
-      if (!st[1] && sample < total_rows) {
-        launch_dict_build(ctx, dc.data.get(), dc.width, sample, total_rows, cd.keys.get(), kDictCapacity, kMaxDictEntries,
-                          d_state.get());
-        copy_d2h(ctx, st, d_state.get(), 16);
-        sync_stream(ctx);
-      }
-      }  // !ready
       if (st[1]) {
         cd.keys.release();
         continue;

@@ -45,6 +45,7 @@ struct Table {
   int64_t nrows = 0;
   std::vector<DevColumn> cols;
   std::vector<int64_t> file_row_begin;  // nfiles+1: row range of every source file
+  int64_t global_rows = -1;             // rows of all ranks together, when the ranks exchanged that while decoding
   Buf<uint8_t> rec;                     // nrows x 4 uint16 codes of the carried columns (after the partition)
 };
 
@@ -72,6 +73,12 @@ struct IndexedRows {
   unsigned long long key_or_and[2] = {0, ~0ull};
   uint64_t* sorted_keys = nullptr;    // points into keys or keys_alt
   uint32_t* sorted_perm = nullptr;
+  // stage timers whose events are read at the call's next synchronisation (reading one synchronises)
+  struct DeferredTimer {
+    std::unique_ptr<StageTimer> t;
+    float hs_stats::*field;
+  };
+  std::vector<DeferredTimer> pending_timers;
 };
 
 struct OutFile {

@@ -309,8 +309,8 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   const int64_t nrows = table.nrows;
   const int ncols = (int)table.cols.size();
   const int nb = num_buckets;
-  StageTimer t_hash(ctx), t_x(ctx);
-  t_hash.start();
+  auto t_hash = std::make_unique<StageTimer>(ctx), t_x = std::make_unique<StageTimer>(ctx);
+  t_hash->start();
   std::vector<KeyColumn> h_keys(nkeys);
   for (int k = 0; k < nkeys; k++) {
     DevColumn& c = table.cols[k];
@@ -320,62 +320,16 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   copy_h2d(ctx, d_keys.get(), h_keys.data(), sizeof(KeyColumn) * nkeys);
   const int64_t ntiles = ceil_div(nrows, fused_tile_rows(true));  // runs leave over NVLink: the large tile shape
   Buf<uint32_t> tile_hist(ctx, std::max<int64_t>(1, ntiles) * nb);
-  // gathered payload per rank: nb bucket counts followed by ncols has-nulls flags
-  const int msg = nb + ncols;
-  Buf<unsigned long long> d_mine(ctx, msg), d_all(ctx, (size_t)msg * world);
-  std::vector<unsigned long long> h_mine(msg, 0), h_all((size_t)msg * world);
-  for (int c = 0; c < ncols; c++) h_mine[nb + c] = table.cols[c].has_nulls ? 1 : 0;
-  copy_h2d(ctx, d_mine.get(), h_mine.data(), 8 * msg);
-  Buf<uint16_t> bin_ids(ctx, std::max<int64_t>(1, nrows));  // bucket of every row: hashed once, read back by the partition
-  launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_mine.get(), nullptr,
-                   single_key_type_of(h_keys.data(), nkeys), bin_ids.get(), /*peer_tiles=*/true);
-  HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), msg, kNcclUint64, ctx->comm->comm, ctx->stream));
-  copy_d2h(ctx, h_all.data(), d_all.get(), 8 * (size_t)msg * world);
-  sync_stream(ctx);
-  t_hash.stop();
 
-  // ---- layout of every owner's receive buffers ------------------------------------------------------------------
-  t_x.start();
-  auto cnt = [&](int r, int b) { return h_all[(size_t)r * msg + b]; };
-  std::vector<unsigned long long> my_base(nb, 0);        // where MY rows of bucket b start inside the owner's buffers
-  std::vector<uint64_t> my_bucket_offsets(nb + 1, 0);    // bucket-major layout of the rows THIS rank receives
-  std::vector<uint64_t> owner_cursor(world, 0);
-  for (int b = 0; b < nb; b++) {
-    const int o = b % world;
-    const uint64_t start = owner_cursor[o];
-    uint64_t before_me = 0, total = 0;
-    for (int r = 0; r < world; r++) {
-      if (r < me) before_me += cnt(r, b);
-      total += cnt(r, b);
-    }
-    my_base[b] = start + before_me;
-    owner_cursor[o] += total;
-    my_bucket_offsets[b] = (o == me) ? start : (b ? my_bucket_offsets[b] : 0);
-    if (o == me) my_bucket_offsets[b + 1] = start + total;
-    else my_bucket_offsets[b + 1] = my_bucket_offsets[b];
-  }
-  // non-owned buckets are empty segments: make the offsets monotone (owned buckets are laid out in increasing b)
-  {
-    uint64_t run = 0;
-    for (int b = 0; b < nb; b++) {
-      const bool owned = (b % world) == me;
-      uint64_t total = 0;
-      if (owned)
-        for (int r = 0; r < world; r++) total += cnt(r, b);
-      my_bucket_offsets[b] = run;
-      run += total;
-    }
-    my_bucket_offsets[nb] = run;
-  }
-  const int64_t n_recv = (int64_t)owner_cursor[me];
-  for (int o = 0; o < world; o++)
-    if (owner_cursor[o] >= (1ull << 32)) fail(HS_EUNSUPPORTED, "more than 2^32-1 rows land on one GPU");
-  std::vector<bool> any_nulls(ncols, false);
-  for (int c = 0; c < ncols; c++)
-    for (int r = 0; r < world; r++) any_nulls[c] = any_nulls[c] || h_all[(size_t)r * msg + nb + c] != 0;
-
-  // ---- receive buffers + IPC handle exchange -----------------------------------------------------------------------
-  out->part.nrows = n_recv;
+  // ---- receive buffers, allocated BEFORE the ranks talk ---------------------------------------------------------------
+  // Their capacity is a bound derived from the global row count the ranks exchanged while decoding (a uniform hash puts
+  // total / world rows on every GPU give or take a per-mille), so that the IPC handles can travel in the SAME all-gather as
+  // the bucket histograms; same sizes every call also mean the pool returns the same blocks and the peers' mappings of
+  // them stay cached.  Should the bound not hold on some rank (or a column hold nulls somewhere, which needs validity
+  // buffers too), every rank sees it in the gathered message and all take the second round below.
+  const int64_t total_rows = table.global_rows;
+  const int64_t cap_rows = total_rows >= 0 ? (int64_t)((double)ceil_div(nb, world) * ((double)total_rows / nb) * 1.10) + 4096 : 0;
+  if (cap_rows >= (1ll << 32)) fail(HS_EUNSUPPORTED, "more than 2^32-1 rows land on one GPU");
   out->part.cols.clear();
   out->part.cols.resize(ncols);
   std::vector<PartColumn> h_pc;          // what the kernel moves (data columns, then validity where needed)
@@ -389,7 +343,6 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
     dst.type = src.type;
     dst.width = src.width;
     dst.schema = src.schema;
-    dst.has_nulls = any_nulls[c];
     if (src.carried) {  // every rank carries the same columns with the same dictionary (decode_sources agreed on both)
       if (c < nkeys || pack.n >= kMaxCarried) fail(HS_EINVAL, "column '%s' cannot be late-materialised here", src.name.c_str());
       dst.carried = true;
@@ -399,40 +352,162 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
       pack.src[pack.n++] = src.codes.get();
       continue;
     }
-    dst.data.alloc(ctx, (size_t)n_recv * src.width + 16);
-    ctx->pool.mark_exported(dst.data.get());
+    if (cap_rows > 0) {
+      dst.data.alloc(ctx, (size_t)cap_rows * src.width + 16);
+      ctx->pool.mark_exported(dst.data.get());
+    }
     h_pc.push_back(PartColumn{src.data.get(), nullptr, src.width, 0, src.zero_copy ? src.zc_tiles.get() : nullptr});
     my_recv.push_back(dst.data.get());
-    if (any_nulls[c]) {
-      dst.valid.alloc(ctx, (size_t)n_recv + 16);
-      ctx->pool.mark_exported(dst.valid.get());
-      if (!src.valid) {  // this rank saw no nulls in the column but another did: ship all-ones
-        src.valid.alloc(ctx, (size_t)nrows + 16);
-        fill_bytes(ctx, src.valid.get(), 1, (size_t)nrows + 16);
-      }
-      h_pc.push_back(PartColumn{src.valid.get(), nullptr, 1, 0});
-      my_recv.push_back(dst.valid.get());
-    }
   }
-  const int ncolmoved = (int)h_pc.size();  // the kernel's column rounds; the code records (if any) follow them
+  const int ndata = (int)h_pc.size();
   if (pack.n > 0) {
-    out->part.rec.alloc(ctx, (size_t)n_recv * 8 + 16);
-    ctx->pool.mark_exported(out->part.rec.get());
+    if (cap_rows > 0) {
+      out->part.rec.alloc(ctx, (size_t)cap_rows * 8 + 16);
+      ctx->pool.mark_exported(out->part.rec.get());
+    }
     my_recv.push_back(out->part.rec.get());
   }
-  const int nmoved = (int)my_recv.size();
-  std::vector<cudaIpcMemHandle_t> my_handles(nmoved), all_handles((size_t)nmoved * world);
-  for (int i = 0; i < nmoved; i++) HS_CUDA(cudaIpcGetMemHandle(&my_handles[i], my_recv[i]));
-  const size_t hbytes = sizeof(cudaIpcMemHandle_t) * nmoved;
-  Buf<uint8_t> d_h(ctx, hbytes), d_hall(ctx, hbytes * world);
-  copy_h2d(ctx, d_h.get(), my_handles.data(), hbytes);
-  HS_NCCL(nccl().AllGather(d_h.get(), d_hall.get(), hbytes, kNcclUint8, ctx->comm->comm, ctx->stream));
-  copy_d2h(ctx, all_handles.data(), d_hall.get(), hbytes * world);
+  const int nfast = (int)my_recv.size();  // buffers whose handles ride in the first message
+  constexpr int kHandleWords = (int)(sizeof(cudaIpcMemHandle_t) / 8);
+  static_assert(sizeof(cudaIpcMemHandle_t) % 8 == 0, "handle size");
+
+  // ---- ONE message per rank: bucket histogram, has-nulls flags, OR / AND of the encoded key, capacity, IPC handles --------
+  const int o_nulls = nb, o_bits = nb + ncols, o_cap = o_bits + 2, o_handles = o_cap + 1;
+  const int msg = o_handles + nfast * kHandleWords;
+  Buf<unsigned long long> d_mine(ctx, msg), d_all(ctx, (size_t)msg * world);
+  std::vector<unsigned long long> h_mine(msg, 0), h_all((size_t)msg * world);
+  for (int c = 0; c < ncols; c++) h_mine[o_nulls + c] = table.cols[c].has_nulls ? 1 : 0;
+  h_mine[o_bits] = 0ull;
+  h_mine[o_bits + 1] = ~0ull;
+  h_mine[o_cap] = (unsigned long long)cap_rows;
+  if (cap_rows > 0)
+    for (int i = 0; i < nfast; i++) {
+      cudaIpcMemHandle_t h;
+      HS_CUDA(cudaIpcGetMemHandle(&h, my_recv[i]));
+      memcpy(&h_mine[o_handles + (size_t)i * kHandleWords], &h, sizeof h);
+    }
+  copy_h2d(ctx, d_mine.get(), h_mine.data(), 8 * (size_t)msg);
+  Buf<uint16_t> bin_ids(ctx, std::max<int64_t>(1, nrows));  // bucket of every row: hashed once, read back by the partition
+  launch_tile_hist(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_mine.get(), d_mine.get() + o_bits,
+                   single_key_type_of(h_keys.data(), nkeys), bin_ids.get(), /*peer_tiles=*/true);
+  HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), msg, kNcclUint64, ctx->comm->comm, ctx->stream));
+  copy_d2h(ctx, h_all.data(), d_all.get(), 8 * (size_t)msg * world);
   sync_stream(ctx);
-  std::vector<void*> h_peer((size_t)nmoved * world);
-  for (int i = 0; i < nmoved; i++)
-    for (int r = 0; r < world; r++)
-      h_peer[(size_t)i * world + r] = (r == me) ? my_recv[i] : open_peer(ctx, all_handles[(size_t)r * nmoved + i]);
+  t_hash->stop();
+
+  // ---- layout of every owner's receive buffers ------------------------------------------------------------------
+  t_x->start();
+  auto cnt = [&](int r, int b) { return h_all[(size_t)r * msg + b]; };
+  std::vector<unsigned long long> my_base(nb, 0);        // where MY rows of bucket b start inside the owner's buffers
+  std::vector<uint64_t> my_bucket_offsets(nb + 1, 0);    // bucket-major layout of the rows THIS rank receives
+  std::vector<uint64_t> owner_cursor(world, 0);
+  for (int b = 0; b < nb; b++) {
+    const int o = b % world;
+    uint64_t before_me = 0, total = 0;
+    for (int r = 0; r < world; r++) {
+      if (r < me) before_me += cnt(r, b);
+      total += cnt(r, b);
+    }
+    my_base[b] = owner_cursor[o] + before_me;
+    owner_cursor[o] += total;
+  }
+  {  // non-owned buckets are empty segments: the offsets stay monotone (owned buckets are laid out in increasing b)
+    uint64_t run = 0;
+    for (int b = 0; b < nb; b++) {
+      uint64_t total = 0;
+      if ((b % world) == me)
+        for (int r = 0; r < world; r++) total += cnt(r, b);
+      my_bucket_offsets[b] = run;
+      run += total;
+    }
+    my_bucket_offsets[nb] = run;
+  }
+  const int64_t n_recv = (int64_t)owner_cursor[me];
+  bool second_round = cap_rows <= 0;
+  for (int o = 0; o < world; o++) {
+    if (owner_cursor[o] >= (1ull << 32)) fail(HS_EUNSUPPORTED, "more than 2^32-1 rows land on one GPU");
+    if (owner_cursor[o] > h_all[(size_t)o * msg + o_cap]) second_round = true;  // some rank's bound did not hold
+  }
+  std::vector<bool> any_nulls(ncols, false);
+  unsigned long long key_or = 0ull, key_and = ~0ull;
+  for (int r = 0; r < world; r++) {
+    for (int c = 0; c < ncols; c++) any_nulls[c] = any_nulls[c] || h_all[(size_t)r * msg + o_nulls + c] != 0;
+    key_or |= h_all[(size_t)r * msg + o_bits];
+    key_and &= h_all[(size_t)r * msg + o_bits + 1];
+  }
+  for (int c = 0; c < ncols; c++) second_round = second_round || any_nulls[c];
+  // OR / AND of the encoded (last) key over ALL rows of all ranks: a superset of the bits that vary among the rows this rank
+  // receives, which is all the sort needs to pick its passes (saves a pass over the received keys and a synchronisation)
+  out->key_or_and[0] = key_or;
+  out->key_or_and[1] = key_and;
+  out->have_key_bits = single_key_type_of(h_keys.data(), nkeys) >= 0 || nkeys >= 1;
+
+  out->part.nrows = n_recv;
+  std::vector<void*> h_peer;
+  int ncolmoved = ndata, nmoved = nfast;
+  if (!second_round) {
+    h_peer.resize((size_t)nfast * world);
+    for (int i = 0; i < nfast; i++)
+      for (int r = 0; r < world; r++) {
+        if (r == me) {
+          h_peer[(size_t)i * world + r] = my_recv[i];
+          continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, &h_all[(size_t)r * msg + o_handles + (size_t)i * kHandleWords], sizeof h);
+        h_peer[(size_t)i * world + r] = open_peer(ctx, h);
+      }
+    for (int c = 0; c < ncols; c++) out->part.cols[c].has_nulls = false;
+  } else {
+    // second round: exact sizes, validity buffers where a column holds nulls on some rank; handles in their own all-gather
+    h_pc.clear();
+    my_recv.clear();
+    for (int c = 0; c < ncols; c++) {
+      DevColumn& src = table.cols[c];
+      DevColumn& dst = out->part.cols[c];
+      dst.has_nulls = any_nulls[c];
+      if (dst.carried) continue;
+      dst.data.alloc(ctx, (size_t)n_recv * src.width + 16);
+      ctx->pool.mark_exported(dst.data.get());
+      h_pc.push_back(PartColumn{src.data.get(), nullptr, src.width, 0, src.zero_copy ? src.zc_tiles.get() : nullptr});
+      my_recv.push_back(dst.data.get());
+      if (any_nulls[c]) {
+        dst.valid.alloc(ctx, (size_t)n_recv + 16);
+        ctx->pool.mark_exported(dst.valid.get());
+        if (!src.valid) {  // this rank saw no nulls in the column but another did: ship all-ones
+          src.valid.alloc(ctx, (size_t)nrows + 16);
+          fill_bytes(ctx, src.valid.get(), 1, (size_t)nrows + 16);
+        }
+        h_pc.push_back(PartColumn{src.valid.get(), nullptr, 1, 0});
+        my_recv.push_back(dst.valid.get());
+      }
+    }
+    ncolmoved = (int)h_pc.size();  // the kernel's column rounds; the code records (if any) follow them
+    if (pack.n > 0) {
+      out->part.rec.alloc(ctx, (size_t)n_recv * 8 + 16);
+      ctx->pool.mark_exported(out->part.rec.get());
+      my_recv.push_back(out->part.rec.get());
+    }
+    nmoved = (int)my_recv.size();
+    std::vector<cudaIpcMemHandle_t> my_handles(nmoved), all_handles((size_t)nmoved * world);
+    for (int i = 0; i < nmoved; i++) HS_CUDA(cudaIpcGetMemHandle(&my_handles[i], my_recv[i]));
+    const size_t hbytes = sizeof(cudaIpcMemHandle_t) * nmoved;
+    Buf<uint8_t> d_h(ctx, hbytes), d_hall(ctx, hbytes * world);
+    copy_h2d(ctx, d_h.get(), my_handles.data(), hbytes);
+    HS_NCCL(nccl().AllGather(d_h.get(), d_hall.get(), hbytes, kNcclUint8, ctx->comm->comm, ctx->stream));
+    copy_d2h(ctx, all_handles.data(), d_hall.get(), hbytes * world);
+    sync_stream(ctx);
+    h_peer.resize((size_t)nmoved * world);
+    for (int i = 0; i < nmoved; i++)
+      for (int r = 0; r < world; r++)
+        h_peer[(size_t)i * world + r] = (r == me) ? my_recv[i] : open_peer(ctx, all_handles[(size_t)r * nmoved + i]);
+  }
+  // HS_DEBUG_LOCAL_PEERS=1 (timing experiments only, the index comes out WRONG): every run is written to this GPU's own
+  // buffers instead of its owner's -- the same kernel without the NVLink traffic
+  static const bool local_peers = getenv("HS_DEBUG_LOCAL_PEERS") != nullptr;
+  if (local_peers)
+    for (int i = 0; i < nmoved; i++)
+      for (int r = 0; r < world; r++) h_peer[(size_t)i * world + r] = my_recv[i];
 
   // ---- one kernel: partition + exchange ------------------------------------------------------------------------
   Buf<unsigned long long> d_base(ctx, nb);
@@ -445,10 +520,11 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   // the peer table holds one row of `world` pointers per column round, then one row for the code records
   launch_partition_rows(ctx, d_keys.get(), nkeys, nrows, nb, 0, tile_hist.get(), d_pc.get(), ncolmoved,
                         (void* const*)d_peer.get(), world, single_key_type_of(h_keys.data(), nkeys), &pack, bin_ids.get());
-  // closing barrier: nobody reads its receive buffers before every peer's kernel has completed
+  // closing barrier: nobody reads its receive buffers before every peer's kernel has completed.  Stream-ordered -- the
+  // sort that follows is enqueued behind it, the host does not wait here.
   HS_NCCL(nccl().AllGather(d_mine.get(), d_all.get(), 1, kNcclUint64, ctx->comm->comm, ctx->stream));
-  t_x.stop();
-  sync_stream(ctx);
+  t_x->stop();
+  // (the source columns go back to the pool; it hands them out again only to work enqueued later on this stream)
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data.release();
     table.cols[c].valid.release();
@@ -458,14 +534,14 @@ void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_bucket
   out->bucket_offsets = my_bucket_offsets;
   out->d_bucket_offsets.alloc(ctx, nb + 1);
   copy_h2d(ctx, out->d_bucket_offsets.get(), my_bucket_offsets.data(), 8 * (nb + 1));
-  sync_stream(ctx);
   for (int r = 0; r < world; r++)
     if (r != me)
       for (int b = r; b < nb; b += world)
         for (int c = 0; c < ncols; c++)
           stats->bytes_exchanged += (int64_t)(cnt(me, b) * ((out->part.cols[c].carried ? 2 : table.cols[c].width) + (any_nulls[c] ? 1 : 0)));
-  stats->ms_hash += t_hash.ms();
-  stats->ms_exchange += t_x.ms();
+  // the two stage timers are read after the call's next synchronisation (sort_partitioned_rows)
+  out->pending_timers.push_back(IndexedRows::DeferredTimer{std::move(t_hash), &hs_stats::ms_hash});
+  out->pending_timers.push_back(IndexedRows::DeferredTimer{std::move(t_x), &hs_stats::ms_exchange});
 }
 
 }  // namespace hs

@@ -741,7 +741,12 @@ size_t fused_smem_bytes(int nb, bool bulk = true) {
 
 bool fused_partition_supported(int nbins) { return nbins <= kFusedMaxBins; }
 
-int fused_tile_rows(bool peer_tiles) { return peer_tiles ? kFusedTilePeer : kFusedTileLocal; }
+// HS_PEER_TILE=small: experiments -- rows that leave over NVLink are partitioned with the local tile shape too
+bool peer_tile_shape() {
+  static const char* e = getenv("HS_PEER_TILE");
+  return !(e && strcmp(e, "small") == 0);
+}
+int fused_tile_rows(bool peer_tiles) { return peer_tiles && peer_tile_shape() ? kFusedTilePeer : kFusedTileLocal; }
 
 template <bool PEER>
 static void launch_tile_hist_t(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t nrows, int num_buckets, int owner_mod,
@@ -768,7 +773,7 @@ void launch_tile_hist(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int64_t n
                       int single_key_type, uint16_t* bin_ids, bool peer_tiles) {
   KernelScope _ks(ctx, "k_tile_hist");
   if (nrows == 0) return;
-  if (peer_tiles)
+  if (peer_tiles && peer_tile_shape())
     launch_tile_hist_t<true>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_hist, global_hist, key_or_and, single_key_type, bin_ids);
   else
     launch_tile_hist_t<false>(ctx, d_keys, nkeys, nrows, num_buckets, owner_mod, tile_hist, global_hist, key_or_and, single_key_type, bin_ids);
@@ -842,7 +847,7 @@ void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int6
   memset(&a.pack, 0, sizeof a.pack);
   if (pack_round) a.pack = *pack_round;
   // tiles that leave over NVLink use the large shape (the tile histogram must have been taken with peer_tiles = true)
-  if (d_peer_out) launch_partition_rows_cfg<true>(ctx, a, single_key_type);
+  if (d_peer_out && peer_tile_shape()) launch_partition_rows_cfg<true>(ctx, a, single_key_type);
   else launch_partition_rows_cfg<false>(ctx, a, single_key_type);
 }
 

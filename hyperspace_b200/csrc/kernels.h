@@ -241,8 +241,9 @@ void launch_dict_build(hs_ctx* ctx, const void* src, int width, int64_t begin, i
 void launch_dict_build_from_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, int col, int width,
                                   unsigned long long* keys, uint32_t capacity, uint32_t max_distinct, uint32_t* state);
 // compacts the distinct values out of the hash set (counter must be zeroed); then slot -> rank in the sorted dictionary
+// (at most max_out values are written; the counter still counts all of them)
 void launch_dict_collect(hs_ctx* ctx, const unsigned long long* keys, uint32_t capacity, unsigned long long* out,
-                         uint32_t* counter);
+                         uint32_t* counter, uint32_t max_out = 0xffffffffu);
 // entries: capacity x 16 bytes {key lo, key hi, dictionary index, 0}
 // all dictionary columns of a table in one map + one pack launch (up to 8 columns per call)
 struct DictMapArgs {

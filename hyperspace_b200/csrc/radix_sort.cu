@@ -402,8 +402,7 @@ ChunkPlan build_chunks(hs_ctx* ctx, const std::vector<uint32_t>& seg_tile_begin)
   cp.chunk_sums.alloc(ctx, std::max<size_t>(1, chunks.size()) * 256);
   if (!chunks.empty())
     copy_h2d(ctx, cp.chunks.get(), chunks.data(), chunks.size() * sizeof(SortChunk));
-  copy_h2d(ctx, cp.seg_chunk_begin.get(), scb.data(), scb.size() * 4);
-  sync_stream(ctx);  // host vectors go out of scope
+  copy_h2d(ctx, cp.seg_chunk_begin.get(), scb.data(), scb.size() * 4);  // (snapshots: the vectors may go out of scope)
   return cp;
 }
 
@@ -448,8 +447,7 @@ void build_sort_plan(hs_ctx* ctx, const uint64_t* seg_offsets, int nseg, SortPla
     k_build_tiles<<<nseg, 256, 0, ctx->stream>>>(plan->seg_start.get(), plan->seg_tile_begin.get(), plan->tiles.get());
     HS_LAUNCH_CHECK(ctx);
   }
-  sync_stream(ctx);  // the host vectors go out of scope
-  plan->h_seg_tile_begin = stb;
+  plan->h_seg_tile_begin = stb;  // (copy_h2d took snapshots of the host vectors)
 }
 
 void segmented_sort_pairs(hs_ctx* ctx, SortPlan* plan, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals,
