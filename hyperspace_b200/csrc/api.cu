@@ -516,6 +516,9 @@ int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** o
       SourceSet src;
       open_sources(ctx, spec->files, spec->n_files, &src, &st);
       decode_sources(ctx, src, cols, nullptr, &table, &st, &carry);
+      const bool has_strings = table.has_strings;
+      if (has_strings && ctx->world > 1)
+        fail(HS_EUNSUPPORTED, "string / binary columns are not exchanged between GPUs yet: build this index on one GPU");
       if (spec->lineage) fill_lineage(ctx, table, spec->files, spec->n_files);
       if (spec->n_deleted_file_ids > 0) drop_deleted_rows(ctx, table, spec->deleted_file_ids, spec->n_deleted_file_ids);
       IndexedRows rows;
@@ -527,7 +530,8 @@ int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** o
         if (ctx->world > 1) exchange_rows(ctx, table, spec->n_indexed, spec->num_buckets, &st);  // NCCL all-to-all
         index_rows(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
       }
-      src.release_images();  // every column is materialised bucket-major now
+      if (!has_strings) src.release_images();  // every column is materialised bucket-major now (string
+                                                         // references keep pointing into the images until the encode)
 
       EncodeRequest req;
       req.table = &rows.part;

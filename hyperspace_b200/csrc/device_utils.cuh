@@ -49,6 +49,49 @@ HS_HD int32_t spark_pmod(uint32_t h, int32_t n) {
   return r < 0 ? r + n : r;
 }
 
+// ---- strings (Parquet BYTE_ARRAY) --------------------------------------------------------------------------------------
+// A string never moves between decode and encode: a row's value is a 64-bit REFERENCE into the source file image (the
+// PLAIN page body or the dictionary page it was read from): device address in the low 48 bits (canonical on every CUDA
+// platform), length in the high 16 (longer values are rejected with HS_EUNSUPPORTED when they are decoded).  References
+// are ordinary 8-byte column values for the partition and the sort's row bookkeeping.
+constexpr uint32_t kMaxStringLen = 0xffffu;
+HS_HD uint64_t string_ref(const void* p, uint32_t len) { return ((uint64_t)(uintptr_t)p & 0xffffffffffffull) | ((uint64_t)len << 48); }
+HS_HD const uint8_t* ref_ptr(uint64_t ref) { return (const uint8_t*)(uintptr_t)(ref & 0xffffffffffffull); }
+HS_HD uint32_t ref_len(uint64_t ref) { return (uint32_t)(ref >> 48); }
+
+// Spark's Murmur3_x86_32.hashUnsafeBytes (the function Murmur3Hash applies to StringType / BinaryType): whole little-endian
+// 4-byte words first, then EVERY tail byte mixed on its own as a sign-extended int -- Spark's legacy, non-standard tail
+// (oracle: hso_hash_bytes; golden vector hash('Spark', array(123), 2) in tests/test_oracle.py).
+HS_HD uint32_t mm3_hash_bytes(const uint8_t* p, uint32_t len, uint32_t seed) {
+  uint32_t h1 = seed;
+  const uint32_t aligned = len & ~3u;
+  for (uint32_t i = 0; i < aligned; i += 4) {
+    const uint32_t w = (uint32_t)p[i] | ((uint32_t)p[i + 1] << 8) | ((uint32_t)p[i + 2] << 16) | ((uint32_t)p[i + 3] << 24);
+    h1 = mm3_mix_h1(h1, mm3_mix_k1(w));
+  }
+  for (uint32_t i = aligned; i < len; i++) h1 = mm3_mix_h1(h1, mm3_mix_k1((uint32_t)(int32_t)(int8_t)p[i]));
+  return mm3_fmix(h1, len);
+}
+
+// UTF8String.compareTo: unsigned byte-wise, a proper prefix sorts first.  -1 / 0 / +1
+HS_HD int string_compare(uint64_t ra, uint64_t rb) {
+  const uint8_t *a = ref_ptr(ra), *b = ref_ptr(rb);
+  const uint32_t la = ref_len(ra), lb = ref_len(rb), n = la < lb ? la : lb;
+  for (uint32_t i = 0; i < n; i++)
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return la == lb ? 0 : (la < lb ? -1 : 1);
+}
+
+// the `chunk`-th 8-byte piece of a string as a big-endian integer, zero-padded: comparing the pieces in order, then the
+// lengths, is the byte-wise order above (this is how the radix sort sees a string key)
+HS_HD uint64_t string_chunk(uint64_t ref, uint32_t chunk) {
+  const uint8_t* p = ref_ptr(ref);
+  const uint32_t len = ref_len(ref), begin = chunk * 8;
+  uint64_t v = 0;
+  for (uint32_t i = 0; i < 8; i++) v = (v << 8) | (begin + i < len ? (uint64_t)p[begin + i] : 0ull);
+  return v;
+}
+
 // raw bits of one key value (type = HS_TYPE_*), as stored in the decoded column
 HS_HD uint32_t mm3_hash_value(int type, uint64_t raw, uint32_t seed) {
   switch (type) {
@@ -67,6 +110,7 @@ HS_HD uint32_t mm3_hash_value(int type, uint64_t raw, uint32_t seed) {
       return mm3_hash_long(b, seed);
     }
     case 4: return mm3_hash_int((raw & 0xff) ? 1u : 0u, seed);
+    case 5: return mm3_hash_bytes(ref_ptr(raw), ref_len(raw), seed);  // string / binary: raw is a reference
   }
   return seed;
 }
@@ -102,6 +146,7 @@ HS_HD int type_width(int type) {
     case 0: case 2: return 4;
     case 1: case 3: return 8;
     case 4: return 1;
+    case 5: return 8;  // a string column holds 8-byte references
   }
   return 0;
 }

@@ -41,8 +41,9 @@ int hs_type_of(const pq::SchemaColumn& c, const char* file) {
     case pq::INT64: return HS_TYPE_INT64;
     case pq::FLOAT: return HS_TYPE_FLOAT;
     case pq::DOUBLE: return HS_TYPE_DOUBLE;
+    case pq::BYTE_ARRAY: return HS_TYPE_STRING;  // Spark string / binary
     default:
-      fail(HS_EUNSUPPORTED, "%s: column '%s' has Parquet physical type %d; the GPU path handles BOOLEAN/INT32/INT64/FLOAT/DOUBLE",
+      fail(HS_EUNSUPPORTED, "%s: column '%s' has Parquet physical type %d; the GPU path handles BOOLEAN/INT32/INT64/FLOAT/DOUBLE/BYTE_ARRAY",
            file, c.name.c_str(), c.type);
   }
 }
@@ -72,6 +73,7 @@ const char* decode_error_text(uint32_t code) {
     case DERR_DICT_INDEX: return "dictionary index out of range or missing dictionary page";
     case DERR_UNSUPPORTED_TYPE: return "unsupported physical type";
     case DERR_SNAPPY: return "corrupt snappy stream";
+    case DERR_STRING_TOO_LONG: return "string / binary value longer than 65535 bytes";
   }
   return "unknown decode error";
 }
@@ -103,16 +105,26 @@ void read_whole_file(const char* path, uint8_t* dst, uint64_t size) {
 struct SourceSet::Impl {
   std::vector<FileImage> imgs;
   Buf<uint8_t> d_images;
+  Buf<uint8_t> d_scratch;  // decompressed pages: string references may point into them, like into the images
 };
 SourceSet::SourceSet() : impl(new Impl()) {}
 SourceSet::~SourceSet() { delete impl; }
-void SourceSet::release_images() { impl->d_images.release(); }
+void SourceSet::release_images() {
+  impl->d_images.release();
+  impl->d_scratch.release();
+}
 
 void load_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, const std::vector<std::string>& columns,
                   Table* out, hs_stats* stats, const CarryOptions* carry) {
   SourceSet src;
   open_sources(ctx, files, n_files, &src, stats);
   decode_sources(ctx, src, columns, nullptr, out, stats, carry);
+  // string columns hold references into the file images, which die with `src`: callers that handle strings keep their own
+  // SourceSet (hs_create_index, hs_verify_index)
+  for (const DevColumn& c : out->cols)
+    if (c.type == HS_TYPE_STRING)
+      fail(HS_EUNSUPPORTED, "column '%s' is a string / binary column; the index scans and joins of the GPU path do not read those yet",
+           c.name.c_str());
 }
 
 // ---- dictionary helpers shared by the decoder (late-materialised columns) and the page encoder -------------------------
@@ -467,7 +479,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
     }
   };
   // ---- snappy: decompress the compressed page bodies (and dictionary pages) into a scratch buffer, repoint the pages ----
-  Buf<uint8_t> d_scratch;
+  Buf<uint8_t>& d_scratch = set.impl->d_scratch;
   if (any_compressed && n_pages > 0) {
     std::vector<PageDesc> h_pages((size_t)n_pages);
     copy_d2h(ctx, h_pages.data(), d_pages.get(), sizeof(PageDesc) * (size_t)n_pages);
@@ -517,6 +529,46 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
     launch_snappy_decompress(ctx, d_blobs.get(), (int64_t)blobs.size(), d_scratch.get(), d_flags.get());
     sync_stream(ctx);  // host vectors go out of scope
   }
+  // ---- strings: the dictionary pages of BYTE_ARRAY columns become tables of references --------------------------------------
+  Buf<uint64_t> d_string_dicts;
+  bool any_string = false;
+  for (int c = 0; c < ncols; c++) any_string = any_string || out->cols[c].type == HS_TYPE_STRING;
+  out->has_strings = any_string;
+  if (any_string && n_pages > 0) {
+    std::vector<PageDesc> h_pages((size_t)n_pages);
+    copy_d2h(ctx, h_pages.data(), d_pages.get(), sizeof(PageDesc) * (size_t)n_pages);
+    sync_stream(ctx);
+    check_walk();
+    std::map<const uint8_t*, size_t> job_of;  // dictionary page -> job
+    std::vector<StringDictJob> jobs;
+    std::vector<size_t> job_off;
+    size_t total = 0;
+    for (PageDesc& pg : h_pages) {
+      if (pg.phys_type != pq::BYTE_ARRAY || !pg.dict || pg.encoding == pq::ENC_PLAIN) continue;
+      auto it = job_of.find(pg.dict);
+      if (it == job_of.end()) {
+        it = job_of.emplace(pg.dict, jobs.size()).first;
+        jobs.push_back(StringDictJob{pg.dict, nullptr, pg.dict_size, pg.dict_count});
+        job_off.push_back(total);
+        total += (size_t)std::max(0, pg.dict_count);
+      }
+    }
+    if (!jobs.empty()) {
+      d_string_dicts.alloc(ctx, std::max<size_t>(1, total));
+      for (size_t j = 0; j < jobs.size(); j++) jobs[j].refs = d_string_dicts.get() + job_off[j];
+      for (PageDesc& pg : h_pages) {
+        if (pg.phys_type != pq::BYTE_ARRAY || !pg.dict || pg.encoding == pq::ENC_PLAIN) continue;
+        const StringDictJob& job = jobs[job_of[pg.dict]];
+        pg.dict = (const uint8_t*)job.refs;  // decodes as a dictionary of 8-byte values from here on
+        pg.dict_size = job.count * 8;
+      }
+      Buf<StringDictJob> d_jobs(ctx, jobs.size());
+      copy_h2d(ctx, d_jobs.get(), jobs.data(), sizeof(StringDictJob) * jobs.size());
+      launch_build_string_dicts(ctx, d_jobs.get(), (int64_t)jobs.size(), d_flags.get());
+      copy_h2d(ctx, d_pages.get(), h_pages.data(), sizeof(PageDesc) * (size_t)n_pages);
+      if (sizeof(PageDesc) * (size_t)n_pages > (16u << 20)) sync_stream(ctx);  // too big for a snapshot: keep h_pages alive
+    }
+  }
   // ---- late-materialised dictionary columns --------------------------------------------------------------------------
   // A candidate column whose every page is dictionary-encoded and free of nulls, and whose chunk dictionaries unite to a
   // dictionary that pays off, is decoded to 16-bit codes of that dictionary: its values are never written to HBM, the
@@ -552,7 +604,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       fill_bytes(ctx, d_cnt.get(), 0, 4 * (size_t)nspec);
       for (int i = 0; i < nspec; i++) {
         const DevColumn& dc = out->cols[spec[i]];
-        if (dc.width != 4 && dc.width != 8) continue;
+        if ((dc.width != 4 && dc.width != 8) || dc.type == HS_TYPE_STRING) continue;
         sets[i].alloc(ctx, kDictCapacity);
         fill_bytes(ctx, sets[i].get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
         launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, spec[i], dc.width, sets[i].get(), kDictCapacity, kMaxDictEntries,
@@ -579,7 +631,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       const DevColumn& dc = out->cols[spec[i]];
       uint64_t* m = &mine[(size_t)ncols + 1 + (size_t)i * per_cand];
       m[0] = (uint64_t)(int64_t)dc.type;
-      m[1] = (uint64_t)dc.width;
+      m[1] = dc.type == HS_TYPE_STRING ? 0ull : (uint64_t)dc.width;  // string references are not values: never carried
       m[2] = spec_state[4 * i];                                                    // distinct values in the set (excl. ~0)
       m[3] = (spec_state[4 * i + 1] || spec_count[i] > kAgreeCap) ? 1 : 0;         // overflow: no carry for this column
       m[4] = spec_state[4 * i + 2];                                                // the value ~0 occurs
@@ -677,7 +729,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   sync_stream(ctx);
   if (flags[0]) {
     const uint32_t code = flags[0] >> 24, detail = flags[0] & 0xffffffu;
-    const int ecode = (code == DERR_COMPRESSED || code == DERR_UNSUPPORTED_ENCODING || code == DERR_UNSUPPORTED_TYPE)
+    const int ecode = (code == DERR_COMPRESSED || code == DERR_UNSUPPORTED_ENCODING || code == DERR_UNSUPPORTED_TYPE || code == DERR_STRING_TOO_LONG)
                           ? HS_EUNSUPPORTED
                           : HS_EFORMAT;
     fail(ecode, "Parquet decode failed: %s (detail %u)", decode_error_text(code), detail);
@@ -690,7 +742,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
     fill_bytes(ctx, d_states.get(), 0, 16 * (size_t)std::max(1, ncols));
     for (int c = 0; c < ncols; c++) {
       DevColumn& dc = out->cols[c];
-      if (dc.carried || dc.zero_copy || (flags[1 + c] & 2u) || (dc.width != 4 && dc.width != 8)) continue;
+      if (dc.carried || dc.zero_copy || dc.type == HS_TYPE_STRING || (flags[1 + c] & 2u) || (dc.width != 4 && dc.width != 8)) continue;
       dc.dict_keys.alloc(ctx, kDictCapacity);
       fill_bytes(ctx, dc.dict_keys.get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
       launch_dict_build_from_pages(ctx, d_pages.get(), n_pages, c, dc.width, dc.dict_keys.get(), kDictCapacity, kMaxDictEntries,
@@ -846,6 +898,27 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
     // beforehand; only the OR / AND of the encoded keys is needed to pick the passes.
     const bool from_raw = k == nkeys - 1 && kc.type >= HS_TYPE_INT32 && kc.type <= HS_TYPE_DOUBLE;
     if (k == nkeys - 1 && !from_raw) launch_iota_u32(ctx, perm, nrows);
+    if (kc.type == HS_TYPE_STRING) {
+      // A string key is sorted piecewise: stable LSD passes on the length, then on its 8-byte pieces from the last to the
+      // first (each piece a big-endian integer; digits that are constant over all rows cost nothing).  Short keys -- the
+      // usual case -- take one piece.
+      auto sort_piece = [&](int piece, unsigned long long* bits_or) {
+        const unsigned long long init[2] = {0ull, ~0ull};
+        unsigned long long oa[2] = {0, 0};
+        copy_h2d(ctx, d_or_and.get(), init, sizeof init);
+        launch_string_piece_keys(ctx, (const uint64_t*)kc.data.get(), perm, nrows, piece, keys, d_or_and.get());
+        copy_d2h(ctx, oa, d_or_and.get(), sizeof oa);
+        sync_stream(ctx);
+        if (bits_or) *bits_or = oa[0];
+        const uint64_t varying = nrows ? (oa[0] ^ oa[1]) : 0;
+        if (varying) segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying);
+      };
+      unsigned long long len_or = 0;
+      sort_piece(-1, &len_or);  // the OR of the lengths bounds the longest key from above
+      for (int piece = (int)((len_or + 7) / 8) - 1; piece >= 0; piece--) sort_piece(piece, nullptr);
+      if (kc.has_nulls) segmented_sort_pass_by_table(ctx, &out->plan, keys, keys_alt, perm, perm_alt, kc.valid.get());
+      continue;
+    }
     unsigned long long or_and[2] = {0, 0};
     if (from_raw && out->have_key_bits) {  // the partition's histogram pass has them already
       or_and[0] = out->key_or_and[0];
@@ -931,6 +1004,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       case HS_TYPE_INT64: schema[c].type = pq::INT64; break;
       case HS_TYPE_FLOAT: schema[c].type = pq::FLOAT; break;
       case HS_TYPE_DOUBLE: schema[c].type = pq::DOUBLE; break;
+      case HS_TYPE_STRING: schema[c].type = pq::BYTE_ARRAY; break;  // converted type (UTF8 or none) comes from the source
     }
   }
   const std::string schema_json = pq::spark_schema_json(schema);
@@ -938,12 +1012,28 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
   // nullable columns: per-tile non-null counts (tiles are kSortTile-aligned inside a segment and P is a multiple of
   // kSortTile, so a tile never straddles a page)
   const int64_t ntiles = req.plan->ntiles;
-  std::vector<std::vector<uint32_t>> tile_valid(ncols);
+  std::vector<std::vector<uint32_t>> tile_valid(ncols), tile_bytes(ncols);  // tile_bytes: string columns only
   std::vector<std::vector<uint64_t>> tile_val_off(ncols), tile_def_off(ncols);
   {
-    std::vector<Buf<uint32_t>> d_counts(ncols);
+    std::vector<Buf<uint32_t>> d_counts(ncols), d_bytes(ncols);
     bool any = false;
     for (int c = 0; c < ncols; c++) {
+      if (table.cols[c].type == HS_TYPE_STRING) {  // always laid out tile by tile: the value sizes are data
+        any = true;
+        d_counts[c].alloc(ctx, std::max<int64_t>(1, ntiles));
+        d_bytes[c].alloc(ctx, std::max<int64_t>(1, ntiles));
+        launch_tile_string_sizes(ctx, req.plan->tiles.get(), ntiles, req.d_perm, (const uint64_t*)table.cols[c].data.get(),
+                                 table.cols[c].has_nulls ? table.cols[c].valid.get() : nullptr, d_bytes[c].get(), d_counts[c].get());
+        tile_valid[c].resize(ntiles);
+        tile_bytes[c].resize(ntiles);
+        tile_val_off[c].assign(ntiles, 0);
+        tile_def_off[c].assign(ntiles, 0);
+        if (ntiles) {
+          copy_d2h(ctx, tile_valid[c].data(), d_counts[c].get(), sizeof(uint32_t) * ntiles);
+          copy_d2h(ctx, tile_bytes[c].data(), d_bytes[c].get(), sizeof(uint32_t) * ntiles);
+        }
+        continue;
+      }
       if (!table.cols[c].has_nulls) continue;
       any = true;
       d_counts[c].alloc(ctx, std::max<int64_t>(1, ntiles));
@@ -993,7 +1083,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     bool any_sampled = false;
     for (int c = 0; c < ncols; c++) {
       const DevColumn& dc = table.cols[c];
-      if (dc.has_nulls || dc.carried) continue;
+      if (dc.has_nulls || dc.carried || dc.type == HS_TYPE_STRING) continue;
       ColDict& cd = dicts[c];
       if (dc.dict_ready && dc.dict_keys) {
         cd.keys_ptr = dc.dict_keys.get();
@@ -1010,7 +1100,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     if (any_sampled) sync_stream(ctx);
     for (int c = 0; c < ncols; c++) {
       const DevColumn& dc = table.cols[c];
-      if (dc.has_nulls || dc.carried) continue;
+      if (dc.has_nulls || dc.carried || dc.type == HS_TYPE_STRING) continue;
       ColDict& cd = dicts[c];
       uint32_t* st = &h_states[4 * (size_t)c];
       const bool ready = dc.dict_ready && dc.dict_keys;
@@ -1126,6 +1216,30 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
             cursor += skeleton.size() - b;
             page_value_offset[c][page_counter + (p0 / P)] = cursor;
             cursor += (uint64_t)((np + 7) / 8) * dicts[c].bw;
+          } else if (table.cols[c].type == HS_TYPE_STRING) {
+            // PLAIN BYTE_ARRAY: definition bits for every row, then [u32 length][bytes] per non-null value, tile by tile
+            const int64_t t0 = seg_tile_begin[s] + p0 / kSortTile, t1 = seg_tile_begin[s] + ceil_div(p0 + np, (int64_t)kSortTile);
+            int64_t non_null = 0;
+            uint64_t value_bytes = 0;
+            for (int64_t t = t0; t < t1; t++) {
+              non_null += tile_valid[c][t];
+              value_bytes += tile_bytes[c][t];
+            }
+            if (value_bytes + (uint64_t)np / 8 + 64 >= (1ull << 31)) fail(HS_EUNSUPPORTED, "column '%s': a page of strings exceeds 2 GiB", table.cols[c].name.c_str());
+            pq::write_nullable_page_prefix_bytes(skeleton, np, value_bytes);
+            emit(cursor, b);
+            cursor += skeleton.size() - b;
+            const uint64_t def_bits = cursor;
+            cursor += (uint64_t)((np + 7) / 8);
+            page_value_offset[c][page_counter + (p0 / P)] = cursor;
+            uint64_t voff = cursor;
+            for (int64_t t = t0; t < t1; t++) {
+              tile_def_off[c][t] = def_bits + (uint64_t)(t - t0) * (kSortTile / 8);
+              tile_val_off[c][t] = voff;
+              voff += tile_bytes[c][t];
+            }
+            cursor += value_bytes;
+            ch.null_count += np - non_null;
           } else if (!table.cols[c].has_nulls) {
             pq::write_plain_page_prefix(skeleton, cursor, np, W);  // file images start 64-byte aligned in the arena
             emit(cursor, b);
@@ -1226,6 +1340,16 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     gc.width = dc.width;
     gc.page_value_offset = d_pvo.get() + (size_t)c * page_counter;
     if (dicts[c].use) continue;  // handled below, all dictionary columns together
+    if (dc.type == HS_TYPE_STRING) {
+      Buf<uint64_t> d_voff(ctx, std::max<int64_t>(1, ntiles)), d_doff(ctx, std::max<int64_t>(1, ntiles));
+      if (ntiles) {
+        copy_h2d(ctx, d_voff.get(), tile_val_off[c].data(), 8 * ntiles);
+        copy_h2d(ctx, d_doff.get(), tile_def_off[c].data(), 8 * ntiles);
+      }
+      launch_gather_encode_strings(ctx, req.plan->tiles.get(), ntiles, req.d_perm, (const uint64_t*)dc.data.get(),
+                                   dc.has_nulls ? dc.valid.get() : nullptr, d_voff.get(), d_doff.get(), out->arena.get());
+      continue;
+    }
     if (dc.has_nulls) {
       Buf<uint64_t> d_voff(ctx, std::max<int64_t>(1, ntiles)), d_doff(ctx, std::max<int64_t>(1, ntiles));
       if (ntiles) {

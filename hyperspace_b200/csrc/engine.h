@@ -46,6 +46,7 @@ struct Table {
   std::vector<DevColumn> cols;
   std::vector<int64_t> file_row_begin;  // nfiles+1: row range of every source file
   int64_t global_rows = -1;             // rows of all ranks together, when the ranks exchanged that while decoding
+  bool has_strings = false;             // some column holds string references into the source images (keep those alive)
   Buf<uint8_t> rec;                     // nrows x 4 uint16 codes of the carried columns (after the partition)
 };
 

@@ -152,6 +152,88 @@ __global__ void __launch_bounds__(kThreads) k_gather_encode_nullable(const SortT
   }
 }
 
+// ---- string columns -----------------------------------------------------------------------------------------------
+// PLAIN BYTE_ARRAY: every non-null value is [u32 length][bytes].  First the tiles are measured (the host needs every
+// page's byte size to lay the files out), then each tile writes its definition bits and its values: a block scan of the
+// value sizes gives every row its place, and each thread copies its own string out of the source image.
+__global__ void __launch_bounds__(kThreads) k_tile_string_sizes(const SortTile* __restrict__ tiles, const uint32_t* __restrict__ perm,
+                                                                 const uint64_t* __restrict__ refs,
+                                                                 const uint8_t* __restrict__ valid,
+                                                                 uint32_t* __restrict__ bytes, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t s_bytes, s_count;
+  if (threadIdx.x == 0) s_bytes = s_count = 0;
+  __syncthreads();
+  const SortTile t = tiles[blockIdx.x];
+  uint32_t b = 0, c = 0;
+  for (uint32_t i = threadIdx.x; i < t.count; i += kThreads) {
+    const uint32_t row = perm[t.start + i];
+    if (!valid || valid[row]) {
+      b += 4u + ref_len(refs[row]);
+      c++;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0 && c) {
+    atomicAdd(&s_bytes, b);
+    atomicAdd(&s_count, c);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bytes[blockIdx.x] = s_bytes;
+    counts[blockIdx.x] = s_count;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_gather_encode_strings(const SortTile* __restrict__ tiles,
+                                                                     const uint32_t* __restrict__ perm,
+                                                                     const uint64_t* __restrict__ refs,
+                                                                     const uint8_t* __restrict__ valid,
+                                                                     const uint64_t* __restrict__ tile_value_offset,
+                                                                     const uint64_t* __restrict__ tile_def_offset,
+                                                                     uint8_t* __restrict__ arena) {
+  __shared__ uint32_t warp_sums[40];
+  const SortTile t = tiles[blockIdx.x];
+  uint8_t* const def_out = arena + tile_def_offset[blockIdx.x];
+  uint8_t* const val_out = arena + tile_value_offset[blockIdx.x];
+  uint32_t base = 0;
+  const uint32_t iters = (t.count + kThreads - 1) / kThreads;
+  for (uint32_t it = 0; it < iters; it++) {
+    const uint32_t i = it * kThreads + threadIdx.x;
+    const bool active = i < t.count;
+    uint32_t flag = 0;
+    uint64_t r = 0;
+    if (active) {
+      const uint32_t row = perm[t.start + i];
+      flag = (!valid || valid[row]) ? 1u : 0u;
+      if (flag) r = refs[row];
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, flag != 0);
+    if ((threadIdx.x & 31) == 0) {  // 32 levels = 4 bytes, LSB first; the last warp of a page may own fewer bytes
+      const uint32_t first = it * kThreads + (threadIdx.x & ~31u);
+      if (first < t.count) {
+        const uint32_t nbytes = min(4u, (t.count - first + 7) / 8);
+        for (uint32_t b = 0; b < nbytes; b++) def_out[first / 8 + b] = (uint8_t)(bits >> (8 * b));
+      }
+    }
+    const uint32_t len = ref_len(r), size = flag ? 4u + len : 0u;
+    uint32_t total = 0;
+    const uint32_t pos = block_exclusive_scan(size, warp_sums, &total);
+    if (flag) {
+      uint8_t* o = val_out + base + pos;
+      o[0] = (uint8_t)len;
+      o[1] = (uint8_t)(len >> 8);
+      o[2] = (uint8_t)(len >> 16);
+      o[3] = (uint8_t)(len >> 24);
+      const uint8_t* src = ref_ptr(r);
+      for (uint32_t b = 0; b < len; b++) o[4 + b] = src[b];
+    }
+    base += total;
+  }
+}
+
 // width-1 columns (BOOLEAN is bit-packed in PLAIN; handled by a byte-per-row staging column + k_pack_bits)
 template <typename T>
 __global__ void k_gather_plain(const T* __restrict__ src, const uint32_t* __restrict__ perm, int64_t n,
@@ -253,6 +335,24 @@ void launch_gather_encode_nullable(hs_ctx* ctx, const SortTile* tiles, int64_t n
                                                                                  tile_def_offset, arena);
   else
     fail(HS_EUNSUPPORTED, "gather_encode_nullable: column width %d", width);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_tile_string_sizes(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint32_t* perm, const uint64_t* refs,
+                              const uint8_t* valid, uint32_t* bytes, uint32_t* counts) {
+  KernelScope _ks(ctx, "k_tile_string_sizes");
+  if (ntiles == 0) return;
+  k_tile_string_sizes<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, perm, refs, valid, bytes, counts);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_gather_encode_strings(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint32_t* perm, const uint64_t* refs,
+                                  const uint8_t* valid, const uint64_t* tile_value_offset, const uint64_t* tile_def_offset,
+                                  uint8_t* arena) {
+  KernelScope _ks(ctx, "k_gather_encode_strings");
+  if (ntiles == 0) return;
+  k_gather_encode_strings<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, perm, refs, valid, tile_value_offset,
+                                                                          tile_def_offset, arena);
   HS_LAUNCH_CHECK(ctx);
 }
 

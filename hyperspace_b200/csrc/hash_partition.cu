@@ -225,6 +225,31 @@ __global__ void k_encode_keys(const void* __restrict__ in, int type, int width, 
   }
 }
 
+// One radix-sortable piece of a string key per row: piece < 0 -> the length, else the piece-th 8 bytes as a big-endian
+// integer (zero-padded).  Sorting stably by length, then by the pieces from the last to the first, is the byte-wise order
+// with a proper prefix first (UTF8String.compareTo).
+__global__ void k_string_piece_keys(const uint64_t* __restrict__ refs, const uint32_t* __restrict__ perm, int64_t n, int piece,
+                                    uint64_t* __restrict__ out, unsigned long long* __restrict__ or_and) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  uint64_t vor = 0, vand = ~0ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t r = refs[perm[i]];
+    const uint64_t e = piece < 0 ? (uint64_t)ref_len(r) : string_chunk(r, (uint32_t)piece);
+    out[i] = e;
+    vor |= e;
+    vand &= e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vor |= __shfl_xor_sync(0xffffffffu, (unsigned long long)vor, o);
+    vand &= __shfl_xor_sync(0xffffffffu, (unsigned long long)vand, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicOr(&or_and[0], (unsigned long long)vor);
+    atomicAnd(&or_and[1], (unsigned long long)vand);
+  }
+}
+
 __global__ void k_iota(uint32_t* out, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint32_t)i;
@@ -314,6 +339,14 @@ void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* s
   if (nrows == 0) return;
   k_encode_keys<<<grid_for(ctx, nrows, 256, 16), 256, 0, ctx->stream>>>(in, type, type_width(type), src, nrows, out,
                                                                          or_and);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_string_piece_keys(hs_ctx* ctx, const uint64_t* refs, const uint32_t* perm, int64_t nrows, int piece, uint64_t* out,
+                              unsigned long long* or_and) {
+  KernelScope _ks(ctx, "k_string_piece_keys");
+  if (nrows == 0) return;
+  k_string_piece_keys<<<grid_for(ctx, nrows, 256, 16), 256, 0, ctx->stream>>>(refs, perm, nrows, piece, out, or_and);
   HS_LAUNCH_CHECK(ctx);
 }
 

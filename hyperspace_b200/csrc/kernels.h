@@ -36,7 +36,7 @@ struct PageDesc {           // one per data page
   int32_t dict_size, dict_uncompressed_size;
   int32_t is_compressed;      // this page's values are snappy-compressed
   int32_t codec;
-  int32_t pad;
+  int32_t chunk;              // index of the column chunk (ChunkDesc) the page belongs to
 };
 
 struct ColumnOut {          // decoded column destination
@@ -75,8 +75,16 @@ void launch_fill_zc_tiles(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, Z
 // device error word: 0 = ok, else (code << 24 | detail)
 enum DecodeError : uint32_t {
   DERR_NONE = 0, DERR_BAD_HEADER = 1, DERR_UNSUPPORTED_ENCODING = 2, DERR_VALUE_COUNT = 3, DERR_COMPRESSED = 4,
-  DERR_OVERRUN = 5, DERR_DICT_INDEX = 6, DERR_UNSUPPORTED_TYPE = 7, DERR_SNAPPY = 8
+  DERR_OVERRUN = 5, DERR_DICT_INDEX = 6, DERR_UNSUPPORTED_TYPE = 7, DERR_SNAPPY = 8, DERR_STRING_TOO_LONG = 9
 };
+// BYTE_ARRAY dictionary pages -> tables of string references (device_utils.cuh: string_ref): one job per dictionary page,
+// walked by one thread (the entries are length-prefixed, so their positions are only found sequentially)
+struct StringDictJob {
+  const uint8_t* page;   // PLAIN byte arrays: [u32 length][bytes] ...
+  uint64_t* refs;        // count references out
+  int32_t size, count;
+};
+void launch_build_string_dicts(hs_ctx* ctx, const StringDictJob* jobs, int64_t n, uint32_t* d_error);
 
 // ---- snappy (snappy.cu) ---------------------------------------------------------------------------------------------
 struct SnappyBlob {
@@ -171,6 +179,10 @@ void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int6
 void launch_encode_keys(hs_ctx* ctx, const void* in, int type, const uint32_t* src, int64_t nrows, uint64_t* out,
                         unsigned long long* or_and);
 void launch_iota_u32(hs_ctx* ctx, uint32_t* out, int64_t n);
+// out[i] = piece of the string refs[perm[i]]: its length (piece < 0) or its piece-th 8 bytes, big-endian, zero-padded
+// (+ OR / AND reduction); see k_string_piece_keys
+void launch_string_piece_keys(hs_ctx* ctx, const uint64_t* refs, const uint32_t* perm, int64_t nrows, int piece, uint64_t* out,
+                              unsigned long long* or_and);
 
 // ---- segmented radix sort (radix_sort.cu) ---------------------------------------------------------------------------
 constexpr int kSortTile = 4096;  // pairs per tile (256 threads x 16)
@@ -230,6 +242,13 @@ void launch_tile_valid_counts(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles
 void launch_gather_encode_nullable(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint32_t* perm,
                                    const void* src, const uint8_t* valid, int width, const uint64_t* tile_value_offset,
                                    const uint64_t* tile_def_offset, uint8_t* arena);
+// string columns (8-byte references, device_utils.cuh): per tile the bytes its non-null values take as PLAIN BYTE_ARRAY
+// ([u32 length][bytes] each) and their number; then definition bits + values per tile.  valid == nullptr: no nulls
+void launch_tile_string_sizes(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint32_t* perm, const uint64_t* refs,
+                              const uint8_t* valid, uint32_t* bytes, uint32_t* counts);
+void launch_gather_encode_strings(hs_ctx* ctx, const SortTile* tiles, int64_t ntiles, const uint32_t* perm, const uint64_t* refs,
+                                  const uint8_t* valid, const uint64_t* tile_value_offset, const uint64_t* tile_def_offset,
+                                  uint8_t* arena);
 // ---- dictionary encoding (dict_encode.cu) -------------------------------------------------------------------------
 constexpr uint32_t kMaxDictEntries = 65536;          // bit width <= 16
 constexpr uint32_t kDictCapacity = 8 * kMaxDictEntries;  // open-addressing slots (power of two)

@@ -144,7 +144,7 @@ __global__ void k_walk_pages(const ChunkDesc* __restrict__ chunks, int n_chunks,
         pd.codec = ch.codec;
         // v1 pages of a compressed chunk are always compressed; v2 pages say so in their header
         pd.is_compressed = ch.codec != pq::UNCOMPRESSED && (h.type == pq::DATA_PAGE || h.is_compressed) ? 1 : 0;
-        pd.pad = 0;
+        pd.chunk = c;
         pages[out + n_pages] = pd;
       }
       if (ch.codec == pq::UNCOMPRESSED && h.compressed_size != h.uncompressed_size) set_error(d_error, DERR_COMPRESSED, (uint32_t)c);
@@ -713,6 +713,121 @@ __device__ void decode_page(const PageDesc& pg, const ColumnOut& co, uint32_t* c
   }
 }
 
+// ---- strings ---------------------------------------------------------------------------------------------------------
+// PLAIN BYTE_ARRAY values are length-prefixed: where value i starts is known only after values 0..i-1 have been walked.  One
+// thread walks a page (pages are walked in parallel with each other); every row gets a reference to its bytes inside the
+// page -- the bytes themselves are not copied anywhere until the index pages are written.
+__device__ __forceinline__ uint32_t load_u32_bytes(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+__device__ void decode_byte_array_plain(const PageDesc& pg, const ColumnOut& co, uint32_t* col_has_nulls, uint32_t* d_error) {
+  if (threadIdx.x != 0) return;
+  atomicOr(col_has_nulls, 2u);  // not a dictionary page
+  const int n = pg.num_values;
+  const uint8_t* p = pg.data;
+  const uint8_t* pend = pg.data + pg.size;
+  const uint8_t *def_p = nullptr, *def_end = nullptr;
+  if (n < 0 || pg.size < 0 || !locate_def_levels(pg, p, def_p, def_end)) {
+    set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+    return;
+  }
+  uint64_t* out = (uint64_t*)co.data + pg.first_row;
+  uint8_t* valid = co.valid ? co.valid + pg.first_row : nullptr;
+  // definition levels (bit width 1), walked serially alongside the values: run_left values of the current run remain
+  uint32_t run_left = 0, run_val = 1, bit_pos = 0;
+  const uint8_t* bits = nullptr;
+  bool run_rle = true, saw_null = false;
+  for (int i = 0; i < n; i++) {
+    bool is_valid = true;
+    if (def_p) {
+      if (run_left == 0) {
+        if (def_p >= def_end) {
+          set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+          return;
+        }
+        uint32_t h = 0;
+        int shift = 0;
+        while (def_p < def_end) {
+          const uint8_t b = *def_p++;
+          h |= (uint32_t)(b & 0x7f) << shift;
+          if (!(b & 0x80)) break;
+          shift += 7;
+          if (shift > 28) break;
+        }
+        if (h & 1) {
+          uint32_t groups = h >> 1;
+          if ((uint64_t)groups > (uint64_t)(def_end - def_p)) groups = (uint32_t)(def_end - def_p);
+          run_rle = false;
+          run_left = groups * 8;
+          bits = def_p;
+          bit_pos = 0;
+          def_p += groups;
+        } else {
+          run_rle = true;
+          run_left = h >> 1;
+          run_val = def_p < def_end ? (*def_p++ & 1u) : 0u;
+        }
+        if (run_left == 0) {
+          set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+          return;
+        }
+      }
+      is_valid = run_rle ? run_val != 0 : ((bits[bit_pos >> 3] >> (bit_pos & 7)) & 1u) != 0;
+      bit_pos++;
+      run_left--;
+    }
+    uint64_t ref = 0;
+    if (is_valid) {
+      if (pend - p < 4) {
+        set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+        return;
+      }
+      const uint32_t len = load_u32_bytes(p);
+      if ((uint64_t)len > (uint64_t)(pend - p - 4)) {
+        set_error(d_error, DERR_OVERRUN, (uint32_t)pg.col);
+        return;
+      }
+      if (len > kMaxStringLen) {
+        set_error(d_error, DERR_STRING_TOO_LONG, (uint32_t)pg.col);
+        return;
+      }
+      ref = string_ref(p + 4, len);
+      p += 4 + (size_t)len;
+    } else {
+      saw_null = true;
+    }
+    out[i] = ref;
+    if (valid) valid[i] = is_valid ? 1 : 0;
+  }
+  if (saw_null) atomicOr(col_has_nulls, 1u);
+}
+
+__global__ void k_build_string_dicts(const StringDictJob* __restrict__ jobs, int64_t n, uint32_t* d_error) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const StringDictJob job = jobs[j];
+  const uint8_t* p = job.page;
+  const uint8_t* pend = job.page + job.size;
+  for (int i = 0; i < job.count; i++) {
+    if (pend - p < 4) {
+      set_error(d_error, DERR_OVERRUN, 0xfffffdu);
+      return;
+    }
+    const uint32_t len = load_u32_bytes(p);
+    if ((uint64_t)len > (uint64_t)(pend - p - 4)) {
+      set_error(d_error, DERR_OVERRUN, 0xfffffdu);
+      return;
+    }
+    if (len > kMaxStringLen) {
+      set_error(d_error, DERR_STRING_TOO_LONG, 0xfffffdu);
+      return;
+    }
+    job.refs[i] = string_ref(p + 4, len);
+    p += 4 + (size_t)len;
+  }
+}
+
 __global__ void __launch_bounds__(kDecodeThreads) k_decode_pages(const PageDesc* __restrict__ pages,
                                                                  const ColumnOut* __restrict__ cols,
                                                                  uint32_t* col_has_nulls,
@@ -733,6 +848,12 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_pages(const PageDesc*
     case pq::INT32:
     case pq::FLOAT: decode_page<4>(pg, co, col_has_nulls + pg.col, d_error, sm); break;
     case pq::BOOLEAN: decode_page<1>(pg, co, col_has_nulls + pg.col, d_error, sm); break;
+    case pq::BYTE_ARRAY:
+      // dictionary-encoded strings: the dictionary has been turned into a table of 8-byte references (decode_sources), so
+      // the page decodes like any dictionary page of 8-byte values; PLAIN pages are walked
+      if (pg.encoding == pq::ENC_PLAIN) decode_byte_array_plain(pg, co, col_has_nulls + pg.col, d_error);
+      else decode_page<8>(pg, co, col_has_nulls + pg.col, d_error, sm);
+      break;
     default:
       if (threadIdx.x == 0) set_error(d_error, DERR_UNSUPPORTED_TYPE, (uint32_t)pg.phys_type);
   }
@@ -754,6 +875,13 @@ void launch_classify_pages(hs_ctx* ctx, const PageDesc* pages, int64_t n_pages, 
   KernelScope _ks(ctx, "k_classify_pages");
   if (n_pages == 0) return;
   k_classify_pages<<<(unsigned)ceil_div(n_pages, 128), 128, 0, ctx->stream>>>(pages, n_pages, col_flags, zc_tile_rows);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_build_string_dicts(hs_ctx* ctx, const StringDictJob* jobs, int64_t n, uint32_t* d_error) {
+  KernelScope _ks(ctx, "k_build_string_dicts");
+  if (n == 0) return;
+  k_build_string_dicts<<<(unsigned)ceil_div(n, 64), 64, 0, ctx->stream>>>(jobs, n, d_error);
   HS_LAUNCH_CHECK(ctx);
 }
 

@@ -356,6 +356,24 @@ inline void write_nullable_page_prefix(std::vector<uint8_t>& out, int64_t n, int
   out.insert(out.end(), hv, hv + hl);
 }
 
+// the same for a page whose values take `value_bytes` bytes in all (PLAIN BYTE_ARRAY: [u32 length][bytes] per non-null value)
+inline void write_nullable_page_prefix_bytes(std::vector<uint8_t>& out, int64_t n, uint64_t value_bytes) {
+  const uint64_t groups = (uint64_t)(n + 7) / 8;
+  uint8_t hv[10];
+  int hl = 0;
+  uint64_t h = (groups << 1) | 1;
+  while (h >= 0x80) {
+    hv[hl++] = (uint8_t)(h | 0x80);
+    h >>= 7;
+  }
+  hv[hl++] = (uint8_t)h;
+  const uint32_t def_len = (uint32_t)(hl + groups);
+  write_data_page_header(out, (int32_t)(4 + def_len + value_bytes), (int32_t)n, ENC_PLAIN);
+  const uint8_t* lp = (const uint8_t*)&def_len;
+  out.insert(out.end(), lp, lp + 4);
+  out.insert(out.end(), hv, hv + hl);
+}
+
 // [page header][all-valid definition levels][bit width byte][bit-packed run header] of a PLAIN_DICTIONARY v1 data page of
 // `n` non-null values whose indices are written as ONE bit-packed run of ceil(n/8) groups of `bw` bits (the packed bytes
 // follow this prefix).

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ t
   // again only for the rows an out-of-order run actually moves.  With 5 M-row buckets one row in eight heads a run: doing
   // all of that through dependent global loads was latency-bound (4.9 ms per 1 B rows for 8 B/row of traffic).
   __shared__ uint64_t s_key[kSortTile + 2];
-  __shared__ uint16_t s_heads[kSortTile / 2 + 32];
+  __shared__ uint16_t s_heads[kSortTile / 2 + 32], s_len[kSortTile / 2 + 32];
   __shared__ uint32_t s_n;
   const SortTile t = tiles[blockIdx.x];
   const uint64_t segb = seg_start[t.seg], sege = seg_start[t.seg + 1];
@@ -287,14 +287,26 @@ __global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ t
   }
   __syncthreads();
   const uint32_t nheads = s_n;
+  // first every run is measured (reads only: a walk looks one key past its run, i.e. at the head of the next one), then,
+  // behind a barrier, every run is sorted (writes stay inside the run)
+  for (uint32_t e = threadIdx.x; e < nheads; e += 256) {
+    const uint32_t i = s_heads[e];
+    const uint64_t* sk = s_key + 1 + i;
+    const uint64_t kh = sk[0] & high_mask;
+    uint32_t len = 1;
+    while (i + len < t.count && len <= max_run && (sk[len] & high_mask) == kh) len++;
+    const bool crosses = i + len == t.count && (sk[len] & high_mask) == kh;  // sk[len] is the next tile's first key here
+    s_len[e] = crosses ? (uint16_t)0xffffu : (uint16_t)len;
+  }
+  __syncthreads();
   for (uint32_t e = threadIdx.x; e < nheads; e += 256) {
     const uint32_t i = s_heads[e];
     const uint64_t p = t.start + i;
     uint64_t* sk = s_key + 1 + i;  // the run starts at sk[0]
     const uint64_t kh = sk[0] & high_mask;
-    uint32_t len = 1;
-    while (i + len < t.count && len <= max_run && (sk[len] & high_mask) == kh) len++;
-    if (i + len == t.count && (sk[len] & high_mask) == kh) {  // sk[len] is the next tile's first key here
+    uint32_t len = s_len[e];
+    if (len == 0xffffu) {
+      len = t.count - i;
       // the run continues into the next tile (at most one per tile): settle it in global memory, as a whole.  The next
       // tile never touches these rows -- none of them heads a run there -- and reads only their (unchanging) prefixes.
       uint64_t q = p + len;

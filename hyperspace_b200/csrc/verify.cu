@@ -22,8 +22,18 @@ struct VerifyCols {
   const void* data[kMaxVerifyCols];
   const uint8_t* valid[kMaxVerifyCols];
   int32_t width[kMaxVerifyCols];
+  int32_t type[kMaxVerifyCols];
   int32_t ncols;
 };
+
+// what a string contributes to the checksums: a 64-bit digest of its bytes and its length (never its address)
+__device__ __forceinline__ uint64_t string_digest(uint64_t ref) {
+  const uint8_t* p = ref_ptr(ref);
+  const uint32_t len = ref_len(ref);
+  uint64_t h = 0xCBF29CE484222325ull ^ len;
+  for (uint32_t i = 0; i < len; i++) h = (h ^ p[i]) * 0x100000001B3ull;
+  return h;
+}
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -51,7 +61,8 @@ __global__ void __launch_bounds__(256) k_row_checksums(VerifyCols cols, int64_t 
     for (int c = 0; c < kMaxVerifyCols; c++) {
       if (c < cols.ncols) {
         const bool null = cols.valid[c] && !cols.valid[c][i];
-        const uint64_t v = null ? 0x6C6C756E6C6C756Eull : raw_value(cols.data[c], cols.width[c], i);
+        uint64_t v = null ? 0x6C6C756E6C6C756Eull : raw_value(cols.data[c], cols.width[c], i);
+        if (!null && cols.type[c] == HS_TYPE_STRING) v = string_digest(v);
         const uint64_t salted = v + (uint64_t)(c + 1) * 0xD6E8FEB86659FD93ull + (null ? 1ull : 0ull);
         acc[1 + c] += mix64(salted);
         h = mix64(h ^ salted);
@@ -76,6 +87,11 @@ __device__ __forceinline__ int compare_rows(const KeyColumn* keys, int nkeys, in
     const bool va = !kc.valid || kc.valid[a], vb = !kc.valid || kc.valid[b];
     if (va != vb) return va ? 1 : -1;
     if (!va) continue;
+    if (kc.type == HS_TYPE_STRING) {
+      const int r = string_compare(raw_value(kc.data, 8, a), raw_value(kc.data, 8, b));
+      if (r) return r;
+      continue;
+    }
     const uint64_t ea = sort_encode(kc.type, raw_value(kc.data, kc.width, a));
     const uint64_t eb = sort_encode(kc.type, raw_value(kc.data, kc.width, b));
     if (ea != eb) return ea < eb ? -1 : 1;
@@ -128,6 +144,7 @@ void checksum_table(hs_ctx* ctx, const Table& t, unsigned long long* d_sums) {
     vc.data[c] = t.cols[c].data.get();
     vc.valid[c] = t.cols[c].has_nulls ? t.cols[c].valid.get() : nullptr;
     vc.width[c] = t.cols[c].width;
+    vc.type[c] = t.cols[c].type;
   }
   const int grid = (int)std::min<int64_t>(ceil_div(t.nrows, 256), (int64_t)ctx->sm_count * 8);
   k_row_checksums<<<grid, 256, 0, ctx->stream>>>(vc, t.nrows, d_sums);
@@ -178,7 +195,9 @@ int hs_verify_index(hs_ctx* ctx, const hs_source_file* files, const int32_t* buc
     hs_stats st;
     memset(&st, 0, sizeof st);
     Table t;
-    load_sources(ctx, files, n_files, cols, &t, &st);
+    SourceSet src;  // outlives the kernels below: string columns hold references into its images
+    open_sources(ctx, files, n_files, &src, &st);
+    decode_sources(ctx, src, cols, nullptr, &t, &st);
     out->rows = t.nrows;
     Buf<unsigned long long> d_sums(ctx, 2 + 1 + kMaxVerifyCols);
     fill_bytes(ctx, d_sums.get(), 0, 8 * (3 + kMaxVerifyCols));

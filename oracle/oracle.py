@@ -211,14 +211,25 @@ def _as_columns(cols: Sequence[np.ndarray], valids: Optional[Sequence[Optional[n
     keep = []
     arr = (_Column * len(cols))()
     for i, c in enumerate(cols):
-        c = np.ascontiguousarray(c)
-        keep.append(c)
-        arr[i].type = _NP_TYPE[c.dtype]
-        arr[i].data = c.ctypes.data
-        arr[i].aux = None
+        c = np.asarray(c)
+        if c.dtype.kind in "OUS":  # strings / binary: int64 offsets[n + 1] + the bytes (utf-8 for str)
+            raw = [(x if isinstance(x, (bytes, bytearray)) else ("" if x is None else str(x)).encode("utf-8")) for x in c.tolist()]
+            offs = np.zeros(len(raw) + 1, dtype=np.int64)
+            np.cumsum([len(b) for b in raw], out=offs[1:])
+            blob = np.frombuffer(b"".join(raw) + b"\0", dtype=np.uint8).copy()
+            keep += [offs, blob]
+            arr[i].type = HSO_STRING
+            arr[i].data = offs.ctypes.data
+            arr[i].aux = blob.ctypes.data
+        else:
+            c = np.ascontiguousarray(c)
+            keep.append(c)
+            arr[i].type = _NP_TYPE[c.dtype]
+            arr[i].data = c.ctypes.data
+            arr[i].aux = None
         v = None if valids is None else valids[i]
         if v is not None:
-            v = np.ascontiguousarray(v.astype(np.uint8))
+            v = np.ascontiguousarray(np.asarray(v).astype(np.uint8))
             keep.append(v)
             arr[i].valid = v.ctypes.data
         else:
