@@ -271,6 +271,10 @@ class Rig:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback); use --impl reference for the CPU arm")
         torch.cuda.set_device(self.local_rank)
+        # host threads and pinned file images next to this rank's GPU (matters once several ranks copy at the same time)
+        from hyperspace_b200.distributed import bind_to_gpu_numa_node
+
+        self.numa_node = bind_to_gpu_numa_node(self.local_rank) if self.world > 1 else None
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist_mod
@@ -538,7 +542,7 @@ def run_create_index(rig, args):
         e2e = {"value": total_rows / (ms_e2e / 1e3), "unit": "rows/s", "h2d_bytes_per_step": int(src_bytes),
                "d2h_bytes_per_step": int(out_bytes[0]), "ms_per_step": ms_e2e,
                "h2d_GBps_per_rank": src_bytes / (ms_e2e / 1e3) / 1e9, "d2h_GBps_per_rank": out_bytes[0] / (ms_e2e / 1e3) / 1e9,
-               "calls_in_flight": 3, "single_call_ms": ms_single,
+               "calls_in_flight": 3, "single_call_ms": ms_single, "numa_node_bound": rig.numa_node,
                "pipelined_ms": {"h2d_copy": avg(copy_ms["h2d"]), "d2h_copy": avg(copy_ms["d2h"]), "build": avg(copy_ms["build"])},
                "single_call_copy_ms": {"h2d": st_single.get("ms_h2d"), "d2h": st_single.get("ms_d2h")},
                "note": "pinned HOST Parquet images in, HOST index images out, per-rank bytes; timed over K steps software-pipelined "

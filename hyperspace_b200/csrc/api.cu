@@ -281,6 +281,8 @@ void hs_shutdown(hs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   xfer_release(ctx);
+  if (ctx->decode_cache && ctx->decode_cache_free) ctx->decode_cache_free(ctx->decode_cache);
+  ctx->decode_cache = nullptr;
   comm_destroy(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   if (ctx->h2d_stream) {

@@ -344,6 +344,24 @@ void open_sources(hs_ctx* ctx, const hs_source_file* files, int n_files, SourceS
   stats->ms_h2d += t_h2d.ms();
 }
 
+// The outcome of the late-materialisation agreement for one gathered message: which columns travel as codes, their merged
+// dictionaries and the device look-up tables.  Builds over the same sources (a refresh cycle, a benchmark loop) gather the
+// same message again; merging eight ranks' dictionaries and rebuilding the tables took ~3 ms of host time per call on 8 GPUs,
+// comparing 2 MB takes 0.1.  The key is the message itself (content, not identity): nothing stale can match.
+struct DecodeCache {
+  struct Column {
+    int col = -1;
+    std::vector<uint64_t> values;
+    uint32_t bw = 0, mask = 0, empty_index = 0;
+    Buf<uint8_t> table;
+  };
+  std::vector<uint64_t> message;
+  int num_segments = 0, first_col = 0;
+  int64_t total_rows = 0;
+  std::vector<Column> carried;
+};
+static void free_decode_cache(void* p) { delete static_cast<DecodeCache*>(p); }
+
 void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>& columns,
                     const std::vector<std::pair<int64_t, int64_t>>* file_windows, Table* out, hs_stats* stats,
                     const CarryOptions* carry) {
@@ -419,7 +437,6 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
   stats->rows_in += nrows;
 
   std::vector<ColumnOut> h_cols(ncols);
-  std::vector<Buf<uint8_t>> carry_tables(ncols);  // look-up tables of the late-materialised columns (decode only)
   // destinations are allocated once the late-materialised columns are known (they get 2-byte codes, not values)
   auto alloc_destinations = [&]() {
     for (int c = 0; c < ncols; c++) {
@@ -637,19 +654,45 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       m[4] = spec_state[4 * i + 2];                                                // the value ~0 occurs
       const uint32_t nv = std::min<uint32_t>(spec_count[i], kAgreeCap);
       for (uint32_t j = 0; j < nv; j++) m[5 + j] = spec_vals[(size_t)i * kAgreeCap + j];
+      std::sort(m + 5, m + 5 + nv);  // the hash set yields them in no particular order: a canonical message can be cached
       m[2] = nv;
     }
     comm_allgather_host(ctx, mine.data(), 8 * words, all.data());
+    DecodeCache* cache = static_cast<DecodeCache*>(ctx->decode_cache);
+    const bool hit = cache && cache->num_segments == carry->num_segments && cache->first_col == carry->first_col &&
+                     cache->message.size() == all.size() && memcmp(cache->message.data(), all.data(), 8 * all.size()) == 0;
     std::vector<uint32_t> cls(ncols, 0u);
     int64_t total_rows = 0;
-    for (int r = 0; r < W; r++) {
-      const uint64_t* a = &all[(size_t)r * words];
-      for (int c = 0; c < ncols; c++) cls[c] |= (uint32_t)a[c];
-      total_rows += (int64_t)a[ncols];
+    if (hit) {
+      total_rows = cache->total_rows;
+      for (DecodeCache::Column& cc : cache->carried) {
+        DevColumn& dc = out->cols[cc.col];
+        dc.carried = true;
+        dc.dict_values = cc.values;
+        dc.dict_bw = cc.bw;
+        dc.codes.alloc(ctx, (size_t)std::max<int64_t>(1, nrows) + 16);
+        h_cols[cc.col] = ColumnOut{dc.codes.get(), nullptr, dc.width, dc.type, cc.table.get(), cc.mask, cc.empty_index, 1, 0};
+      }
+    } else {
+      for (int r = 0; r < W; r++) {
+        const uint64_t* a = &all[(size_t)r * words];
+        for (int c = 0; c < ncols; c++) cls[c] |= (uint32_t)a[c];
+        total_rows += (int64_t)a[ncols];
+      }
+      if (!cache) {
+        cache = new DecodeCache();
+        ctx->decode_cache = cache;
+        ctx->decode_cache_free = free_decode_cache;
+      }
+      cache->carried.clear();  // (the previous entry's tables were last read by kernels of an earlier, completed call)
+      cache->message = all;
+      cache->num_segments = carry->num_segments;
+      cache->first_col = carry->first_col;
+      cache->total_rows = total_rows;
     }
     out->global_rows = total_rows;
     int ncarried = 0;
-    for (int i = 0; i < nspec && ncarried < kMaxCarried && total_rows > 0; i++) {
+    for (int i = 0; !hit && i < nspec && ncarried < kMaxCarried && total_rows > 0; i++) {
       const int c = spec[i];
       DevColumn& dc = out->cols[c];
       if (cls[c] != 0) continue;
@@ -670,13 +713,17 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
       values.erase(std::unique(values.begin(), values.end()), values.end());
       const uint32_t bw = bits_for((uint32_t)values.size());
       if (!dictionary_pays_off((uint32_t)values.size(), bw, width, total_rows, carry->num_segments)) continue;
-      uint32_t mask = 0, empty_index = 0;
-      upload_lookup_table(ctx, values, &carry_tables[c], &mask, &empty_index);
+      cache->carried.emplace_back();
+      DecodeCache::Column& cc = cache->carried.back();
+      cc.col = c;
+      cc.bw = bw;
+      upload_lookup_table(ctx, values, &cc.table, &cc.mask, &cc.empty_index);
+      cc.values = values;
       dc.carried = true;
       dc.dict_values = std::move(values);
       dc.dict_bw = bw;
       dc.codes.alloc(ctx, (size_t)std::max<int64_t>(1, nrows) + 16);
-      h_cols[c] = ColumnOut{dc.codes.get(), nullptr, dc.width, dc.type, carry_tables[c].get(), mask, empty_index, 1, 0};
+      h_cols[c] = ColumnOut{dc.codes.get(), nullptr, dc.width, dc.type, cc.table.get(), cc.mask, cc.empty_index, 1, 0};
       ncarried++;
     }
   }

@@ -159,6 +159,9 @@ struct hs_ctx {
   size_t xfer_cap = 0, xfer_head = 0;
   std::vector<uint8_t*> xfer_retired; // outgrown rings, recycled at the next synchronisation
   std::vector<PendingD2H> xfer_pending;
+  // what the ranks agreed on when the same dictionaries were last seen (engine.cu: DecodeCache); freed by hs_shutdown
+  void* decode_cache = nullptr;
+  void (*decode_cache_free)(void*) = nullptr;
 };
 
 namespace hs {

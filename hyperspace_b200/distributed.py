@@ -5,7 +5,9 @@ the shuffle behind ``indexData.repartition(numBuckets, indexedColumns)``
 (src/main/scala/com/microsoft/hyperspace/index/covering/CoveringIndex.scala:60)."""
 from __future__ import annotations
 
-from typing import List, Sequence, TypeVar
+import os
+import subprocess
+from typing import List, Optional, Sequence, TypeVar
 
 T = TypeVar("T")
 
@@ -45,3 +47,39 @@ def gather_file_lists(dist, local_files: List[str], world: int) -> List[str]:
     box = [None] * world
     dist.all_gather_object(box, local_files)
     return [f for part in box for f in part]
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    out: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            out.extend(range(int(a), int(b) + 1))
+        else:
+            out.append(int(part))
+    return out
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pins this process to the CPUs of the NUMA node the GPU hangs off, BEFORE any pinned host memory is allocated, so that
+    the file images a rank stages (hs_stage_sources) and drains (hs_pending_wait) live in memory local to its GPU's PCIe
+    root.  With eight ranks copying in both directions at once, images on the far socket make every byte cross the
+    inter-socket link as well.  What ``numactl --cpunodebind --membind`` does for a Spark executor; a no-op (returns None)
+    when the topology cannot be read.  Returns the node."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device_index)],
+                                      text=True, timeout=20).strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set(_parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())) & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
