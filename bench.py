@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 
 INDEXED = ["k"]
 INCLUDED = ["v1", "v2", "v3", "v4"]
-NUM_BUCKETS = 200
+NUM_BUCKETS = int(os.environ.get("HS_BENCH_BUCKETS", "200"))  # (override: experiments only; the benchmark config is 200)
 ROW_BYTES = 32  # decoded bytes per row of T
 ALGO_BYTES_PER_ROW = 64  # 32 read + 32 written
 

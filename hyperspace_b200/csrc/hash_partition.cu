@@ -762,214 +762,6 @@ __global__ void __launch_bounds__(FusedCfg<PEER>::kThreads, FusedCfg<PEER>::kMin
   }
 }
 
-// ---- streaming variant for rows that leave over NVLink -------------------------------------------------------------
-// The bulk copies of k_partition_rows leave shared memory at the pace the NVLink accepts them, and the CTA that issued them
-// stands still until they have (wait_group.read before the exchange buffer is reused): measured, kernel time = ranking +
-// copy-engine drain + link time, added up.  Here ONE persistent CTA per SM (1024 threads, 8192-row tiles as before) owns two
-// exchange buffers and alternates between them from column to column: while the copy engine drains one, the threads fill
-// the other -- or rank the next tile.  Before a buffer is written again, `wait_group.read 1` lets only the most recent
-// group (the other buffer's) stay in flight.  Needs the bucket ids stored by the histogram pass (bin_ids) and nb <= 256.
-constexpr int kStreamThreads = 1024;
-constexpr int kStreamWarps = kStreamThreads / 32;
-constexpr int kStreamItems = kFusedTilePeer / kStreamThreads;  // 8
-constexpr int kStreamWarpRows = kFusedTilePeer / kStreamWarps; // 256
-constexpr int kStreamMaxBins = 256;
-
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-
-template <int BITS>
-__global__ void __launch_bounds__(kStreamThreads, 1) k_partition_stream(int64_t nrows, int nb, int64_t ntiles,
-                                                                         const uint32_t* __restrict__ tile_dst,
-                                                                         const PartColumn* __restrict__ cols, int ncols,
-                                                                         void* const* __restrict__ peer_out, int out_world,
-                                                                         CodePackRound pack, const uint16_t* __restrict__ bin_ids) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  constexpr int kTile = kFusedTilePeer;
-  const uint32_t XN = (uint32_t)kTile + 2u * (uint32_t)nb + 2u;
-  uint64_t* xbuf0 = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* xbuf1 = xbuf0 + XN + (XN & 1);  // keeps the second buffer 16-byte aligned
-  uint16_t* pos_bin = reinterpret_cast<uint16_t*>(xbuf1 + XN + (XN & 1));
-  uint16_t* cnt = pos_bin + XN;
-  uint32_t* out_adj = reinterpret_cast<uint32_t*>(cnt + (size_t)kStreamWarps * nb + ((XN + (size_t)kStreamWarps * nb) & 1));
-  uint32_t* bin_owner = out_adj + nb;
-  uint16_t* run_start = reinterpret_cast<uint16_t*>(bin_owner + nb);
-  uint16_t* run_len = run_start + nb;
-  uint32_t* warp_sums = reinterpret_cast<uint32_t*>(run_len + nb);
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1;
-  uint32_t round = 0;  // exchange rounds so far: picks the buffer
-  for (int b = threadIdx.x; b < nb; b += kStreamThreads) bin_owner[b] = out_world > 1 ? (uint32_t)b % (uint32_t)out_world : 0u;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    __syncthreads();  // the previous tile's position tables are no longer read (its last copies were ISSUED before this point)
-    for (int i = threadIdx.x; i < kStreamWarps * nb; i += kStreamThreads) cnt[i] = 0;
-    for (uint32_t i = threadIdx.x; i < XN; i += kStreamThreads) pos_bin[i] = 0xffffu;
-    const int64_t tile_base = tile * kTile;
-    const uint32_t first = warp * kStreamWarpRows + lane;
-    const int64_t wbase = tile_base + first;
-    const uint32_t tile_count = (uint32_t)min((int64_t)kTile, nrows - tile_base);
-    uint32_t bin[kStreamItems];
-#pragma unroll
-    for (int j = 0; j < kStreamItems; j++) bin[j] = first + j * 32 < tile_count ? (uint32_t)bin_ids[wbase + j * 32] : (uint32_t)nb - 1;
-    __syncthreads();
-    uint16_t* wcnt = cnt + (size_t)warp * nb;
-#pragma unroll
-    for (int j = 0; j < kStreamItems; j++) {
-      const unsigned peers = match_any_bits<BITS>(0xffffffffu, bin[j]);
-      const uint32_t before = __popc(peers & lt);
-      const uint32_t pre = wcnt[bin[j]];
-      __syncwarp();
-      if (before == 0) wcnt[bin[j]] = (uint16_t)(pre + __popc(peers));
-      __syncwarp();
-      bin[j] |= (pre + before) << 16;
-    }
-    __syncthreads();
-    {  // nb <= 256 <= blockDim: one scan round
-      const int b = threadIdx.x;
-      uint32_t total = 0;
-      if (b < nb) {
-#pragma unroll 8
-        for (int w = 0; w < kStreamWarps; w++) total += cnt[(size_t)w * nb + b];
-      }
-      const uint32_t P = block_exclusive_scan(total, warp_sums, nullptr);
-      if (b < nb) {
-        const uint32_t dst = tile_dst[(size_t)tile * nb + b];
-        uint32_t run = P + 2u * (uint32_t)b + ((P ^ dst) & 1u);
-        out_adj[b] = dst - run;
-        run_start[b] = (uint16_t)run;
-        run_len[b] = (uint16_t)(b == nb - 1 ? total - ((uint32_t)kTile - tile_count) : total);
-#pragma unroll 8
-        for (int w = 0; w < kStreamWarps; w++) {
-          const uint16_t c = cnt[(size_t)w * nb + b];
-          cnt[(size_t)w * nb + b] = (uint16_t)run;
-          run += c;
-        }
-      }
-    }
-    __syncthreads();
-    const uint32_t x_end = (uint32_t)run_start[nb - 1] + run_len[nb - 1];
-#pragma unroll
-    for (int j = 0; j < kStreamItems; j++) {
-      const uint32_t b = bin[j] & 0xffffu;
-      bin[j] = wcnt[b] + (bin[j] >> 16);
-      if (first + j * 32 < tile_count) pos_bin[bin[j]] = (uint16_t)b;
-    }
-    const uint32_t(&pos)[kStreamItems] = bin;
-    const int nrounds = ncols + (pack.n > 0 ? 1 : 0);
-    for (int c = 0; c < nrounds; c++) {
-      const bool is_pack = c == ncols;
-      PartColumn pc;
-      if (!is_pack) pc = cols[c];
-      else pc = PartColumn{nullptr, pack.out, 8, 0, nullptr};
-      uint64_t* xbuf = (round & 1) ? xbuf1 : xbuf0;
-      round++;
-      // this buffer was last read by the copies issued two rounds ago: all but the latest group must have left
-      if (threadIdx.x < (unsigned)nb) bulk_wait_read_1();
-      __syncthreads();
-      if (is_pack) {
-#pragma unroll
-        for (int j = 0; j < kStreamItems; j++) {
-          if (first + j * 32 < tile_count) {
-            const int64_t row = wbase + j * 32;
-            uint32_t lo = pack.src[0][row], hi = 0;
-            if (pack.n > 1) lo |= (uint32_t)pack.src[1][row] << 16;
-            if (pack.n > 2) hi = pack.src[2][row];
-            if (pack.n > 3) hi |= (uint32_t)pack.src[3][row] << 16;
-            xbuf[pos[j]] = (uint64_t)lo | ((uint64_t)hi << 32);
-          }
-        }
-      } else if (pc.tiles) {
-        const ZcTile z = pc.tiles[tile];
-        if (pc.width == 8) {
-#pragma unroll
-          for (int j = 0; j < kStreamItems; j++)
-            if (first + j * 32 < tile_count) {
-              const int64_t row = wbase + j * 32;
-              xbuf[pos[j]] = *(const uint64_t*)((row < z.split ? z.p0 : z.p1) + row * 8);
-            }
-        } else {
-          uint32_t* xb = reinterpret_cast<uint32_t*>(xbuf);
-#pragma unroll
-          for (int j = 0; j < kStreamItems; j++)
-            if (first + j * 32 < tile_count) {
-              const int64_t row = wbase + j * 32;
-              xb[pos[j]] = *(const uint32_t*)((row < z.split ? z.p0 : z.p1) + row * 4);
-            }
-        }
-      } else if (pc.width == 8) {
-        const uint64_t* in = (const uint64_t*)pc.in + wbase;
-#pragma unroll
-        for (int j = 0; j < kStreamItems; j++)
-          if (first + j * 32 < tile_count) xbuf[pos[j]] = in[j * 32];
-      } else if (pc.width == 4) {
-        const uint32_t* in = (const uint32_t*)pc.in + wbase;
-        uint32_t* xb = reinterpret_cast<uint32_t*>(xbuf);
-#pragma unroll
-        for (int j = 0; j < kStreamItems; j++)
-          if (first + j * 32 < tile_count) xb[pos[j]] = in[j * 32];
-      } else {
-        const uint8_t* in = (const uint8_t*)pc.in + wbase;
-        uint8_t* xb = reinterpret_cast<uint8_t*>(xbuf);
-#pragma unroll
-        for (int j = 0; j < kStreamItems; j++)
-          if (first + j * 32 < tile_count) xb[pos[j]] = in[j * 32];
-      }
-      if (pc.width == 8) fence_async_smem();
-      __syncthreads();
-      void* const* pout = peer_out + (size_t)c * out_world;
-      if (pc.width == 8) {
-        if (threadIdx.x < (unsigned)nb) {
-          const int b = threadIdx.x;
-          const uint32_t n = run_len[b];
-          if (n) {
-            const uint32_t s = run_start[b];
-            uint64_t* dst = (uint64_t*)pout[bin_owner[b]] + (out_adj[b] + s);
-            const uint32_t h = (uint32_t)(((uintptr_t)dst >> 3) & 1u);
-            if ((h ^ s) & 1u) {
-              for (uint32_t i = 0; i < n; i++) dst[i] = xbuf[s + i];
-            } else {
-              if (h) dst[0] = xbuf[s];
-              const uint32_t body = (n - h) & ~1u;
-              if (body) bulk_store_s2g(dst + h, xbuf + s + h, body * 8u);
-              if ((n - h) & 1u) dst[n - 1] = xbuf[s + n - 1];
-            }
-          }
-          bulk_commit();  // one group per round and issuing thread, empty or not: wait_group.read counts groups
-        }
-      } else if (pc.width == 4) {
-        const uint32_t* xb = reinterpret_cast<const uint32_t*>(xbuf);
-        for (uint32_t i = threadIdx.x; i < x_end; i += kStreamThreads) {
-          const uint32_t b0 = pos_bin[i];
-          const bool real = b0 != 0xffffu;
-          const uint32_t b = real ? b0 : 0u;
-          uint32_t* out = (uint32_t*)pout[bin_owner[b]];
-          const uint32_t v = xb[i];
-          if (real) out[out_adj[b] + i] = v;
-        }
-        if (threadIdx.x < (unsigned)nb) bulk_commit();
-      } else {
-        const uint8_t* xb = reinterpret_cast<const uint8_t*>(xbuf);
-        for (uint32_t i = threadIdx.x; i < x_end; i += kStreamThreads) {
-          const uint32_t b0 = pos_bin[i];
-          const bool real = b0 != 0xffffu;
-          const uint32_t b = real ? b0 : 0u;
-          uint8_t* out = (uint8_t*)pout[bin_owner[b]];
-          const uint8_t v = xb[i];
-          if (real) out[out_adj[b] + i] = v;
-        }
-        if (threadIdx.x < (unsigned)nb) bulk_commit();
-      }
-    }
-  }
-  if (threadIdx.x < (unsigned)nb) bulk_wait_read();  // shared memory must outlive the last copies' reads
-}
-
-size_t stream_smem_bytes(int nb) {
-  const size_t XN = (size_t)kFusedTilePeer + 2 * (size_t)nb + 2, XA = XN + (XN & 1);
-  size_t u16s = XN + (size_t)kStreamWarps * nb;
-  u16s += u16s & 1;
-  return 2 * XA * 8 + u16s * 2 + (size_t)nb * 4 * 2 + (size_t)nb * 2 * 2 + 40 * 4;
-}
-
 template <bool PEER>
 size_t fused_smem_bytes(int nb, bool bulk = true) {
   const size_t XN = (size_t)FusedCfg<PEER>::kTile + (bulk ? 2 * (size_t)nb + 2 : 0);
@@ -1087,29 +879,6 @@ void launch_partition_rows(hs_ctx* ctx, const KeyColumn* d_keys, int nkeys, int6
   PartitionLaunch a{d_keys, nkeys, nrows, num_buckets, owner_mod, tile_dst, d_cols, ncols, d_peer_out, out_world, {}, bin_ids, bulk};
   memset(&a.pack, 0, sizeof a.pack);
   if (pack_round) a.pack = *pack_round;
-  // rows that leave over NVLink: the persistent double-buffered kernel (HS_PART_STREAM=0: the one-tile-per-CTA kernel)
-  static const char* stream_env = getenv("HS_PART_STREAM");
-  const int nbins = owner_mod > 0 ? owner_mod : num_buckets;
-  if (d_peer_out && peer_tile_shape() && bulk && bin_ids && nbins <= kStreamMaxBins && !(stream_env && atoi(stream_env) == 0)) {
-    const int64_t ntiles = ceil_div(nrows, kFusedTilePeer);
-    const size_t smem = stream_smem_bytes(nbins);
-    static DeviceOnce attr_once;
-    bool& attr = attr_once(ctx->device);
-    if (!attr) {
-      HS_CUDA(cudaFuncSetAttribute(k_partition_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(kStreamMaxBins)));
-      HS_CUDA(cudaFuncSetAttribute(k_partition_stream<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(kStreamMaxBins)));
-      attr = true;
-    }
-    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, ctx->sm_count);
-    if (nbins <= 16)
-      k_partition_stream<4><<<grid, kStreamThreads, smem, ctx->stream>>>(nrows, nbins, ntiles, tile_dst, d_cols, ncols, d_peer_out,
-                                                                        out_world, a.pack, bin_ids);
-    else
-      k_partition_stream<8><<<grid, kStreamThreads, smem, ctx->stream>>>(nrows, nbins, ntiles, tile_dst, d_cols, ncols, d_peer_out,
-                                                                        out_world, a.pack, bin_ids);
-    HS_LAUNCH_CHECK(ctx);
-    return;
-  }
   // tiles that leave over NVLink use the large shape (the tile histogram must have been taken with peer_tiles = true)
   if (d_peer_out && peer_tile_shape()) launch_partition_rows_cfg<true>(ctx, a, single_key_type);
   else launch_partition_rows_cfg<false>(ctx, a, single_key_type);
