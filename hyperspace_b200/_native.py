@@ -21,6 +21,7 @@ HS_OK, HS_EINVAL, HS_ENODEVICE, HS_ECUDA, HS_EFORMAT, HS_EIO, HS_EUNSUPPORTED, H
 HS_TYPE_INT32, HS_TYPE_INT64, HS_TYPE_FLOAT, HS_TYPE_DOUBLE, HS_TYPE_BOOL, HS_TYPE_STRING = range(6)
 HS_SAVE_OVERWRITE, HS_SAVE_APPEND = 0, 1
 HS_OUT_FILES, HS_OUT_HOST, HS_OUT_DEVICE = 0, 1, 2
+HS_CODEC_UNCOMPRESSED, HS_CODEC_SNAPPY = 0, 1
 
 _NP_OF_TYPE = {HS_TYPE_INT32: np.int32, HS_TYPE_INT64: np.int64, HS_TYPE_FLOAT: np.float32, HS_TYPE_DOUBLE: np.float64,
                HS_TYPE_BOOL: np.uint8}
@@ -47,7 +48,8 @@ class IndexSpec(C.Structure):
                 ("num_buckets", C.c_int32), ("save_mode", C.c_int32), ("output", C.c_int32), ("lineage", C.c_int32),
                 ("out_dir", C.c_char_p), ("job_uuid", C.c_char_p),
                 ("rows_per_page", C.c_int64), ("rows_per_row_group", C.c_int64),
-                ("deleted_file_ids", C.POINTER(C.c_int64)), ("n_deleted_file_ids", C.c_int32), ("disable_dictionary", C.c_int32)]
+                ("deleted_file_ids", C.POINTER(C.c_int64)), ("n_deleted_file_ids", C.c_int32), ("disable_dictionary", C.c_int32),
+                ("compression", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -101,6 +103,7 @@ EXPORTED_SYMBOLS = [
     "hs_k_bucket_ids", "hs_k_sort_perm", "hs_synth_table",
     "hs_stage_sources", "hs_staged_num_files", "hs_staged_file", "hs_staged_wait", "hs_staged_free",
     "hs_create_index_async", "hs_pending_wait", "hs_pending_cancel", "hs_verify_index", "hs_synth_checksum",
+    "hs_synth_table_ex", "hs_k_snappy_compress",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -188,6 +191,11 @@ def load_library() -> C.CDLL:
                                   C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.POINTER(VerifyReport), *err]
     L.hs_synth_checksum.restype = C.c_int
     L.hs_synth_checksum.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.POINTER(VerifyReport), *err]
+    L.hs_synth_table_ex.restype = C.c_int
+    L.hs_synth_table_ex.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_void_p), *err]
+    L.hs_k_snappy_compress.restype = C.c_int
+    L.hs_k_snappy_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), *err]
     if L.hs_abi_version() != 1:
         raise HyperspaceGpuError(HS_EINVAL, f"ABI version mismatch: library {L.hs_abi_version()}, binding 1")
     _lib = L
@@ -507,7 +515,7 @@ class Context:
 
     def _index_spec(self, files, indexed, included, num_buckets, out_dir=None, output=HS_OUT_FILES, job_uuid=None,
                     save_mode=HS_SAVE_OVERWRITE, lineage=False, deleted_file_ids=(), rows_per_page=0, rows_per_row_group=0,
-                    dictionary=True):
+                    dictionary=True, compression=HS_CODEC_UNCOMPRESSED):
         src, keep = _source_array(files)
         ic, nc = _cstr_array(indexed), _cstr_array(included)
         spec = IndexSpec()
@@ -521,40 +529,36 @@ class Context:
         dl = (C.c_int64 * max(1, len(deleted_file_ids)))(*deleted_file_ids)
         spec.deleted_file_ids, spec.n_deleted_file_ids = dl, len(deleted_file_ids)
         spec.disable_dictionary = 0 if dictionary else 1
+        spec.compression = compression
         return spec, (src, keep, ic, nc, dl)
 
     def create_index(self, files: Sequence[FileImage], indexed: Sequence[str], included: Sequence[str], num_buckets: int,
-                     out_dir: Optional[str] = None, output: int = HS_OUT_FILES, job_uuid: Optional[str] = None,
-                     save_mode: int = HS_SAVE_OVERWRITE, lineage: bool = False, deleted_file_ids: Sequence[int] = (),
-                     rows_per_page: int = 0, rows_per_row_group: int = 0, dictionary: bool = True
-                     ) -> Tuple[IndexResult, Dict[str, float]]:
-        L = load_library()
-        src, keep = _source_array(files)
-        ic, nc = _cstr_array(indexed), _cstr_array(included)
-        spec = IndexSpec()
-        spec.files, spec.n_files = src, len(files)
-        spec.indexed_columns, spec.n_indexed = ic, len(indexed)
-        spec.included_columns, spec.n_included = nc, len(included)
-        spec.num_buckets, spec.save_mode, spec.output, spec.lineage = num_buckets, save_mode, output, 1 if lineage else 0
-        spec.out_dir = out_dir.encode() if out_dir else None
-        spec.job_uuid = job_uuid.encode() if job_uuid else None
-        spec.rows_per_page, spec.rows_per_row_group = rows_per_page, rows_per_row_group
-        dl = (C.c_int64 * max(1, len(deleted_file_ids)))(*deleted_file_ids)
-        spec.deleted_file_ids, spec.n_deleted_file_ids = dl, len(deleted_file_ids)
-        spec.disable_dictionary = 0 if dictionary else 1
+                     **kw) -> Tuple[IndexResult, Dict[str, float]]:
+        """hs_create_index.  Keywords: out_dir, output (HS_OUT_*), job_uuid, save_mode, lineage, deleted_file_ids,
+        rows_per_page, rows_per_row_group, dictionary, compression (HS_CODEC_*)."""
+        spec, keep = self._index_spec(files, indexed, included, num_buckets, **kw)
         res, st = C.c_void_p(), Stats()
         err = C.create_string_buffer(1024)
-        _check(L.hs_create_index(self._h, C.byref(spec), C.byref(res), C.byref(st), err, len(err)), err)
-        return IndexResult(self, res.value, output), st.as_dict()
+        _check(load_library().hs_create_index(self._h, C.byref(spec), C.byref(res), C.byref(st), err, len(err)), err)
+        return IndexResult(self, res.value, spec.output), st.as_dict()
 
     def synth_table(self, first_row: int, nrows: int, ncols: int = 5, n_files: int = 1, row_groups_per_file: int = 1,
-                    output: int = HS_OUT_HOST, dictionary: bool = True) -> IndexResult:
+                    output: int = HS_OUT_HOST, dictionary: bool = True, compression: int = HS_CODEC_UNCOMPRESSED) -> IndexResult:
         L = load_library()
         res = C.c_void_p()
         err = C.create_string_buffer(1024)
-        _check(L.hs_synth_table(self._h, first_row, nrows, ncols, n_files, row_groups_per_file, 1 if dictionary else 0, output,
-                                C.byref(res), err, len(err)), err)
+        _check(L.hs_synth_table_ex(self._h, first_row, nrows, ncols, n_files, row_groups_per_file, 1 if dictionary else 0,
+                                   compression, output, C.byref(res), err, len(err)), err)
         return IndexResult(self, res.value, output)
+
+    def k_snappy_compress(self, data: bytes) -> bytes:
+        """The GPU page compressor on a host buffer (parity tests: any Snappy decoder must give `data` back)."""
+        cap = 64 + len(data) + len(data) // 5
+        out = C.create_string_buffer(cap)
+        n = C.c_uint64(0)
+        err = C.create_string_buffer(1024)
+        _check(load_library().hs_k_snappy_compress(self._h, data, len(data), out, cap, C.byref(n), err, len(err)), err)
+        return out.raw[:n.value]
 
     # ---- read side ----------------------------------------------------------------------------------
     def filter_scan(self, files: Sequence[FileImage], key: str, projected: Sequence[str], lo: Optional[int] = None,

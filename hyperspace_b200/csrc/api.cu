@@ -544,13 +544,16 @@ int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** o
       req.rows_per_page = spec->rows_per_page;
       req.rows_per_row_group = spec->rows_per_row_group;
       req.use_dictionary = spec->disable_dictionary == 0;
+      if (spec->compression != HS_CODEC_UNCOMPRESSED && spec->compression != HS_CODEC_SNAPPY)
+        fail(HS_EUNSUPPORTED, "compression codec %d; the GPU path writes UNCOMPRESSED and SNAPPY pages", spec->compression);
+      req.codec = spec->compression == HS_CODEC_SNAPPY ? pq::SNAPPY : pq::UNCOMPRESSED;
       const std::string uuid = spec->job_uuid ? spec->job_uuid : make_uuid();
       req.seg_names.resize(spec->num_buckets);
       for (int b = 0; b < spec->num_buckets; b++) {
         // Spark FileFormatWriter: part-<task>-<jobUUID>_<bucket>.c000<codec ext>.parquet ; bucket id parsed back by
         // BucketingUtils.getBucketId (relied on by actions/OptimizeAction.scala:110)
         char nm[160];
-        snprintf(nm, sizeof nm, "part-%05d-%s_%05d.c000.parquet", b, uuid.c_str(), b);
+        snprintf(nm, sizeof nm, "part-%05d-%s_%05d.c000%s.parquet", b, uuid.c_str(), b, req.codec == pq::SNAPPY ? ".snappy" : "");
         req.seg_names[b] = nm;
       }
       encode_segments(ctx, req, &enc, &st);  // synchronises the stream before it returns
@@ -1109,6 +1112,53 @@ int hs_k_sort_perm(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64
 int hs_synth_table(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, int32_t n_files,
                    int32_t row_groups_per_file, int32_t dictionary, int32_t output, hs_index_result** out, char* err,
                    size_t errlen) {
+  return hs_synth_table_ex(ctx, first_row, nrows, ncols, n_files, row_groups_per_file, dictionary, HS_CODEC_UNCOMPRESSED, output, out,
+                           err, errlen);
+}
+
+int hs_k_snappy_compress(hs_ctx* ctx, const void* in, uint64_t n, void* out_buf, uint64_t cap, uint64_t* out_len, char* err,
+                         size_t errlen) {
+  if (!ctx || !out_len || (n && !in)) return HS_EINVAL;
+  return guarded(ctx, err, errlen, [&] {
+    std::vector<SnappyFragment> frags;
+    uint64_t slot = 0;
+    for (uint64_t o = 0; o < n; o += kSnappyFragment) {
+      const uint32_t len = (uint32_t)std::min<uint64_t>(kSnappyFragment, n - o);
+      frags.push_back(SnappyFragment{o, slot, len, 0});
+      slot += round_up(snappy_max_compressed(len), 16);
+    }
+    Buf<uint8_t> d_in(ctx, std::max<uint64_t>(n, 16) + 16), d_slots(ctx, std::max<uint64_t>(slot, 16));
+    Buf<SnappyFragment> d_frags(ctx, std::max<size_t>(1, frags.size()));
+    Buf<uint32_t> d_len(ctx, std::max<size_t>(1, frags.size()));
+    std::vector<uint32_t> lens(frags.size());
+    if (n) copy_h2d(ctx, d_in.get(), in, n);
+    copy_h2d(ctx, d_frags.get(), frags.data(), sizeof(SnappyFragment) * frags.size());
+    launch_snappy_compress(ctx, d_frags.get(), (int64_t)frags.size(), d_in.get(), d_slots.get(), d_len.get());
+    copy_d2h(ctx, lens.data(), d_len.get(), 4 * frags.size());
+    sync_stream(ctx);
+    std::vector<uint8_t> stream;
+    for (uint64_t v = n;; v >>= 7) {  // preamble: the uncompressed length
+      if (v >= 0x80) stream.push_back((uint8_t)(v | 0x80));
+      else {
+        stream.push_back((uint8_t)v);
+        break;
+      }
+    }
+    std::vector<uint8_t> piece;
+    for (size_t f = 0; f < frags.size(); f++) {
+      piece.resize(lens[f]);
+      HS_CUDA(cudaMemcpy(piece.data(), d_slots.get() + frags[f].dst_off, lens[f], cudaMemcpyDeviceToHost));
+      stream.insert(stream.end(), piece.begin(), piece.end());
+    }
+    *out_len = stream.size();
+    if (stream.size() > cap) fail(HS_ENOMEM, "output buffer too small: %zu bytes needed", stream.size());
+    if (out_buf) memcpy(out_buf, stream.data(), stream.size());
+  });
+}
+
+int hs_synth_table_ex(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, int32_t n_files,
+                      int32_t row_groups_per_file, int32_t dictionary, int32_t compression, int32_t output,
+                      hs_index_result** out, char* err, size_t errlen) {
   if (!ctx || !out) return HS_EINVAL;
   *out = nullptr;
   std::unique_ptr<hs_index_result> res(new hs_index_result());
@@ -1148,6 +1198,8 @@ int hs_synth_table(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols,
     req.seg_offsets = seg;
     req.rows_per_page = P;
     req.use_dictionary = dictionary != 0;
+    if (compression != HS_CODEC_UNCOMPRESSED && compression != HS_CODEC_SNAPPY) fail(HS_EUNSUPPORTED, "compression codec %d", compression);
+    req.codec = compression == HS_CODEC_SNAPPY ? pq::SNAPPY : pq::UNCOMPRESSED;
     req.rows_per_row_group = std::max<int64_t>(P, (int64_t)round_up((size_t)ceil_div(per_file, row_groups_per_file), (size_t)P));
     req.seg_names.resize(n_files);
     for (int f = 0; f < n_files; f++) {

@@ -1191,6 +1191,27 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
   std::vector<StatPatch> stat_patches;
   std::vector<uint8_t> skeleton;
   std::vector<ByteCopy> copies;
+  // every page of every file, in file order (needed only when the pages are compressed afterwards)
+  struct PagePlan {
+    uint64_t hdr_off;   // arena offset of the page header
+    uint32_t hdr_len;   // Thrift header bytes
+    uint32_t body_len;  // page bytes behind the header
+  };
+  struct FilePlan {
+    int seg = 0;
+    int64_t rows = 0;
+    std::vector<pq::OutRowGroup> rgs;
+    std::vector<std::pair<size_t, size_t>> chunk_pages;  // per (row group, column): first page, page count
+  };
+  const bool compress = req.codec == pq::SNAPPY;
+  std::vector<PagePlan> page_plans;
+  std::vector<FilePlan> file_plans;
+  auto header_len_at = [&](size_t skel_pos) -> uint32_t {  // length of the Thrift struct (page header) that starts there
+    thrift::Reader r(skeleton.data() + skel_pos, skeleton.data() + skeleton.size());
+    r.skip(thrift::T_STRUCT);
+    if (r.bad) fail(HS_EINVAL, "internal: page header does not parse");
+    return (uint32_t)(r.p - (skeleton.data() + skel_pos));
+  };
   std::vector<uint32_t> seg_page_begin(nseg + 1, 0);
   std::vector<std::vector<uint64_t>> page_value_offset(ncols);
   uint64_t cursor = 0;
@@ -1247,16 +1268,22 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         // GPU after the sort); this is what lets a Spark reader prune row groups on the key
         ch.has_minmax = stats_on_key && c == 0;
         const uint64_t chunk_begin = cursor;
+        const size_t chunk_first_page = page_plans.size();
         if (dicts[c].use) {  // every chunk of the column carries the same (global) dictionary page
           ch.has_dictionary = true;
           ch.dictionary_page_offset = (int64_t)(cursor - file_off);
           copies.push_back(ByteCopy{cursor, (uint32_t)dicts[c].skel_off, (uint32_t)dicts[c].skel_len});
+          if (compress) {
+            const uint32_t hl = header_len_at(dicts[c].skel_off);
+            page_plans.push_back(PagePlan{cursor, hl, (uint32_t)(dicts[c].skel_len - hl)});
+          }
           cursor += dicts[c].skel_len;
           ch.data_page_offset = (int64_t)(cursor - file_off);
         }
         for (int64_t p0 = r0; p0 < r1; p0 += P) {
           const int64_t np = std::min(P, r1 - p0);
           const size_t b = skeleton.size();
+          const uint64_t page_begin = cursor;
           if (dicts[c].use) {
             pq::write_dict_data_page_prefix(skeleton, np, dicts[c].bw);
             emit(cursor, b);
@@ -1313,9 +1340,21 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
             cursor += (uint64_t)non_null * W;
             ch.null_count += np - non_null;
           }
+          if (compress) {
+            const uint32_t hl = header_len_at(b);
+            page_plans.push_back(PagePlan{page_begin, hl, (uint32_t)(cursor - page_begin - hl)});
+          }
         }
         ch.total_size = (int64_t)(cursor - chunk_begin);
         g.chunks.push_back(ch);
+        if (compress) {
+          if (file_plans.empty() || file_plans.back().seg != s) {
+            file_plans.emplace_back();
+            file_plans.back().seg = s;
+            file_plans.back().rows = n;
+          }
+          file_plans.back().chunk_pages.emplace_back(chunk_first_page, page_plans.size() - chunk_first_page);
+        }
       }
       g.total_byte_size = (int64_t)(cursor - rg_begin);
       rgs.push_back(std::move(g));
@@ -1338,6 +1377,7 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
         sp.pad = 0;
         stat_patches.push_back(sp);
       }
+      if (compress) file_plans.back().rgs = rgs;
       skeleton.insert(skeleton.end(), footer.begin(), footer.end());
       uint32_t flen = (uint32_t)footer.size();
       const uint8_t* lp = (const uint8_t*)&flen;
@@ -1453,6 +1493,179 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       launch_dict_encode_all(ctx, req.plan->tiles.get(), ntiles, req.plan->seg_start.get(), req.d_perm, ma, pa, table.nrows,
                              kDictCapacity, rec.get(), d_page_begin.get(), P, out->arena.get());
     }
+  }
+  // ---- SNAPPY: the pages just written are compressed and the files laid out again ------------------------------------------
+  // Compressed sizes are data: the files cannot be laid out before the pages exist.  So the uncompressed images above serve
+  // as the compressor's input; every page body is cut into 64 KB fragments that compress in parallel into worst-case sized
+  // slots; their lengths come back to the host, which lays the files out again (new page headers, new footers, the codec in
+  // every chunk) and a copy kernel moves the fragments into place.
+  if (compress && !page_plans.empty()) {
+    std::vector<SnappyFragment> frags;
+    std::vector<size_t> page_first_frag(page_plans.size() + 1, 0);
+    uint64_t slot_cursor = 0;
+    for (size_t i = 0; i < page_plans.size(); i++) {
+      page_first_frag[i] = frags.size();
+      const PagePlan& pp = page_plans[i];
+      for (uint32_t o = 0; o < pp.body_len; o += kSnappyFragment) {
+        const uint32_t len = std::min<uint32_t>(kSnappyFragment, pp.body_len - o);
+        frags.push_back(SnappyFragment{pp.hdr_off + pp.hdr_len + o, slot_cursor, len, 0});
+        slot_cursor += round_up(snappy_max_compressed(len), 16);
+      }
+    }
+    page_first_frag[page_plans.size()] = frags.size();
+    Buf<uint8_t> d_slots(ctx, std::max<uint64_t>(slot_cursor, 16));
+    Buf<SnappyFragment> d_frags(ctx, std::max<size_t>(1, frags.size()));
+    Buf<uint32_t> d_flen(ctx, std::max<size_t>(1, frags.size()));
+    std::vector<uint32_t> flen(frags.size());
+    copy_h2d(ctx, d_frags.get(), frags.data(), sizeof(SnappyFragment) * frags.size());
+    launch_snappy_compress(ctx, d_frags.get(), (int64_t)frags.size(), out->arena.get(), d_slots.get(), d_flen.get());
+    copy_d2h(ctx, flen.data(), d_flen.get(), 4 * frags.size());
+    sync_stream(ctx);
+    // second layout
+    std::vector<uint8_t> skel2;
+    std::vector<ByteCopy> copies2;
+    std::vector<BlobCopy> blobs;
+    std::vector<StatPatch> patches2;
+    uint64_t cur2 = 0;
+    auto emit2 = [&](size_t skel_begin) {
+      copies2.push_back(ByteCopy{cur2, (uint32_t)skel_begin, (uint32_t)(skel2.size() - skel_begin)});
+      cur2 += skel2.size() - skel_begin;
+    };
+    // header fields by destination offset
+    std::map<uint64_t, size_t> skel_at;  // arena offset -> skeleton position of the bytes copied there
+    for (const ByteCopy& bc : copies) skel_at[bc.dst] = bc.src;
+    size_t page_i = 0;
+    std::vector<OutFile> files2;
+    for (size_t fi = 0; fi < file_plans.size(); fi++) {
+      FilePlan& fp = file_plans[fi];
+      const uint64_t file_off = round_up(cur2, 64);
+      cur2 = file_off;
+      {
+        const size_t b0 = skel2.size();
+        skel2.insert(skel2.end(), {'P', 'A', 'R', '1'});
+        emit2(b0);
+      }
+      size_t chunk_i = 0;
+      for (pq::OutRowGroup& g : fp.rgs) {
+        g.file_offset = (int64_t)(cur2 - file_off);
+        int64_t rg_comp = 0, rg_uncomp = 0;
+        for (pq::OutChunk& ch : g.chunks) {
+          const auto range = fp.chunk_pages[chunk_i++];
+          const uint64_t chunk_begin = cur2;
+          int64_t uncomp = 0;
+          bool first_data = true;
+          for (size_t pi = range.first; pi < range.first + range.second; pi++, page_i++) {
+            const PagePlan& pp = page_plans[pi];
+            // parse the first layout's header of this page
+            auto it = skel_at.find(pp.hdr_off);
+            if (it == skel_at.end()) fail(HS_EINVAL, "internal: page header not found in the layout");
+            thrift::Reader r(skeleton.data() + it->second, skeleton.data() + it->second + pp.hdr_len);
+            int32_t ptype = -1, nvals = 0, enc = 0;
+            int16_t fid = 0;
+            for (;;) {
+              const uint8_t t = r.field(fid);
+              if (r.bad || t == thrift::T_STOP) break;
+              if (fid == 1) ptype = (int32_t)r.zigzag();
+              else if (fid == 5 || fid == 7) {
+                int16_t f2 = 0;
+                for (;;) {
+                  const uint8_t t2 = r.field(f2);
+                  if (r.bad || t2 == thrift::T_STOP) break;
+                  if (f2 == 1) nvals = (int32_t)r.zigzag();
+                  else if (f2 == 2) enc = (int32_t)r.zigzag();
+                  else r.skip(t2);
+                }
+              } else r.skip(t);
+            }
+            // compressed body = varint(uncompressed length) + the fragments' element streams
+            uint8_t pre[5];
+            int pl = 0;
+            for (uint32_t v = pp.body_len;; v >>= 7) {
+              if (v >= 0x80) pre[pl++] = (uint8_t)(v | 0x80);
+              else {
+                pre[pl++] = (uint8_t)v;
+                break;
+              }
+            }
+            uint64_t comp = (uint64_t)pl;
+            for (size_t f = page_first_frag[pi]; f < page_first_frag[pi + 1]; f++) comp += flen[f];
+            if (comp >= (1ull << 31)) fail(HS_EUNSUPPORTED, "a compressed page exceeds 2 GiB");
+            const size_t b0 = skel2.size();
+            if (ptype == pq::DICTIONARY_PAGE) {
+              ch.dictionary_page_offset = (int64_t)(cur2 - file_off);
+              pq::write_dict_page_header(skel2, (int32_t)pp.body_len, nvals, (int32_t)comp);
+            } else {
+              if (first_data) ch.data_page_offset = (int64_t)(cur2 - file_off);
+              first_data = false;
+              pq::write_data_page_header(skel2, (int32_t)pp.body_len, nvals, enc, (int32_t)comp);
+            }
+            uncomp += (int64_t)(skel2.size() - b0) + pp.body_len;
+            skel2.insert(skel2.end(), pre, pre + pl);
+            emit2(b0);
+            for (size_t f = page_first_frag[pi]; f < page_first_frag[pi + 1]; f++) {
+              blobs.push_back(BlobCopy{frags[f].dst_off, cur2, flen[f], 0});
+              cur2 += flen[f];
+            }
+          }
+          ch.total_size = (int64_t)(cur2 - chunk_begin);
+          ch.total_uncompressed = uncomp;
+          ch.codec = pq::SNAPPY;
+          rg_comp += ch.total_size;
+          rg_uncomp += uncomp;
+        }
+        g.total_byte_size = rg_uncomp;
+        g.total_compressed = rg_comp;
+      }
+      {
+        const size_t b0 = skel2.size();
+        std::vector<pq::StatSlot> slots;
+        std::vector<uint8_t> footer = pq::write_footer(schema, fp.rgs, fp.rows, schema_json, &slots);
+        for (const pq::StatSlot& sl : slots) {
+          StatPatch sp;
+          int64_t row0 = 0;
+          for (int g = 0; g < sl.row_group; g++) row0 += fp.rgs[g].num_rows;
+          sp.first_pos = req.seg_offsets[fp.seg] + (uint64_t)row0;
+          sp.last_pos = sp.first_pos + (uint64_t)fp.rgs[sl.row_group].num_rows - 1;
+          for (int j = 0; j < 2; j++) {
+            sp.min_off[j] = cur2 + sl.min_off[j];
+            sp.max_off[j] = cur2 + sl.max_off[j];
+          }
+          sp.width = sl.width;
+          sp.pad = 0;
+          patches2.push_back(sp);
+        }
+        skel2.insert(skel2.end(), footer.begin(), footer.end());
+        const uint32_t flen32 = (uint32_t)footer.size();
+        const uint8_t* lp = (const uint8_t*)&flen32;
+        skel2.insert(skel2.end(), lp, lp + 4);
+        skel2.insert(skel2.end(), {'P', 'A', 'R', '1'});
+        emit2(b0);
+      }
+      OutFile of = out->files[fi];
+      of.offset = file_off;
+      of.size = cur2 - file_off;
+      files2.push_back(std::move(of));
+    }
+    if (skel2.size() >= (1ull << 32)) fail(HS_EUNSUPPORTED, "index metadata exceeds 4 GiB");
+    Buf<uint8_t> arena2(ctx, std::max<uint64_t>(cur2, 16) + 64);
+    Buf<uint8_t> d_skel2(ctx, std::max<size_t>(1, skel2.size()));
+    Buf<ByteCopy> d_copies2(ctx, std::max<size_t>(1, copies2.size()));
+    Buf<BlobCopy> d_blobs(ctx, std::max<size_t>(1, blobs.size()));
+    copy_h2d(ctx, d_skel2.get(), skel2.data(), skel2.size());
+    copy_h2d(ctx, d_copies2.get(), copies2.data(), copies2.size() * sizeof(ByteCopy));
+    copy_h2d(ctx, d_blobs.get(), blobs.data(), blobs.size() * sizeof(BlobCopy));
+    launch_scatter_bytes(ctx, d_copies2.get(), (int64_t)copies2.size(), d_skel2.get(), arena2.get());
+    launch_copy_blobs(ctx, d_blobs.get(), (int64_t)blobs.size(), d_slots.get(), arena2.get());
+    if (!patches2.empty()) {
+      Buf<StatPatch> d_sp(ctx, patches2.size());
+      copy_h2d(ctx, d_sp.get(), patches2.data(), sizeof(StatPatch) * patches2.size());
+      launch_patch_key_stats(ctx, d_sp.get(), (int64_t)patches2.size(), req.d_sorted_keys, table.cols[0].type, arena2.get());
+    }
+    sync_stream(ctx);  // (large plan arrays may have gone through cudaMemcpyAsync: keep them alive until here)
+    out->arena = std::move(arena2);
+    out->arena_bytes = cur2;
+    out->files = std::move(files2);
+    cursor = cur2;
   }
   t_enc.stop();
   sync_stream(ctx);  // host plan vectors are about to go out of scope

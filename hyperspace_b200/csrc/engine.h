@@ -135,6 +135,7 @@ struct EncodeRequest {
   int64_t rows_per_row_group = 0;
   std::vector<int64_t> seg_rows_per_row_group;  // optional per-segment override
   bool use_dictionary = true;                   // dictionary-encode columns whose distinct values fit (like parquet-mr)
+  int codec = 0;                                // pq::Codec of the written pages: UNCOMPRESSED or SNAPPY (Spark's default)
 };
 struct EncodedFiles {
   Buf<uint8_t> arena;       // device

@@ -251,6 +251,22 @@ __global__ void k_scatter_bytes(const ByteCopy* __restrict__ copies, int64_t n, 
   for (uint32_t i = lane; i < c.len; i += 32) arena[c.dst + i] = skeleton[c.src + i];
 }
 
+__global__ void __launch_bounds__(256) k_copy_blobs(const BlobCopy* __restrict__ blobs, const uint8_t* __restrict__ src_base,
+                                                     uint8_t* __restrict__ dst_base) {
+  const BlobCopy b = blobs[blockIdx.x];
+  const uint8_t* src = src_base + b.src;
+  uint8_t* dst = dst_base + b.dst;
+  // bytes up to the destination's first 4-byte boundary, then whole words assembled from the two aligned source words
+  // around them, then the tail
+  const uint32_t head = min(b.len, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+  for (uint32_t i = threadIdx.x; i < head; i += 256) dst[i] = src[i];
+  const uint32_t nwords = (b.len - head) / 4;
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + head);
+  const uint8_t* s0 = src + head;
+  for (uint32_t w = threadIdx.x; w < nwords; w += 256) d32[w] = load_le32_unaligned(s0 + 4 * (size_t)w);
+  for (uint32_t i = head + 4 * nwords + threadIdx.x; i < b.len; i += 256) dst[i] = src[i];
+}
+
 // min / max statistics of the (sorted) indexed column: first and last key of every row group, written over the
 // placeholders the host left in the footer
 __global__ void k_patch_key_stats(const StatPatch* __restrict__ patches, int64_t n, const uint64_t* __restrict__ sorted_keys,
@@ -353,6 +369,13 @@ void launch_gather_encode_strings(hs_ctx* ctx, const SortTile* tiles, int64_t nt
   if (ntiles == 0) return;
   k_gather_encode_strings<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(tiles, perm, refs, valid, tile_value_offset,
                                                                           tile_def_offset, arena);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_copy_blobs(hs_ctx* ctx, const BlobCopy* blobs, int64_t n, const uint8_t* src_base, uint8_t* dst_base) {
+  KernelScope _ks(ctx, "k_copy_blobs");
+  if (n == 0) return;
+  k_copy_blobs<<<(unsigned)n, 256, 0, ctx->stream>>>(blobs, src_base, dst_base);
   HS_LAUNCH_CHECK(ctx);
 }
 

@@ -97,6 +97,17 @@ struct SnappyBlob {
 };
 void launch_snappy_decompress(hs_ctx* ctx, const SnappyBlob* blobs, int64_t n, uint8_t* scratch, uint32_t* d_error);
 
+// compression of page bodies: one warp per fragment (<= 65536 bytes) of a page; fragment f of raw bytes [src_off, src_off +
+// len) is written to scratch at dst_off (room for 32 + len + len / 6 bytes), its compressed length to out_len[f]
+struct SnappyFragment {
+  uint64_t src_off, dst_off;
+  uint32_t len, pad;
+};
+constexpr uint32_t kSnappyFragment = 65536;
+inline uint64_t snappy_max_compressed(uint64_t len) { return 32 + len + len / 6; }
+void launch_snappy_compress(hs_ctx* ctx, const SnappyFragment* frags, int64_t n, const uint8_t* raw, uint8_t* scratch,
+                            uint32_t* out_len);
+
 // Walks the page headers of every chunk.  mode 0: page_counts[chunk] = number of data pages.
 // mode 1: fills pages[page_offsets[chunk] ...].
 void launch_walk_pages(hs_ctx* ctx, const ChunkDesc* chunks, int n_chunks, int32_t* page_counts,
@@ -301,6 +312,12 @@ struct ByteCopy {
   uint32_t len;
 };
 void launch_scatter_bytes(hs_ctx* ctx, const ByteCopy* copies, int64_t n, const uint8_t* skeleton, uint8_t* arena);
+// larger pieces at any alignment (compressed page fragments moving into their place in the file): one CTA per blob
+struct BlobCopy {
+  uint64_t src, dst;  // byte offsets into src_base / dst_base
+  uint32_t len, pad;
+};
+void launch_copy_blobs(hs_ctx* ctx, const BlobCopy* blobs, int64_t n, const uint8_t* src_base, uint8_t* dst_base);
 // Synthetic table generator: rows [first_row, first_row+n) of column `col` (0..4) of table T
 void launch_synth_column(hs_ctx* ctx, int col, int64_t first_row, int64_t n, void* out);
 

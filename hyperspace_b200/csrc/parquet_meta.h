@@ -220,12 +220,14 @@ inline FileMeta parse_footer(const uint8_t* file, uint64_t size, const char* wha
 // ---- writing ---------------------------------------------------------------------------------------------
 
 // v1 data page header for `num_values` values: PLAIN (or dictionary) values, RLE definition levels.
-inline void write_data_page_header(std::vector<uint8_t>& out, int32_t page_bytes, int32_t num_values, int32_t encoding) {
+// compressed_bytes < 0: the page is stored as it is (compressed size == uncompressed size)
+inline void write_data_page_header(std::vector<uint8_t>& out, int32_t page_bytes, int32_t num_values, int32_t encoding,
+                                   int32_t compressed_bytes = -1) {
   thrift::Writer w;
   w.struct_begin();
   w.f_i32(1, DATA_PAGE);
   w.f_i32(2, page_bytes);
-  w.f_i32(3, page_bytes);
+  w.f_i32(3, compressed_bytes < 0 ? page_bytes : compressed_bytes);
   w.f_struct_begin(5);
   w.f_i32(1, num_values);
   w.f_i32(2, encoding);
@@ -236,12 +238,12 @@ inline void write_data_page_header(std::vector<uint8_t>& out, int32_t page_bytes
   out.insert(out.end(), w.buf.begin(), w.buf.end());
 }
 
-inline void write_dict_page_header(std::vector<uint8_t>& out, int32_t page_bytes, int32_t num_values) {
+inline void write_dict_page_header(std::vector<uint8_t>& out, int32_t page_bytes, int32_t num_values, int32_t compressed_bytes = -1) {
   thrift::Writer w;
   w.struct_begin();
   w.f_i32(1, DICTIONARY_PAGE);
   w.f_i32(2, page_bytes);
-  w.f_i32(3, page_bytes);
+  w.f_i32(3, compressed_bytes < 0 ? page_bytes : compressed_bytes);
   w.f_struct_begin(7);
   w.f_i32(1, num_values);
   w.f_i32(2, ENC_PLAIN_DICTIONARY);
@@ -407,7 +409,9 @@ inline void write_dict_data_page_prefix(std::vector<uint8_t>& real_out, int64_t 
 struct OutChunk {
   int32_t type;
   int64_t num_values;
-  int64_t total_size;       // bytes of all pages incl. headers
+  int64_t total_size;       // bytes of all pages incl. headers, as stored (compressed)
+  int64_t total_uncompressed = -1;  // the same with every page uncompressed (-1: equal to total_size)
+  int32_t codec = UNCOMPRESSED;
   int64_t data_page_offset; // absolute file offset of the first data page header
   int64_t dictionary_page_offset = -1;
   bool has_dictionary = false;
@@ -419,7 +423,8 @@ struct OutChunk {
 
 struct OutRowGroup {
   int64_t num_rows;
-  int64_t total_byte_size;
+  int64_t total_byte_size;        // uncompressed
+  int64_t total_compressed = -1;  // -1: equal to total_byte_size
   int64_t file_offset;
   std::vector<OutChunk> chunks;
 };
@@ -478,9 +483,9 @@ inline std::vector<uint8_t> write_footer(const std::vector<SchemaColumn>& cols, 
       }
       w.f_list_begin(3, thrift::T_BINARY, 1);
       w.string_elem(cols[ci].name);
-      w.f_i32(4, UNCOMPRESSED);
+      w.f_i32(4, ch.codec);
       w.f_i64(5, ch.num_values);
-      w.f_i64(6, ch.total_size);
+      w.f_i64(6, ch.total_uncompressed >= 0 ? ch.total_uncompressed : ch.total_size);
       w.f_i64(7, ch.total_size);
       w.f_i64(9, ch.data_page_offset);
       if (ch.has_dictionary) w.f_i64(11, ch.dictionary_page_offset);
@@ -508,7 +513,7 @@ inline std::vector<uint8_t> write_footer(const std::vector<SchemaColumn>& cols, 
     w.f_i64(2, g.total_byte_size);
     w.f_i64(3, g.num_rows);
     w.f_i64(5, g.file_offset);
-    w.f_i64(6, g.total_byte_size);
+    w.f_i64(6, g.total_compressed >= 0 ? g.total_compressed : g.total_byte_size);
     w.struct_end();
   }
   w.f_list_begin(5, thrift::T_STRUCT, 2);

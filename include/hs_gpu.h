@@ -48,7 +48,8 @@ extern "C" {
 #define HS_TYPE_FLOAT 2
 #define HS_TYPE_DOUBLE 3
 #define HS_TYPE_BOOL 4
-#define HS_TYPE_STRING 5 /* BYTE_ARRAY; not yet supported on the GPU path -> HS_EUNSUPPORTED */
+#define HS_TYPE_STRING 5 /* BYTE_ARRAY (Spark string / binary): write path (keys and included columns, one GPU); the index
+                            scans and joins do not read it yet -> HS_EUNSUPPORTED */
 
 typedef struct hs_ctx hs_ctx;
 typedef struct hs_index_result hs_index_result;
@@ -104,6 +105,9 @@ typedef struct {
 #define HS_SAVE_OVERWRITE 0 /* create / refresh full / optimize  (covering/CoveringIndexTrait.scala:45-47) */
 #define HS_SAVE_APPEND 1    /* incremental refresh into an existing version dir (CoveringIndexTrait.scala:87-93) */
 
+#define HS_CODEC_UNCOMPRESSED 0
+#define HS_CODEC_SNAPPY 1
+
 #define HS_OUT_FILES 0  /* write <out_dir>/part-<bbbbb>-<uuid>_<bbbbb>.c000.parquet (the reference's effect) */
 #define HS_OUT_HOST 1   /* keep the bucket file images in pinned host memory owned by the result handle */
 #define HS_OUT_DEVICE 2 /* keep the bucket file images in device memory owned by the result handle */
@@ -129,6 +133,9 @@ typedef struct {
   int32_t n_deleted_file_ids;
   int32_t disable_dictionary; /* 0 (default): dictionary-encode columns whose distinct values fit a dictionary page, as
                                  parquet-mr does; != 0: PLAIN only */
+  int32_t compression;        /* HS_CODEC_*: codec of the index pages.  HS_CODEC_SNAPPY is what Spark writes by default
+                                 (files are then named ...c000.snappy.parquet, T/index/VacuumOutdatedActionTest.scala:67) */
+  int32_t reserved;
 } hs_index_spec;
 
 typedef struct {
@@ -296,6 +303,14 @@ int hs_k_sort_perm(hs_ctx* ctx, const hs_host_column* keys, int32_t nkeys, int64
 int hs_synth_table(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, int32_t n_files,
                    int32_t row_groups_per_file, int32_t dictionary, int32_t output, hs_index_result** out, char* err,
                    size_t errlen);
+/* the same with a page codec (HS_CODEC_*): the SNAPPY variant of T that SURVEY.md 8d asks for */
+int hs_synth_table_ex(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, int32_t n_files,
+                      int32_t row_groups_per_file, int32_t dictionary, int32_t compression, int32_t output,
+                      hs_index_result** out, char* err, size_t errlen);
+/* Snappy-compresses n bytes of host memory on the GPU (the page compressor, fragment by fragment) into out (capacity cap);
+ * kernel-level entry point for the parity tests: any Snappy decoder must give the input back. */
+int hs_k_snappy_compress(hs_ctx* ctx, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* out_len, char* err,
+                         size_t errlen);
 
 #ifdef __cplusplus
 }
