@@ -263,10 +263,72 @@ def run_refresh(rig, args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# SNAPPY variants of the createIndex workload ("two variants: UNCOMPRESSED and SNAPPY (Spark's default)")
+# ---------------------------------------------------------------------------------------------------------------------
+
+def run_snappy(rig, args):
+    N, ctx = rig.N, rig.ctx
+    fr, my_rows, my_files = _my_share(rig, 0, args.rows // args.files * args.files, args.files)
+    total_rows = args.rows // args.files * args.files
+    inc = ["v1", "v2", "v3", "v4"]
+    out = {}
+
+    def timed_builds(sources, **kw):
+        def one():
+            res, st = ctx.create_index(sources, ["k"], inc, NB, output=N.HS_OUT_DEVICE, job_uuid="z", **kw)
+            nbytes = sum(f.size for f in res.files)
+            res.free()
+            return st, nbytes
+        one()
+        one()
+        ctx.profile_enable(True)
+        acc = [None, 0]
+
+        def loop():
+            for _ in range(3):
+                acc[0], acc[1] = one()
+        ms, _ = rig.timed(loop)
+        kernels = ctx.profile_report()
+        ctx.profile_enable(False)
+        return ms / 3, {k: v["ms"] / 3 for k, v in kernels.items()}, acc[1]
+
+    usrc = ctx.synth_table(fr, my_rows, 5, n_files=max(1, my_files), row_groups_per_file=4, output=N.HS_OUT_DEVICE)
+    ms_u, k_u, bytes_u = timed_builds(usrc.as_sources())
+    ms_o, k_o, bytes_o = timed_builds(usrc.as_sources(), compression=N.HS_CODEC_SNAPPY)
+    src_bytes_u = sum(f.size for f in usrc.files)
+    usrc.free()
+    ctx.trim()
+    ssrc = ctx.synth_table(fr, my_rows, 5, n_files=max(1, my_files), row_groups_per_file=4, output=N.HS_OUT_DEVICE,
+                           compression=N.HS_CODEC_SNAPPY)
+    src_bytes_s = sum(f.size for f in ssrc.files)
+    ms_s, k_s, _ = timed_builds(ssrc.as_sources())
+    ssrc.free()
+    ctx.trim()
+    dec_ms = k_s.get("k_snappy_decompress", 0.0)
+    comp_ms = k_o.get("k_snappy_compress", 0.0)
+    out = {
+        "workload": f"createIndex over {total_rows} rows of T: UNCOMPRESSED source and index (reference point), SNAPPY index, SNAPPY source; "
+                    f"{rig.world} GPU(s), images resident in HBM",
+        "uncompressed": {"rows_per_s": total_rows / (ms_u / 1e3), "ms": ms_u},
+        "snappy_index": {"rows_per_s": total_rows / (ms_o / 1e3), "ms": ms_o, "relative": ms_u / ms_o,
+                         "index_bytes_per_rank": bytes_o, "uncompressed_index_bytes_per_rank": bytes_u,
+                         "k_snappy_compress_ms": comp_ms,
+                         "compress_GBps_per_gpu": (bytes_u / (comp_ms / 1e3) / 1e9) if comp_ms else None,
+                         "compress_frac_of_hbm_peak": (2 * bytes_u / (comp_ms / 1e3) / 1e9 / _peak()) if comp_ms else None},
+        "snappy_source": {"rows_per_s": total_rows / (ms_s / 1e3), "ms": ms_s, "relative": ms_u / ms_s,
+                          "source_bytes_per_rank": src_bytes_s, "uncompressed_source_bytes_per_rank": src_bytes_u,
+                          "k_snappy_decompress_ms": dec_ms,
+                          "decompress_GBps_per_gpu": (src_bytes_u / (dec_ms / 1e3) / 1e9) if dec_ms else None,
+                          "decompress_frac_of_hbm_peak": ((src_bytes_s + src_bytes_u) / (dec_ms / 1e3) / 1e9 / _peak()) if dec_ms else None},
+    }
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 
 def run_all(rig, args):
     out = {}
-    for name, fn in (("filter_C3", run_filter), ("join_C4", run_join), ("refresh_C5", run_refresh)):
+    for name, fn in (("filter_C3", run_filter), ("join_C4", run_join), ("refresh_C5", run_refresh), ("snappy_variants", run_snappy)):
         try:
             out[name] = fn(rig, args)
         except Exception as ex:
