@@ -304,7 +304,7 @@ def run_snappy(rig, args):
     ms_s, k_s, _ = timed_builds(ssrc.as_sources())
     ssrc.free()
     ctx.trim()
-    dec_ms = k_s.get("k_snappy_decompress", 0.0)
+    dec_ms = k_s.get("k_snappy_index", 0.0) + k_s.get("k_snappy_blocks", 0.0)
     comp_ms = k_o.get("k_snappy_compress", 0.0)
     out = {
         "workload": f"createIndex over {total_rows} rows of T: UNCOMPRESSED source and index (reference point), SNAPPY index, SNAPPY source; "
@@ -317,7 +317,8 @@ def run_snappy(rig, args):
                          "compress_frac_of_hbm_peak": (2 * bytes_u / (comp_ms / 1e3) / 1e9 / _peak()) if comp_ms else None},
         "snappy_source": {"rows_per_s": total_rows / (ms_s / 1e3), "ms": ms_s, "relative": ms_u / ms_s,
                           "source_bytes_per_rank": src_bytes_s, "uncompressed_source_bytes_per_rank": src_bytes_u,
-                          "k_snappy_decompress_ms": dec_ms,
+                          "k_snappy_decompress_ms": dec_ms, "k_snappy_index_ms": k_s.get("k_snappy_index", 0.0),
+                          "k_snappy_blocks_ms": k_s.get("k_snappy_blocks", 0.0),
                           "decompress_GBps_per_gpu": (src_bytes_u / (dec_ms / 1e3) / 1e9) if dec_ms else None,
                           "decompress_frac_of_hbm_peak": ((src_bytes_s + src_bytes_u) / (dec_ms / 1e3) / 1e9 / _peak()) if dec_ms else None},
     }
@@ -343,9 +344,11 @@ def run_all(rig, args):
 def run_one(rig, args):
     import bench
 
-    fn = {"filter": run_filter, "join": run_join, "refresh": run_refresh}[args.workload]
+    fn = {"filter": run_filter, "join": run_join, "refresh": run_refresh, "snappy": run_snappy}[args.workload]
     res = fn(rig, args)
-    if args.workload == "filter":
+    if args.workload == "snappy":
+        metric, value, unit = "createIndex rows/sec over a SNAPPY source", res["snappy_source"]["rows_per_s"], "rows/s"
+    elif args.workload == "filter":
         metric, value, unit = "filter queries/sec", res["result_to_host"]["queries_per_s"], "queries/s"
     elif args.workload == "join":
         metric, value, unit = "join queries/sec", res["result_to_host"]["joins_per_s"], "joins/s"

@@ -103,7 +103,7 @@ EXPORTED_SYMBOLS = [
     "hs_k_bucket_ids", "hs_k_sort_perm", "hs_synth_table",
     "hs_stage_sources", "hs_staged_num_files", "hs_staged_file", "hs_staged_wait", "hs_staged_free",
     "hs_create_index_async", "hs_pending_wait", "hs_pending_cancel", "hs_verify_index", "hs_synth_checksum",
-    "hs_synth_table_ex", "hs_k_snappy_compress",
+    "hs_synth_table_ex", "hs_k_snappy_compress", "hs_k_snappy_decompress",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -196,6 +196,8 @@ def load_library() -> C.CDLL:
                                     C.POINTER(C.c_void_p), *err]
     L.hs_k_snappy_compress.restype = C.c_int
     L.hs_k_snappy_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), *err]
+    L.hs_k_snappy_decompress.restype = C.c_int
+    L.hs_k_snappy_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), *err]
     if L.hs_abi_version() != 1:
         raise HyperspaceGpuError(HS_EINVAL, f"ABI version mismatch: library {L.hs_abi_version()}, binding 1")
     _lib = L
@@ -559,6 +561,15 @@ class Context:
         err = C.create_string_buffer(1024)
         _check(load_library().hs_k_snappy_compress(self._h, data, len(data), out, cap, C.byref(n), err, len(err)), err)
         return out.raw[:n.value]
+
+    def k_snappy_decompress(self, stream: bytes, uncompressed_len: int) -> Tuple[bytes, bool]:
+        """The GPU page decompressor on one raw Snappy stream; returns (bytes, decoded front-to-back by one warp?)."""
+        out = C.create_string_buffer(max(1, uncompressed_len))
+        seq = C.c_int32(0)
+        err = C.create_string_buffer(1024)
+        _check(load_library().hs_k_snappy_decompress(self._h, stream, len(stream), out, uncompressed_len, C.byref(seq), err,
+                                                     len(err)), err)
+        return out.raw[:uncompressed_len], bool(seq.value)
 
     # ---- read side ----------------------------------------------------------------------------------
     def filter_scan(self, files: Sequence[FileImage], key: str, projected: Sequence[str], lo: Optional[int] = None,

@@ -1156,6 +1156,29 @@ int hs_k_snappy_compress(hs_ctx* ctx, const void* in, uint64_t n, void* out_buf,
   });
 }
 
+int hs_k_snappy_decompress(hs_ctx* ctx, const void* in, uint64_t n, void* out_buf, uint64_t out_len, int32_t* sequential,
+                           char* err, size_t errlen) {
+  if (!ctx || !in || n == 0 || n > 0xffffffffull || out_len > 0xfffffff0ull || (out_len && !out_buf)) return HS_EINVAL;
+  return guarded(ctx, err, errlen, [&] {
+    Buf<uint8_t> d_in(ctx, n + 16), d_out(ctx, out_len + 32);
+    copy_h2d(ctx, d_in.get(), in, n);
+    SnappyBlob blob{d_in.get(), 0, (uint32_t)n, (uint32_t)out_len, 0u, 1u, 0u, 0u};
+    const int64_t blocks = snappy_blocks_of(blob.dst_len, 0);
+    Buf<SnappyBlob> d_blob(ctx, 1);
+    Buf<uint32_t> d_block_in(ctx, (size_t)blocks + 1), d_seq(ctx, 1), d_error(ctx, 1);
+    copy_h2d(ctx, d_blob.get(), &blob, sizeof blob);
+    fill_bytes(ctx, d_error.get(), 0, 4);
+    launch_snappy_decompress(ctx, d_blob.get(), 1, blocks, false, d_block_in.get(), d_seq.get(), d_out.get(), d_error.get());
+    uint32_t error = 0, seq = 0;
+    copy_d2h(ctx, &error, d_error.get(), 4);
+    copy_d2h(ctx, &seq, d_seq.get(), 4);
+    sync_stream(ctx);
+    if (error) fail(HS_EFORMAT, "corrupt snappy stream (check %u)", error & 0xffffffu);
+    if (out_len) HS_CUDA(cudaMemcpy(out_buf, d_out.get(), out_len, cudaMemcpyDeviceToHost));
+    if (sequential) *sequential = (int32_t)seq;
+  });
+}
+
 int hs_synth_table_ex(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t ncols, int32_t n_files,
                       int32_t row_groups_per_file, int32_t dictionary, int32_t compression, int32_t output,
                       hs_index_result** out, char* err, size_t errlen) {

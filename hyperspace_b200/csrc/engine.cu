@@ -511,7 +511,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
         auto it = dict_off.find(pg.dict);
         if (it == dict_off.end()) {
           it = dict_off.emplace(pg.dict, cursor).first;
-          blobs.push_back(SnappyBlob{pg.dict, cursor, (uint32_t)pg.dict_size, (uint32_t)pg.dict_uncompressed_size, 0u, 1u});
+          blobs.push_back(SnappyBlob{pg.dict, cursor, (uint32_t)pg.dict_size, (uint32_t)pg.dict_uncompressed_size, 0u, 1u, 0u, 0u});
           cursor += round_up((size_t)pg.dict_uncompressed_size, 16) + 16;
         }
         pg.dict = (const uint8_t*)(uintptr_t)(it->second + 1);  // patched to a pointer below (offset + 1 marks "relocated")
@@ -522,7 +522,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
         if (prefix > (uint32_t)pg.size || prefix > (uint32_t)pg.uncompressed_size)
           fail(HS_EFORMAT, "compressed page has level bytes beyond its size");
         blobs.push_back(SnappyBlob{pg.data, cursor, (uint32_t)pg.size, (uint32_t)pg.uncompressed_size, prefix,
-                                   (uint32_t)(pg.is_compressed ? 1 : 0)});
+                                   (uint32_t)(pg.is_compressed ? 1 : 0), 0u, 0u});
         pg.data = (const uint8_t*)(uintptr_t)(cursor + 1);
         pg.size = -pg.uncompressed_size;  // negative: data is a scratch offset (+1)
         cursor += round_up((size_t)pg.uncompressed_size, 16) + 16;
@@ -540,10 +540,21 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
         pg.size = pg.uncompressed_size;
       }
     }
+    uint64_t total_blocks = 0;  // 64 KB output blocks, the unit of the decoder's parallelism
+    bool any_verbatim = false;
+    for (SnappyBlob& b : blobs) {
+      any_verbatim = any_verbatim || b.prefix != 0 || !b.compressed;
+      b.first_block = (uint32_t)total_blocks;
+      total_blocks += snappy_blocks_of(b.dst_len, b.prefix);
+    }
+    if (total_blocks >= 0xffffffffull) fail(HS_EUNSUPPORTED, "more than 256 TB of compressed pages in one call");
     Buf<SnappyBlob> d_blobs(ctx, std::max<size_t>(1, blobs.size()));
+    Buf<uint32_t> d_block_in(ctx, (size_t)total_blocks + 1), d_sequential(ctx, std::max<size_t>(1, blobs.size()));
     copy_h2d(ctx, d_blobs.get(), blobs.data(), sizeof(SnappyBlob) * blobs.size());
     copy_h2d(ctx, d_pages.get(), h_pages.data(), sizeof(PageDesc) * (size_t)n_pages);
-    launch_snappy_decompress(ctx, d_blobs.get(), (int64_t)blobs.size(), d_scratch.get(), d_flags.get());
+    launch_snappy_decompress(ctx, d_blobs.get(), (int64_t)blobs.size(), (int64_t)total_blocks, any_verbatim, d_block_in.get(),
+                             d_sequential.get(),
+                             d_scratch.get(), d_flags.get());
     sync_stream(ctx);  // host vectors go out of scope
   }
   // ---- strings: the dictionary pages of BYTE_ARRAY columns become tables of references --------------------------------------

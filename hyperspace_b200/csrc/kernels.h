@@ -94,8 +94,17 @@ struct SnappyBlob {
   uint32_t dst_len;     // prefix + decompressed length
   uint32_t prefix;      // leading bytes copied verbatim (v2 level bytes)
   uint32_t compressed;  // 0: copy, 1: snappy
+  uint32_t first_block; // index of this page's first 64 KB output block in the block table (ascending over the blobs)
+  uint32_t pad;
 };
-void launch_snappy_decompress(hs_ctx* ctx, const SnappyBlob* blobs, int64_t n, uint8_t* scratch, uint32_t* d_error);
+__host__ __device__ inline uint32_t snappy_blocks_of(uint32_t dst_len, uint32_t prefix) {
+  const uint32_t body = dst_len - prefix;
+  return body == 0 ? 1u : (body + 65535u) / 65536u;
+}
+// block_in: one uint32 per block (+1), sequential: one uint32 per blob -- scratch of the two launches
+// any_verbatim: some blob has a prefix or is stored uncompressed
+void launch_snappy_decompress(hs_ctx* ctx, const SnappyBlob* blobs, int64_t n, int64_t total_blocks, bool any_verbatim,
+                              uint32_t* block_in, uint32_t* sequential, uint8_t* scratch, uint32_t* d_error);
 
 // compression of page bodies: one warp per fragment (<= 65536 bytes) of a page; fragment f of raw bytes [src_off, src_off +
 // len) is written to scratch at dst_off (room for 32 + len + len / 6 bytes), its compressed length to out_len[f]

@@ -311,6 +311,11 @@ int hs_synth_table_ex(hs_ctx* ctx, int64_t first_row, int64_t nrows, int32_t nco
  * kernel-level entry point for the parity tests: any Snappy decoder must give the input back. */
 int hs_k_snappy_compress(hs_ctx* ctx, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* out_len, char* err,
                          size_t errlen);
+/* The page decompressor on one raw Snappy stream of n bytes whose uncompressed length is out_len (Parquet's page header
+ * carries it); *sequential = 1 when the stream's 64 KB blocks were not independent and one warp decoded it front to back.
+ * HS_EFORMAT for a damaged stream.  Kernel-level entry point for the parity tests. */
+int hs_k_snappy_decompress(hs_ctx* ctx, const void* in, uint64_t n, void* out, uint64_t out_len, int32_t* sequential, char* err,
+                           size_t errlen);
 
 #ifdef __cplusplus
 }

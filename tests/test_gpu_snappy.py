@@ -117,3 +117,86 @@ def test_snappy_source_table_and_compressible_columns(ctx):
             assert got.column(c).to_numpy().tobytes() == cols[c][perm[int(offs[f.bucket]):int(offs[f.bucket + 1])]].tobytes()
     plain.free()
     snap.free()
+
+
+def _varint(n):
+    out = bytearray()
+    while n >= 0x80:
+        out.append((n & 0x7f) | 0x80)
+        n >>= 7
+    out.append(n)
+    return bytes(out)
+
+
+def _literal(data):
+    n = len(data) - 1
+    if n < 60:
+        return bytes([n << 2]) + data
+    nb = (n.bit_length() + 7) // 8
+    return bytes([(59 + nb) << 2]) + n.to_bytes(nb, "little") + data
+
+
+def _copy(offset, length):  # 4-byte-offset form: any offset, length 1..64
+    return bytes([((length - 1) << 2) | 3]) + offset.to_bytes(4, "little")
+
+
+def test_page_decompressor_on_reference_streams_block_by_block(ctx):
+    """Streams of the C++ snappy library (pyarrow's codec, the one behind snappy-java): 64 KB blocks are independent, so
+    the decoder takes one warp per block; the result is the input."""
+    codec = pa.Codec("snappy")
+    for data in _inputs():
+        comp = codec.compress(data, asbytes=True)
+        back, sequential = ctx.k_snappy_decompress(comp, len(data))
+        assert back == data, len(data)
+        assert not sequential
+        mine = ctx.k_snappy_compress(data)  # and the engine's own compressor's streams
+        back, sequential = ctx.k_snappy_decompress(mine, len(data))
+        assert back == data and not sequential
+
+
+def test_page_decompressor_falls_back_for_streams_whose_blocks_depend_on_each_other(ctx):
+    """Legal snappy that no mainstream writer produces: a back-reference reaching into the previous 64 KB block, an element
+    straddling a block boundary, an overlapping (run-length) copy.  Decoded front to back by one warp, same bytes."""
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, size=70_000, dtype=np.uint8).tobytes()
+    # 70 000 literal bytes (straddles 65 536), then 64 bytes copied from 69 000 back (crosses the boundary), then a run
+    want = a + a[1000:1064]
+    want += want[-3:] * 20
+    stream = _varint(len(want)) + _literal(a) + _copy(69_000, 64) + _copy(3, 60)
+    back, sequential = ctx.k_snappy_decompress(stream, len(want))
+    assert sequential and back == want
+    # blocks aligned by construction but the second one copies from the first
+    b0, b1 = a[:65_536], a[:1000]
+    want = b0 + b1[:64] + b1
+    stream = _varint(len(want)) + _literal(b0) + _copy(65_536, 64) + _literal(b1)
+    back, sequential = ctx.k_snappy_decompress(stream, len(want))
+    assert sequential and back == want
+
+
+def test_page_decompressor_rejects_damaged_streams(ctx):
+    from hyperspace_b200 import _native as N
+
+    codec = pa.Codec("snappy")
+    data = (b"0123456789abcdef" * 20_000)[:300_000]
+    comp = codec.compress(data, asbytes=True)
+    bad = [
+        comp[:len(comp) // 2],                                  # truncated
+        _varint(len(data) + 1) + comp[len(_varint(len(data))):],  # preamble disagrees with the page header
+        _varint(100) + _copy(50, 60) + _literal(b"x" * 40),     # back-reference before the start of the output
+        _varint(10) + _literal(b"y" * 30),                      # element longer than the output
+        _varint(50) + _literal(b"z" * 10),                      # stream ends early
+    ]
+    lens = [len(data), len(data), 100, 10, 50]
+    for stream, n in zip(bad, lens):
+        with pytest.raises(N.HyperspaceGpuError) as e:
+            ctx.k_snappy_decompress(stream, n)
+        assert e.value.code == N.HS_EFORMAT
+    rng = np.random.default_rng(9)
+    for _ in range(200):  # random damage: an error or some bytes, never a crash (compute-sanitizer run in profiles/)
+        m = bytearray(comp[:40_000])
+        for p in rng.integers(1, len(m), size=3):
+            m[p] = int(rng.integers(0, 256))
+        try:
+            ctx.k_snappy_decompress(bytes(m), len(data))
+        except N.HyperspaceGpuError as e:
+            assert e.code == N.HS_EFORMAT
