@@ -10,7 +10,8 @@
  * function returns 0 on success or a negative HS_E* code and writes a message into (err, errlen) when non-NULL.
  * The library owns all device memory and every handle it returns until the matching *_free call.  There is no
  * CPU fallback: without a CUDA device hs_init fails with HS_ENODEVICE and nothing else can be called.
- * One hs_ctx drives one GPU on one CUDA stream; use one ctx per host thread / per rank.
+ * One hs_ctx drives one GPU: a main stream for the kernels plus one copy stream per direction for the staged / asynchronous
+ * entry points; use one ctx per host thread / per rank.
  *
  * Environment switches (diagnostics and A/B measurements only; results are identical either way):
  *   HS_EXCHANGE=nccl   multi-GPU: NCCL all-to-all instead of the fused partition + NVLink peer stores
@@ -18,6 +19,13 @@
  *                      (on several GPUs all ranks must agree)
  *   HS_FULL_SORT=1     radix-sort every varying key byte instead of the high bytes + tie fix-up
  *   HS_PART_REHASH=1   partition kernel hashes the keys again instead of reading the stored bucket ids
+ *   HS_NO_ZEROCOPY=1   decode aligned PLAIN pages into column arrays instead of reading them in place
+ *   HS_PART_BULK=0|1   partition kernel: per-thread stores (0) or cp.async.bulk stores of whole runs (1); default: bulk only for
+ *                      runs that leave over NVLink
+ *   HS_PEER_TILE=small multi-GPU: the 4096-row partition tile of the single-GPU path instead of the 8192-row one
+ *   HS_DEBUG_LOCAL_PEERS=1  multi-GPU: every rank keeps its rows (peer stores go to local memory; wrong results, isolates
+ *                      the NVLink share of the exchange time) -- the one switch that changes results
+ *   HS_TIMELINE=1      print the event timeline (H2D / build / D2H begin and end) of every staged or asynchronous call
  */
 #ifndef HS_GPU_H
 #define HS_GPU_H
