@@ -527,11 +527,14 @@ int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** o
       if (p2p_exchange_supported(ctx, spec->num_buckets)) {
         // partition + exchange fused over NVLink peer memory, then the local sort
         exchange_partition_p2p(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
-        sort_partitioned_rows(ctx, spec->n_indexed, spec->num_buckets, &rows, &st);
+        sort_partitioned_rows(ctx, spec->n_indexed, spec->num_buckets, &rows, &st, /*defer_settle=*/true);
       } else {
         if (ctx->world > 1) exchange_rows(ctx, table, spec->n_indexed, spec->num_buckets, &st);  // NCCL all-to-all
-        index_rows(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st);
+        index_rows(ctx, table, spec->n_indexed, spec->num_buckets, &rows, &st, /*defer_settle=*/true);
       }
+      // From here to the end of encode_segments the host does not wait for the GPU unless it has to: the sort kernels are
+      // queued, the verdict of the tie fix-up is on its way (settle_sort below), and the encoder lays the pages out on the
+      // host while the rows are still being sorted.
       if (!has_strings) src.release_images();  // every column is materialised bucket-major now (string
                                                          // references keep pointing into the images until the encode)
 
@@ -556,7 +559,15 @@ int hs_create_index_async(hs_ctx* ctx, const hs_index_spec* spec, hs_pending** o
         snprintf(nm, sizeof nm, "part-%05d-%s_%05d.c000%s.parquet", b, uuid.c_str(), b, req.codec == pq::SNAPPY ? ".snappy" : "");
         req.seg_names[b] = nm;
       }
+      req.probe = rows.probe.get();
       encode_segments(ctx, req, &enc, &st);  // synchronises the stream before it returns
+      if (settle_sort(ctx, &rows, &st)) {    // (rare) the fix-up gave up on a long run of equal key prefixes: the rows were sorted
+        req.probe = nullptr;                 // again with full passes, so the pages are gathered again
+        req.d_perm = rows.sorted_perm;
+        req.d_sorted_keys = rows.sorted_keys;
+        enc = EncodedFiles();
+        encode_segments(ctx, req, &enc, &st);
+      }
       st.rows_out = rows.part.nrows;
       // the decoded / partitioned / sorted intermediates go back to the pool here: while this call's index files drain to
       // the host, the next call can already build in the same memory

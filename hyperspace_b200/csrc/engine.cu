@@ -825,7 +825,7 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
 
 // ---------------------------------------------------------------------------------------------------------------------
 
-void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats) {
+void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats, bool defer_settle) {
   const int64_t nrows = table.nrows;
   const int ncols = (int)table.cols.size();
   if (num_buckets < 1 || num_buckets > kMaxBuckets)
@@ -921,6 +921,7 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
     for (const PartColumn& pc : h_pc) launch_scatter_column(ctx, pc.in, pc.out, dest.get(), nrows, pc.width);
   }
   t_part.stop();
+  if (defer_settle) launch_dictionary_probes(ctx, out->part, true, &out->probe);  // results ride on the synchronisation below
   sync_stream(ctx);  // h_pc is read by the async copy; bucket_offsets now valid on the host
   for (int c = 0; c < ncols; c++) {
     table.cols[c].data.release();
@@ -931,14 +932,14 @@ void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRo
 
   stats->ms_hash += t_hash.ms();
   stats->ms_partition += t_part.ms();
-  sort_partitioned_rows(ctx, nkeys, num_buckets, out, stats);
+  sort_partitioned_rows(ctx, nkeys, num_buckets, out, stats, defer_settle);
 }
 
-void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats) {
+void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats, bool defer_settle) {
   const int64_t nrows = out->part.nrows;
-  StageTimer t_sort(ctx);
+  auto t_sort = std::make_unique<StageTimer>(ctx);
   // ---- K4: segmented sort on the indexed columns, last column first ---------------------------------------------
-  t_sort.start();
+  t_sort->start();
   build_sort_plan(ctx, out->bucket_offsets.data(), num_buckets, &out->plan);
   out->keys.alloc(ctx, std::max<int64_t>(1, nrows));
   out->keys_alt.alloc(ctx, std::max<int64_t>(1, nrows));
@@ -1015,13 +1016,25 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
       const uint64_t high_mask = ~0ull << (8 * fourth_from_top);
       const uint64_t low_mask = ~high_mask;
       segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying & high_mask, first_src);
-      Buf<uint32_t> d_flag(ctx, 1);
-      fill_bytes(ctx, d_flag.get(), 0, 4);
-      launch_fix_runs(ctx, &out->plan, keys, perm, high_mask, low_mask, 64, d_flag.get());
-      uint32_t flag = 0;
-      copy_d2h(ctx, &flag, d_flag.get(), 4);
-      sync_stream(ctx);
-      if (flag) segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying);
+      out->d_fix_flag.alloc(ctx, 1);
+      fill_bytes(ctx, out->d_fix_flag.get(), 0, 4);
+      launch_fix_runs(ctx, &out->plan, keys, perm, high_mask, low_mask, 64, out->d_fix_flag.get());
+      out->fix_flag = 0;
+      out->fix_varying = varying;
+      out->fix_queued_at = ctx->sync_count;
+      out->fix_pending = true;
+      copy_d2h(ctx, &out->fix_flag, out->d_fix_flag.get(), 4);
+      // a single, null-free key column is the last thing this function sorts: the verdict can wait for the caller's next
+      // synchronisation (the encoder plans its pages on the host meanwhile); otherwise later passes build on this order
+      if (!(defer_settle && nkeys == 1 && !kc.has_nulls)) {
+        out->sorted_keys = keys;
+        out->sorted_perm = perm;
+        settle_sort(ctx, out, stats);
+        keys = out->sorted_keys;
+        perm = out->sorted_perm;
+        keys_alt = keys == out->keys.get() ? out->keys_alt.get() : out->keys.get();
+        perm_alt = perm == out->perm.get() ? out->perm_alt.get() : out->perm.get();
+      }
     } else {
       segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, varying, first_src);
     }
@@ -1030,11 +1043,69 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
   }
   out->sorted_keys = keys;
   out->sorted_perm = perm;
-  t_sort.stop();
+  t_sort->stop();
+  if (out->fix_pending) {  // no synchronisation here: the stage timers are read in settle_sort
+    out->pending_timers.push_back(IndexedRows::DeferredTimer{std::move(t_sort), &hs_stats::ms_sort});
+    return;
+  }
   sync_stream(ctx);
-  stats->ms_sort += t_sort.ms();
+  stats->ms_sort += t_sort->ms();
   for (auto& d : out->pending_timers) stats->*(d.field) += d.t->ms();
   out->pending_timers.clear();
+}
+
+bool settle_sort(hs_ctx* ctx, IndexedRows* out, hs_stats* stats) {
+  bool again = false;
+  if (out->fix_pending) {
+    if (ctx->sync_count <= out->fix_queued_at) sync_stream(ctx);  // the flag has not been delivered yet
+    out->fix_pending = false;
+    if (out->fix_flag) {
+      StageTimer t(ctx);
+      t.start();
+      uint64_t* keys = out->sorted_keys;
+      uint32_t* perm = out->sorted_perm;
+      uint64_t* keys_alt = keys == out->keys.get() ? out->keys_alt.get() : out->keys.get();
+      uint32_t* perm_alt = perm == out->perm.get() ? out->perm_alt.get() : out->perm.get();
+      segmented_sort_pairs(ctx, &out->plan, keys, keys_alt, perm, perm_alt, out->fix_varying);
+      out->sorted_keys = keys;
+      out->sorted_perm = perm;
+      t.stop();
+      sync_stream(ctx);
+      stats->ms_sort += t.ms();
+      again = true;
+    }
+  }
+  for (auto& d : out->pending_timers) stats->*(d.field) += d.t->ms();
+  out->pending_timers.clear();
+  return again;
+}
+
+// see DictProbe
+void launch_dictionary_probes(hs_ctx* ctx, const Table& part, bool use_dictionary, std::unique_ptr<DictProbe>* out) {
+  out->reset();
+  const int ncols = (int)part.cols.size();
+  if (!use_dictionary || part.nrows == 0) return;
+  auto pr = std::make_unique<DictProbe>();
+  pr->mini = std::min<int64_t>(part.nrows, 1 << 14);
+  pr->d_states.alloc(ctx, 4 * (size_t)ncols);
+  pr->h_states.assign(4 * (size_t)ncols, 0u);
+  pr->keys.resize(ncols);
+  fill_bytes(ctx, pr->d_states.get(), 0, 16 * (size_t)ncols);
+  bool any = false;
+  for (int c = 0; c < ncols; c++) {
+    const DevColumn& dc = part.cols[c];
+    if (dc.has_nulls || dc.carried || dc.type == HS_TYPE_STRING || (dc.dict_ready && dc.dict_keys)) continue;
+    if (dc.width != 4 && dc.width != 8) continue;
+    pr->keys[c].alloc(ctx, kDictCapacity);
+    fill_bytes(ctx, pr->keys[c].get(), 0xFF, sizeof(unsigned long long) * kDictCapacity);
+    launch_dict_build(ctx, dc.data.get(), dc.width, 0, pr->mini, pr->keys[c].get(), kDictCapacity, kMaxDictEntries,
+                      pr->d_states.get() + 4 * c);
+    copy_d2h(ctx, &pr->h_states[4 * (size_t)c], pr->d_states.get() + 4 * c, 16);
+    any = true;
+  }
+  if (!any) return;
+  pr->queued_at = ctx->sync_count;
+  *out = std::move(pr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1134,9 +1205,16 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
     // staged sampling: 16 K rows that are (nearly) all distinct mark a key-like column at once; a 256 K-row sample then
     // lets the remaining high-cardinality columns overflow cheaply (the overflow path serialises on one counter).  The
     // first stage runs for ALL columns before the host looks at any result: one synchronisation instead of one per column.
-    Buf<uint32_t> d_states(ctx, 4 * (size_t)ncols);
+    DictProbe* early = req.probe;  // first stage already launched behind the partition (see DictProbe)?
+    if (early && ((int)early->keys.size() != ncols || early->mini != std::min<int64_t>(total_rows, 1 << 14))) early = nullptr;
+    if (early && !early->delivered(ctx)) sync_stream(ctx);
+    Buf<uint32_t> own_states;
+    if (early) own_states = std::move(early->d_states);
+    else own_states.alloc(ctx, 4 * (size_t)ncols);
+    Buf<uint32_t>& d_states = own_states;
     std::vector<uint32_t> h_states(4 * (size_t)ncols, 0u);
-    fill_bytes(ctx, d_states.get(), 0, 16 * (size_t)ncols);
+    if (early) h_states = early->h_states;
+    else fill_bytes(ctx, d_states.get(), 0, 16 * (size_t)ncols);
     const int64_t mini = std::min<int64_t>(total_rows, 1 << 14);
     bool any_sampled = false;
     for (int c = 0; c < ncols; c++) {
@@ -1146,6 +1224,11 @@ void encode_segments(hs_ctx* ctx, const EncodeRequest& req, EncodedFiles* out, h
       if (dc.dict_ready && dc.dict_keys) {
         cd.keys_ptr = dc.dict_keys.get();
         memcpy(&h_states[4 * (size_t)c], dc.dict_state, 16);
+        continue;
+      }
+      if (early && early->keys[c]) {
+        cd.keys = std::move(early->keys[c]);
+        cd.keys_ptr = cd.keys.get();
         continue;
       }
       cd.keys.alloc(ctx, kDictCapacity);

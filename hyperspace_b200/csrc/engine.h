@@ -62,6 +62,18 @@ struct CarryOptions {
 };
 
 // Rows in bucket-major, key-sorted order (result of K2-K4).
+// First stage of the encoder's dictionary analysis (a 16 K-row probe per column that is neither late-materialised nor
+// nullable), launched as soon as the partitioned columns exist so that its results reach the host with a synchronisation
+// the path performs anyway -- the encoder's page-layout plan can then run on the host while the GPU still sorts.
+struct DictProbe {
+  int64_t mini = 0;
+  Buf<uint32_t> d_states;                             // 4 words per column
+  std::vector<uint32_t> h_states;                     // valid once delivered()
+  std::vector<Buf<unsigned long long>> keys;          // per column: the hash set the probe filled (empty: not probed)
+  uint64_t queued_at = 0;
+  bool delivered(const hs_ctx* ctx) const { return ctx->sync_count > queued_at; }
+};
+
 struct IndexedRows {
   Table part;                         // partitioned columns (bucket-major, source order inside a bucket)
   std::vector<uint64_t> bucket_offsets;  // host, nb+1
@@ -80,6 +92,14 @@ struct IndexedRows {
     float hs_stats::*field;
   };
   std::vector<DeferredTimer> pending_timers;
+  std::unique_ptr<DictProbe> probe;   // see DictProbe
+  // deferred verdict of the tie fix-up (sort_partitioned_rows(..., defer_settle)): k_fix_runs raises the flag when a run of
+  // equal prefixes is too long for it; the flag travels with the call's next synchronisation and settle_sort() re-sorts
+  // with full passes if it is set (never for keys that spread over their high bytes)
+  Buf<uint32_t> d_fix_flag;
+  uint32_t fix_flag = 0;
+  uint64_t fix_queued_at = 0, fix_varying = 0;
+  bool fix_pending = false;
 };
 
 struct OutFile {
@@ -120,7 +140,8 @@ void decode_sources(hs_ctx* ctx, SourceSet& set, const std::vector<std::string>&
                     const CarryOptions* carry = nullptr);
 
 // K2-K4 on a decoded table whose first nkeys columns are the indexed columns.
-void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats);
+// defer_settle: see IndexedRows::fix_pending -- the caller must call settle_sort() after its next synchronisation
+void index_rows(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats, bool defer_settle = false);
 
 // K5+K6: encode every segment (bucket or source file) as one Parquet file image inside one device arena.
 struct EncodeRequest {
@@ -136,6 +157,7 @@ struct EncodeRequest {
   std::vector<int64_t> seg_rows_per_row_group;  // optional per-segment override
   bool use_dictionary = true;                   // dictionary-encode columns whose distinct values fit (like parquet-mr)
   int codec = 0;                                // pq::Codec of the written pages: UNCOMPRESSED or SNAPPY (Spark's default)
+  DictProbe* probe = nullptr;                   // optional: first-stage dictionary probes already launched (consumed)
 };
 struct EncodedFiles {
   Buf<uint8_t> arena;       // device
@@ -155,7 +177,10 @@ void comm_allgather_host(hs_ctx* ctx, const void* in, size_t bytes, void* out);
 bool p2p_exchange_supported(hs_ctx* ctx, int num_buckets);
 void exchange_partition_p2p(hs_ctx* ctx, Table& table, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats);
 // K4 only: sorts out->part (already bucket-major, offsets in out->bucket_offsets) on the first nkeys columns.
-void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats);
+void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows* out, hs_stats* stats, bool defer_settle = false);
+// true when the rows had to be sorted again (whatever was derived from sorted_keys / sorted_perm must be redone)
+bool settle_sort(hs_ctx* ctx, IndexedRows* out, hs_stats* stats);
+void launch_dictionary_probes(hs_ctx* ctx, const Table& part, bool use_dictionary, std::unique_ptr<DictProbe>* out);
 
 std::string make_uuid();
 

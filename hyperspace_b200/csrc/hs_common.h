@@ -159,6 +159,7 @@ struct hs_ctx {
   size_t xfer_cap = 0, xfer_head = 0;
   std::vector<uint8_t*> xfer_retired; // outgrown rings, recycled at the next synchronisation
   std::vector<PendingD2H> xfer_pending;
+  uint64_t sync_count = 0;            // sync_stream calls so far: a copy_d2h queued at count c has been delivered once sync_count > c
   // what the ranks agreed on when the same dictionaries were last seen (engine.cu: DecodeCache); freed by hs_shutdown
   void* decode_cache = nullptr;
   void (*decode_cache_free)(void*) = nullptr;

@@ -105,6 +105,7 @@ void sync_stream(hs_ctx* ctx) {
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
   for (const hs_ctx::PendingD2H& p : ctx->xfer_pending) memcpy(p.dst, p.slot, p.bytes);
   ctx->xfer_pending.clear();
+  ctx->sync_count++;
   recycle(ctx);
 }
 

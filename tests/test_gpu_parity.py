@@ -217,6 +217,24 @@ def test_create_index_matches_oracle(ctx, tmp_path, variant):
     res.free()
 
 
+def test_create_index_when_the_tie_fixup_gives_up(ctx):
+    """createIndex does not wait for the verdict of the tie fix-up before it lays out and gathers the pages; when the fix-up
+    gives up (long runs of equal key prefixes) the rows are sorted again with full passes and the pages are written again.
+    Keys: three values in the top byte, 30 random low bits -> runs of ~n/3/256 rows on the sorted top bytes."""
+    rng = np.random.default_rng(78)
+    n = 300_000
+    cols = {"k": (rng.integers(0, 3, size=n, dtype=np.int64) << 60) | rng.integers(0, 1 << 30, size=n, dtype=np.int64),
+            "v": rng.integers(0, 50, size=n, dtype=np.int32), "w": rng.standard_normal(n)}
+    for nb in (1, 8):
+        res = _index_in_memory(ctx, cols, ["k"], ["v", "w"], nb, "u")
+        _check_index(res, cols, ["k"], ["v", "w"], nb, "u")
+        res.free()
+    short = dict(cols, k=(rng.integers(0, 1 << 16, size=n, dtype=np.int64) << 44) | (rng.integers(0, 5, size=n, dtype=np.int64) << 8))
+    res = _index_in_memory(ctx, short, ["k"], ["v", "w"], 8, "u")   # the usual case: short runs, nothing to redo
+    _check_index(res, short, ["k"], ["v", "w"], 8, "u")
+    res.free()
+
+
 def test_create_index_c1_config_and_files_on_disk(ctx, tmp_path):
     """BASELINE.json configs[0]: 10k rows x 3 columns; written to disk like the reference does."""
     from hyperspace_b200 import _native
