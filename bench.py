@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- createIndex rows/s on the synthetic table T of SURVEY.md section 8d (BASELINE.json configs[1]).
 
-    python bench.py --gpus N --steps K --warmup W [--rows R] [--impl reference] [--workload createIndex|filter|join|refresh|snappy]
+    python bench.py --gpus N --steps K --warmup W [--rows R] [--impl reference] [--workload createIndex|filter|join|refresh|snappy|files]
 
 A "step" is one createIndex over the whole table: scan (Parquet decode) -> project -> hash-repartition into 200 buckets
 -> sort within bucket -> Parquet encode, through the C ABI (hs_create_index).
@@ -68,7 +68,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=1_000_000_000)
     ap.add_argument("--files", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="createIndex", choices=["createIndex", "filter", "join", "refresh", "snappy"])
+    ap.add_argument("--workload", default="createIndex", choices=["createIndex", "filter", "join", "refresh", "snappy", "files"])
     ap.add_argument("--cpu-sample-rows", type=int, default=128_000_000)
     ap.add_argument("--cpu-sample-files", type=int, default=128)
     ap.add_argument("--no-e2e", action="store_true")

@@ -325,11 +325,72 @@ def run_snappy(rig, args):
     return out
 
 
+def run_files(rig, args):
+    """The reference's actual effect: Parquet files in, bucket files out (index/DataFrameWriterExtensions.scala:50-68 writes
+    them under <index>/v__=N).  createIndex with path sources and HS_OUT_FILES: file reads (a few host threads into pinned
+    memory), H2D, build, D2H, file writes (a few host threads) -- one blocking call, nothing pipelined.  tmpfs and, where a
+    writable disk with room exists, the local file system; a quarter of --rows to keep the run short."""
+    import shutil
+    import tempfile
+    import time
+
+    N, ctx = rig.N, rig.ctx
+    if rig.world > 1:
+        return {"skipped": "measured on one GPU (the ranks of a multi-GPU build write disjoint bucket files the same way)"}
+    rows = max(1 << 20, (args.rows // 4) // 64 * 64)
+    n_files = 64
+    src = ctx.synth_table(0, rows, 5, n_files=n_files, row_groups_per_file=4, output=N.HS_OUT_HOST)
+    src_bytes = sum(f.size for f in src.files)
+    out = {"workload": f"createIndex over {rows} rows of T from {n_files} Parquet files on a file system to {NB} index files on "
+                       f"the same file system (hs_create_index, HS_OUT_FILES), one blocking call", "source_bytes": src_bytes}
+    for label, base in (("tmpfs", "/dev/shm"), ("local_fs", tempfile.gettempdir())):
+        try:
+            if not os.path.isdir(base) or shutil.disk_usage(base).free < 3 * src_bytes + (1 << 30):
+                out[label] = {"skipped": f"no room under {base}"}
+                continue
+            root = tempfile.mkdtemp(prefix="hs_bench_", dir=base)
+        except Exception as ex:
+            out[label] = {"skipped": f"{type(ex).__name__}: {ex}"}
+            continue
+        try:
+            paths = []
+            for i, f in enumerate(src.files):
+                p = os.path.join(root, f"src-{i:03d}.parquet")
+                with open(p, "wb") as fh:
+                    fh.write(src.host_bytes(i))
+                paths.append(p)
+            files = [N.FileImage(path=p, file_id=i) for i, p in enumerate(paths)]
+            best, stats = None, None
+            for rep in range(3):
+                out_dir = os.path.join(root, f"v__={rep}")
+                t0 = time.perf_counter()
+                res, st = ctx.create_index(files, ["k"], ["v1", "v2", "v3", "v4"], NB, out_dir=out_dir, output=N.HS_OUT_FILES,
+                                           job_uuid="f")
+                dt = time.perf_counter() - t0
+                n_out = len(res.files)
+                res.free()
+                if rep and (best is None or dt < best):
+                    best, stats = dt, st
+            idx_bytes = sum(os.path.getsize(os.path.join(out_dir, n)) for n in os.listdir(out_dir) if n.endswith(".parquet"))
+            out[label] = {"rows_per_s": rows / best, "ms": best * 1e3, "index_files": n_out, "index_bytes": idx_bytes,
+                          "GBps_in_plus_out": (src_bytes + idx_bytes) / best / 1e9,
+                          "stage_ms": {k: round(v, 2) for k, v in stats.items() if k.startswith("ms_")},
+                          "note": "wall clock of the call, best of 2 after one warm-up; files come from / go to the page cache"}
+        except Exception as ex:
+            out[label] = {"failed": f"{type(ex).__name__}: {ex}"}
+        finally:
+            shutil.rmtree(root, ignore_errors=True)
+    src.free()
+    ctx.trim()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 
 def run_all(rig, args):
     out = {}
-    for name, fn in (("filter_C3", run_filter), ("join_C4", run_join), ("refresh_C5", run_refresh), ("snappy_variants", run_snappy)):
+    for name, fn in (("filter_C3", run_filter), ("join_C4", run_join), ("refresh_C5", run_refresh), ("snappy_variants", run_snappy),
+                     ("files_in_files_out", run_files)):
         try:
             out[name] = fn(rig, args)
         except Exception as ex:
@@ -344,9 +405,12 @@ def run_all(rig, args):
 def run_one(rig, args):
     import bench
 
-    fn = {"filter": run_filter, "join": run_join, "refresh": run_refresh, "snappy": run_snappy}[args.workload]
+    fn = {"filter": run_filter, "join": run_join, "refresh": run_refresh, "snappy": run_snappy, "files": run_files}[args.workload]
     res = fn(rig, args)
-    if args.workload == "snappy":
+    if args.workload == "files":
+        best = max((v.get("rows_per_s", 0.0) for v in res.values() if isinstance(v, dict)), default=0.0)
+        metric, value, unit = "createIndex rows/sec, files in -> files out", best, "rows/s"
+    elif args.workload == "snappy":
         metric, value, unit = "createIndex rows/sec over a SNAPPY source", res["snappy_source"]["rows_per_s"], "rows/s"
     elif args.workload == "filter":
         metric, value, unit = "filter queries/sec", res["result_to_host"]["queries_per_s"], "queries/s"

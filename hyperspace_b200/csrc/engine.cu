@@ -939,6 +939,13 @@ void sort_partitioned_rows(hs_ctx* ctx, int nkeys, int num_buckets, IndexedRows*
   const int64_t nrows = out->part.nrows;
   auto t_sort = std::make_unique<StageTimer>(ctx);
   // ---- K4: segmented sort on the indexed columns, last column first ---------------------------------------------
+  if (defer_settle && !out->probe) {
+    // rows that arrived through the fused exchange: the probes need the peers' rows (i.e. the closing barrier), and their
+    // results must be on the host before the sort is queued if the encoder is to plan while the GPU sorts -- one
+    // synchronisation here (the ranks are in step anyway) buys the overlap
+    launch_dictionary_probes(ctx, out->part, true, &out->probe);
+    if (out->probe) sync_stream(ctx);
+  }
   t_sort->start();
   build_sort_plan(ctx, out->bucket_offsets.data(), num_buckets, &out->plan);
   out->keys.alloc(ctx, std::max<int64_t>(1, nrows));

@@ -245,8 +245,7 @@ __global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ t
   // again only for the rows an out-of-order run actually moves.  With 5 M-row buckets one row in eight heads a run: doing
   // all of that through dependent global loads was latency-bound (4.9 ms per 1 B rows for 8 B/row of traffic).
   __shared__ uint64_t s_key[kSortTile + 2];
-  __shared__ uint16_t s_heads[kSortTile / 2 + 32], s_len[kSortTile / 2 + 32];
-  __shared__ uint32_t s_n;
+  __shared__ uint16_t s_heads[kSortTile / 2], s_len[kSortTile / 2];  // 8 warps x 256 entries
   const SortTile t = tiles[blockIdx.x];
   const uint64_t segb = seg_start[t.seg], sege = seg_start[t.seg + 1];
   const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1;
@@ -263,12 +262,18 @@ __global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ t
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    s_n = 0;
     const uint64_t flip = high_mask & (~high_mask + 1);  // lowest bit of the prefix: flipping it makes a different prefix
     s_key[0] = t.start > segb ? keys[t.start - 1] : (s_key[1] ^ flip);
     s_key[t.count + 1] = t.start + t.count < sege ? keys[t.start + t.count] : (s_key[t.count] ^ flip);
   }
   __syncthreads();
+  // every warp keeps its own list of heads (a warp's rows give at most 256: a head needs a row behind it), so building the
+  // lists takes no atomics and no block-wide counter -- 128 contended shared-memory atomics per tile, each followed by a
+  // dependent shuffle, were a third of this kernel's time
+  const uint32_t wid = threadIdx.x >> 5;
+  uint16_t* my_heads = s_heads + wid * (kSortTile / 16);
+  uint16_t* my_len = s_len + wid * (kSortTile / 16);
+  uint32_t my_n = 0;
 #pragma unroll 4
   for (uint32_t i0 = 0; i0 < kSortTile; i0 += 256) {  // uniform trip count: the ballot below needs whole warps
     const uint32_t i = i0 + threadIdx.x;
@@ -278,33 +283,28 @@ __global__ void __launch_bounds__(256) k_fix_runs(const SortTile* __restrict__ t
       head = (s_key[i] & high_mask) != kh && (s_key[2 + i] & high_mask) == kh;
     }
     const unsigned m = __ballot_sync(0xffffffffu, head);
-    if (m) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&s_n, (uint32_t)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (head) s_heads[base + __popc(m & lt)] = (uint16_t)i;
-    }
+    if (head) my_heads[my_n + __popc(m & lt)] = (uint16_t)i;
+    my_n += __popc(m);
   }
-  __syncthreads();
-  const uint32_t nheads = s_n;
+  __syncwarp();
   // first every run is measured (reads only: a walk looks one key past its run, i.e. at the head of the next one), then,
   // behind a barrier, every run is sorted (writes stay inside the run)
-  for (uint32_t e = threadIdx.x; e < nheads; e += 256) {
-    const uint32_t i = s_heads[e];
+  for (uint32_t e = lane; e < my_n; e += 32) {
+    const uint32_t i = my_heads[e];
     const uint64_t* sk = s_key + 1 + i;
     const uint64_t kh = sk[0] & high_mask;
     uint32_t len = 1;
     while (i + len < t.count && len <= max_run && (sk[len] & high_mask) == kh) len++;
     const bool crosses = i + len == t.count && (sk[len] & high_mask) == kh;  // sk[len] is the next tile's first key here
-    s_len[e] = crosses ? (uint16_t)0xffffu : (uint16_t)len;
+    my_len[e] = crosses ? (uint16_t)0xffffu : (uint16_t)len;
   }
   __syncthreads();
-  for (uint32_t e = threadIdx.x; e < nheads; e += 256) {
-    const uint32_t i = s_heads[e];
+  for (uint32_t e = lane; e < my_n; e += 32) {
+    const uint32_t i = my_heads[e];
     const uint64_t p = t.start + i;
     uint64_t* sk = s_key + 1 + i;  // the run starts at sk[0]
     const uint64_t kh = sk[0] & high_mask;
-    uint32_t len = s_len[e];
+    uint32_t len = my_len[e];
     if (len == 0xffffu) {
       len = t.count - i;
       // the run continues into the next tile (at most one per tile): settle it in global memory, as a whole.  The next

@@ -25,6 +25,7 @@
  *   HS_PEER_TILE=small multi-GPU: the 4096-row partition tile of the single-GPU path instead of the 8192-row one
  *   HS_DEBUG_LOCAL_PEERS=1  multi-GPU: every rank keeps its rows (peer stores go to local memory; wrong results, isolates
  *                      the NVLink share of the exchange time) -- the one switch that changes results
+ *   HS_IO_THREADS=n    host threads that read source files / write bucket files (default 16, at most half the cores)
  *   HS_TIMELINE=1      print the event timeline (H2D / build / D2H begin and end) of every staged or asynchronous call
  */
 #ifndef HS_GPU_H
