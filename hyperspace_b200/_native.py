@@ -67,7 +67,8 @@ class ScanSpec(C.Structure):
     _fields_ = [("files", C.POINTER(SourceFile)), ("n_files", C.c_int32), ("sorted_on_key", C.c_int32),
                 ("key_column", C.c_char_p), ("projected_columns", C.POINTER(C.c_char_p)), ("n_projected", C.c_int32),
                 ("has_lo", C.c_int32), ("has_hi", C.c_int32), ("lo", C.c_int64), ("hi", C.c_int64),
-                ("deleted_file_ids", C.POINTER(C.c_int64)), ("n_deleted_file_ids", C.c_int32), ("output", C.c_int32)]
+                ("deleted_file_ids", C.POINTER(C.c_int64)), ("n_deleted_file_ids", C.c_int32), ("output", C.c_int32),
+                ("lo_bytes", C.c_char_p), ("hi_bytes", C.c_char_p), ("lo_len", C.c_uint32), ("hi_len", C.c_uint32)]
 
 
 class JoinSpec(C.Structure):
@@ -103,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "hs_k_bucket_ids", "hs_k_sort_perm", "hs_synth_table",
     "hs_stage_sources", "hs_staged_num_files", "hs_staged_file", "hs_staged_wait", "hs_staged_free",
     "hs_create_index_async", "hs_pending_wait", "hs_pending_cancel", "hs_verify_index", "hs_synth_checksum",
-    "hs_synth_table_ex", "hs_k_snappy_compress", "hs_k_snappy_decompress",
+    "hs_synth_table_ex", "hs_k_snappy_compress", "hs_k_snappy_decompress", "hs_batch_string_offsets",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -196,6 +197,8 @@ def load_library() -> C.CDLL:
                                     C.POINTER(C.c_void_p), *err]
     L.hs_k_snappy_compress.restype = C.c_int
     L.hs_k_snappy_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), *err]
+    L.hs_batch_string_offsets.restype = C.c_int
+    L.hs_batch_string_offsets.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.hs_k_snappy_decompress.restype = C.c_int
     L.hs_k_snappy_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), *err]
     if L.hs_abi_version() != 1:
@@ -386,6 +389,20 @@ class Batch:
             if self.on_device:
                 self.device_columns.append((nm.value.decode(), ty.value, d.value))
                 continue
+            if ty.value == HS_TYPE_STRING:  # bytes back to back + num_rows + 1 offsets -> an object array of bytes
+                off_p, total = C.c_void_p(), C.c_uint64()
+                L.hs_batch_string_offsets(handle, i, C.byref(off_p), C.byref(total))
+                offs = np.ctypeslib.as_array((C.c_uint64 * (n + 1)).from_address(off_p.value)) if n else np.zeros(1, np.uint64)
+                blob = C.string_at(d.value, total.value) if total.value else b""
+                data = np.empty(n, dtype=object)
+                o = offs.tolist()
+                for r in range(n):
+                    data[r] = blob[o[r]:o[r + 1]]
+                valid = None
+                if v.value:
+                    valid = np.ctypeslib.as_array((C.c_uint8 * n).from_address(v.value)).copy() if n else np.empty(0, np.uint8)
+                self.columns.append((nm.value.decode(), data, valid))
+                continue
             dt = np.dtype(_NP_OF_TYPE[ty.value])
             if n:
                 data = np.ctypeslib.as_array((C.c_uint8 * (n * dt.itemsize)).from_address(d.value)).view(dt)
@@ -572,8 +589,7 @@ class Context:
         return out.raw[:uncompressed_len], bool(seq.value)
 
     # ---- read side ----------------------------------------------------------------------------------
-    def filter_scan(self, files: Sequence[FileImage], key: str, projected: Sequence[str], lo: Optional[int] = None,
-                    hi: Optional[int] = None, sorted_on_key: bool = True, deleted_file_ids: Sequence[int] = (),
+    def filter_scan(self, files: Sequence[FileImage], key: str, projected: Sequence[str], lo=None, hi=None, sorted_on_key: bool = True, deleted_file_ids: Sequence[int] = (),
                     output: int = HS_OUT_HOST) -> Tuple[Batch, Dict[str, float]]:
         L = load_library()
         src, keep = _source_array(files)
@@ -583,7 +599,13 @@ class Context:
         spec.key_column = key.encode()
         spec.projected_columns, spec.n_projected = pc, len(projected)
         spec.has_lo, spec.has_hi = int(lo is not None), int(hi is not None)
-        spec.lo, spec.hi = lo or 0, hi or 0
+        if isinstance(lo, (str, bytes)) or isinstance(hi, (str, bytes)):  # string / binary key: bounds as bytes
+            lob = (lo.encode() if isinstance(lo, str) else lo) if lo is not None else b""
+            hib = (hi.encode() if isinstance(hi, str) else hi) if hi is not None else b""
+            spec.lo_bytes, spec.lo_len, spec.hi_bytes, spec.hi_len = lob, len(lob), hib, len(hib)
+            spec.lo, spec.hi = 0, 0
+        else:
+            spec.lo, spec.hi = lo or 0, hi or 0
         dl = (C.c_int64 * max(1, len(deleted_file_ids)))(*deleted_file_ids)
         spec.deleted_file_ids, spec.n_deleted_file_ids = dl, len(deleted_file_ids)
         spec.output = output

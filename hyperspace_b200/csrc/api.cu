@@ -778,8 +778,29 @@ static void batch_from_gather(hs_ctx* ctx, const Table& t, const std::vector<int
                               int64_t n_out, hs_batch* b) {
   // all gathers first, then all copies, one synchronisation at the end
   std::vector<Buf<uint8_t>> d_data, d_valid;
-  for (int ci : col_idx) {
+  std::vector<Buf<uint64_t>> d_offsets(col_idx.size());
+  std::vector<uint64_t> str_bytes(col_idx.size(), 0);
+  for (size_t k = 0; k < col_idx.size(); k++) {
+    const int ci = col_idx[k];
     const DevColumn& c = t.cols[ci];
+    if (c.type == HS_TYPE_STRING) {
+      // values are references into the source images (still alive here): lengths -> offsets -> one copy of the bytes
+      const uint8_t* valid = c.has_nulls ? c.valid.get() : nullptr;
+      Buf<uint32_t> lens(ctx, (size_t)std::max<int64_t>(1, n_out));
+      d_offsets[k].alloc(ctx, (size_t)n_out + 1);
+      launch_string_lengths(ctx, (const uint64_t*)c.data.get(), valid, d_idx, n_out, lens.get());
+      exclusive_scan_u32_u64(ctx, lens.get(), n_out, d_offsets[k].get());
+      copy_d2h(ctx, &str_bytes[k], d_offsets[k].get() + n_out, 8);
+      sync_stream(ctx);
+      d_data.emplace_back(ctx, std::max<uint64_t>(1, str_bytes[k]));
+      launch_copy_strings(ctx, (const uint64_t*)c.data.get(), valid, d_idx, n_out, d_offsets[k].get(), d_data.back().get());
+      d_valid.emplace_back();
+      if (c.has_nulls) {
+        d_valid.back().alloc(ctx, (size_t)std::max<int64_t>(1, n_out));
+        launch_gather_plain(ctx, c.valid.get(), d_idx, n_out, 1, d_valid.back().get());
+      }
+      continue;
+    }
     d_data.emplace_back(ctx, (size_t)std::max<int64_t>(1, n_out) * c.width);
     launch_gather_plain(ctx, c.data.get(), d_idx, n_out, c.width, d_data.back().get());
     d_valid.emplace_back();
@@ -794,12 +815,20 @@ static void batch_from_gather(hs_ctx* ctx, const Table& t, const std::vector<int
     bc.name = c.name;
     bc.type = c.type;
     bc.has_valid = c.has_nulls;
+    const bool is_str = c.type == HS_TYPE_STRING;
+    const size_t data_bytes = is_str ? (size_t)str_bytes[i] : (size_t)n_out * c.width;
+    bc.total_bytes = is_str ? str_bytes[i] : 0;
     if (b->on_device) {  // the next GPU operator consumes the columns where they are
       bc.data = std::move(d_data[i]);
+      if (is_str) bc.offsets = std::move(d_offsets[i]);
       if (c.has_nulls) bc.valid = std::move(d_valid[i]);
     } else {
-      bc.data.alloc(ctx, (size_t)std::max<int64_t>(1, n_out) * c.width, true);
-      if (n_out) copy_d2h(ctx, bc.data.get(), d_data[i].get(), (size_t)n_out * c.width);
+      bc.data.alloc(ctx, std::max<size_t>(1, data_bytes), true);
+      if (data_bytes) copy_d2h(ctx, bc.data.get(), d_data[i].get(), data_bytes);
+      if (is_str) {
+        bc.offsets.alloc(ctx, (size_t)n_out + 1, true);
+        copy_d2h(ctx, bc.offsets.get(), d_offsets[i].get(), 8 * ((size_t)n_out + 1));
+      }
       if (c.has_nulls) {
         bc.valid.alloc(ctx, (size_t)std::max<int64_t>(1, n_out), true);
         if (n_out) copy_d2h(ctx, bc.valid.get(), d_valid[i].get(), (size_t)n_out);
@@ -885,11 +914,26 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
     } else {
       decode_sources(ctx, src, cols, nullptr, &t, &st);
     }
-    if (t.cols[0].type != HS_TYPE_INT64 && t.cols[0].type != HS_TYPE_INT32)
-      fail(HS_EUNSUPPORTED, "filter scan: key column must be int32/int64");
+    const bool str_key = t.cols[0].type == HS_TYPE_STRING;
+    if (!str_key && t.cols[0].type != HS_TYPE_INT64 && t.cols[0].type != HS_TYPE_INT32)
+      fail(HS_EUNSUPPORTED, "filter scan: key column must be int32 / int64 / string");
     const int64_t n = t.nrows;
     Buf<int64_t> k64;
-    const int64_t* d_keys = widened_key(ctx, t.cols[0], n, &k64);
+    const int64_t* d_keys = str_key ? nullptr : widened_key(ctx, t.cols[0], n, &k64);
+    // string bounds: device copies of the bytes, addressed like every string value (a reference)
+    Buf<uint8_t> d_bound_bytes;
+    uint64_t lo_ref = 0, hi_ref = 0;
+    if (str_key) {
+      if ((spec->has_lo && spec->lo_len && !spec->lo_bytes) || (spec->has_hi && spec->hi_len && !spec->hi_bytes))
+        fail(HS_EINVAL, "filter scan: string key '%s' needs lo_bytes / hi_bytes", t.cols[0].name.c_str());
+      if (spec->lo_len > kMaxStringLen || spec->hi_len > kMaxStringLen) fail(HS_EUNSUPPORTED, "string bound longer than 65535 bytes");
+      const uint32_t ll = spec->has_lo ? spec->lo_len : 0, hl = spec->has_hi ? spec->hi_len : 0;
+      d_bound_bytes.alloc(ctx, (size_t)ll + hl + 16);
+      if (ll) copy_h2d(ctx, d_bound_bytes.get(), spec->lo_bytes, ll);
+      if (hl) copy_h2d(ctx, d_bound_bytes.get() + ll, spec->hi_bytes, hl);
+      lo_ref = string_ref(d_bound_bytes.get(), ll);
+      hi_ref = string_ref(d_bound_bytes.get() + ll, hl);
+    }
     StageTimer t_scan(ctx);
     t_scan.start();
     Buf<uint32_t> idx;
@@ -899,7 +943,7 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
       Table full;
       decode_sources(ctx, src, cols, nullptr, &full, &st);
       t = std::move(full);
-      d_keys = widened_key(ctx, t.cols[0], n, &k64);
+      if (!str_key) d_keys = widened_key(ctx, t.cols[0], n, &k64);
     }
     if (sorted) {
       // K7: two binary searches per file
@@ -909,7 +953,11 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
       Buf<uint64_t> d_seg(ctx, nseg + 1);
       Buf<int64_t> d_bounds(ctx, 2 * std::max(1, nseg));
       copy_h2d(ctx, d_seg.get(), seg.data(), 8 * (nseg + 1));
-      launch_range_bounds(ctx, d_keys, d_seg.get(), nseg, spec->has_lo, spec->lo, spec->has_hi, spec->hi, d_bounds.get());
+      if (str_key)
+        launch_range_bounds_strings(ctx, (const uint64_t*)t.cols[0].data.get(), d_seg.get(), nseg, spec->has_lo, lo_ref, spec->has_hi,
+                                    hi_ref, d_bounds.get());
+      else
+        launch_range_bounds(ctx, d_keys, d_seg.get(), nseg, spec->has_lo, spec->lo, spec->has_hi, spec->hi, d_bounds.get());
       std::vector<int64_t> bounds(2 * std::max(1, nseg));
       copy_d2h(ctx, bounds.data(), d_bounds.get(), 16 * nseg);
       sync_stream(ctx);
@@ -936,8 +984,12 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
       // full predicate scan (appended source files under Hybrid Scan, or lineage NOT-IN filter)
       Buf<uint32_t> mask(ctx, std::max<int64_t>(1, n));
       Buf<uint64_t> offs(ctx, n + 1);
-      launch_filter_mask(ctx, d_keys, t.cols[0].has_nulls ? t.cols[0].valid.get() : nullptr, n, spec->has_lo, spec->lo,
-                         spec->has_hi, spec->hi, mask.get());
+      if (str_key)
+        launch_filter_mask_strings(ctx, (const uint64_t*)t.cols[0].data.get(), t.cols[0].has_nulls ? t.cols[0].valid.get() : nullptr, n,
+                                   spec->has_lo, lo_ref, spec->has_hi, hi_ref, mask.get());
+      else
+        launch_filter_mask(ctx, d_keys, t.cols[0].has_nulls ? t.cols[0].valid.get() : nullptr, n, spec->has_lo, spec->lo,
+                           spec->has_hi, spec->hi, mask.get());
       if (spec->n_deleted_file_ids > 0) {
         Buf<int64_t> d_del(ctx, spec->n_deleted_file_ids);
         copy_h2d(ctx, d_del.get(), spec->deleted_file_ids, 8 * spec->n_deleted_file_ids);
@@ -1125,6 +1177,13 @@ int hs_batch_column(const hs_batch* b, int32_t i, const char** name, int32_t* ty
   if (valid) *valid = c.has_valid ? c.valid.get() : nullptr;
   return HS_OK;
 }
+int hs_batch_string_offsets(const hs_batch* b, int32_t i, const uint64_t** offsets, uint64_t* total_bytes) {
+  if (!b || i < 0 || i >= (int32_t)b->cols.size() || b->cols[i].type != HS_TYPE_STRING) return HS_EINVAL;
+  if (offsets) *offsets = b->cols[i].offsets.get();
+  if (total_bytes) *total_bytes = b->cols[i].total_bytes;
+  return HS_OK;
+}
+
 void hs_batch_free(hs_batch* b) {
   if (!b) return;
   if (b->ctx) {

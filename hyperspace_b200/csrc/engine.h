@@ -233,6 +233,8 @@ struct hs_batch {
     hs::Buf<uint8_t> data;
     hs::Buf<uint8_t> valid;
     bool has_valid = false;
+    hs::Buf<uint64_t> offsets;  // HS_TYPE_STRING: nrows + 1 byte offsets into data
+    uint64_t total_bytes = 0;
   };
   std::vector<Col> cols;
 };

@@ -344,6 +344,17 @@ void exclusive_scan_u32_u64(hs_ctx* ctx, const uint32_t* in, int64_t n, uint64_t
 // mask[i] = lo <= keys[i] <= hi (and file id not deleted); compaction index list
 void launch_filter_mask(hs_ctx* ctx, const int64_t* keys, const uint8_t* valid, int64_t n, int has_lo, int64_t lo,
                         int has_hi, int64_t hi, uint32_t* mask);
+// string / binary keys (values are references into the source images, device_utils.cuh: string_ref): the bounds are
+// references to device copies of the bound bytes; order = unsigned byte order, shorter first on a common prefix
+void launch_range_bounds_strings(hs_ctx* ctx, const uint64_t* refs, const uint64_t* seg_offsets, int nseg, int has_lo,
+                                 uint64_t lo_ref, int has_hi, uint64_t hi_ref, int64_t* bounds);
+void launch_filter_mask_strings(hs_ctx* ctx, const uint64_t* refs, const uint8_t* valid, int64_t n, int has_lo,
+                                uint64_t lo_ref, int has_hi, uint64_t hi_ref, uint32_t* mask);
+// lens[i] = length of refs[idx[i]] (0 for a null);  then, with offsets = exclusive scan of lens: out[offsets[i] ..] = bytes
+void launch_string_lengths(hs_ctx* ctx, const uint64_t* refs, const uint8_t* valid, const uint32_t* idx, int64_t n,
+                           uint32_t* lens);
+void launch_copy_strings(hs_ctx* ctx, const uint64_t* refs, const uint8_t* valid, const uint32_t* idx, int64_t n,
+                         const uint64_t* offsets, uint8_t* out);
 void launch_compact_indices(hs_ctx* ctx, const uint32_t* mask, const uint64_t* offsets, int64_t n, uint32_t* out_idx);
 void launch_not_in_mask(hs_ctx* ctx, const int64_t* file_ids, int64_t n, const int64_t* deleted, int ndeleted,
                         uint32_t* mask /* and-ed in place */);

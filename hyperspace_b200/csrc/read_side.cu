@@ -191,7 +191,105 @@ inline int grid_for(hs_ctx* ctx, int64_t n, int threads, int per_sm) {
   return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 
+// ---- string keys: the same scans over references, compared in UTF8String byte order ------------------------------------
+__global__ void k_range_bounds_str(const uint64_t* __restrict__ refs, const uint64_t* __restrict__ seg_offsets, int nseg,
+                                   int has_lo, uint64_t lo_ref, int has_hi, uint64_t hi_ref, int64_t* __restrict__ bounds) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const int64_t b = (int64_t)seg_offsets[s], n = (int64_t)seg_offsets[s + 1] - b;
+  const uint64_t* a = refs + b;
+  int64_t first = 0, last = n;
+  if (has_lo) {  // first row with value >= lo
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      if (string_compare(a[mid], lo_ref) < 0) lo = mid + 1;
+      else hi = mid;
+    }
+    first = lo;
+  }
+  if (has_hi) {  // first row with value > hi
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      if (string_compare(a[mid], hi_ref) <= 0) lo = mid + 1;
+      else hi = mid;
+    }
+    last = lo;
+  }
+  if (last < first) last = first;
+  bounds[2 * s] = first;
+  bounds[2 * s + 1] = last;
+}
+
+__global__ void k_filter_mask_str(const uint64_t* __restrict__ refs, const uint8_t* __restrict__ valid, int64_t n, int has_lo,
+                                  uint64_t lo_ref, int has_hi, uint64_t hi_ref, uint32_t* __restrict__ mask) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    bool ok = !valid || valid[i];  // a null key never satisfies a comparison
+    if (ok) {
+      const uint64_t r = refs[i];
+      if (has_lo) ok = string_compare(r, lo_ref) >= 0;
+      if (ok && has_hi) ok = string_compare(r, hi_ref) <= 0;
+    }
+    mask[i] = ok ? 1u : 0u;
+  }
+}
+
+__global__ void k_string_lengths(const uint64_t* __restrict__ refs, const uint8_t* __restrict__ valid,
+                                 const uint32_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ lens) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t r = idx[i];
+    lens[i] = (!valid || valid[r]) ? ref_len(refs[r]) : 0u;
+  }
+}
+
+// one warp per output value: short values are a single coalesced pass, long ones loop
+__global__ void k_copy_strings(const uint64_t* __restrict__ refs, const uint8_t* __restrict__ valid,
+                               const uint32_t* __restrict__ idx, int64_t n, const uint64_t* __restrict__ offsets,
+                               uint8_t* __restrict__ out) {
+  const unsigned lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const uint32_t r = idx[i];
+    if (valid && !valid[r]) continue;
+    const uint64_t ref = refs[r];
+    const uint8_t* src = ref_ptr(ref);
+    uint8_t* dst = out + offsets[i];
+    for (uint32_t j = lane, len = ref_len(ref); j < len; j += 32) dst[j] = src[j];
+  }
+}
+
 }  // namespace
+
+void launch_range_bounds_strings(hs_ctx* ctx, const uint64_t* refs, const uint64_t* seg_offsets, int nseg, int has_lo,
+                                 uint64_t lo_ref, int has_hi, uint64_t hi_ref, int64_t* bounds) {
+  if (nseg == 0) return;
+  k_range_bounds_str<<<(nseg + 127) / 128, 128, 0, ctx->stream>>>(refs, seg_offsets, nseg, has_lo, lo_ref, has_hi, hi_ref, bounds);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_filter_mask_strings(hs_ctx* ctx, const uint64_t* refs, const uint8_t* valid, int64_t n, int has_lo,
+                                uint64_t lo_ref, int has_hi, uint64_t hi_ref, uint32_t* mask) {
+  if (n == 0) return;
+  k_filter_mask_str<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(refs, valid, n, has_lo, lo_ref, has_hi, hi_ref, mask);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_string_lengths(hs_ctx* ctx, const uint64_t* refs, const uint8_t* valid, const uint32_t* idx, int64_t n,
+                           uint32_t* lens) {
+  if (n == 0) return;
+  k_string_lengths<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(refs, valid, idx, n, lens);
+  HS_LAUNCH_CHECK(ctx);
+}
+
+void launch_copy_strings(hs_ctx* ctx, const uint64_t* refs, const uint8_t* valid, const uint32_t* idx, int64_t n,
+                         const uint64_t* offsets, uint8_t* out) {
+  if (n == 0) return;
+  k_copy_strings<<<grid_for(ctx, n * 32, 256, 16), 256, 0, ctx->stream>>>(refs, valid, idx, n, offsets, out);
+  HS_LAUNCH_CHECK(ctx);
+}
 
 void launch_range_bounds(hs_ctx* ctx, const int64_t* keys, const uint64_t* seg_offsets, int nseg, int has_lo,
                          int64_t lo, int has_hi, int64_t hi, int64_t* bounds) {

@@ -197,7 +197,15 @@ class ScanExec:
         lo, hi = self._bounds(key)
         batch, _ = self.session.gpu.filter_scan(files, key, out_cols, lo=lo, hi=hi, sorted_on_key=sorted_on_key,
                                                 deleted_file_ids=list(deleted_ids))
-        out = {n: d.copy() for n, d, _ in batch.columns}
+        out = {}
+        for n, d, _ in batch.columns:
+            if d.dtype == object:  # string / binary column: text when every value is UTF-8, bytes otherwise
+                try:
+                    out[n] = np.array([v.decode("utf-8") for v in d], dtype=object)
+                except UnicodeDecodeError:
+                    out[n] = d.copy()
+            else:
+                out[n] = d.copy()
         batch.free()
         return out
 
@@ -205,7 +213,7 @@ class ScanExec:
         out_cols = self.lin.output
         pred_cols = self.lin.predicate.columns if self.lin.predicate else []
         if len(pred_cols) > 1:
-            raise LE.HyperspaceException("the GPU scan handles range predicates on one integer column")
+            raise LE.HyperspaceException("the GPU scan handles range predicates on one integer or string column")
         if self.cand is None:
             key = pred_cols[0] if pred_cols else self.lin.relation.column_names[0]
             return self._scan(_file_images([f[0] for f in self.lin.relation.files]), key, out_cols, False)

@@ -108,30 +108,47 @@ class Predicate:
         return list(self.bounds)
 
 
+def _as_bytes(v) -> bytes:
+    return v.encode("utf-8") if isinstance(v, str) else bytes(v)
+
+
 class Column:
     def __init__(self, name: str):
         self.name = name
 
     # integer key columns: a non-integral literal is rounded in the direction that keeps the predicate's meaning
-    # (k < 1.5  <=>  k <= 1;  k >= 1.5  <=>  k >= 2)
+    # (k < 1.5  <=>  k <= 1;  k >= 1.5  <=>  k >= 2).  String / binary literals give byte bounds in UTF8String order --
+    # `col("Query") == "facebook"` is the predicate of the reference's own filter-rule tests (T/index/E2EHyperspaceRulesTest.scala).
     def __ge__(self, v):
+        if isinstance(v, (str, bytes)):
+            return Predicate({self.name: (_as_bytes(v), None)})
         return Predicate({self.name: (math.ceil(v), None)})
 
     def __gt__(self, v):
+        if isinstance(v, (str, bytes)):
+            return Predicate({self.name: (_as_bytes(v) + b"\x00", None)})  # the smallest value above v
         return Predicate({self.name: (math.floor(v) + 1, None)})
 
     def __le__(self, v):
+        if isinstance(v, (str, bytes)):
+            return Predicate({self.name: (None, _as_bytes(v))})
         return Predicate({self.name: (None, math.floor(v))})
 
     def __lt__(self, v):
+        if isinstance(v, (str, bytes)):
+            raise ValueError("a strict upper bound on a string column has no inclusive form: use <= or between")
         return Predicate({self.name: (None, math.ceil(v) - 1)})
 
     def __eq__(self, v):  # noqa: A003
+        if isinstance(v, (str, bytes)):
+            return Predicate({self.name: (_as_bytes(v), _as_bytes(v))})
         if v != math.floor(v):
             return Predicate({self.name: (1, 0)})  # an integer never equals a fraction: empty range
         return Predicate({self.name: (int(v), int(v))})
 
     def between(self, lo, hi):
+        if isinstance(lo, (str, bytes)) or isinstance(hi, (str, bytes)):
+            return Predicate({self.name: (_as_bytes(lo), _as_bytes(hi))})
         return Predicate({self.name: (math.ceil(lo), math.floor(hi))})
 
 

@@ -223,6 +223,13 @@ typedef struct {
   int32_t n_deleted_file_ids;
   int32_t output;              /* HS_OUT_HOST (or 0): result columns in pinned host memory; HS_OUT_DEVICE: left in device
                                   memory for the next GPU operator (hs_batch_column then yields device pointers) */
+  /* string / binary key column (HS_TYPE_STRING): the inclusive bounds as bytes, compared in UTF8String byte order (unsigned
+   * bytes, the shorter value first on a common prefix); has_lo / has_hi say which are set, lo / hi are ignored.  Equality
+   * -- the predicate of the reference's own filter-rule tests, `c3 == "facebook"` (T/index/E2EHyperspaceRulesTest.scala) --
+   * is lo == hi. */
+  const void* lo_bytes;
+  const void* hi_bytes;
+  uint32_t lo_len, hi_len;
 } hs_scan_spec;
 
 /* Executes the scan FilterIndexRule.applyIndex substitutes for the source scan
@@ -258,6 +265,9 @@ int32_t hs_batch_num_columns(const hs_batch* b);
  * has no nulls); host pointers unless hs_batch_on_device. */
 int hs_batch_column(const hs_batch* b, int32_t i, const char** name, int32_t* type, const void** data,
                     const uint8_t** valid);
+/* A HS_TYPE_STRING column: `data` of hs_batch_column points to the values' bytes back to back, and value r occupies
+ * bytes [offsets[r], offsets[r + 1]) (num_rows + 1 offsets; a null has length 0).  HS_EINVAL for other columns. */
+int hs_batch_string_offsets(const hs_batch* b, int32_t i, const uint64_t** offsets, uint64_t* total_bytes);
 void hs_batch_free(hs_batch* b);
 
 /* ------------------------------------------------------------------------------------------------------------

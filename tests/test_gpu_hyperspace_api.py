@@ -237,3 +237,42 @@ def test_hybrid_scan_join_with_appended_files(env):
     base = j.collect()
     assert len(got["v1"]) == len(base["v1"]) > 0
     assert np.array_equal(_rows(got, ["v1", "w"]), _rows(base, ["v1", "w"]))
+
+
+def test_string_index_through_the_api_like_the_reference_examples(env):
+    """The reference's canonical flow (its README and T/index/E2EHyperspaceRulesTest.scala): index a string column, filter on
+    it, the plan uses the index and the answer does not change.  Data: T/SampleData.scala:25-35."""
+    from hyperspace_b200.index_config import IndexConfig
+    from hyperspace_b200.session import col
+
+    s, hs, tmp = env
+    sample = [("2017-09-03", "810a20a2baa24ff3ad493bfbf064569a", "donde", 2, 1000),
+              ("2017-09-03", "fd093f8a05604515957083e70cb3dceb", "facebook", 1, 3000),
+              ("2017-09-03", "af3ed6a197a8447cba8bc8ea21fad208", "facebook", 1, 3000),
+              ("2017-09-03", "975134eca06c4711a0406d0464cbe7d6", "facebook", 1, 4000),
+              ("2018-09-03", "e90a6028e15b4f4593eef557daf5166d", "ibraco", 2, 3000),
+              ("2018-09-03", "576ed96b0d5340aa98a47de15c9f87ce", "facebook", 2, 3000),
+              ("2018-09-03", "50d690516ca641438166049a6303650c", "ibraco", 2, 1000),
+              ("2019-10-03", "380786e6495d4cd8a5dd4cc8d3d12917", "facebook", 2, 3000),
+              ("2019-10-03", "ff60e4838b92421eafc3e6ee59a9e9f1", "miperro", 2, 2000),
+              ("2019-10-03", "187696fe0a6a40cc9516bc6e47c70bc1", "facebook", 4, 3000)]
+    c = list(zip(*sample))
+    cols = {"Date": pa.array(c[0]), "RGUID": pa.array(c[1]), "Query": pa.array(c[2]), "imprs": pa.array(c[3], pa.int32()),
+            "clicks": pa.array(c[4], pa.int32())}
+    os.makedirs(tmp / "sample", exist_ok=True)
+    pq.write_table(pa.table(cols), str(tmp / "sample" / "part-0.parquet"), compression="snappy")
+    df = s.read.parquet(str(tmp / "sample"))
+    hs.createIndex(df, IndexConfig("qidx", ["Query"], ["RGUID", "clicks"]))
+    q = df.filter(col("Query") == "facebook").select("RGUID", "clicks", "Query")
+    s.disableHyperspace()
+    assert "GpuSourceScan" in q.explain()
+    base = q.collect()
+    s.enableHyperspace()
+    assert "Name: qidx" in q.explain()
+    got = q.collect()
+    want = sorted((r[1], r[4], r[2]) for r in sample if r[2] == "facebook")
+    assert sorted(zip(got["RGUID"], (int(x) for x in got["clicks"]), got["Query"])) == want
+    assert sorted(zip(base["RGUID"], (int(x) for x in base["clicks"]), base["Query"])) == want
+    rng_q = df.filter(col("Query").between("e", "j")).select("Query", "clicks")
+    got = rng_q.collect()
+    assert sorted(zip(got["Query"], (int(x) for x in got["clicks"]))) == sorted((r[2], r[4]) for r in sample if "e" <= r[2] <= "j")

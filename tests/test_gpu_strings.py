@@ -193,3 +193,73 @@ def test_nullable_string_key_and_long_values(ctx):
     with pytest.raises(N.HyperspaceGpuError) as e:
         ctx.create_index([N.FileImage(data=sink.getvalue().to_pybytes())], ["k"], ["v"], 3, output=N.HS_OUT_HOST)
     assert e.value.code == N.HS_EUNSUPPORTED
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# read side: FilterIndexRule's scan over an index on a string column (index/covering/FilterIndexRule.scala:135-149)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _scan_rows(batch, names):
+    cols = {n: d for n, d, _ in batch.columns}
+    valid = {n: v for n, _, v in batch.columns}
+    out = []
+    for r in range(batch.num_rows):
+        out.append(tuple(None if (valid[n] is not None and not valid[n][r]) else
+                         (bytes(cols[n][r]) if cols[n].dtype == object else cols[n][r].item()) for n in names))
+    return sorted(out, key=repr)
+
+
+def test_filter_scan_on_a_string_key_like_the_filter_rule_tests(ctx, tmp_path):
+    """`SELECT ... WHERE Query = 'facebook'` over an index on Query (the predicate of the reference's filter-rule tests,
+    T/index/E2EHyperspaceRulesTest.scala; data T/SampleData.scala:25-35): two binary searches per sorted index file, string
+    and integer columns projected; the same predicate as a full scan over the source (Hybrid Scan's appended files)."""
+    from hyperspace_b200 import _native as N
+
+    table = _sample_table()
+    src = _write(table, str(tmp_path / "src.parquet"))
+    res, _ = ctx.create_index([N.FileImage(path=src)], ["Query"], ["RGUID", "imprs", "clicks"], 3, output=N.HS_OUT_HOST)
+    idx = res.as_sources()
+    rows = [(q.encode(), g.encode(), i, c) for (_, g, q, i, c) in SAMPLE]
+    names = ["Query", "RGUID", "imprs", "clicks"]
+    for lo, hi in (("facebook", "facebook"), ("donde", "facebook"), ("g", None), (None, "e"), ("zzz", "zzzz"), ("", "\xff")):
+        want = sorted([r for r in rows if (lo is None or r[0] >= lo.encode()) and (hi is None or r[0] <= hi.encode())], key=repr)
+        b, st = ctx.filter_scan(idx, "Query", names, lo=lo, hi=hi, sorted_on_key=True)
+        assert _scan_rows(b, names) == want, (lo, hi)
+        b.free()
+        b, _ = ctx.filter_scan([N.FileImage(path=src)], "Query", names, lo=lo, hi=hi, sorted_on_key=False)
+        assert _scan_rows(b, names) == want, (lo, hi)
+        b.free()
+    res.free()
+
+
+def test_filter_scan_on_random_binary_keys(ctx):
+    """300 K binary keys (shared prefixes, empty values, bytes >= 0x80), nullable string payload: ranges and equalities
+    against numpy on the source rows."""
+    from hyperspace_b200 import _native as N
+
+    rng = np.random.default_rng(12)
+    n, nb = 300_000, 16
+    keys = _random_strings(rng, n, max_len=12)
+    words = [b"alpha", b"beta", b"", b"delta-delta"]
+    s = [words[i] for i in rng.integers(0, len(words), size=n)]
+    smask = rng.random(n) < 0.2
+    v = rng.integers(0, 10**6, size=n, dtype=np.int64)
+    table = pa.table({"k": pa.array(keys, pa.binary()), "s": pa.array(s, pa.binary(), mask=smask), "v": pa.array(v)})
+    sink = pa.BufferOutputStream()
+    pq.write_table(table, sink, compression="SNAPPY", data_page_size=32 << 10)
+    res, _ = ctx.create_index([N.FileImage(data=sink.getvalue().to_pybytes())], ["k"], ["s", "v"], nb, output=N.HS_OUT_HOST)
+    idx = res.as_sources()
+    karr = np.array(keys, dtype=object)
+    probes = [(keys[5], keys[5]), (b"a", b"b"), (b"", b""), (b"m", None), (None, b"0"), (keys[77][:2], keys[77][:2] + b"\xff\xff")]
+    for lo, hi in probes:
+        sel = np.ones(n, bool)
+        if lo is not None:
+            sel &= np.array([k >= lo for k in karr])
+        if hi is not None:
+            sel &= np.array([k <= hi for k in karr])
+        want = sorted([(keys[i], None if smask[i] else s[i], int(v[i])) for i in np.flatnonzero(sel)], key=repr)
+        b, _ = ctx.filter_scan(idx, "k", ["k", "s", "v"], lo=lo, hi=hi, sorted_on_key=True)
+        assert b.num_rows == len(want)
+        assert _scan_rows(b, ["k", "s", "v"]) == want, (lo, hi)
+        b.free()
+    res.free()
