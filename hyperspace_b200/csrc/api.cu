@@ -1022,7 +1022,7 @@ int hs_filter_scan(hs_ctx* ctx, const hs_scan_spec* spec, hs_batch** out, hs_sta
 // Orders the decoded rows of one join side bucket-major and key-sorted.  When every bucket holds exactly one file the
 // files are already sorted (they are index files) and only need to be visited in bucket order; otherwise the rows go
 // through K2-K4 again, which is what Spark's SortExec does for multi-file buckets.
-static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_files, const int32_t* buckets, int nb,
+static void prepare_join_side(hs_ctx* ctx, SourceSet* src, const hs_source_file* files, int n_files, const int32_t* buckets, int nb,
                               const std::vector<std::string>& cols, Table* t, IndexedRows* rows, hs_stats* st,
                               std::vector<uint64_t>* seg, const int64_t** d_keys, const uint32_t** d_perm, Buf<uint32_t>* iota,
                               Buf<int64_t>* k64) {
@@ -1037,9 +1037,13 @@ static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_fi
     if (buckets[order[i]] < 0 || buckets[order[i]] >= nb) fail(HS_EINVAL, "bucket id %d out of range", buckets[order[i]]);
     per_bucket[buckets[order[i]]]++;
   }
-  load_sources(ctx, sorted_files.data(), n_files, cols, t, st);
-  if (t->cols[0].type != HS_TYPE_INT64 && t->cols[0].type != HS_TYPE_INT32)
-    fail(HS_EUNSUPPORTED, "bucket join: key column must be int32 or int64");
+  // string values are references into the file images: the caller's SourceSet keeps those alive until the result batch exists
+  open_sources(ctx, sorted_files.data(), n_files, src, st);
+  decode_sources(ctx, *src, cols, nullptr, t, st);
+  if (!t->has_strings) src->release_images();
+  const bool str_key = t->cols[0].type == HS_TYPE_STRING;
+  if (!str_key && t->cols[0].type != HS_TYPE_INT64 && t->cols[0].type != HS_TYPE_INT32)
+    fail(HS_EUNSUPPORTED, "bucket join: key column must be int32, int64 or string");
   if (t->cols[0].has_nulls) fail(HS_EUNSUPPORTED, "bucket join: null join keys are not handled yet");
   const bool single = std::all_of(per_bucket.begin(), per_bucket.end(), [](int c) { return c <= 1; });
   if (single) {
@@ -1050,7 +1054,7 @@ static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_fi
       if (per_bucket[b]) fi++;
     }
     (*seg)[nb] = (uint64_t)t->nrows;
-    *d_keys = widened_key(ctx, t->cols[0], t->nrows, k64);
+    *d_keys = str_key ? (const int64_t*)t->cols[0].data.get() : widened_key(ctx, t->cols[0], t->nrows, k64);
     iota->alloc(ctx, std::max<int64_t>(1, t->nrows));
     launch_iota_u32(ctx, iota->get(), t->nrows);
     *d_perm = iota->get();
@@ -1073,7 +1077,7 @@ static void prepare_join_side(hs_ctx* ctx, const hs_source_file* files, int n_fi
     kc.width = kw;
     kc.data = std::move(sk);
     t->cols.push_back(std::move(kc));
-    *d_keys = widened_key(ctx, t->cols.back(), t->nrows, k64);
+    *d_keys = str_key ? (const int64_t*)t->cols.back().data.get() : widened_key(ctx, t->cols.back(), t->nrows, k64);
     *d_perm = rows->sorted_perm;
   }
 }
@@ -1118,8 +1122,9 @@ int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_sta
     const uint32_t *lperm = nullptr, *rperm = nullptr;
     Buf<uint32_t> liota, riota;
     Buf<int64_t> lk64, rk64;
-    prepare_join_side(ctx, spec->left_files, spec->n_left, spec->left_buckets, nb, lcols, &lt, &lrows, &st, &lseg, &lkeys, &lperm, &liota, &lk64);
-    prepare_join_side(ctx, spec->right_files, spec->n_right, spec->right_buckets, nb, rcols, &rt, &rrows, &st, &rseg, &rkeys, &rperm, &riota, &rk64);
+    SourceSet lsrc, rsrc;
+    prepare_join_side(ctx, &lsrc, spec->left_files, spec->n_left, spec->left_buckets, nb, lcols, &lt, &lrows, &st, &lseg, &lkeys, &lperm, &liota, &lk64);
+    prepare_join_side(ctx, &rsrc, spec->right_files, spec->n_right, spec->right_buckets, nb, rcols, &rt, &rrows, &st, &rseg, &rkeys, &rperm, &riota, &rk64);
     // hashInt and hashLong put equal values into different buckets: both sides must have been bucketed on the same type
     // (JoinIndexRule only pairs indexes whose indexed columns have the same data type)
     if (lt.cols[0].type != rt.cols[0].type) fail(HS_EUNSUPPORTED, "bucket join: key columns have different types");
@@ -1132,7 +1137,8 @@ int hs_bucket_join(hs_ctx* ctx, const hs_join_spec* spec, hs_batch** out, hs_sta
     copy_h2d(ctx, d_rseg.get(), rseg.data(), 8 * (nb + 1));
     Buf<uint32_t> counts(ctx, std::max<int64_t>(1, nl)), first(ctx, std::max<int64_t>(1, nl));
     Buf<uint64_t> offs(ctx, nl + 1);
-    launch_join_count(ctx, lkeys, d_lseg.get(), rkeys, d_rseg.get(), nb, nl, counts.get(), first.get());
+    launch_join_count(ctx, lkeys, d_lseg.get(), rkeys, d_rseg.get(), nb, nl, counts.get(), first.get(),
+                      lt.cols[0].type == HS_TYPE_STRING);
     exclusive_scan_u32_u64(ctx, counts.get(), nl, offs.get());
     uint64_t total_out = 0;
     copy_d2h(ctx, &total_out, offs.get() + nl, 8);

@@ -335,8 +335,9 @@ void launch_synth_column(hs_ctx* ctx, int col, int64_t first_row, int64_t n, voi
 void launch_range_bounds(hs_ctx* ctx, const int64_t* keys, const uint64_t* seg_offsets, int nseg, int has_lo,
                          int64_t lo, int has_hi, int64_t hi, int64_t* bounds);
 // match counts of every left row against the right rows of the same bucket
+// string_keys: lkeys / rkeys hold string references (device_utils.cuh) compared in byte order
 void launch_join_count(hs_ctx* ctx, const int64_t* lkeys, const uint64_t* lseg, const int64_t* rkeys,
-                       const uint64_t* rseg, int nseg, int64_t nl, uint32_t* counts, uint32_t* first_match);
+                       const uint64_t* rseg, int nseg, int64_t nl, uint32_t* counts, uint32_t* first_match, bool string_keys = false);
 void launch_join_emit(hs_ctx* ctx, const uint32_t* counts, const uint32_t* first_match, const uint64_t* out_offsets,
                       int64_t nl, uint32_t* out_li, uint32_t* out_ri);
 // exclusive scan of uint32 counts into uint64 offsets (n+1 entries; last = total)

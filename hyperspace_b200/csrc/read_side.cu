@@ -46,6 +46,7 @@ __global__ void k_range_bounds(const int64_t* __restrict__ keys, const uint64_t*
 }
 
 // one thread per left row; the segment of a row is found by binary search over the (few hundred) segment offsets
+template <bool STR>
 __global__ void k_join_count(const int64_t* __restrict__ lkeys, const uint64_t* __restrict__ lseg,
                              const int64_t* __restrict__ rkeys, const uint64_t* __restrict__ rseg, int nseg, int64_t nl,
                              uint32_t* __restrict__ counts, uint32_t* __restrict__ first_match) {
@@ -58,9 +59,29 @@ __global__ void k_join_count(const int64_t* __restrict__ lkeys, const uint64_t* 
       else hi = mid;
     }
     const int64_t rb = (int64_t)rseg[lo], rn = (int64_t)rseg[lo + 1] - rb;
-    const int64_t k = lkeys[i];
-    const int64_t f = lower_bound_i64(rkeys + rb, rn, k);
-    const int64_t l = upper_bound_i64(rkeys + rb, rn, k);
+    int64_t f, l;
+    if (STR) {  // keys are string references: the same two searches in byte order
+      const uint64_t k = (uint64_t)lkeys[i];
+      const uint64_t* a = (const uint64_t*)rkeys + rb;
+      int64_t x = 0, y = rn;
+      while (x < y) {
+        const int64_t mid = x + ((y - x) >> 1);
+        if (string_compare(a[mid], k) < 0) x = mid + 1;
+        else y = mid;
+      }
+      f = x;
+      y = rn;
+      while (x < y) {
+        const int64_t mid = x + ((y - x) >> 1);
+        if (string_compare(a[mid], k) <= 0) x = mid + 1;
+        else y = mid;
+      }
+      l = x;
+    } else {
+      const int64_t k = lkeys[i];
+      f = lower_bound_i64(rkeys + rb, rn, k);
+      l = upper_bound_i64(rkeys + rb, rn, k);
+    }
     counts[i] = (uint32_t)(l - f);
     first_match[i] = (uint32_t)(rb + f);
   }
@@ -299,11 +320,13 @@ void launch_range_bounds(hs_ctx* ctx, const int64_t* keys, const uint64_t* seg_o
 }
 
 void launch_join_count(hs_ctx* ctx, const int64_t* lkeys, const uint64_t* lseg, const int64_t* rkeys,
-                       const uint64_t* rseg, int nseg, int64_t nl, uint32_t* counts, uint32_t* first_match) {
+                       const uint64_t* rseg, int nseg, int64_t nl, uint32_t* counts, uint32_t* first_match, bool string_keys) {
   KernelScope _ks(ctx, "k_join_count");
   if (nl == 0) return;
-  k_join_count<<<grid_for(ctx, nl, 256, 16), 256, 0, ctx->stream>>>(lkeys, lseg, rkeys, rseg, nseg, nl, counts,
-                                                                     first_match);
+  if (string_keys)
+    k_join_count<true><<<grid_for(ctx, nl, 256, 16), 256, 0, ctx->stream>>>(lkeys, lseg, rkeys, rseg, nseg, nl, counts, first_match);
+  else
+    k_join_count<false><<<grid_for(ctx, nl, 256, 16), 256, 0, ctx->stream>>>(lkeys, lseg, rkeys, rseg, nseg, nl, counts, first_match);
   HS_LAUNCH_CHECK(ctx);
 }
 

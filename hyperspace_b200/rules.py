@@ -173,6 +173,17 @@ def _concat(parts: List[Dict[str, np.ndarray]], columns: List[str]) -> Dict[str,
     return {c: np.concatenate([p[c] for p in parts]) for c in columns}
 
 
+def _host_column(d: np.ndarray) -> np.ndarray:
+    """A result column copied out of the batch; string / binary columns (object arrays of bytes) become text when every
+    value is UTF-8 and stay bytes otherwise."""
+    if d.dtype != object:
+        return d.copy()
+    try:
+        return np.array([v.decode("utf-8") for v in d], dtype=object)
+    except UnicodeDecodeError:
+        return d.copy()
+
+
 class ScanExec:
     """Filter / projection over a relation: index-only scan, Hybrid Scan, or plain source scan -- always hs_filter_scan."""
 
@@ -197,15 +208,7 @@ class ScanExec:
         lo, hi = self._bounds(key)
         batch, _ = self.session.gpu.filter_scan(files, key, out_cols, lo=lo, hi=hi, sorted_on_key=sorted_on_key,
                                                 deleted_file_ids=list(deleted_ids))
-        out = {}
-        for n, d, _ in batch.columns:
-            if d.dtype == object:  # string / binary column: text when every value is UTF-8, bytes otherwise
-                try:
-                    out[n] = np.array([v.decode("utf-8") for v in d], dtype=object)
-                except UnicodeDecodeError:
-                    out[n] = d.copy()
-            else:
-                out[n] = d.copy()
+        out = {n: _host_column(d) for n, d, _ in batch.columns}
         batch.free()
         return out
 
@@ -281,7 +284,7 @@ class BucketJoinExec:
         out: Dict[str, np.ndarray] = {}
         for i, (n, d, _) in enumerate(batch.columns):
             name = n if n not in out else f"{n}_right"
-            out[name] = d.copy()
+            out[name] = _host_column(d)
         batch.free()
         return out
 

@@ -245,7 +245,7 @@ typedef struct {
   const int32_t* right_buckets;
   int32_t num_buckets;
   int32_t output;                    /* HS_OUT_HOST (or 0) / HS_OUT_DEVICE, as in hs_scan_spec */
-  const char* left_key;              /* single integer join key on each side */
+  const char* left_key;              /* single join key on each side: int32 / int64 / string, the same type on both */
   const char* right_key;
   const char* const* left_columns;   /* projected from the left side */
   int32_t n_left_columns;

@@ -276,3 +276,19 @@ def test_string_index_through_the_api_like_the_reference_examples(env):
     rng_q = df.filter(col("Query").between("e", "j")).select("Query", "clicks")
     got = rng_q.collect()
     assert sorted(zip(got["Query"], (int(x) for x in got["clicks"]))) == sorted((r[2], r[4]) for r in sample if "e" <= r[2] <= "j")
+    # the reference's E2E join tests join the sample data with itself on the string column (leftDf("c3") === rightDf("c3"))
+    os.makedirs(tmp / "sample2", exist_ok=True)
+    pq.write_table(pa.table({"Query": cols["Query"], "shown": cols["imprs"]}), str(tmp / "sample2" / "part-0.parquet"),
+                   compression="snappy")
+    dr = s.read.parquet(str(tmp / "sample2"))
+    hs.createIndex(dr, IndexConfig("qidx2", ["Query"], ["shown"]))
+    j = df.join(dr, on="Query").select("RGUID", "shown")
+    s.disableHyperspace()
+    jb = j.collect()
+    s.enableHyperspace()
+    plan = j.explain()
+    assert "Name: qidx" in plan and "Name: qidx2" in plan and "exchange=none" in plan
+    jg = j.collect()
+    want = sorted((a[1], b[3]) for a in sample for b in sample if a[2] == b[2])
+    assert sorted(zip(jg["RGUID"], (int(x) for x in jg["shown"]))) == want
+    assert sorted(zip(jb["RGUID"], (int(x) for x in jb["shown"]))) == want

@@ -263,3 +263,42 @@ def test_filter_scan_on_random_binary_keys(ctx):
         assert _scan_rows(b, ["k", "s", "v"]) == want, (lo, hi)
         b.free()
     res.free()
+
+
+def test_bucket_join_on_string_keys(ctx):
+    """JoinIndexRule's join over two indexes on a string column (the reference's E2E join tests join SampleData on c3 = Query,
+    T/index/E2EHyperspaceRulesTest.scala): per-bucket merge join on byte order, string and integer columns projected; one
+    side with two files per bucket (after an incremental refresh) is re-sorted first."""
+    from hyperspace_b200 import _native as N
+
+    rng = np.random.default_rng(21)
+    nl, nr, nb = 40_000, 30_000, 8
+    vocab = _random_strings(rng, 3000, max_len=10)
+    lk = [vocab[i] for i in rng.integers(0, 2500, size=nl)]          # keys 2500..2999 never appear on the left
+    rk = [vocab[i] for i in rng.integers(500, 3000, size=nr)]        # keys 0..499 never appear on the right
+    lv = rng.integers(0, 10**6, size=nl, dtype=np.int64)
+    rs = [b"r-%d" % i for i in range(nr)]
+    L = pa.table({"k": pa.array(lk, pa.binary()), "lv": pa.array(lv)})
+    R = pa.table({"k": pa.array(rk, pa.binary()), "rs": pa.array(rs, pa.binary())})
+
+    def image(t):
+        sink = pa.BufferOutputStream()
+        pq.write_table(t, sink, compression="NONE")
+        return N.FileImage(data=sink.getvalue().to_pybytes())
+
+    li, _ = ctx.create_index([image(L)], ["k"], ["lv"], nb, output=N.HS_OUT_HOST)
+    r1, _ = ctx.create_index([image(R.slice(0, nr // 2))], ["k"], ["rs"], nb, output=N.HS_OUT_HOST)
+    r2, _ = ctx.create_index([image(R.slice(nr // 2))], ["k"], ["rs"], nb, output=N.HS_OUT_HOST)
+    right = r1.as_sources() + r2.as_sources()
+    right_b = [f.bucket for f in r1.files] + [f.bucket for f in r2.files]
+    b, st = ctx.bucket_join(li.as_sources(), [f.bucket for f in li.files], right, right_b, nb, "k", "k", ["k", "lv"], ["rs"])
+    by_key = {}
+    for k, s in zip(rk, rs):
+        by_key.setdefault(k, []).append(s)
+    want = sorted((k, int(v), s) for k, v in zip(lk, lv) for s in by_key.get(k, ()))
+    cols = {n: d for n, d, _ in b.columns}
+    got = sorted((bytes(k), int(v), bytes(s)) for k, v, s in zip(cols["k"], cols["lv"], cols["rs"]))
+    assert b.num_rows == len(want) and got == want
+    b.free()
+    for r in (li, r1, r2):
+        r.free()
