@@ -160,3 +160,17 @@ def test_comparison_operators_round_fractional_literals_correctly():
     lo, hi = b(col("k") == 1.5)
     assert lo > hi  # empty
     assert b(col("k") == 3) == (3, 3)
+
+
+def test_string_literals_give_byte_bounds_in_utf8_order():
+    """Predicates on string columns (the reference's filter-rule tests filter on `c3 == "facebook"`): inclusive byte bounds in
+    UTF8String order, which is what hs_filter_scan's lo_bytes / hi_bytes take."""
+    b = lambda p: p.bounds["q"]  # noqa: E731
+    assert b(col("q") == "facebook") == (b"facebook", b"facebook")
+    assert b(col("q") >= "é") == ("é".encode("utf-8"), None)
+    assert b(col("q") <= b"\xff\x00") == (None, b"\xff\x00")
+    assert b(col("q") > "abc") == (b"abc\x00", None)  # the smallest value above "abc"
+    assert b(col("q").between("a", "b")) == (b"a", b"b")
+    assert b((col("q") >= "b") & (col("q") <= "y") & (col("q") >= "c")) == (b"c", b"y")  # conjunction keeps the tighter bound
+    with pytest.raises(ValueError):
+        col("q") < "x"  # noqa: B015  (no inclusive form; the message says to use <= or between)
