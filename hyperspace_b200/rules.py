@@ -362,6 +362,14 @@ def join_index_rule(session, left: Linear, right: Linear, lkey: str, rkey: str):
     rc = [c for c in candidates_for(session, right.relation)
           if [x.lower() for x in c.entry.indexedColumns] == [rkey.lower()] and _covers(c.entry, right.referenced())
           and not c.deleted_ids]
+    # Spark's analyzer puts a Cast on one side when the key types differ, and a condition over a Cast is not the plain
+    # attribute equality the rule asks for (JoinIndexRule.scala:143-163): no index then.  It also matters physically:
+    # hashInt and hashLong (and hashUnsafeBytes) send equal values to different buckets.
+    def key_type(lin: Linear, key: str):
+        return next((t for n, t in lin.relation.schema if n.lower() == key.lower()), None)
+
+    if key_type(left, lkey) != key_type(right, rkey):
+        return None
     ranked = rank_join_pairs(session, [(a, b) for a in lc for b in rc])
     if not ranked or ranked[0][0].entry.numBuckets != ranked[0][1].entry.numBuckets:
         return None

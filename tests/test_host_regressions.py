@@ -174,3 +174,21 @@ def test_string_literals_give_byte_bounds_in_utf8_order():
     assert b((col("q") >= "b") & (col("q") <= "y") & (col("q") >= "c")) == (b"c", b"y")  # conjunction keeps the tighter bound
     with pytest.raises(ValueError):
         col("q") < "x"  # noqa: B015  (no inclusive form; the message says to use <= or between)
+
+
+def test_join_rule_needs_equal_key_types(tmp_path):
+    """Spark casts one side of `int = long` (or `string = long`), and a condition over a Cast is not what JoinIndexRule accepts
+    (index/covering/JoinIndexRule.scala:143-163); physically hashInt / hashLong / hashUnsafeBytes bucket equal values
+    differently.  Same types: both indexes are used."""
+    s = HyperspaceSession({"spark.hyperspace.system.path": str(tmp_path / "indexes")})
+    s.enableHyperspace()
+    lrel = _rel(tmp_path / "l", ("k", "a"))
+    rrel = _rel(tmp_path / "r", ("k", "b"))
+    _fabricate(tmp_path, s, "lidx", lrel, ["k"], ["a"])
+    _fabricate(tmp_path, s, "ridx", rrel, ["k"], ["b"])
+    plan = DataFrame(s, lrel).join(DataFrame(s, rrel), on="k").select("a", "b").explain()
+    assert "Name: lidx" in plan and "Name: ridx" in plan
+    for other in ("integer", "string"):
+        rrel.schema[0] = ("k", other)
+        plan = DataFrame(s, lrel).join(DataFrame(s, rrel), on="k").select("a", "b").explain()
+        assert "Name: lidx" not in plan and "Name: ridx" not in plan, other
