@@ -149,3 +149,26 @@ def test_spark_documented_hash_example():
     h = L.hso_hash_int(123, h)   # an array hashes its elements in order, each seeded with the running hash
     h = L.hso_hash_int(2, h)
     assert h == -1321691492
+
+
+def test_string_keys_bucket_and_order_like_spark():
+    """The oracle's string path, which the GPU string tests are held against: bucket = pmod(hashUnsafeBytes(bytes, 42), n) --
+    pinned through Spark's documented hash('Spark', ...) vector above and the pure-Python restatement here -- and order =
+    UTF8String.compareTo: unsigned bytes, the shorter value first on a common prefix, nulls first, ties in source order."""
+    rng = np.random.default_rng(3)
+    vocab = [b"", b"a", b"ab", b"abc", b"b", b"\xc3\xa9", b"\xff", b"\x7f", b"zz", b"facebook", b"donde", b"ibraco", b"miperro"]
+    n, nb = 5000, 7
+    keys = np.array([vocab[i] for i in rng.integers(0, len(vocab), size=n)], dtype=object)
+    valid = rng.random(n) > 0.1
+    b = O.bucket_ids([keys], nb, [valid])
+    for i in range(0, n, 37):
+        h = O.py_hash_bytes(keys[i], 42) if valid[i] else 42  # a null leaves the running hash (the seed) unchanged
+        h = h - (1 << 32) if h >= (1 << 31) else h
+        assert b[i] == ((h % nb) + nb) % nb, (i, keys[i])
+    perm, offs = O.sort_perm([keys], nb, b, [valid])
+    assert sorted(perm.tolist()) == list(range(n)) and offs[-1] == n
+    for q in range(nb):
+        rows = perm[offs[q]:offs[q + 1]]
+        assert np.all(b[rows] == q)
+        want = sorted(rows.tolist(), key=lambda r: (bool(valid[r]), keys[r] if valid[r] else b"", r))
+        assert rows.tolist() == want  # Python's bytes order is the unsigned byte order with shorter-first
